@@ -1,0 +1,157 @@
+/*
+ * qradient_b200.h -- C ABI of libqradient_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * The reference (frederikwilde/qradient) is pure Python with no FFI: its drop-in boundary is
+ * the Python class surface `qradient.physical_components.{State,Gates,Observable}` and
+ * `qradient.circuit_logic.{McClean,Qaoa}`.  The Python package `qradient_b200` re-creates that
+ * surface and binds these entry points through ctypes; each entry point
+ * cites the reference code it replaces (paths relative to /root/reference/qradient).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; the message is available from
+ *     qr_last_error() (thread-local).  The Python layer raises ValueError for QR_EINVAL and
+ *     RuntimeError otherwise.
+ *   - qr_ctx owns one CUDA stream and all device buffers of one state register (the state
+ *     vector psi, the co-state lambda of the adjoint sweep, ping-pong scratch, the diagonal
+ *     Hamiltonian table, reduction scratch).  A context must not be used from two threads at
+ *     once (same rule as the reference objects).
+ *   - host pointers are caller-owned and only read/written during the call; every call is
+ *     synchronous at return.
+ *   - amplitudes are complex128, interleaved (re, im); amplitude index j = sum_q b_q 2^(n-1-q)
+ *     (qubit 0 is the most significant bit; physical_components/state.py:84-88,163).
+ *   - there is NO CPU fallback: every compute entry point launches CUDA kernels.
+ */
+#ifndef QRADIENT_B200_H
+#define QRADIENT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qr_ctx qr_ctx;
+typedef struct qr_obs qr_obs;
+
+enum { QR_OK = 0, QR_EINVAL = 1, QR_ECUDA = 2, QR_ENOMEM = 3, QR_ESTATE = 4 };
+
+/* observable term kinds (physical_components/observable.py:45-73) */
+enum { QR_TERM_X = 0, QR_TERM_Y = 1, QR_TERM_Z = 2, QR_TERM_ZZ = 3 };
+
+/* qr_set_option keys */
+enum {
+    QR_OPT_FUSION = 0,        /* 1 (default): fused tile passes; 0: one kernel per gate          */
+    QR_OPT_TILE_BITS = 1,     /* log2 amplitudes per shared-memory tile (default 12)            */
+    QR_OPT_PREFETCH = 2,      /* 1: L2-prefetch the next tile while computing the current one   */
+    QR_OPT_CTAS_PER_SM_FWD = 3,
+    QR_OPT_CTAS_PER_SM_BWD = 4,
+    QR_OPT_FINAL_LADDER = 5,  /* 1 (default): leave state.vec exactly as mc_clean.py:77 does     */
+    QR_OPT_HAM_LUT = 6        /* 1 (default): integer-valued diagonal Hamiltonians use a phase LUT */
+};
+
+typedef struct qr_perf {
+    double ms_total;          /* device time of the last fused call (CUDA events on the ctx stream) */
+    double ms_forward;
+    double ms_observable;
+    double ms_backward;
+    double algorithmic_bytes; /* bytes the schedule moves by construction (B_sched)  */
+    double bwd_pass_ms_avg;   /* average duration of one backward tile-pass launch                  */
+    double bwd_pass_bytes;    /* algorithmic bytes of one backward tile-pass launch                 */
+    double fwd_pass_ms_avg;
+    double fwd_pass_bytes;
+    long long kernel_launches;/* kernels launched by the last fused call                            */
+    int passes_per_layer;
+    int tile_bits;
+} qr_perf;
+
+const char* qr_last_error(void);
+int qr_version(void);
+int qr_device_count(int* out);
+
+/* ---- context ------------------------------------------------------------------------- */
+/* replaces State.__init__ (state.py:34-37): allocates psi on `device` and resets it to |0..0> */
+int qr_ctx_create(int n_qubits, int device, qr_ctx** out);
+int qr_ctx_destroy(qr_ctx* ctx);
+int qr_set_option(qr_ctx* ctx, int key, long long value);
+int qr_get_option(qr_ctx* ctx, int key, long long* value);
+int qr_perf_last(qr_ctx* ctx, qr_perf* out);
+int qr_sync(qr_ctx* ctx);
+
+/* ---- state vector (physical_components/state.py) -------------------------------------- */
+/* State.reset (state.py:61-71): which = 0 -> |0..0>, 1 -> |+..+> */
+int qr_state_init(qr_ctx* ctx, int which);
+/* State.vec setter / getter: n_amps must equal 2^n */
+int qr_state_upload(qr_ctx* ctx, const double* re_im, size_t n_amps);
+int qr_state_download(qr_ctx* ctx, double* re_im, size_t n_amps);
+/* device address of the current state vector (for torch / NCCL plumbing; complex128[2^n]) */
+int qr_state_device_ptr(qr_ctx* ctx, void** out);
+/* xrot / yrot / zrot (state.py:90-92,142-144,168-170): axis 0,1,2 = X,Y,Z; exp(-i angle P/2) */
+int qr_apply_rot(qr_ctx* ctx, int axis, double angle, int qubit);
+/* dxrot / dyrot / dzrot (state.py:94-97,146-149,172-175): derivative of the rotation */
+int qr_apply_drot(qr_ctx* ctx, int axis, double angle, int qubit);
+/* cnot (state.py:198-199,336-356): control, target */
+int qr_apply_cnot(qr_ctx* ctx, int control, int target);
+/* cnot_ladder (state.py:209-251): stacking 0 or 1 (its inverse); periodic needs even n */
+int qr_apply_cnot_ladder(qr_ctx* ctx, int stacking, int periodic);
+/* xrot_all / x_summed (state.py:107-123): vec = sum_q 1/2 (-i X_q) vec */
+int qr_apply_x_summed(qr_ctx* ctx);
+/* norm_error (state.py:331-332) needs ||vec||^2 */
+int qr_norm2(qr_ctx* ctx, double* out);
+
+/* ---- observable (physical_components/observable.py) ------------------------------------ */
+/* Observable.load_matrix (observable.py:34-79) in term-list form: kind[k], qubit i[k],
+ * second qubit j[k] (ZZ only, i<j), weight w[k]; order = projector order (observable.py:90-101) */
+int qr_obs_create(int n_qubits, int n_terms, const int32_t* kind, const int32_t* qi, const int32_t* qj,
+                  const double* w, qr_obs** out);
+int qr_obs_destroy(qr_obs* obs);
+/* State.multiply_matrix(observable.matrix) (mc_clean.py:65): vec = O vec */
+int qr_apply_observable(qr_ctx* ctx, const qr_obs* obs);
+/* ParametrizedCircuit.expec_val (base.py:17-20): Re <vec|O|vec> */
+int qr_expec_val(qr_ctx* ctx, const qr_obs* obs, double* out);
+/* per-term <P_k> in projector order; prob_k = (1 + <P_k>)/2 is what base.py:28 computes */
+int qr_term_expecs(qr_ctx* ctx, const qr_obs* obs, double* out_terms);
+
+/* ---- diagonal ("classical") Hamiltonian (state.py:261-321) ------------------------------ */
+/* load_classical_ham / Gates.add_classical_ham: builds H[j] on the device; z and zz terms only */
+int qr_ham_load(qr_ctx* ctx, const qr_obs* obs);
+int qr_ham_download(qr_ctx* ctx, double* out, size_t n_amps);
+/* rot_classical_ham / exp_ham_classical (state.py:299-301): vec *= exp(-i angle H) */
+int qr_apply_exp_ham(qr_ctx* ctx, double angle);
+/* rot_classical_ham_component (state.py:309-311): same with the k-th term of obs only */
+int qr_apply_exp_ham_component(qr_ctx* ctx, const qr_obs* obs, int k, double angle);
+/* classical_ham() / ham_classical (state.py:319-321): mode 0: vec *= -i H ; mode 1: vec *= H
+ * (the latter is `state.vec *= gates.classical_ham`, qaoa.py:56) */
+int qr_apply_ham(qr_ctx* ctx, int mode);
+
+/* ---- fused circuit paths (circuit_logic/mc_clean.py, qaoa.py) --------------------------- */
+/* McClean.run_expec_val (mc_clean.py:27-45).  axes/angles: [L*n] row-major.  If
+ * use_current_state != 0 the current vector is the ini_state (mc_clean.py:32), else reset. */
+int qr_mcclean_expec(qr_ctx* ctx, int n_layers, const int32_t* axes, const double* angles,
+                     const qr_obs* obs, int use_current_state, double* e_out);
+/* McClean.grad_run (mc_clean.py:47-78): E and dE/d angles[L*n]; afterwards the state vector holds
+ * the back-propagated co-state exactly as the reference leaves it. */
+int qr_mcclean_grad(qr_ctx* ctx, int n_layers, const int32_t* axes, const double* angles,
+                    const qr_obs* obs, int use_current_state, double* e_out, double* grad_out);
+/* batched extension (timing-test.ipynb cell 6 loop): B independent parameter sets on one device.
+ * axes/angles: [B*L*n]; e_out[B]; grad_out[B*L*n].  ctx must have been created with n qubits. */
+int qr_mcclean_grad_batch(qr_ctx* ctx, int batch, int n_layers, const int32_t* axes, const double* angles,
+                          const qr_obs* obs, double* e_out, double* grad_out);
+/* Qaoa.run_expec_val (qaoa.py:23-38); requires qr_ham_load(ctx, obs) first */
+int qr_qaoa_expec(qr_ctx* ctx, int n_layers, const double* betas, const double* gammas,
+                  int use_current_state, double* e_out);
+/* Qaoa.grad_run (qaoa.py:40-70): grad_out[p*2], column 0 = d/d beta, column 1 = d/d gamma */
+int qr_qaoa_grad(qr_ctx* ctx, int n_layers, const double* betas, const double* gammas,
+                 int use_current_state, double* e_out, double* grad_out);
+
+/* ---- finite-shot sampling (qaoa.py:196-198, mc_clean.py:259-261) ------------------------ */
+/* index = first k with cumsum(|vec|^2)[k] >= u  (scipy rv_discrete inverse CDF); uniforms are
+ * supplied by the caller from the numpy stream so the draw order matches the reference. */
+int qr_sample_bitstrings(qr_ctx* ctx, int n_shots, const double* uniforms, int64_t* out_idx);
+/* mean of H[idx] over the sampled indices, computed on the device from the loaded H table */
+int qr_ham_gather(qr_ctx* ctx, int n, const int64_t* idx, double* out_vals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QRADIENT_B200_H */

@@ -1,0 +1,4 @@
+"""Device-backed counterparts of qradient.circuit_logic (McClean, Qaoa)."""
+from .base import ParametrizedCircuit, progbar_range  # noqa: F401
+from .mc_clean import McClean  # noqa: F401
+from .qaoa import Qaoa  # noqa: F401

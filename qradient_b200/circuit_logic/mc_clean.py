@@ -1,0 +1,139 @@
+"""McClean random-Pauli-rotation ansatz (reference: circuit_logic/mc_clean.py).
+
+Circuit (mc_clean.py:35-41): Ry(pi/4) on every qubit, then L x [CNOT ladder, one Pauli rotation
+per qubit with axis axes[i,q] in {0,1,2} = {X,Y,Z} and angle angles[i,q]].
+
+grad_run replaces the reference's (L+1)-copy history algorithm (mc_clean.py:47-78) by the
+two-vector adjoint recurrence  grad[i,q] = Im<lambda_i| P_q |psi_i>  executed in fused CUDA
+tile passes (qradient_b200/csrc/qr_tile.cuh); results agree to ~1e-15.
+"""
+import ctypes
+
+import numpy as np
+
+from .. import _lib
+from ..physical_components import Gates
+from .base import ParametrizedCircuit
+
+
+class McClean(ParametrizedCircuit):
+    def __init__(self, qubit_number, observable, layer_number, use_observable_components=False, **kwargs):
+        ParametrizedCircuit.init(self, qubit_number, observable, use_observable_components,
+                                 device=kwargs.get('device', 0))
+        self.lnum = layer_number
+        # same draws, same order as mc_clean.py:13-14 (axes first, then angles, global numpy stream)
+        self.axes = kwargs.get('axes', (3 * np.random.rand(self.lnum, self.qnum)).astype('int'))
+        self.angles = kwargs.get('angles', 2 * np.pi * np.random.rand(self.lnum, self.qnum))
+        self.state.gates = Gates(self.qnum) \
+            .add_xrots() \
+            .add_yrots() \
+            .add_zrots() \
+            .add_cnot_ladder()
+
+    # -- helpers ------------------------------------------------------------------------------
+    def _params(self):
+        axes = np.asarray(self.axes)
+        angles = np.asarray(self.angles, dtype=np.float64)
+        if axes.shape != (self.lnum, self.qnum) or angles.shape != (self.lnum, self.qnum):
+            raise ValueError('axes and angles must have shape ({}, {})'.format(self.lnum, self.qnum))
+        bad = (axes < 0) | (axes > 2)
+        if np.any(bad):
+            raise ValueError('Invalid axis {}'.format(axes[bad].ravel()[0]))   # mc_clean.py:392
+        return _lib.as_i32(axes), np.ascontiguousarray(angles)
+
+    def _adopt(self, ini_state):
+        if ini_state is None:
+            return 0
+        self.state.vec = ini_state      # mc_clean.py:32
+        return 1
+
+    # -- mc_clean.py:27-45 --------------------------------------------------------------------
+    def run_expec_val(self, hide_progbar=True, exact_expec_val=True, shot_num=1, ini_state=None):
+        '''Runs the circuit and returns the expectation value under observable'''
+        axes, angles = self._params()
+        use_current = self._adopt(ini_state)
+        e = ctypes.c_double()
+        self._lib.call('qr_mcclean_expec', self.state._ctx, self.lnum, _lib.ptr(axes), _lib.ptr(angles),
+                       self.observable._handle, use_current, ctypes.byref(e))
+        if exact_expec_val:
+            return e.value
+        return self.sample_expec_val(shot_num)
+
+    # -- mc_clean.py:47-78 --------------------------------------------------------------------
+    def grad_run(self, hide_progbar=True, ini_state=None):
+        axes, angles = self._params()
+        use_current = self._adopt(ini_state)
+        e = ctypes.c_double()
+        grad = np.empty([self.lnum, self.qnum], dtype='double')
+        self._lib.call('qr_mcclean_grad', self.state._ctx, self.lnum, _lib.ptr(axes), _lib.ptr(angles),
+                       self.observable._handle, use_current, ctypes.byref(e), _lib.ptr(grad))
+        return e.value, grad
+
+    # -- extension: many parameter sets at once (timing-test.ipynb cell 6 host loop) -------------
+    def grad_run_batch(self, angles, axes=None):
+        """angles: [B, L, n]; axes: [B, L, n] or [L, n] (default: self.axes).
+        Returns (float64[B], float64[B, L, n])."""
+        angles = np.ascontiguousarray(angles, dtype=np.float64)
+        if angles.ndim != 3 or angles.shape[1:] != (self.lnum, self.qnum):
+            raise ValueError('angles must have shape (B, {}, {})'.format(self.lnum, self.qnum))
+        B = angles.shape[0]
+        axes = np.asarray(self.axes if axes is None else axes)
+        if axes.ndim == 2:
+            axes = np.broadcast_to(axes, angles.shape)
+        if axes.shape != angles.shape:
+            raise ValueError('axes must have shape (B, L, n) or (L, n)')
+        if np.any((axes < 0) | (axes > 2)):
+            raise ValueError('Invalid axis')
+        axes = _lib.as_i32(axes)
+        e = np.empty(B, dtype=np.float64)
+        grad = np.empty(angles.shape, dtype=np.float64)
+        self._lib.call('qr_mcclean_grad_batch', self.state._ctx, B, self.lnum, _lib.ptr(axes), _lib.ptr(angles),
+                       self.observable._handle, _lib.ptr(e), _lib.ptr(grad))
+        return e, grad
+
+    # -- mc_clean.py:117-156: parameter-shift gradient with finite shots ------------------------
+    def sample_grad(self, hide_progbar=True, shot_num=1, exact_expec_val=True, ini_state=None):
+        axes, angles = self._params()
+        n, L = self.qnum, self.lnum
+        st = self.state
+        if ini_state is None:
+            st.reset()
+        else:
+            st.vec = ini_state
+        grad = np.ndarray([L, n], dtype='double')
+        for q in range(n):
+            st.yrot(np.pi / 4., q)
+        history = []
+        for i in range(L):
+            st.cnot_ladder(0)
+            for q in range(n):
+                self._rot(i, q)
+            history.append(np.array(st.vec))            # mc_clean.py:132
+        expec_val = self.expec_val() if exact_expec_val else self.sample_expec_val(shot_num)
+        for i in range(L):
+            for dq in range(n):
+                shifted = []
+                for shift in (np.pi / 2, -np.pi / 2):
+                    st.vec = history[i]
+                    self._manual_rot(i, dq, shift)
+                    for j in range(i + 1, L):
+                        st.cnot_ladder(0)
+                        for q in range(n):
+                            self._rot(j, q)
+                    shifted.append(self.sample_expec_val(shot_num))
+                grad[i, dq] = .5 * (shifted[0] - shifted[1])
+        return expec_val, grad
+
+    def _rot(self, i, q, angle_sign=1.):
+        self._manual_rot(i, q, angle_sign * self.angles[i, q])
+
+    def _manual_rot(self, i, q, angle):                 # mc_clean.py:394-403
+        ax = self.axes[i, q]
+        if ax == 0:
+            self.state.xrot(angle, q)
+        elif ax == 1:
+            self.state.yrot(angle, q)
+        elif ax == 2:
+            self.state.zrot(angle, q)
+        else:
+            raise ValueError('Invalid axis {}'.format(ax))

@@ -1,0 +1,70 @@
+"""QAOA ansatz (reference: circuit_logic/qaoa.py).
+
+Circuit (qaoa.py:32-34): |+>^n, then p x [exp(-i gamma_i H), Rx(beta_i) on every qubit] with H
+the diagonal Hamiltonian of the observable ('z' / 'zz' terms).  grad_run returns
+(E, grad[p, 2]) with grad[:, 0] = dE/dbeta, grad[:, 1] = dE/dgamma (qaoa.py:62-68), computed by
+the two-vector adjoint recurrence in fused CUDA tile passes.
+"""
+import ctypes
+
+import numpy as np
+
+from .. import _lib
+from ..physical_components import Gates
+from .base import ParametrizedCircuit
+
+
+class Qaoa(ParametrizedCircuit):
+    def __init__(self, qubit_number, observable, layer_number, **kwargs):
+        ParametrizedCircuit.init(self, qubit_number, observable, device=kwargs.get('device', 0))
+        self.state.gates = Gates(qubit_number) \
+            .add_xrots() \
+            .add_x_summed() \
+            .add_classical_ham(self.observable, include_individual_components=True)
+        self.lnum = layer_number
+        self.state.reset('+')   # initialize in uniform-superposition state (qaoa.py:17)
+
+    def _check_parameters(self, betas, gammas):
+        betas, gammas = np.asarray(betas), np.asarray(gammas)
+        if (betas.size != self.lnum) or (gammas.size != self.lnum):   # qaoa.py:186-191
+            raise ValueError('Wrong amount of parameters. Expected {0} and {0}, found {1} and {2}.'.format(
+                self.lnum, betas.size, gammas.size))
+        return (np.ascontiguousarray(betas, dtype=np.float64).ravel(),
+                np.ascontiguousarray(gammas, dtype=np.float64).ravel())
+
+    def _adopt(self, ini_state):
+        if ini_state is None:
+            return 0
+        self.state.vec = ini_state      # qaoa.py:28
+        return 1
+
+    # -- qaoa.py:23-38 ------------------------------------------------------------------------
+    def run_expec_val(self, betas, gammas, hide_progbar=True, exact_expec_val=True, shot_num=1, ini_state=None):
+        '''Runs the circuit and returns the expectation value under observable'''
+        use_current = self._adopt(ini_state)
+        betas, gammas = self._check_parameters(betas, gammas)
+        e = ctypes.c_double()
+        self._lib.call('qr_qaoa_expec', self.state._ctx, self.lnum, _lib.ptr(betas), _lib.ptr(gammas), use_current,
+                       ctypes.byref(e))
+        if exact_expec_val:
+            return e.value
+        return self.sample_expec_val(shot_num)
+
+    # -- qaoa.py:40-70 ------------------------------------------------------------------------
+    def grad_run(self, betas, gammas, hide_progbar=True, ini_state=None):
+        use_current = self._adopt(ini_state)
+        betas, gammas = self._check_parameters(betas, gammas)
+        e = ctypes.c_double()
+        grad = np.empty([self.lnum, 2], dtype='double')
+        self._lib.call('qr_qaoa_grad', self.state._ctx, self.lnum, _lib.ptr(betas), _lib.ptr(gammas), use_current,
+                       ctypes.byref(e), _lib.ptr(grad))
+        return e.value, grad
+
+    # -- qaoa.py:196-198 applied to the current state --------------------------------------------
+    def sample_cost(self, shot_num, uniforms=None):
+        """Mean of H over `shot_num` bitstrings drawn from |psi|^2 (the reference's private
+        ``__sample(dist, shot_num)`` with dist = |state.vec|^2), entirely on the device."""
+        idx = self.sample_bitstrings(shot_num, uniforms)
+        vals = np.empty(idx.size, dtype=np.float64)
+        self._lib.call('qr_ham_gather', self.state._ctx, int(idx.size), _lib.ptr(idx), _lib.ptr(vals))
+        return vals.mean()

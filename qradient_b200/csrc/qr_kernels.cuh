@@ -1,0 +1,384 @@
+// Gate-at-a-time kernels, reductions and the sampling kernels (complex128 state vector).
+//
+// These implement the `State` / `Observable` method surface one call at a time
+// (physical_components/state.py, observable.py) and are the un-fused cross-check for the
+// fused tile passes in qr_tile.cuh.  All kernels are grid-stride, one 16-byte amplitude per
+// load/store instruction (LDG.128/STG.128), coalesced along the fastest-varying index bit.
+#pragma once
+#include "qr_platform.cuh"
+
+#define QR_BLOCK 256
+
+struct ObsTerm {
+    int kind;     // QR_TERM_X/Y/Z/ZZ
+    int bit_i;    // index-bit position of qubit i  (n-1-i)
+    int bit_j;    // index-bit position of qubit j  (ZZ only)
+    int pad;
+    double w;
+};
+
+// ------------------------------------------------------------------------------------------
+// block-wide sum; result valid in thread 0.  blockDim.x is a power of two.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_reduce_sum(double v) {
+    __shared__ double red[32];
+    const int tid = threadIdx.x;
+    if (blockDim.x >= 32) {
+        const int lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[w] = v;
+        __syncthreads();
+        v = (lane < nw) ? red[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+    } else {
+        red[tid] = v;
+        __syncthreads();
+        if (tid == 0) { v = 0.0; for (unsigned t = 0; t < blockDim.x; ++t) v += red[t]; }
+        __syncthreads();
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// State.reset (state.py:61-71) and the McClean input layer prod_q Ry_q(pi/4)|0..0>
+// ------------------------------------------------------------------------------------------
+__global__ void k_init_basis(double2* __restrict__ v, u64 N, int which, double amp) {
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (u64)gridDim.x * blockDim.x) {
+        double re = which == 0 ? (j == 0 ? 1.0 : 0.0) : amp;
+        v[j] = make_double2(re, 0.0);
+    }
+}
+
+// amplitude_j = table[popcount(j)]: product state of identical single-qubit states (mc_clean.py:35-36)
+__global__ void k_init_product(double2* __restrict__ v, u64 N, const double* __restrict__ table, u64 state_mask) {
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (u64)gridDim.x * blockDim.x)
+        v[j] = make_double2(table[__popcll(j & state_mask)], 0.0);
+}
+
+// ------------------------------------------------------------------------------------------
+// general single-qubit matrix on index bit `bit`:  (a,b) -> (m00 a + m01 b, m10 a + m11 b)
+// used for xrot/yrot/zrot and dxrot/dyrot/dzrot (state.py:90-97,142-149,168-175)
+// ------------------------------------------------------------------------------------------
+struct Mat2 { double2 m00, m01, m10, m11; };
+
+__global__ void k_apply_1q(double2* __restrict__ v, u64 npairs, int bit, Mat2 m) {
+    const u64 lowmask = ((u64)1 << bit) - 1;
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += (u64)gridDim.x * blockDim.x) {
+        const u64 i0 = ((p & ~lowmask) << 1) | (p & lowmask);
+        const u64 i1 = i0 | ((u64)1 << bit);
+        const double2 a = v[i0], b = v[i1];
+        v[i0] = cadd(cmul(m.m00, a), cmul(m.m01, b));
+        v[i1] = cadd(cmul(m.m10, a), cmul(m.m11, b));
+    }
+}
+
+// CNOT (state.py:336-356): swap target pair where the control bit is set
+__global__ void k_cnot(double2* __restrict__ v, u64 nquads, int cbit, int tbit) {
+    const int lo = cbit < tbit ? cbit : tbit, hi = cbit < tbit ? tbit : cbit;
+    const u64 m_lo = ((u64)1 << lo) - 1, m_hi = ((u64)1 << (hi - 1)) - 1;
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < nquads; p += (u64)gridDim.x * blockDim.x) {
+        // insert zero bits at positions lo and hi
+        u64 x = ((p & ~m_lo) << 1) | (p & m_lo);
+        x = ((x & ~((m_hi << 1) | 1)) << 1) | (x & ((m_hi << 1) | 1));
+        const u64 i0 = x | ((u64)1 << cbit);
+        const u64 i1 = i0 | ((u64)1 << tbit);
+        const double2 a = v[i0], b = v[i1];
+        v[i0] = b;
+        v[i1] = a;
+    }
+}
+
+// CNOT ladder as one gather permutation (state.py:229-251): dst[i] = src[map(i)]
+__global__ void k_ladder_gather(const double2* __restrict__ src, double2* __restrict__ dst, u64 N, u64 m1, u64 m2) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (u64)gridDim.x * blockDim.x)
+        dst[i] = src[ladder_map(i, m1, m2)];
+}
+
+// x_summed (state.py:107-123): dst_j = sum_q (-i/2) src_{j ^ bit_q}
+__global__ void k_x_summed(const double2* __restrict__ src, double2* __restrict__ dst, u64 N, int n) {
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (u64)gridDim.x * blockDim.x) {
+        double sx = 0.0, sy = 0.0;
+        for (int b = 0; b < n; ++b) {
+            const double2 p = src[j ^ ((u64)1 << b)];
+            sx += p.x; sy += p.y;
+        }
+        dst[j] = make_double2(0.5 * sy, -0.5 * sx);   // (-i/2)(sx + i sy)
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// diagonal Hamiltonian (state.py:261-321)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double diag_value(u64 j, const ObsTerm* __restrict__ terms, int nterms) {
+    double d = 0.0;
+    for (int k = 0; k < nterms; ++k) {
+        const ObsTerm t = terms[k];
+        if (t.kind == 2) d += ((j >> t.bit_i) & 1) ? -t.w : t.w;
+        else if (t.kind == 3) d += (((j >> t.bit_i) ^ (j >> t.bit_j)) & 1) ? -t.w : t.w;
+    }
+    return d;
+}
+
+__global__ void k_ham_build(double* __restrict__ ham, u64 N, const ObsTerm* __restrict__ terms, int nterms) {
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (u64)gridDim.x * blockDim.x)
+        ham[j] = diag_value(j, terms, nterms);
+}
+
+// vec *= exp(-i angle H)   (state.py:299-301)
+__global__ void k_exp_ham(double2* __restrict__ v, const double* __restrict__ ham, u64 N, double angle) {
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (u64)gridDim.x * blockDim.x) {
+        double s, c;
+        sincos(angle * ham[j], &s, &c);
+        v[j] = cmul(v[j], make_double2(c, -s));
+    }
+}
+
+// mode 0: vec *= -i H (state.py:319-321);  mode 1: vec *= H (qaoa.py:56)
+__global__ void k_mul_ham(double2* __restrict__ v, const double* __restrict__ ham, u64 N, int mode) {
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (u64)gridDim.x * blockDim.x) {
+        const double h = ham[j];
+        const double2 a = v[j];
+        v[j] = mode == 0 ? make_double2(h * a.y, -h * a.x) : make_double2(h * a.x, h * a.y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// observable application (mc_clean.py:65) fused with Re<src|O src> (mc_clean.py:66)
+//   dst = O src ; partial[block] = sum_j Re(conj(src_j) dst_j)
+// dst may be null (expectation only).
+// ------------------------------------------------------------------------------------------
+__global__ void k_apply_obs(const double2* __restrict__ src, double2* __restrict__ dst, u64 N,
+                            const ObsTerm* __restrict__ terms, int nterms, double* __restrict__ partial) {
+    double acc = 0.0;
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (u64)gridDim.x * blockDim.x) {
+        const double2 a = src[j];
+        double d = 0.0, ox = 0.0, oy = 0.0;
+        for (int k = 0; k < nterms; ++k) {
+            const ObsTerm t = terms[k];
+            if (t.kind == 2) d += ((j >> t.bit_i) & 1) ? -t.w : t.w;
+            else if (t.kind == 3) d += (((j >> t.bit_i) ^ (j >> t.bit_j)) & 1) ? -t.w : t.w;
+            else {
+                const double2 p = src[j ^ ((u64)1 << t.bit_i)];
+                if (t.kind == 0) { ox += t.w * p.x; oy += t.w * p.y; }
+                else {  // Y = [[0,-i],[i,0]]: bit 0 row gets -i p, bit 1 row gets +i p
+                    const double sgn = ((j >> t.bit_i) & 1) ? 1.0 : -1.0;
+                    ox += -sgn * t.w * p.y;   // (i sgn w)(p.x + i p.y) = sgn w (-p.y + i p.x)
+                    oy += sgn * t.w * p.x;
+                }
+            }
+        }
+        const double2 o = make_double2(d * a.x + ox, d * a.y + oy);
+        if (dst) dst[j] = o;
+        acc += re_conj_mul(a, o);
+    }
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// per-term expectations <P_k> for up to 8 terms per launch (base.py:22-33 probabilities)
+#define QR_TERMS_PER_LAUNCH 8
+__global__ void k_term_expecs(const double2* __restrict__ v, u64 N, const ObsTerm* __restrict__ terms, int nterms,
+                              double* __restrict__ partial /*[grid][8]*/) {
+    double acc[QR_TERMS_PER_LAUNCH];
+#pragma unroll
+    for (int k = 0; k < QR_TERMS_PER_LAUNCH; ++k) acc[k] = 0.0;
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (u64)gridDim.x * blockDim.x) {
+        const double2 a = v[j];
+        const double p2 = a.x * a.x + a.y * a.y;
+#pragma unroll
+        for (int k = 0; k < QR_TERMS_PER_LAUNCH; ++k) {
+            if (k < nterms) {
+                const ObsTerm t = terms[k];
+                if (t.kind == 2) acc[k] += ((j >> t.bit_i) & 1) ? -p2 : p2;
+                else if (t.kind == 3) acc[k] += (((j >> t.bit_i) ^ (j >> t.bit_j)) & 1) ? -p2 : p2;
+                else {
+                    const double2 p = v[j ^ ((u64)1 << t.bit_i)];
+                    if (t.kind == 0) acc[k] += re_conj_mul(a, p);
+                    else acc[k] += (((j >> t.bit_i) & 1) ? -1.0 : 1.0) * im_conj_mul(a, p);  // Re(conj(a)(-+i p))
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < QR_TERMS_PER_LAUNCH; ++k) {
+        const double s = block_reduce_sum(acc[k]);
+        if (threadIdx.x == 0) partial[(u64)blockIdx.x * QR_TERMS_PER_LAUNCH + k] = s;
+    }
+}
+
+// ||v||^2 partials
+__global__ void k_norm2(const double2* __restrict__ v, u64 N, double* __restrict__ partial) {
+    double acc = 0.0;
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (u64)gridDim.x * blockDim.x) {
+        const double2 a = v[j];
+        acc += a.x * a.x + a.y * a.y;
+    }
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// QAOA lambda = H psi and E = <psi|H|psi> (qaoa.py:56-57)
+__global__ void k_ham_costate(const double2* __restrict__ psi, double2* __restrict__ lam, const double* __restrict__ ham,
+                              u64 N, double* __restrict__ partial) {
+    double acc = 0.0;
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (u64)gridDim.x * blockDim.x) {
+        const double2 a = psi[j];
+        const double h = ham[j];
+        if (lam) lam[j] = make_double2(h * a.x, h * a.y);
+        acc += h * (a.x * a.x + a.y * a.y);
+    }
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// Im<lam| P |psi> for one Pauli on one index bit (un-fused gradient path, mc_clean.py:75)
+__global__ void k_pauli_inner(const double2* __restrict__ psi, const double2* __restrict__ lam, u64 npairs, int bit,
+                              int axis, double* __restrict__ partial) {
+    const u64 lowmask = ((u64)1 << bit) - 1;
+    double acc = 0.0;
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += (u64)gridDim.x * blockDim.x) {
+        const u64 i0 = ((p & ~lowmask) << 1) | (p & lowmask);
+        const u64 i1 = i0 | ((u64)1 << bit);
+        const double2 p0 = psi[i0], p1 = psi[i1], l0 = lam[i0], l1 = lam[i1];
+        if (axis == 0) acc += im_conj_mul(l0, p1) + im_conj_mul(l1, p0);
+        else if (axis == 1) acc += re_conj_mul(l1, p0) - re_conj_mul(l0, p1);
+        else acc += im_conj_mul(l0, p0) - im_conj_mul(l1, p1);
+    }
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// sum_j H_j Im(conj(lam_j) psi_j)  (un-fused QAOA gamma gradient, qaoa.py:67-68)
+__global__ void k_ham_inner(const double2* __restrict__ psi, const double2* __restrict__ lam,
+                            const double* __restrict__ ham, u64 N, double* __restrict__ partial) {
+    double acc = 0.0;
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (u64)gridDim.x * blockDim.x)
+        acc += ham[j] * im_conj_mul(lam[j], psi[j]);
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// deterministic second stage: out[v] = sum_u partial[u*nvals + v], one block, fixed order
+__global__ void k_reduce_partials(const double* __restrict__ partial, int nunits, int nvals, double* __restrict__ out) {
+    for (int v = 0; v < nvals; ++v) {
+        double acc = 0.0;
+        for (int u = threadIdx.x; u < nunits; u += blockDim.x) acc += partial[(u64)u * nvals + v];
+        acc = block_reduce_sum(acc);
+        if (threadIdx.x == 0) out[v] = acc;
+    }
+}
+
+// grouped variant for batches: out[g*out_stride + v] = sum over the units of group g
+__global__ void k_reduce_partials_grouped(const double* __restrict__ partial, int units_per_group, int nvals,
+                                          double* __restrict__ out, int out_stride) {
+    const u64 base = (u64)blockIdx.x * units_per_group * nvals;
+    for (int v = 0; v < nvals; ++v) {
+        double acc = 0.0;
+        for (int u = threadIdx.x; u < units_per_group; u += blockDim.x) acc += partial[base + (u64)u * nvals + v];
+        acc = block_reduce_sum(acc);
+        if (threadIdx.x == 0) out[(u64)blockIdx.x * out_stride + v] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// finite-shot bitstring sampling (qaoa.py:196-198): inverse CDF of |psi|^2.
+//   stage 1: chunk sums of |psi|^2 (chunk = QR_SCAN_CHUNK amplitudes, one block each)
+//   stage 2: exclusive scan of the chunk sums by one block (sequential per thread + block scan)
+//   stage 3: one block per shot: binary-search the chunk, then scan inside the chunk
+// "first k with cdf[k] >= u" is evaluated on prefix sums accumulated in index order inside a
+// chunk and chunk-wise across chunks, i.e. the same left-to-right order as numpy.cumsum up to
+// the association of the partial sums.
+// ------------------------------------------------------------------------------------------
+#define QR_SCAN_CHUNK 4096
+
+__global__ void k_prob_chunk_sums(const double2* __restrict__ v, u64 N, double* __restrict__ sums) {
+    for (u64 chunk = blockIdx.x; chunk * QR_SCAN_CHUNK < N; chunk += gridDim.x) {
+        const u64 base = chunk * QR_SCAN_CHUNK;
+        double acc = 0.0;
+        for (u64 j = base + threadIdx.x; j < base + QR_SCAN_CHUNK && j < N; j += blockDim.x) {
+            const double2 a = v[j];
+            acc += a.x * a.x + a.y * a.y;
+        }
+        acc = block_reduce_sum(acc);
+        if (threadIdx.x == 0) sums[chunk] = acc;
+    }
+}
+
+// in-place inclusive scan of `sums[0..n)` by a single block (n up to a few million)
+__global__ void k_scan_inclusive_single(double* __restrict__ sums, u64 n) {
+    __shared__ double tot[1024];
+    const u64 per = (n + blockDim.x - 1) / blockDim.x;
+    const u64 lo = (u64)threadIdx.x * per, hi = (lo + per < n) ? lo + per : n;
+    double acc = 0.0;
+    for (u64 i = lo; i < hi; ++i) acc += sums[i];
+    tot[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double run = 0.0;
+        for (unsigned t = 0; t < blockDim.x; ++t) { const double x = tot[t]; tot[t] = run; run += x; }
+    }
+    __syncthreads();
+    double run = tot[threadIdx.x];
+    for (u64 i = lo; i < hi; ++i) { run += sums[i]; sums[i] = run; }
+}
+
+__global__ void k_sample_search(const double2* __restrict__ v, u64 N, const double* __restrict__ chunk_cdf,
+                                u64 nchunks, const double* __restrict__ uniforms, i64* __restrict__ out) {
+    __shared__ double tot[QR_BLOCK];
+    __shared__ i64 hits[QR_BLOCK];
+    const int shot = blockIdx.x;
+    const double u = uniforms[shot];
+    // chunk = first c with chunk_cdf[c] >= u
+    u64 lo = 0, hi = nchunks;   // search in [lo, hi)
+    while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        if (chunk_cdf[mid] >= u) hi = mid; else lo = mid + 1;
+    }
+    if (lo >= nchunks) {   // u above the last cdf value: scipy's argmax over all-False returns 0
+        if (threadIdx.x == 0) out[shot] = 0;
+        return;
+    }
+    const u64 chunk = lo;
+    const double before = chunk ? chunk_cdf[chunk - 1] : 0.0;
+    const u64 base = chunk * QR_SCAN_CHUNK;
+    const int per = QR_SCAN_CHUNK / QR_BLOCK;
+    double p[QR_SCAN_CHUNK / QR_BLOCK];
+    double acc = 0.0;
+    for (int i = 0; i < per; ++i) {
+        const u64 j = base + (u64)threadIdx.x * per + i;
+        double q = 0.0;
+        if (j < N) { const double2 a = v[j]; q = a.x * a.x + a.y * a.y; }
+        p[i] = q;
+        acc += q;
+    }
+    tot[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double run = before;
+        for (int t = 0; t < QR_BLOCK; ++t) { const double x = tot[t]; tot[t] = run; run += x; }
+    }
+    __syncthreads();
+    // the first thread whose running range crosses u owns the answer
+    double run = tot[threadIdx.x];
+    i64 mine = -1;
+    for (int i = 0; i < per; ++i) {
+        run += p[i];
+        if (mine < 0 && run >= u) mine = (i64)(base + (u64)threadIdx.x * per + i);
+    }
+    // threads are ordered by index: the first thread with a hit owns the answer
+    hits[threadIdx.x] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        i64 r = -1;
+        for (int t = 0; t < QR_BLOCK && r < 0; ++t) r = hits[t];
+        if (r < 0) r = (i64)((base + QR_SCAN_CHUNK < N ? base + QR_SCAN_CHUNK : N) - 1);  // rounding at the chunk edge
+        out[shot] = r;
+    }
+}
+
+__global__ void k_gather_f64(const double* __restrict__ table, const i64* __restrict__ idx, int n, double* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = table[idx[i]];
+}

@@ -1,0 +1,1369 @@
+// libqradient_b200: C ABI (include/qradient_b200.h) + host-side pass planner.
+//
+// Single translation unit: kernels live in qr_kernels.cuh (gate-at-a-time, reductions,
+// sampling) and qr_tile.cuh (fused tile pass).  Everything here is host orchestration: buffer
+// ping-pong, the per-layer pass schedule, gate tables, and the mapping of per-CTA gradient
+// partials back to (layer, qubit).
+#include "../../include/qradient_b200.h"
+#include "qr_kernels.cuh"
+#include "qr_tile.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(x)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (x);                                                                         \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(e_ == cudaErrorMemoryAllocation ? QR_ENOMEM : QR_ECUDA, "%s: %s (%s:%d)", #x, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                  \
+    } while (0)
+#define QR_TRY(x)            \
+    do {                     \
+        int r_ = (x);        \
+        if (r_) return r_;   \
+    } while (0)
+#define KERNEL_CHECK() CUDA_TRY(cudaGetLastError())
+
+// ------------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------------
+struct qr_obs {
+    int n;
+    std::vector<ObsTerm> terms;   // projector order
+    bool diagonal;                // only z / zz terms
+};
+
+struct PassPlan {
+    int k, c, h, nrounds;
+    int g[QR_MAXROUNDS];
+    int gbit[QR_MAXROUNDS * QR_R];   // global index bit handled by (round, register bit) or -1
+};
+
+struct LayerPlan {
+    int n, k, npasses;
+    PassPlan pass[16];
+};
+
+#define QR_NBUF 4
+
+struct qr_ctx {
+    int n = 0;
+    u64 N = 0;
+    int device = 0;
+    int sm_count = 1;
+    cudaStream_t stream = nullptr;
+    double2* buf[QR_NBUF] = {nullptr, nullptr, nullptr, nullptr};
+    u64 buf_amps = 0;            // capacity of each buffer in amplitudes (>= N; batch paths grow it)
+    int psi = 0;                 // buffer holding the state vector
+    double* d_ham = nullptr;     // diagonal Hamiltonian table [N]
+    bool ham_loaded = false;
+    double* d_scratch = nullptr; // reduction partials
+    size_t scratch_cap = 0;      // in doubles
+    double* d_result = nullptr;  // small results
+    size_t result_cap = 0;
+    void* d_small = nullptr;     // gate tables / observable terms / tables
+    size_t small_cap = 0;
+    unsigned char* h_pin = nullptr;
+    size_t pin_cap = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // options
+    long long opt_fusion = 1, opt_tile_bits = QR_MAX_TILE_BITS, opt_prefetch = 0;
+    long long opt_ctas_fwd = 2, opt_ctas_bwd = 1, opt_final_ladder = 1, opt_ham_lut = 1;
+    qr_perf perf;
+};
+
+static inline int use_device(qr_ctx* c) {
+    CUDA_TRY(cudaSetDevice(c->device));
+    return 0;
+}
+
+static int ensure_dev(void** p, size_t* cap, size_t need_bytes) {
+    if (*cap >= need_bytes) return 0;
+    if (*p) CUDA_TRY(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    size_t sz = std::max(need_bytes, (size_t)4096);
+    CUDA_TRY(cudaMalloc(p, sz));
+    *cap = sz;
+    return 0;
+}
+
+static int ensure_scratch(qr_ctx* c, size_t doubles) {
+    size_t cap = c->scratch_cap * sizeof(double);
+    QR_TRY(ensure_dev((void**)&c->d_scratch, &cap, doubles * sizeof(double)));
+    c->scratch_cap = cap / sizeof(double);
+    return 0;
+}
+static int ensure_result(qr_ctx* c, size_t doubles) {
+    size_t cap = c->result_cap * sizeof(double);
+    QR_TRY(ensure_dev((void**)&c->d_result, &cap, doubles * sizeof(double)));
+    c->result_cap = cap / sizeof(double);
+    return 0;
+}
+static int ensure_small(qr_ctx* c, size_t bytes) { return ensure_dev(&c->d_small, &c->small_cap, bytes); }
+
+static int ensure_pin(qr_ctx* c, size_t bytes) {
+    if (c->pin_cap >= bytes) return 0;
+    if (c->h_pin) CUDA_TRY(cudaFreeHost(c->h_pin));
+    c->h_pin = nullptr;
+    c->pin_cap = 0;
+    size_t sz = std::max(bytes, (size_t)1 << 16);
+    CUDA_TRY(cudaMallocHost((void**)&c->h_pin, sz));
+    c->pin_cap = sz;
+    return 0;
+}
+
+static int ensure_buf(qr_ctx* c, int i) {
+    if (c->buf[i]) return 0;
+    cudaError_t e = cudaMalloc((void**)&c->buf[i], c->buf_amps * sizeof(double2));
+    if (e != cudaSuccess) {
+        c->buf[i] = nullptr;
+        return fail(QR_ENOMEM, "cannot allocate state buffer %d of %.2f GiB for %d qubits: %s", i,
+                    (double)(c->buf_amps * sizeof(double2)) / (double)(1ull << 30), c->n, cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+// a buffer index different from a, b, d (pass -1 for unused)
+static int other_buf(qr_ctx* c, int a, int b = -1, int d = -1) {
+    for (int i = 0; i < QR_NBUF; ++i)
+        if (i != a && i != b && i != d) return i;
+    return -1;
+}
+
+static inline int grid_for(const qr_ctx* c, u64 work) {
+    u64 blocks = (work + QR_BLOCK - 1) / QR_BLOCK;
+    u64 cap = (u64)c->sm_count * 8;
+    if (blocks < 1) blocks = 1;
+    return (int)std::min(blocks, cap);
+}
+
+// sum scratch partials [nunits][nvals] -> host
+static int reduce_to_host(qr_ctx* c, int nunits, int nvals, double* out) {
+    QR_TRY(ensure_result(c, nvals));
+    QR_TRY(ensure_pin(c, nvals * sizeof(double)));
+    QR_LAUNCH(k_reduce_partials, 1, QR_BLOCK, 0, c->stream, c->d_scratch, nunits, nvals, c->d_result);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(c->h_pin, c->d_result, nvals * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(out, c->h_pin, nvals * sizeof(double));
+    return 0;
+}
+
+// upload a small host array into d_small at byte offset `off` (stream ordered, via pinned staging)
+static int upload_small(qr_ctx* c, size_t off, const void* src, size_t bytes, size_t pin_off) {
+    memcpy(c->h_pin + pin_off, src, bytes);
+    CUDA_TRY(cudaMemcpyAsync((char*)c->d_small + off, c->h_pin + pin_off, bytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// misc API
+// ------------------------------------------------------------------------------------------
+extern "C" const char* qr_last_error(void) { return g_err.c_str(); }
+extern "C" int qr_version(void) { return 100; }
+
+extern "C" int qr_device_count(int* out) {
+    if (!out) return fail(QR_EINVAL, "null output");
+    CUDA_TRY(cudaGetDeviceCount(out));
+    return 0;
+}
+
+extern "C" int qr_ctx_create(int n_qubits, int device, qr_ctx** out) {
+    if (!out) return fail(QR_EINVAL, "null output");
+    *out = nullptr;
+    if (n_qubits < 1 || n_qubits > 34) return fail(QR_EINVAL, "qubit_number must be in [1, 34], got %d", n_qubits);
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) return fail(QR_ECUDA, "no CUDA device visible: qradient_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(QR_EINVAL, "device %d out of range (%d visible)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    qr_ctx* c = new qr_ctx();
+    c->n = n_qubits;
+    c->N = (u64)1 << n_qubits;
+    c->buf_amps = c->N;
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    memset(&c->perf, 0, sizeof(c->perf));
+    int rc = 0;
+    do {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(QR_ECUDA, "stream creation failed"); break; }
+        for (int i = 0; i < 4; ++i) cudaEventCreate(&c->ev[i]);
+        if ((rc = ensure_buf(c, 0))) break;
+        if ((rc = ensure_scratch(c, (size_t)c->sm_count * 8 * 16))) break;
+        if ((rc = ensure_result(c, 64))) break;
+        if ((rc = ensure_small(c, 1 << 16))) break;
+        if ((rc = ensure_pin(c, 1 << 16))) break;
+    } while (0);
+    if (rc) { qr_ctx_destroy(c); return rc; }
+    *out = c;
+    return qr_state_init(c, 0);
+}
+
+extern "C" int qr_ctx_destroy(qr_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < QR_NBUF; ++i) if (c->buf[i]) cudaFree(c->buf[i]);
+    if (c->d_ham) cudaFree(c->d_ham);
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    if (c->d_result) cudaFree(c->d_result);
+    if (c->d_small) cudaFree(c->d_small);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
+    if (!c) return fail(QR_EINVAL, "null context");
+    switch (key) {
+        case QR_OPT_FUSION: c->opt_fusion = v ? 1 : 0; break;
+        case QR_OPT_TILE_BITS:
+            if (v < QR_R || v > QR_MAX_TILE_BITS) return fail(QR_EINVAL, "tile bits must be in [%d, %d]", QR_R, QR_MAX_TILE_BITS);
+            c->opt_tile_bits = v; break;
+        case QR_OPT_PREFETCH: c->opt_prefetch = v ? 1 : 0; break;
+        case QR_OPT_CTAS_PER_SM_FWD: if (v < 1 || v > 8) return fail(QR_EINVAL, "bad CTAs/SM"); c->opt_ctas_fwd = v; break;
+        case QR_OPT_CTAS_PER_SM_BWD: if (v < 1 || v > 8) return fail(QR_EINVAL, "bad CTAs/SM"); c->opt_ctas_bwd = v; break;
+        case QR_OPT_FINAL_LADDER: c->opt_final_ladder = v ? 1 : 0; break;
+        case QR_OPT_HAM_LUT: c->opt_ham_lut = v ? 1 : 0; break;
+        default: return fail(QR_EINVAL, "unknown option %d", key);
+    }
+    return 0;
+}
+
+extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
+    if (!c || !v) return fail(QR_EINVAL, "null argument");
+    switch (key) {
+        case QR_OPT_FUSION: *v = c->opt_fusion; break;
+        case QR_OPT_TILE_BITS: *v = c->opt_tile_bits; break;
+        case QR_OPT_PREFETCH: *v = c->opt_prefetch; break;
+        case QR_OPT_CTAS_PER_SM_FWD: *v = c->opt_ctas_fwd; break;
+        case QR_OPT_CTAS_PER_SM_BWD: *v = c->opt_ctas_bwd; break;
+        case QR_OPT_FINAL_LADDER: *v = c->opt_final_ladder; break;
+        case QR_OPT_HAM_LUT: *v = c->opt_ham_lut; break;
+        default: return fail(QR_EINVAL, "unknown option %d", key);
+    }
+    return 0;
+}
+
+extern "C" int qr_perf_last(qr_ctx* c, qr_perf* out) {
+    if (!c || !out) return fail(QR_EINVAL, "null argument");
+    *out = c->perf;
+    return 0;
+}
+
+extern "C" int qr_sync(qr_ctx* c) {
+    if (!c) return fail(QR_EINVAL, "null context");
+    QR_TRY(use_device(c));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// state vector
+// ------------------------------------------------------------------------------------------
+extern "C" int qr_state_init(qr_ctx* c, int which) {
+    if (!c) return fail(QR_EINVAL, "null context");
+    if (which != 0 && which != 1) return fail(QR_EINVAL, "Invalid initialization format %d.", which);
+    QR_TRY(use_device(c));
+    const double amp = std::pow(2.0, -0.5 * c->n);   // state.py:69
+    QR_LAUNCH(k_init_basis, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[c->psi], c->N, which, amp);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int qr_state_upload(qr_ctx* c, const double* re_im, size_t n_amps) {
+    if (!c || !re_im) return fail(QR_EINVAL, "null argument");
+    if (n_amps != c->N) return fail(QR_EINVAL, "state vector must have 2^%d = %llu amplitudes, got %llu", c->n, c->N, (u64)n_amps);
+    QR_TRY(use_device(c));
+    CUDA_TRY(cudaMemcpyAsync(c->buf[c->psi], re_im, n_amps * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int qr_state_download(qr_ctx* c, double* re_im, size_t n_amps) {
+    if (!c || !re_im) return fail(QR_EINVAL, "null argument");
+    if (n_amps != c->N) return fail(QR_EINVAL, "state vector has 2^%d = %llu amplitudes, got room for %llu", c->n, c->N, (u64)n_amps);
+    QR_TRY(use_device(c));
+    CUDA_TRY(cudaMemcpyAsync(re_im, c->buf[c->psi], n_amps * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int qr_state_device_ptr(qr_ctx* c, void** out) {
+    if (!c || !out) return fail(QR_EINVAL, "null argument");
+    *out = c->buf[c->psi];
+    return 0;
+}
+
+static int check_axis_qubit(qr_ctx* c, int axis, int qubit) {
+    if (axis < 0 || axis > 2) return fail(QR_EINVAL, "Invalid axis %d", axis);
+    if (qubit < 0 || qubit >= c->n) return fail(QR_EINVAL, "Invalid qubit index %d for %d qubits.", qubit, c->n);
+    return 0;
+}
+
+// rotation matrices exp(-i angle P / 2) (state.py:90-92,142-144,168-170)
+static Mat2 rot_matrix(int axis, double angle) {
+    const double cs = std::cos(0.5 * angle), sn = std::sin(0.5 * angle);
+    Mat2 m;
+    if (axis == 0) {
+        m.m00 = make_double2(cs, 0); m.m01 = make_double2(0, -sn);
+        m.m10 = make_double2(0, -sn); m.m11 = make_double2(cs, 0);
+    } else if (axis == 1) {
+        m.m00 = make_double2(cs, 0); m.m01 = make_double2(-sn, 0);
+        m.m10 = make_double2(sn, 0); m.m11 = make_double2(cs, 0);
+    } else {
+        m.m00 = make_double2(cs, -sn); m.m01 = make_double2(0, 0);
+        m.m10 = make_double2(0, 0); m.m11 = make_double2(cs, sn);
+    }
+    return m;
+}
+
+// derivative matrices (state.py:94-97,146-149,172-175): 1/2 cos G - 1/2 sin 1 ; dz: -+ i/2 e^{-+ i a/2}
+static Mat2 drot_matrix(int axis, double angle) {
+    const double cs = std::cos(0.5 * angle), sn = std::sin(0.5 * angle);
+    Mat2 m;
+    if (axis == 0) {
+        m.m00 = make_double2(-0.5 * sn, 0); m.m01 = make_double2(0, -0.5 * cs);
+        m.m10 = make_double2(0, -0.5 * cs); m.m11 = make_double2(-0.5 * sn, 0);
+    } else if (axis == 1) {
+        m.m00 = make_double2(-0.5 * sn, 0); m.m01 = make_double2(-0.5 * cs, 0);
+        m.m10 = make_double2(0.5 * cs, 0); m.m11 = make_double2(-0.5 * sn, 0);
+    } else {
+        m.m00 = make_double2(-0.5 * sn, -0.5 * cs); m.m01 = make_double2(0, 0);
+        m.m10 = make_double2(0, 0); m.m11 = make_double2(-0.5 * sn, 0.5 * cs);
+    }
+    return m;
+}
+
+static int launch_1q(qr_ctx* c, double2* v, int bit, const Mat2& m) {
+    const u64 npairs = c->N >> 1;
+    QR_LAUNCH(k_apply_1q, grid_for(c, npairs), QR_BLOCK, 0, c->stream, v, npairs, bit, m);
+    KERNEL_CHECK();
+    return 0;
+}
+
+extern "C" int qr_apply_rot(qr_ctx* c, int axis, double angle, int qubit) {
+    if (!c) return fail(QR_EINVAL, "null context");
+    QR_TRY(check_axis_qubit(c, axis, qubit));
+    QR_TRY(use_device(c));
+    QR_TRY(launch_1q(c, c->buf[c->psi], c->n - 1 - qubit, rot_matrix(axis, angle)));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int qr_apply_drot(qr_ctx* c, int axis, double angle, int qubit) {
+    if (!c) return fail(QR_EINVAL, "null context");
+    QR_TRY(check_axis_qubit(c, axis, qubit));
+    QR_TRY(use_device(c));
+    QR_TRY(launch_1q(c, c->buf[c->psi], c->n - 1 - qubit, drot_matrix(axis, angle)));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int launch_cnot(qr_ctx* c, double2* v, int control, int target) {
+    const u64 nquads = c->N >> 2;
+    QR_LAUNCH(k_cnot, grid_for(c, nquads), QR_BLOCK, 0, c->stream, v, nquads, c->n - 1 - control, c->n - 1 - target);
+    KERNEL_CHECK();
+    return 0;
+}
+
+extern "C" int qr_apply_cnot(qr_ctx* c, int control, int target) {
+    if (!c) return fail(QR_EINVAL, "null context");
+    if (control == target || control < 0 || target < 0 || control >= c->n || target >= c->n)
+        return fail(QR_EINVAL, "Invalid CNOT indecies %d and %d, for %d qubits.", control, target, c->n);
+    QR_TRY(use_device(c));
+    QR_TRY(launch_cnot(c, c->buf[c->psi], control, target));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// scatter masks of ladder `stacking`; the gather for stacking s uses the
+// masks of 1-s because ladder(1) = ladder(0)^-1.
+static void ladder_masks(int n, int stacking, u64* m1, u64* m2) {
+    u64 a = 0, b = 0;
+    for (int t = 1; t < n; ++t) {
+        const int p = n - 1 - t;
+        a |= (u64)1 << p;
+        const bool three = stacking == 0 ? (t % 2 == 1) : (t % 2 == 0);
+        if (t >= 2 && three) b |= (u64)1 << p;
+    }
+    *m1 = a;
+    *m2 = b;
+}
+
+// out-of-place ladder on buffer `src` into buffer `dst`
+static int launch_ladder(qr_ctx* c, int src, int dst, int stacking) {
+    u64 m1, m2;
+    ladder_masks(c->n, 1 - stacking, &m1, &m2);
+    QR_LAUNCH(k_ladder_gather, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[src], c->buf[dst], c->N, m1, m2);
+    KERNEL_CHECK();
+    return 0;
+}
+
+extern "C" int qr_apply_cnot_ladder(qr_ctx* c, int stacking, int periodic) {
+    if (!c) return fail(QR_EINVAL, "null context");
+    if (stacking != 0 && stacking != 1) return fail(QR_EINVAL, "Invalid stacking %d", stacking);
+    if (periodic && (c->n % 2 != 0))
+        return fail(QR_EINVAL, "CNOT gates in a ladder structure with periodic boundaries are ambiguous for uneven number of qubits.");
+    QR_TRY(use_device(c));
+    if (!periodic) {
+        if (c->n >= 2) {
+            const int dst = other_buf(c, c->psi);
+            QR_TRY(ensure_buf(c, dst));
+            QR_TRY(launch_ladder(c, c->psi, dst, stacking));
+            c->psi = dst;
+        }
+    } else {
+        // state.py:235-241 with the wrap-around CNOT(n-1 -> 0) in the odd-start group
+        const int n = c->n;
+        for (int phase = 0; phase < 2; ++phase) {
+            const int start = (stacking == 0) ? (phase == 0 ? 1 : 0) : (phase == 0 ? 0 : 1);
+            for (int i = start; i < n; i += 2) QR_TRY(launch_cnot(c, c->buf[c->psi], i, (i + 1) % n));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int qr_apply_x_summed(qr_ctx* c) {
+    if (!c) return fail(QR_EINVAL, "null context");
+    QR_TRY(use_device(c));
+    const int dst = other_buf(c, c->psi);
+    QR_TRY(ensure_buf(c, dst));
+    QR_LAUNCH(k_x_summed, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[c->psi], c->buf[dst], c->N, c->n);
+    KERNEL_CHECK();
+    c->psi = dst;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int qr_norm2(qr_ctx* c, double* out) {
+    if (!c || !out) return fail(QR_EINVAL, "null argument");
+    QR_TRY(use_device(c));
+    const int grid = grid_for(c, c->N);
+    QR_TRY(ensure_scratch(c, grid));
+    QR_LAUNCH(k_norm2, grid, QR_BLOCK, 0, c->stream, c->buf[c->psi], c->N, c->d_scratch);
+    KERNEL_CHECK();
+    return reduce_to_host(c, grid, 1, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// observable
+// ------------------------------------------------------------------------------------------
+extern "C" int qr_obs_create(int n, int n_terms, const int32_t* kind, const int32_t* qi, const int32_t* qj,
+                             const double* w, qr_obs** out) {
+    if (!out) return fail(QR_EINVAL, "null output");
+    *out = nullptr;
+    if (n < 1 || n > 34) return fail(QR_EINVAL, "qubit_number must be in [1, 34], got %d", n);
+    if (n_terms < 0 || (n_terms > 0 && (!kind || !qi || !w))) return fail(QR_EINVAL, "bad term arrays");
+    qr_obs* o = new qr_obs();
+    o->n = n;
+    o->diagonal = true;
+    for (int k = 0; k < n_terms; ++k) {
+        ObsTerm t;
+        t.kind = kind[k];
+        t.pad = 0;
+        t.w = w[k];
+        if (t.kind < 0 || t.kind > 3) { delete o; return fail(QR_EINVAL, "Unknown key for projector %d.", t.kind); }
+        if (qi[k] < 0 || qi[k] >= n) { delete o; return fail(QR_EINVAL, "observable qubit index %d out of range", qi[k]); }
+        t.bit_i = n - 1 - qi[k];
+        t.bit_j = 0;
+        if (t.kind == QR_TERM_ZZ) {
+            if (!qj || qj[k] <= qi[k] || qj[k] >= n) {
+                delete o;
+                return fail(QR_EINVAL, "zz of observable should be a upper triangular %d by %d matrix.", n, n);
+            }
+            t.bit_j = n - 1 - qj[k];
+        }
+        if (t.kind == QR_TERM_X || t.kind == QR_TERM_Y) o->diagonal = false;
+        o->terms.push_back(t);
+    }
+    *out = o;
+    return 0;
+}
+
+extern "C" int qr_obs_destroy(qr_obs* o) {
+    delete o;
+    return 0;
+}
+
+static int check_obs(qr_ctx* c, const qr_obs* o) {
+    if (!c || !o) return fail(QR_EINVAL, "null argument");
+    if (o->n != c->n) return fail(QR_EINVAL, "observable is for %d qubits, state has %d", o->n, c->n);
+    return 0;
+}
+
+// put the observable's terms at the start of d_small; returns device pointer
+static int upload_terms(qr_ctx* c, const std::vector<ObsTerm>& terms, const ObsTerm** d_terms) {
+    const size_t bytes = std::max<size_t>(terms.size(), 1) * sizeof(ObsTerm);
+    QR_TRY(ensure_small(c, bytes));
+    QR_TRY(ensure_pin(c, bytes));
+    if (!terms.empty()) QR_TRY(upload_small(c, 0, terms.data(), terms.size() * sizeof(ObsTerm), 0));
+    *d_terms = (const ObsTerm*)c->d_small;
+    return 0;
+}
+
+// dst = O src (dst < 0: expectation only); E = Re<src|O|src>
+static int observable_pass(qr_ctx* c, const qr_obs* o, int src, int dst, double* e_out) {
+    const ObsTerm* d_terms;
+    QR_TRY(upload_terms(c, o->terms, &d_terms));
+    const int grid = grid_for(c, c->N);
+    QR_TRY(ensure_scratch(c, grid));
+    QR_LAUNCH(k_apply_obs, grid, QR_BLOCK, 0, c->stream, (const double2*)c->buf[src],
+              dst >= 0 ? c->buf[dst] : (double2*)nullptr, c->N, d_terms, (int)o->terms.size(), c->d_scratch);
+    KERNEL_CHECK();
+    return reduce_to_host(c, grid, 1, e_out);
+}
+
+extern "C" int qr_apply_observable(qr_ctx* c, const qr_obs* o) {
+    QR_TRY(check_obs(c, o));
+    QR_TRY(use_device(c));
+    const int dst = other_buf(c, c->psi);
+    QR_TRY(ensure_buf(c, dst));
+    double e;
+    QR_TRY(observable_pass(c, o, c->psi, dst, &e));
+    c->psi = dst;
+    return 0;
+}
+
+extern "C" int qr_expec_val(qr_ctx* c, const qr_obs* o, double* out) {
+    QR_TRY(check_obs(c, o));
+    if (!out) return fail(QR_EINVAL, "null output");
+    QR_TRY(use_device(c));
+    return observable_pass(c, o, c->psi, -1, out);
+}
+
+extern "C" int qr_term_expecs(qr_ctx* c, const qr_obs* o, double* out) {
+    QR_TRY(check_obs(c, o));
+    if (!out && !o->terms.empty()) return fail(QR_EINVAL, "null output");
+    QR_TRY(use_device(c));
+    const ObsTerm* d_terms;
+    QR_TRY(upload_terms(c, o->terms, &d_terms));
+    const int grid = grid_for(c, c->N);
+    QR_TRY(ensure_scratch(c, (size_t)grid * QR_TERMS_PER_LAUNCH));
+    const int K = (int)o->terms.size();
+    for (int k0 = 0; k0 < K; k0 += QR_TERMS_PER_LAUNCH) {
+        const int nk = std::min(QR_TERMS_PER_LAUNCH, K - k0);
+        QR_LAUNCH(k_term_expecs, grid, QR_BLOCK, 0, c->stream, (const double2*)c->buf[c->psi], c->N, d_terms + k0, nk,
+                  c->d_scratch);
+        KERNEL_CHECK();
+        double vals[QR_TERMS_PER_LAUNCH];
+        QR_TRY(reduce_to_host(c, grid, QR_TERMS_PER_LAUNCH, vals));
+        for (int k = 0; k < nk; ++k) out[k0 + k] = vals[k];
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// diagonal Hamiltonian
+// ------------------------------------------------------------------------------------------
+extern "C" int qr_ham_load(qr_ctx* c, const qr_obs* o) {
+    QR_TRY(check_obs(c, o));
+    QR_TRY(use_device(c));
+    if (!c->d_ham) {
+        cudaError_t e = cudaMalloc((void**)&c->d_ham, c->N * sizeof(double));
+        if (e != cudaSuccess) { c->d_ham = nullptr; return fail(QR_ENOMEM, "cannot allocate the Hamiltonian table: %s", cudaGetErrorString(e)); }
+    }
+    const ObsTerm* d_terms;
+    QR_TRY(upload_terms(c, o->terms, &d_terms));
+    QR_LAUNCH(k_ham_build, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->d_ham, c->N, d_terms, (int)o->terms.size());
+    KERNEL_CHECK();
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->ham_loaded = true;
+    return 0;
+}
+
+static int need_ham(qr_ctx* c) {
+    if (!c) return fail(QR_EINVAL, "null context");
+    if (!c->ham_loaded) return fail(QR_ESTATE, "classical Hamiltonian not loaded (call qr_ham_load / Gates.add_classical_ham first)");
+    return 0;
+}
+
+extern "C" int qr_ham_download(qr_ctx* c, double* out, size_t n_amps) {
+    QR_TRY(need_ham(c));
+    if (!out || n_amps != c->N) return fail(QR_EINVAL, "bad output buffer");
+    QR_TRY(use_device(c));
+    CUDA_TRY(cudaMemcpyAsync(out, c->d_ham, c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int qr_apply_exp_ham(qr_ctx* c, double angle) {
+    QR_TRY(need_ham(c));
+    QR_TRY(use_device(c));
+    QR_LAUNCH(k_exp_ham, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[c->psi], (const double*)c->d_ham, c->N, angle);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int qr_apply_exp_ham_component(qr_ctx* c, const qr_obs* o, int k, double angle) {
+    QR_TRY(check_obs(c, o));
+    // components are the diagonal terms in order (state.py:277-294)
+    int idx = -1, seen = 0;
+    for (size_t t = 0; t < o->terms.size(); ++t)
+        if (o->terms[t].kind >= 2) { if (seen == k) { idx = (int)t; break; } ++seen; }
+    if (k < 0 || idx < 0) return fail(QR_EINVAL, "classical Hamiltonian component %d out of range", k);
+    QR_TRY(use_device(c));
+    // vec *= exp(-i angle w z..z): a diagonal with two values = an Rz-like phase by parity; reuse
+    // the generic 1-qubit kernel for z, and a two-step parity phase for zz via CNOT-free masks.
+    const ObsTerm t = o->terms[idx];
+    const double cs = std::cos(angle * t.w), sn = std::sin(angle * t.w);
+    if (t.kind == 2) {
+        Mat2 m;
+        m.m00 = make_double2(cs, -sn); m.m01 = make_double2(0, 0); m.m10 = make_double2(0, 0); m.m11 = make_double2(cs, sn);
+        QR_TRY(launch_1q(c, c->buf[c->psi], t.bit_i, m));
+    } else {
+        // exp(-i a w Z_i Z_j) = CNOT(i->j) . exp(-i a w Z_j) . CNOT(i->j)
+        const int qi = c->n - 1 - t.bit_i, qj = c->n - 1 - t.bit_j;
+        Mat2 m;
+        m.m00 = make_double2(cs, -sn); m.m01 = make_double2(0, 0); m.m10 = make_double2(0, 0); m.m11 = make_double2(cs, sn);
+        QR_TRY(launch_cnot(c, c->buf[c->psi], qi, qj));
+        QR_TRY(launch_1q(c, c->buf[c->psi], t.bit_j, m));
+        QR_TRY(launch_cnot(c, c->buf[c->psi], qi, qj));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int qr_apply_ham(qr_ctx* c, int mode) {
+    QR_TRY(need_ham(c));
+    if (mode != 0 && mode != 1) return fail(QR_EINVAL, "bad mode %d", mode);
+    QR_TRY(use_device(c));
+    QR_LAUNCH(k_mul_ham, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[c->psi], (const double*)c->d_ham, c->N, mode);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// pass planner
+// ------------------------------------------------------------------------------------------
+// Rounds of a pass whose gate bits are the local bits [first, k): the top group first (its
+// threads' lanes cover the lowest local bits -> coalesced global loads), then ascending groups;
+// every gate bit is assigned to the first group that covers it.
+static void plan_rounds(PassPlan& pp, int first) {
+    const int k = pp.k;
+    int assigned[QR_MAX_TILE_BITS];
+    for (int i = 0; i < QR_MAX_TILE_BITS; ++i) assigned[i] = -1;
+    int nr = 0;
+    const int top = std::max(k - QR_R, 0);
+    pp.g[nr++] = top;
+    for (int g = first; g < top; g += QR_R) pp.g[nr++] = g;
+    pp.nrounds = nr;
+    for (int i = 0; i < QR_MAXROUNDS * QR_R; ++i) pp.gbit[i] = -1;
+    for (int r = 0; r < nr; ++r)
+        for (int b = 0; b < QR_R; ++b) {
+            const int lb = pp.g[r] + b;
+            if (lb < first || lb >= k || assigned[lb] >= 0) continue;
+            assigned[lb] = r;
+            pp.gbit[r * QR_R + b] = lb < pp.c ? lb : pp.h + (lb - pp.c);
+        }
+}
+
+static int make_plan(int n, int tile_bits, LayerPlan* lp) {
+    if (n < QR_R) return fail(QR_EINVAL, "fused path needs at least %d qubits", QR_R);
+    const int k = std::min(n, tile_bits);
+    lp->n = n;
+    lp->k = k;
+    int np = 0;
+    PassPlan& p0 = lp->pass[np++];
+    p0.k = k; p0.c = k; p0.h = k;
+    plan_rounds(p0, 0);
+    const int rem = n - k;
+    if (rem > 0) {
+        const int umax = std::max(k - 3, 1);
+        const int nx = (rem + umax - 1) / umax;
+        int h = k;
+        for (int i = 0; i < nx; ++i) {
+            const int m = rem / nx + (i < rem % nx ? 1 : 0);
+            PassPlan& pp = lp->pass[np++];
+            pp.k = k; pp.c = k - m; pp.h = h;
+            plan_rounds(pp, pp.c);
+            h += m;
+        }
+    }
+    lp->npasses = np;
+    for (int i = 0; i < np; ++i)
+        if (lp->pass[i].nrounds > QR_MAXROUNDS) return fail(QR_EINVAL, "internal: pass needs %d rounds", lp->pass[i].nrounds);
+    return 0;
+}
+
+// gate table entries of one (layer, pass): QR_MAXROUNDS*QR_R GateP, from per-qubit (axis, cos, sin)
+template <class F>
+static void fill_gates(const LayerPlan& lp, int pass, GateP* out, F gate_of_qubit) {
+    const PassPlan& pp = lp.pass[pass];
+    for (int i = 0; i < QR_MAXROUNDS * QR_R; ++i) {
+        GateP g;
+        g.c = 1.0; g.s = 0.0; g.axis = -1; g.pad = 0;
+        if (pp.gbit[i] >= 0) g = gate_of_qubit(lp.n - 1 - pp.gbit[i]);
+        out[i] = g;
+    }
+}
+
+typedef void (*tile_fn)(const TilePass);
+
+static tile_fn tile_kernel(int nv, int nr) {
+    if (nv == 1) return nr == 1 ? k_tile_pass<1, 1> : nr == 2 ? k_tile_pass<1, 2> : k_tile_pass<1, 3>;
+    return nr == 1 ? k_tile_pass<2, 1> : nr == 2 ? k_tile_pass<2, 2> : k_tile_pass<2, 3>;
+}
+
+struct PassIO {
+    const double2* src0; const double2* src1; double2* dst0; double2* dst1;
+};
+
+// launch one tile pass; returns the number of partial units written (backward) through *units
+static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const PassIO& io, const GateP* d_gates,
+                       int gate_stride, int ladder_stacking /* -1 none, else gather of ladder(stacking) */,
+                       i64 batch, i64 state_stride, int flush_per_tile, const double* ham, int pre_phase,
+                       double angle_pre, int post_phase, double angle_post, int* units) {
+    const PassPlan& pp = lp.pass[pass];
+    TilePass tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.k = pp.k; tp.c = pp.c; tp.h = pp.h; tp.nrounds = pp.nrounds;
+    for (int r = 0; r < QR_MAXROUNDS; ++r) tp.g[r] = r < pp.nrounds ? pp.g[r] : 0;
+    tp.ladder = 0;
+    if (ladder_stacking >= 0) {
+        tp.ladder = 1;
+        ladder_masks(lp.n, 1 - ladder_stacking, &tp.M1, &tp.M2);
+    }
+    tp.tiles_log2 = lp.n - pp.k;
+    tp.num_tiles = batch << tp.tiles_log2;
+    tp.state_stride = state_stride;
+    tp.src0 = io.src0; tp.src1 = io.src1; tp.dst0 = io.dst0; tp.dst1 = io.dst1;
+    tp.gates = d_gates; tp.gate_stride = gate_stride;
+    tp.ham = ham; tp.pre_phase = pre_phase; tp.post_phase = post_phase;
+    tp.angle_pre = angle_pre; tp.angle_post = angle_post;
+    tp.flush_per_tile = flush_per_tile;
+    tp.prefetch = (int)c->opt_prefetch;
+    const int threads = 1 << (pp.k - QR_R);
+    const long long per_sm = std::min<long long>(16, (nv == 1 ? c->opt_ctas_fwd : c->opt_ctas_bwd) * std::max(1, 256 / threads));
+    const i64 grid = std::min<i64>(tp.num_tiles, (i64)c->sm_count * per_sm);
+    const size_t smem = pp.nrounds > 1 ? (size_t)nv * sizeof(double2) << pp.k : 0;
+    if (nv == 2) {
+        const i64 nunits = flush_per_tile ? tp.num_tiles : grid;
+        QR_TRY(ensure_scratch(c, (size_t)nunits * QR_SLOTS));
+        *units = (int)nunits;
+    }
+    tp.partials = c->d_scratch;
+    tile_fn fn = tile_kernel(nv, pp.nrounds);
+    static bool attr_done[2][QR_MAXROUNDS + 1] = {{false}};
+    if (!attr_done[nv - 1][pp.nrounds]) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(double2) << QR_MAX_TILE_BITS));
+        attr_done[nv - 1][pp.nrounds] = true;
+    }
+    QR_LAUNCH(fn, (unsigned)grid, threads, smem, c->stream, tp);
+    KERNEL_CHECK();
+    c->perf.kernel_launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// McClean (circuit_logic/mc_clean.py)
+// ------------------------------------------------------------------------------------------
+static int check_mcclean_args(qr_ctx* c, int L, const int32_t* axes, const double* angles, const qr_obs* o) {
+    QR_TRY(check_obs(c, o));
+    if (L < 0) return fail(QR_EINVAL, "layer_number must be >= 0");
+    if (L > 0 && (!axes || !angles)) return fail(QR_EINVAL, "null axes/angles");
+    for (i64 i = 0; i < (i64)L * c->n; ++i)
+        if (axes[i] < 0 || axes[i] > 2) return fail(QR_EINVAL, "Invalid axis %d", axes[i]);   // mc_clean.py:392
+    return 0;
+}
+
+static void perf_reset(qr_ctx* c) { memset(&c->perf, 0, sizeof(c->perf)); }
+
+// product state prod_q Ry_q(pi/4)|0>: amplitude cos(pi/8)^(n-w) sin(pi/8)^w, w = popcount(j)
+static int init_mcclean_product(qr_ctx* c) {
+    double table[40];
+    const double cs = std::cos(M_PI / 8.0), sn = std::sin(M_PI / 8.0);
+    for (int w = 0; w <= c->n; ++w) {
+        double v = 1.0;
+        for (int q = 0; q < c->n; ++q) v *= (q < c->n - w) ? cs : sn;
+        table[w] = v;
+    }
+    const size_t off = c->small_cap - 512;   // tail of d_small, away from terms / gate tables
+    QR_TRY(upload_small(c, off, table, sizeof(double) * (c->n + 1), c->pin_cap - 512));
+    QR_LAUNCH(k_init_product, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[c->psi], c->N,
+              (const double*)((char*)c->d_small + off), c->N - 1);
+    KERNEL_CHECK();
+    c->perf.kernel_launches++;
+    return 0;
+}
+
+// --- un-fused McClean (gate-at-a-time kernels): QR_OPT_FUSION=0, n < 4, or cross-checks ---
+static int mcclean_unfused(qr_ctx* c, int L, const int32_t* axes, const double* angles, const qr_obs* o,
+                           int use_current, double* e_out, double* grad) {
+    const int n = c->n;
+    if (!use_current) {
+        QR_LAUNCH(k_init_basis, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[c->psi], c->N, 0, 0.0);
+        KERNEL_CHECK();
+    }
+    for (int q = 0; q < n; ++q) QR_TRY(launch_1q(c, c->buf[c->psi], n - 1 - q, rot_matrix(1, M_PI / 4.0)));
+    for (int i = 0; i < L; ++i) {
+        if (n >= 2) {
+            const int dst = other_buf(c, c->psi);
+            QR_TRY(ensure_buf(c, dst));
+            QR_TRY(launch_ladder(c, c->psi, dst, 0));
+            c->psi = dst;
+        }
+        for (int q = 0; q < n; ++q)
+            QR_TRY(launch_1q(c, c->buf[c->psi], n - 1 - q, rot_matrix(axes[i * n + q], angles[i * n + q])));
+    }
+    if (!grad) return observable_pass(c, o, c->psi, -1, e_out);
+    int lam = other_buf(c, c->psi);
+    QR_TRY(ensure_buf(c, lam));
+    QR_TRY(observable_pass(c, o, c->psi, lam, e_out));
+    const u64 npairs = c->N >> 1;
+    const int grid = grid_for(c, npairs);
+    QR_TRY(ensure_scratch(c, grid));
+    for (int i = L - 1; i >= 0; --i) {
+        for (int q = 0; q < n; ++q) {
+            QR_LAUNCH(k_pauli_inner, grid, QR_BLOCK, 0, c->stream, (const double2*)c->buf[c->psi],
+                      (const double2*)c->buf[lam], npairs, n - 1 - q, (int)axes[i * n + q], c->d_scratch);
+            KERNEL_CHECK();
+            QR_TRY(reduce_to_host(c, grid, 1, &grad[i * n + q]));
+        }
+        for (int q = 0; q < n; ++q) {
+            const Mat2 m = rot_matrix(axes[i * n + q], -angles[i * n + q]);
+            QR_TRY(launch_1q(c, c->buf[c->psi], n - 1 - q, m));
+            QR_TRY(launch_1q(c, c->buf[lam], n - 1 - q, m));
+        }
+        if (n >= 2) {
+            const int d1 = other_buf(c, c->psi, lam);
+            const int d2 = other_buf(c, c->psi, lam, d1);
+            QR_TRY(ensure_buf(c, d1));
+            QR_TRY(launch_ladder(c, lam, d1, 1));
+            lam = d1;
+            if (i > 0) {   // psi is only needed while gradients remain
+                QR_TRY(ensure_buf(c, d2));
+                QR_TRY(launch_ladder(c, c->psi, d2, 1));
+                c->psi = d2;
+            }
+        }
+    }
+    c->psi = lam;   // mc_clean.py leaves the back-propagated co-state in state.vec
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+struct GradLayout {   // where the per-(layer, pass) slot sums land in d_result
+    int slots_per_layer;
+};
+
+// fused McClean forward (+ backward when grad != null) for `batch` parameter sets laid out
+// contiguously in the state buffers (state b at offset b * N)
+static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const double* angles, const qr_obs* o,
+                         int use_current, double* e_out, double* grad) {
+    const int n = c->n;
+    LayerPlan lp;
+    QR_TRY(make_plan(n, (int)c->opt_tile_bits, &lp));
+    const int P = lp.npasses;
+    const int GS = QR_MAXROUNDS * QR_R;           // gate entries per (layer, pass)
+    const bool want_grad = grad != nullptr;
+    const bool ry_layer = use_current != 0;       // ini_state given: apply the Ry(pi/4) layer as gates
+    // ---- gate tables: [batch][ (ry layer) + L forward + L backward ][P][GS] ----
+    const int nlay_tab = (ry_layer ? 1 : 0) + L + (want_grad ? L : 0);
+    const size_t per_batch = (size_t)nlay_tab * P * GS;
+    const size_t tab_bytes = (size_t)batch * per_batch * sizeof(GateP);
+    const size_t terms_bytes = (o->terms.size() + 1) * sizeof(ObsTerm);
+    const size_t tab_off = (terms_bytes + 255) & ~(size_t)255;
+    QR_TRY(ensure_small(c, tab_off + tab_bytes + 1024));
+    QR_TRY(ensure_pin(c, tab_off + tab_bytes + 1024));
+    {
+        GateP* tab = (GateP*)(c->h_pin + tab_off);
+        for (i64 b = 0; b < batch; ++b) {
+            GateP* tb = tab + b * per_batch;
+            int lay = 0;
+            if (ry_layer) {
+                const double cs = std::cos(M_PI / 8.0), sn = std::sin(M_PI / 8.0);
+                for (int p = 0; p < P; ++p)
+                    fill_gates(lp, p, tb + ((size_t)lay * P + p) * GS, [&](int) { GateP g; g.c = cs; g.s = sn; g.axis = 1; g.pad = 0; return g; });
+                ++lay;
+            }
+            for (int dir = 0; dir < (want_grad ? 2 : 1); ++dir)
+                for (int i = 0; i < L; ++i, ++lay) {
+                    const int32_t* ax = axes + ((size_t)b * L + i) * n;
+                    const double* an = angles + ((size_t)b * L + i) * n;
+                    const double sgn = dir == 0 ? 1.0 : -1.0;
+                    for (int p = 0; p < P; ++p)
+                        fill_gates(lp, p, tb + ((size_t)lay * P + p) * GS, [&](int q) {
+                            GateP g; g.c = std::cos(0.5 * an[q]); g.s = sgn * std::sin(0.5 * an[q]); g.axis = ax[q]; g.pad = 0; return g; });
+                }
+        }
+        CUDA_TRY(cudaMemcpyAsync((char*)c->d_small + tab_off, tab, tab_bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    const GateP* d_tab = (const GateP*)((char*)c->d_small + tab_off);
+    const int gate_stride = (int)per_batch;
+    const i64 stride = (i64)c->N;
+    const int flush = batch > 1 ? 1 : 0;
+
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    // ---- forward ----
+    int lay = 0;
+    if (!ry_layer) {
+        if (batch == 1) QR_TRY(init_mcclean_product(c));
+        else {
+            // same product state for every batch element: N*batch amplitudes, popcount of the low n bits
+            double table[40];
+            const double cs = std::cos(M_PI / 8.0), sn = std::sin(M_PI / 8.0);
+            for (int w = 0; w <= n; ++w) { double v = 1.0; for (int q = 0; q < n; ++q) v *= (q < n - w) ? cs : sn; table[w] = v; }
+            const size_t off = c->small_cap - 512;
+            QR_TRY(upload_small(c, off, table, sizeof(double) * (n + 1), c->pin_cap - 512));
+            QR_LAUNCH(k_init_product, grid_for(c, c->N * batch), QR_BLOCK, 0, c->stream, c->buf[c->psi], c->N * (u64)batch,
+                      (const double*)((char*)c->d_small + off), c->N - 1);
+            KERNEL_CHECK();
+            c->perf.kernel_launches++;
+        }
+    } else {
+        for (int p = 0; p < P; ++p) {
+            PassIO io = {c->buf[c->psi], nullptr, c->buf[c->psi], nullptr};
+            QR_TRY(launch_pass(c, lp, p, 1, io, d_tab + ((size_t)lay * P + p) * GS, gate_stride, -1, batch, stride, 0,
+                               nullptr, 0, 0, 0, 0, nullptr));
+        }
+        ++lay;
+    }
+    for (int i = 0; i < L; ++i, ++lay) {
+        for (int p = 0; p < P; ++p) {
+            int dst = c->psi;
+            int lad = -1;
+            if (p == 0 && n >= 2) { dst = other_buf(c, c->psi); QR_TRY(ensure_buf(c, dst)); lad = 0; }
+            PassIO io = {c->buf[c->psi], nullptr, c->buf[dst], nullptr};
+            QR_TRY(launch_pass(c, lp, p, 1, io, d_tab + ((size_t)lay * P + p) * GS, gate_stride, lad, batch, stride, 0,
+                               nullptr, 0, 0, 0, 0, nullptr));
+            c->psi = dst;
+        }
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    // ---- observable: lambda = O psi, E = Re<psi|lambda> ----
+    const ObsTerm* d_terms;
+    QR_TRY(upload_small(c, 0, o->terms.data(), o->terms.size() * sizeof(ObsTerm), 0));
+    d_terms = (const ObsTerm*)c->d_small;
+    int lam = -1;
+    if (want_grad) { lam = other_buf(c, c->psi); QR_TRY(ensure_buf(c, lam)); }
+    const int ogrid = grid_for(c, c->N);
+    QR_TRY(ensure_scratch(c, (size_t)ogrid * std::max<i64>(batch, 1)));
+    QR_TRY(ensure_result(c, (size_t)batch * (1 + (want_grad ? (size_t)L * P * QR_SLOTS : 0)) + 16));
+    for (i64 b = 0; b < batch; ++b) {
+        QR_LAUNCH(k_apply_obs, ogrid, QR_BLOCK, 0, c->stream, (const double2*)(c->buf[c->psi] + b * stride),
+                  want_grad ? c->buf[lam] + b * stride : (double2*)nullptr, c->N, d_terms, (int)o->terms.size(),
+                  c->d_scratch + (size_t)b * ogrid);
+        KERNEL_CHECK();
+        c->perf.kernel_launches++;
+    }
+    // result layout: [batch] E values, then [batch][L][P][QR_SLOTS] slot sums
+    QR_LAUNCH(k_reduce_partials_grouped, (unsigned)batch, QR_BLOCK, 0, c->stream, (const double*)c->d_scratch, ogrid, 1,
+              c->d_result, 1);
+    KERNEL_CHECK();
+    c->perf.kernel_launches++;
+    CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    // ---- backward ----
+    double* d_slots = c->d_result + batch;
+    const int slots_per_state = L * P * QR_SLOTS;
+    int n_bwd_pass = 0;
+    if (want_grad) {
+        for (int i = L - 1; i >= 0; --i, ++lay) {
+            // table index of backward layer i: forward tables come first, backward tables are stored in layer order
+            const int tlay = (ry_layer ? 1 : 0) + L + i;
+            for (int p = 0; p < P; ++p) {
+                int dpsi = c->psi, dlam = lam, lad = -1;
+                if (p == 0 && i < L - 1 && n >= 2) {
+                    dpsi = other_buf(c, c->psi, lam);
+                    dlam = other_buf(c, c->psi, lam, dpsi);
+                    QR_TRY(ensure_buf(c, dpsi));
+                    QR_TRY(ensure_buf(c, dlam));
+                    lad = 1;   // inverse ladder of layer i+1, folded into this load (mc_clean.py:77)
+                }
+                PassIO io = {c->buf[c->psi], c->buf[lam], c->buf[dpsi], c->buf[dlam]};
+                int units = 0;
+                QR_TRY(launch_pass(c, lp, p, 2, io, d_tab + ((size_t)tlay * P + p) * GS, gate_stride, lad, batch, stride,
+                                   flush, nullptr, 0, 0, 0, 0, &units));
+                c->psi = dpsi;
+                lam = dlam;
+                ++n_bwd_pass;
+                if (batch == 1) {
+                    QR_LAUNCH(k_reduce_partials, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_scratch, units, QR_SLOTS,
+                              d_slots + ((size_t)i * P + p) * QR_SLOTS);
+                } else {
+                    const int tiles_per_state = 1 << (n - lp.k);
+                    QR_LAUNCH(k_reduce_partials_grouped, (unsigned)batch, 32, 0, c->stream, (const double*)c->d_scratch,
+                              tiles_per_state, QR_SLOTS, d_slots + ((size_t)i * P + p) * QR_SLOTS, slots_per_state);
+                }
+                KERNEL_CHECK();
+                c->perf.kernel_launches++;
+            }
+        }
+        if (c->opt_final_ladder && n >= 2 && L > 0 && batch == 1) {   // mc_clean.py:77 for layer 0
+            const int d = other_buf(c, c->psi, lam);
+            QR_TRY(ensure_buf(c, d));
+            QR_TRY(launch_ladder(c, lam, d, 1));
+            c->perf.kernel_launches++;
+            lam = d;
+        }
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    // ---- results ----
+    const size_t nres = (size_t)batch * (1 + (want_grad ? slots_per_state : 0));
+    QR_TRY(ensure_pin(c, nres * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(c->h_pin, c->d_result, nres * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const double* res = (const double*)c->h_pin;
+    for (i64 b = 0; b < batch; ++b) e_out[b] = res[b];
+    if (want_grad) {
+        const double* slots = res + batch;
+        for (i64 b = 0; b < batch; ++b)
+            for (int i = 0; i < L; ++i)
+                for (int p = 0; p < P; ++p)
+                    for (int s = 0; s < GS; ++s) {
+                        const int gb = lp.pass[p].gbit[s];
+                        if (gb < 0) continue;
+                        grad[((size_t)b * L + i) * n + (n - 1 - gb)] = slots[(size_t)b * slots_per_state + ((size_t)i * P + p) * QR_SLOTS + s];
+                    }
+        c->psi = lam;   // state.vec = back-propagated co-state (mc_clean.py:68-77)
+    }
+    // ---- perf ----
+    float ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->perf.ms_forward = ms;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->perf.ms_observable = ms;
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->perf.ms_backward = ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); c->perf.ms_total = ms;
+    const double amps = (double)c->N * (double)batch;
+    c->perf.passes_per_layer = P;
+    c->perf.tile_bits = lp.k;
+    c->perf.fwd_pass_bytes = 32.0 * amps;
+    c->perf.bwd_pass_bytes = 64.0 * amps;
+    const int n_fwd_pass = (L + (ry_layer ? 1 : 0)) * P;
+    c->perf.fwd_pass_ms_avg = n_fwd_pass ? c->perf.ms_forward / n_fwd_pass : 0.0;
+    c->perf.bwd_pass_ms_avg = n_bwd_pass ? c->perf.ms_backward / n_bwd_pass : 0.0;
+    // B_sched: init write 16, forward 32 per pass, observable 32 (+16 read-only if no grad), backward 64 per pass
+    c->perf.algorithmic_bytes = amps * (16.0 + 32.0 * n_fwd_pass + (want_grad ? 32.0 : 16.0) + 64.0 * n_bwd_pass +
+                                        (want_grad && c->opt_final_ladder && batch == 1 && L > 0 ? 32.0 : 0.0));
+    return 0;
+}
+
+static bool use_fused(qr_ctx* c) { return c->opt_fusion && c->n >= QR_R; }
+
+extern "C" int qr_mcclean_expec(qr_ctx* c, int L, const int32_t* axes, const double* angles, const qr_obs* o,
+                                int use_current_state, double* e_out) {
+    QR_TRY(check_mcclean_args(c, L, axes, angles, o));
+    if (!e_out) return fail(QR_EINVAL, "null output");
+    QR_TRY(use_device(c));
+    perf_reset(c);
+    if (use_fused(c)) return mcclean_fused(c, 1, L, axes, angles, o, use_current_state, e_out, nullptr);
+    return mcclean_unfused(c, L, axes, angles, o, use_current_state, e_out, nullptr);
+}
+
+extern "C" int qr_mcclean_grad(qr_ctx* c, int L, const int32_t* axes, const double* angles, const qr_obs* o,
+                               int use_current_state, double* e_out, double* grad_out) {
+    QR_TRY(check_mcclean_args(c, L, axes, angles, o));
+    if (!e_out || (!grad_out && L > 0)) return fail(QR_EINVAL, "null output");
+    QR_TRY(use_device(c));
+    perf_reset(c);
+    double dummy;
+    if (use_fused(c)) return mcclean_fused(c, 1, L, axes, angles, o, use_current_state, e_out, grad_out ? grad_out : &dummy);
+    return mcclean_unfused(c, L, axes, angles, o, use_current_state, e_out, grad_out ? grad_out : &dummy);
+}
+
+extern "C" int qr_mcclean_grad_batch(qr_ctx* c, int batch, int L, const int32_t* axes, const double* angles,
+                                     const qr_obs* o, double* e_out, double* grad_out) {
+    QR_TRY(check_obs(c, o));
+    if (batch < 1) return fail(QR_EINVAL, "batch must be >= 1");
+    if (!axes || !angles || !e_out || !grad_out) return fail(QR_EINVAL, "null argument");
+    if (c->n < QR_R) return fail(QR_EINVAL, "batched path needs at least %d qubits", QR_R);
+    for (i64 i = 0; i < (i64)batch * L * c->n; ++i)
+        if (axes[i] < 0 || axes[i] > 2) return fail(QR_EINVAL, "Invalid axis %d", axes[i]);
+    QR_TRY(use_device(c));
+    perf_reset(c);
+    // chunk the batch so the four ping-pong buffers of a chunk stay L2-friendly / within memory
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const u64 per_state = c->N * sizeof(double2) * QR_NBUF;
+    u64 chunk = std::max<u64>(1, std::min<u64>((u64)batch, ((u64)1 << 28) / std::max<u64>(per_state / QR_NBUF, 1)));
+    // (re)allocate the buffers for `chunk` states
+    if (c->buf_amps < c->N * chunk) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < QR_NBUF; ++i) if (c->buf[i]) { cudaFree(c->buf[i]); c->buf[i] = nullptr; }
+        c->buf_amps = c->N * chunk;
+        c->psi = 0;
+        QR_TRY(ensure_buf(c, 0));
+    }
+    qr_perf total;
+    memset(&total, 0, sizeof(total));
+    for (i64 b0 = 0; b0 < batch; b0 += (i64)chunk) {
+        const i64 nb = std::min<i64>((i64)chunk, batch - b0);
+        QR_TRY(mcclean_fused(c, nb, L, axes + (size_t)b0 * L * c->n, angles + (size_t)b0 * L * c->n, o, 0, e_out + b0,
+                             grad_out + (size_t)b0 * L * c->n));
+        total.ms_total += c->perf.ms_total; total.ms_forward += c->perf.ms_forward;
+        total.ms_observable += c->perf.ms_observable; total.ms_backward += c->perf.ms_backward;
+        total.algorithmic_bytes += c->perf.algorithmic_bytes; total.kernel_launches += c->perf.kernel_launches;
+        total.passes_per_layer = c->perf.passes_per_layer; total.tile_bits = c->perf.tile_bits;
+        total.bwd_pass_ms_avg = c->perf.bwd_pass_ms_avg; total.bwd_pass_bytes = c->perf.bwd_pass_bytes;
+        total.fwd_pass_ms_avg = c->perf.fwd_pass_ms_avg; total.fwd_pass_bytes = c->perf.fwd_pass_bytes;
+    }
+    c->perf = total;
+    // leave a valid single state in psi (state 0 of the last chunk)
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// QAOA (circuit_logic/qaoa.py)
+// ------------------------------------------------------------------------------------------
+static int qaoa_unfused(qr_ctx* c, int p, const double* betas, const double* gammas, int use_current, double* e_out,
+                        double* grad) {
+    const int n = c->n;
+    if (!use_current) {
+        QR_LAUNCH(k_init_basis, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[c->psi], c->N, 1, std::pow(2.0, -0.5 * n));
+        KERNEL_CHECK();
+    }
+    const int g = grid_for(c, c->N);
+    for (int i = 0; i < p; ++i) {
+        QR_LAUNCH(k_exp_ham, g, QR_BLOCK, 0, c->stream, c->buf[c->psi], (const double*)c->d_ham, c->N, gammas[i]);
+        KERNEL_CHECK();
+        for (int q = 0; q < n; ++q) QR_TRY(launch_1q(c, c->buf[c->psi], n - 1 - q, rot_matrix(0, betas[i])));
+    }
+    QR_TRY(ensure_scratch(c, g));
+    int lam = -1;
+    if (grad) { lam = other_buf(c, c->psi); QR_TRY(ensure_buf(c, lam)); }
+    QR_LAUNCH(k_ham_costate, g, QR_BLOCK, 0, c->stream, (const double2*)c->buf[c->psi], grad ? c->buf[lam] : (double2*)nullptr,
+              (const double*)c->d_ham, c->N, c->d_scratch);
+    KERNEL_CHECK();
+    QR_TRY(reduce_to_host(c, g, 1, e_out));
+    if (!grad) return 0;
+    const u64 npairs = c->N >> 1;
+    const int gp = grid_for(c, npairs);
+    for (int i = p - 1; i >= 0; --i) {
+        double gb = 0.0;
+        for (int q = 0; q < n; ++q) {
+            QR_LAUNCH(k_pauli_inner, gp, QR_BLOCK, 0, c->stream, (const double2*)c->buf[c->psi], (const double2*)c->buf[lam],
+                      npairs, n - 1 - q, 0, c->d_scratch);
+            KERNEL_CHECK();
+            double v;
+            QR_TRY(reduce_to_host(c, gp, 1, &v));
+            gb += v;
+        }
+        grad[2 * i] = gb;
+        for (int q = 0; q < n; ++q) {
+            const Mat2 m = rot_matrix(0, -betas[i]);
+            QR_TRY(launch_1q(c, c->buf[c->psi], n - 1 - q, m));
+            QR_TRY(launch_1q(c, c->buf[lam], n - 1 - q, m));
+        }
+        QR_LAUNCH(k_ham_inner, g, QR_BLOCK, 0, c->stream, (const double2*)c->buf[c->psi], (const double2*)c->buf[lam],
+                  (const double*)c->d_ham, c->N, c->d_scratch);
+        KERNEL_CHECK();
+        double v;
+        QR_TRY(reduce_to_host(c, g, 1, &v));
+        grad[2 * i + 1] = 2.0 * v;
+        QR_LAUNCH(k_exp_ham, g, QR_BLOCK, 0, c->stream, c->buf[c->psi], (const double*)c->d_ham, c->N, -gammas[i]);
+        KERNEL_CHECK();
+        QR_LAUNCH(k_exp_ham, g, QR_BLOCK, 0, c->stream, c->buf[lam], (const double*)c->d_ham, c->N, -gammas[i]);
+        KERNEL_CHECK();
+    }
+    c->psi = lam;   // qaoa.py leaves the back-propagated co-state in state.vec
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gammas, int use_current, double* e_out,
+                      double* grad) {
+    const int n = c->n;
+    LayerPlan lp;
+    QR_TRY(make_plan(n, (int)c->opt_tile_bits, &lp));
+    const int P = lp.npasses;
+    const int GS = QR_MAXROUNDS * QR_R;
+    const bool want_grad = grad != nullptr;
+    const int nlay_tab = p * (want_grad ? 2 : 1);
+    const size_t tab_bytes = (size_t)nlay_tab * P * GS * sizeof(GateP);
+    QR_TRY(ensure_small(c, tab_bytes + 1024));
+    QR_TRY(ensure_pin(c, tab_bytes + 1024));
+    {
+        GateP* tab = (GateP*)c->h_pin;
+        int lay = 0;
+        for (int dir = 0; dir < (want_grad ? 2 : 1); ++dir)
+            for (int i = 0; i < p; ++i, ++lay) {
+                const double cs = std::cos(0.5 * betas[i]), sn = (dir == 0 ? 1.0 : -1.0) * std::sin(0.5 * betas[i]);
+                for (int q = 0; q < P; ++q)
+                    fill_gates(lp, q, tab + ((size_t)lay * P + q) * GS, [&](int) { GateP g; g.c = cs; g.s = sn; g.axis = 0; g.pad = 0; return g; });
+            }
+        CUDA_TRY(cudaMemcpyAsync(c->d_small, tab, tab_bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    const GateP* d_tab = (const GateP*)c->d_small;
+    const i64 stride = (i64)c->N;
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    if (!use_current) {
+        QR_LAUNCH(k_init_basis, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[c->psi], c->N, 1, std::pow(2.0, -0.5 * n));
+        KERNEL_CHECK();
+        c->perf.kernel_launches++;
+    }
+    for (int i = 0; i < p; ++i)
+        for (int q = 0; q < P; ++q) {
+            PassIO io = {c->buf[c->psi], nullptr, c->buf[c->psi], nullptr};
+            QR_TRY(launch_pass(c, lp, q, 1, io, d_tab + ((size_t)i * P + q) * GS, 0, -1, 1, stride, 0, c->d_ham, q == 0 ? 1 : 0,
+                               gammas[i], 0, 0.0, nullptr));
+        }
+    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    const int g = grid_for(c, c->N);
+    QR_TRY(ensure_scratch(c, g));
+    QR_TRY(ensure_result(c, 1 + (size_t)p * P * QR_SLOTS + 16));
+    int lam = -1;
+    if (want_grad) { lam = other_buf(c, c->psi); QR_TRY(ensure_buf(c, lam)); }
+    QR_LAUNCH(k_ham_costate, g, QR_BLOCK, 0, c->stream, (const double2*)c->buf[c->psi], want_grad ? c->buf[lam] : (double2*)nullptr,
+              (const double*)c->d_ham, c->N, c->d_scratch);
+    KERNEL_CHECK();
+    QR_LAUNCH(k_reduce_partials, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_scratch, g, 1, c->d_result);
+    KERNEL_CHECK();
+    c->perf.kernel_launches += 2;
+    CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    double* d_slots = c->d_result + 1;
+    int n_bwd_pass = 0;
+    if (want_grad) {
+        for (int i = p - 1; i >= 0; --i)
+            for (int q = 0; q < P; ++q) {
+                PassIO io = {c->buf[c->psi], c->buf[lam], c->buf[c->psi], c->buf[lam]};
+                int units = 0;
+                QR_TRY(launch_pass(c, lp, q, 2, io, d_tab + ((size_t)(p + i) * P + q) * GS, 0, -1, 1, stride, 0, c->d_ham, 0, 0.0,
+                                   q == P - 1 ? 1 : 0, -gammas[i], &units));
+                QR_LAUNCH(k_reduce_partials, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_scratch, units, QR_SLOTS,
+                          d_slots + ((size_t)i * P + q) * QR_SLOTS);
+                KERNEL_CHECK();
+                c->perf.kernel_launches++;
+                ++n_bwd_pass;
+            }
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    const size_t nres = 1 + (want_grad ? (size_t)p * P * QR_SLOTS : 0);
+    QR_TRY(ensure_pin(c, nres * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(c->h_pin, c->d_result, nres * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const double* res = (const double*)c->h_pin;
+    *e_out = res[0];
+    if (want_grad) {
+        for (int i = 0; i < p; ++i) {
+            double gb = 0.0;
+            for (int q = 0; q < P; ++q)
+                for (int s = 0; s < GS; ++s)
+                    if (lp.pass[q].gbit[s] >= 0) gb += res[1 + ((size_t)i * P + q) * QR_SLOTS + s];
+            grad[2 * i] = gb;                                                              // qaoa.py:62-63
+            grad[2 * i + 1] = 2.0 * res[1 + ((size_t)i * P + (P - 1)) * QR_SLOTS + (QR_SLOTS - 1)];   // qaoa.py:67-68
+        }
+        c->psi = lam;
+    }
+    float ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->perf.ms_forward = ms;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->perf.ms_observable = ms;
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->perf.ms_backward = ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); c->perf.ms_total = ms;
+    const double amps = (double)c->N;
+    c->perf.passes_per_layer = P;
+    c->perf.tile_bits = lp.k;
+    c->perf.fwd_pass_bytes = 32.0 * amps;
+    c->perf.bwd_pass_bytes = 64.0 * amps;
+    c->perf.fwd_pass_ms_avg = p ? c->perf.ms_forward / (p * P) : 0.0;
+    c->perf.bwd_pass_ms_avg = n_bwd_pass ? c->perf.ms_backward / n_bwd_pass : 0.0;
+    // H table reads: 8 B/amp in the first forward pass and the last backward pass of every layer
+    c->perf.algorithmic_bytes = amps * (16.0 + (32.0 * P + 8.0) * p + (want_grad ? 40.0 : 24.0) + (want_grad ? (64.0 * P + 8.0) * p : 0.0));
+    return 0;
+}
+
+static int check_qaoa_args(qr_ctx* c, int p, const double* betas, const double* gammas) {
+    QR_TRY(need_ham(c));
+    if (p < 0) return fail(QR_EINVAL, "layer_number must be >= 0");
+    if (p > 0 && (!betas || !gammas)) return fail(QR_EINVAL, "null parameters");
+    return 0;
+}
+
+extern "C" int qr_qaoa_expec(qr_ctx* c, int p, const double* betas, const double* gammas, int use_current_state, double* e_out) {
+    QR_TRY(check_qaoa_args(c, p, betas, gammas));
+    if (!e_out) return fail(QR_EINVAL, "null output");
+    QR_TRY(use_device(c));
+    perf_reset(c);
+    if (use_fused(c)) return qaoa_fused(c, p, betas, gammas, use_current_state, e_out, nullptr);
+    return qaoa_unfused(c, p, betas, gammas, use_current_state, e_out, nullptr);
+}
+
+extern "C" int qr_qaoa_grad(qr_ctx* c, int p, const double* betas, const double* gammas, int use_current_state, double* e_out,
+                            double* grad_out) {
+    QR_TRY(check_qaoa_args(c, p, betas, gammas));
+    if (!e_out || (!grad_out && p > 0)) return fail(QR_EINVAL, "null output");
+    QR_TRY(use_device(c));
+    perf_reset(c);
+    double dummy[2];
+    if (use_fused(c)) return qaoa_fused(c, p, betas, gammas, use_current_state, e_out, grad_out ? grad_out : dummy);
+    return qaoa_unfused(c, p, betas, gammas, use_current_state, e_out, grad_out ? grad_out : dummy);
+}
+
+// ------------------------------------------------------------------------------------------
+// sampling
+// ------------------------------------------------------------------------------------------
+extern "C" int qr_sample_bitstrings(qr_ctx* c, int S, const double* uniforms, int64_t* out_idx) {
+    if (!c) return fail(QR_EINVAL, "null context");
+    if (S < 0 || (S > 0 && (!uniforms || !out_idx))) return fail(QR_EINVAL, "bad sample arguments");
+    if (S == 0) return 0;
+    QR_TRY(use_device(c));
+    const u64 nchunks = (c->N + QR_SCAN_CHUNK - 1) / QR_SCAN_CHUNK;
+    QR_TRY(ensure_scratch(c, nchunks + 2 * (size_t)S + 16));
+    double* d_cdf = c->d_scratch;
+    double* d_u = c->d_scratch + nchunks;
+    i64* d_idx = (i64*)(c->d_scratch + nchunks + S);
+    QR_TRY(ensure_pin(c, (size_t)S * 16));
+    memcpy(c->h_pin, uniforms, (size_t)S * sizeof(double));
+    CUDA_TRY(cudaMemcpyAsync(d_u, c->h_pin, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const int grid = (int)std::min<u64>(nchunks, (u64)c->sm_count * 8);
+    QR_LAUNCH(k_prob_chunk_sums, grid, QR_BLOCK, 0, c->stream, (const double2*)c->buf[c->psi], c->N, d_cdf);
+    KERNEL_CHECK();
+    QR_LAUNCH(k_scan_inclusive_single, 1, 1024, 0, c->stream, d_cdf, nchunks);
+    KERNEL_CHECK();
+    QR_LAUNCH(k_sample_search, S, QR_BLOCK, 0, c->stream, (const double2*)c->buf[c->psi], c->N, (const double*)d_cdf, nchunks,
+              (const double*)d_u, d_idx);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(c->h_pin, d_idx, (size_t)S * sizeof(i64), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(out_idx, c->h_pin, (size_t)S * sizeof(i64));
+    return 0;
+}
+
+extern "C" int qr_ham_gather(qr_ctx* c, int n, const int64_t* idx, double* out) {
+    QR_TRY(need_ham(c));
+    if (n < 0 || (n > 0 && (!idx || !out))) return fail(QR_EINVAL, "bad gather arguments");
+    if (n == 0) return 0;
+    for (int i = 0; i < n; ++i)
+        if (idx[i] < 0 || (u64)idx[i] >= c->N) return fail(QR_EINVAL, "index %lld out of range", (long long)idx[i]);
+    QR_TRY(use_device(c));
+    QR_TRY(ensure_scratch(c, 2 * (size_t)n + 16));
+    QR_TRY(ensure_pin(c, (size_t)n * 16));
+    i64* d_idx = (i64*)c->d_scratch;
+    double* d_out = c->d_scratch + n;
+    memcpy(c->h_pin, idx, (size_t)n * sizeof(i64));
+    CUDA_TRY(cudaMemcpyAsync(d_idx, c->h_pin, (size_t)n * sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+    QR_LAUNCH(k_gather_f64, (n + QR_BLOCK - 1) / QR_BLOCK, QR_BLOCK, 0, c->stream, (const double*)c->d_ham, (const i64*)d_idx, n, d_out);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(c->h_pin, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(out, c->h_pin, (size_t)n * sizeof(double));
+    return 0;
+}
