@@ -3,7 +3,8 @@
     python -m qradient_b200.build            # build if stale
     python -m qradient_b200.build --force
 
-The library is a single translation unit (csrc/qr_lib.cu) and links only libcudart.
+The library is a single translation unit (csrc/qr_lib.cu) with the CUDA runtime linked statically,
+so it loads through ctypes without LD_LIBRARY_PATH and without torch.
 """
 import os
 import shutil
@@ -20,7 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
-    "--cudart", "shared",
+    "--cudart", "static",
 ]
 
 

@@ -1,0 +1,148 @@
+"""GPU-only parity at BASELINE.json sizes: golden config 2, and size-independent properties
+(fused == gate-at-a-time, norm preservation, finite differences, E consistency) where the
+oracle would take too long."""
+import numpy as np
+import pytest
+
+from backends import activate
+from conftest import load_golden, obs_from_golden, assert_parity
+from oracle import qr_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _cuda():
+    activate("cuda")
+    yield
+
+
+def zz01(n):
+    m = np.full((n, n), None)
+    m[0, 1] = 1.0
+    return {"zz": m}
+
+
+def test_config2_mcclean_20x20_golden():
+    """BASELINE config 2 against the reference's own output (tests/golden/gv10)."""
+    from qradient_b200.circuit_logic import McClean
+    d = load_golden("gv10_mcclean_20x20")
+    c = McClean(20, obs_from_golden(d), 20, axes=d["axes"], angles=d["angles"])
+    e, g = c.grad_run()
+    assert_parity(e, g, float(d["E"]), d["grad"], 1.0, 1e-10)
+    assert abs(c.run_expec_val() - float(d["E"])) < 1e-10
+    assert abs(c.state.norm_error()) < 1e-12
+    for opt in (("prefetch", 1), ("tile_bits", 10), ("ctas_per_sm_bwd", 2)):
+        c.state.set_option(*opt)
+        e2, g2 = c.grad_run()
+        assert_parity(e2, g2, float(d["E"]), d["grad"], 1.0, 1e-10)
+
+
+def test_mcclean_16x8_mixed_vs_oracle():
+    from qradient_b200.circuit_logic import McClean
+    n, L = 16, 8
+    rng = np.random.default_rng(16)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    obs = zz01(n)
+    obs["x"] = np.array([0.3] + [None] * (n - 1), dtype=object)
+    obs["y"] = np.array([None] * (n - 1) + [0.7], dtype=object)
+    e_ref, g_ref = orc.mcclean_grad_run(n, obs, axes, angles)
+    c = McClean(n, obs, L, axes=axes, angles=angles)
+    e, g = c.grad_run()
+    assert_parity(e, g, e_ref, g_ref, 2.0, 1e-10)
+
+
+def test_fused_equals_gate_at_a_time_24_qubits():
+    from qradient_b200.circuit_logic import McClean
+    n, L = 24, 3
+    rng = np.random.default_rng(24)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    c = McClean(n, zz01(n), L, axes=axes, angles=angles)
+    e1, g1 = c.grad_run()
+    assert c.perf()["passes_per_layer"] == 3
+    c.state.set_option("fusion", 0)
+    e0, g0 = c.grad_run()
+    assert_parity(e1, g1, e0, g0, 1.0, 1e-11)
+
+
+def test_qaoa_20_qubits_vs_oracle_and_sampling():
+    from qradient_b200.circuit_logic import Qaoa
+    from qradient_b200.optimization_problems import MaxCut
+    n, p = 20, 2
+    edges = MaxCut.random_regular(n, 3, seed=20)
+    rng = np.random.default_rng(10)
+    gammas, betas = rng.random(p), rng.random(p)
+    e_ref, g_ref, psi = orc.qaoa_grad_run(n, orc.maxcut_observable(n, edges), betas, gammas, return_state=True)
+    q = Qaoa(n, MaxCut(n, edge_set=edges).to_observable(), p)
+    e, g = q.grad_run(betas, gammas)
+    assert_parity(e, g, e_ref, g_ref, float(len(edges)), 1e-10)
+    q.run_expec_val(betas, gammas)
+    u = np.random.RandomState(0).uniform(size=100)
+    idx = q.sample_bitstrings(100, u)
+    ref = orc.sample_bitstrings(psi, u)
+    assert np.mean(idx == ref) >= 0.99     # ties within rounding of a cdf step are the only allowed difference
+    cdf = np.cumsum(np.abs(psi) ** 2)
+    for a, b, uu in zip(idx, ref, u):
+        if a != b:
+            assert abs(cdf[min(a, b)] - uu) < 1e-12
+
+
+def test_qaoa_config3_26_qubits_properties():
+    """BASELINE config 3 (26 qubits, p=10): fused == gate-at-a-time on the device, FD on gamma_0/beta_3."""
+    from qradient_b200.circuit_logic import Qaoa
+    from qradient_b200.optimization_problems import MaxCut
+    import bench
+    n, p = 26, 10
+    rng = np.random.default_rng(10)
+    gammas, betas = rng.random(p), rng.random(p)
+    q = Qaoa(n, MaxCut(n, edge_set=bench.CONFIG3_EDGES).to_observable(), p)
+    e, g = q.grad_run(betas, gammas)
+    assert abs(q.run_expec_val(betas, gammas) - e) < 1e-10 * 39
+    assert abs(q.state.norm_error()) < 1e-12
+    eps = 1e-5
+    for (arr, col, k) in ((gammas, 1, 0), (betas, 0, 3)):
+        plus, minus = arr.copy(), arr.copy()
+        plus[k] += eps
+        minus[k] -= eps
+        if col == 1:
+            fd = (q.run_expec_val(betas, plus) - q.run_expec_val(betas, minus)) / (2 * eps)
+        else:
+            fd = (q.run_expec_val(plus, gammas) - q.run_expec_val(minus, gammas)) / (2 * eps)
+        assert abs(fd - g[k, col]) < 1e-6 * 39
+    idx = q.sample_bitstrings(100, np.random.RandomState(0).uniform(size=100))
+    assert idx.min() >= 0 and idx.max() < 2 ** n
+
+
+def test_mcclean_30_qubits_properties():
+    """North-star size (16 GiB state): E consistency, unit norm, finite differences on two angles."""
+    from qradient_b200.circuit_logic import McClean
+    n, L = 30, 2
+    rng = np.random.default_rng(30)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    c = McClean(n, zz01(n), L, axes=axes, angles=angles)
+    e, g = c.grad_run()
+    assert c.perf()["passes_per_layer"] == 3
+    assert abs(c.run_expec_val() - e) < 1e-10
+    assert abs(c.state.norm_error()) < 1e-11
+    eps = 1e-5
+    for (i, q) in ((0, 0), (1, 17)):
+        a = angles.copy()
+        a[i, q] += eps
+        c.angles = a
+        ep = c.run_expec_val()
+        a[i, q] -= 2 * eps
+        c.angles = a
+        em = c.run_expec_val()
+        assert abs((ep - em) / (2 * eps) - g[i, q]) < 1e-7
+
+
+def test_batched_14_qubits_matches_single():
+    from qradient_b200.circuit_logic import McClean
+    n, L, B = 14, 4, 64
+    rng = np.random.default_rng(4)
+    axes, angles = rng.integers(0, 3, (B, L, n)), rng.uniform(0, 2 * np.pi, (B, L, n))
+    c = McClean(n, zz01(n), L, axes=axes[0], angles=angles[0])
+    e, g = c.grad_run_batch(angles, axes)
+    for b in (0, 17, 63):
+        e_ref, g_ref = orc.mcclean_grad_run(n, zz01(n), axes[b], angles[b])
+        assert_parity(e[b], g[b], e_ref, g_ref, 1.0, 1e-10)
