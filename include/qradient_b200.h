@@ -47,7 +47,13 @@ enum {
     QR_OPT_CTAS_PER_SM_FWD = 3,
     QR_OPT_CTAS_PER_SM_BWD = 4,
     QR_OPT_FINAL_LADDER = 5,  /* 1 (default): leave state.vec exactly as mc_clean.py:77 does     */
-    QR_OPT_HAM_LUT = 6        /* 1 (default): integer-valued diagonal Hamiltonians use a phase LUT */
+    QR_OPT_HAM_LUT = 6,       /* 1 (default): integer-valued diagonal Hamiltonians use a phase LUT */
+    QR_OPT_REG_BITS_FWD = 7,  /* index bits per round held in registers, forward pass: 3 or 4     */
+    QR_OPT_REG_BITS_BWD = 8,  /* same for the backward pass                                        */
+    QR_OPT_ASYNC_FWD = 9,     /* 1: stage forward tiles with bulk async copies (TMA) + mbarrier    */
+    QR_OPT_ASYNC_BWD = 10,    /* same for the backward pass                                        */
+    QR_OPT_TILE_BITS_STRIDED = 11, /* tile bits of the strided (non-first) passes; 0 = same as first */
+    QR_OPT_MIN_ROW_BITS = 12  /* log2 of the minimum contiguous run (amplitudes) in strided passes */
 };
 
 typedef struct qr_perf {

@@ -57,11 +57,11 @@ struct qr_obs {
 struct PassPlan {
     int k, c, h, nrounds;
     int g[QR_MAXROUNDS];
-    int gbit[QR_MAXROUNDS * QR_R];   // global index bit handled by (round, register bit) or -1
+    int gbit[QR_GATE_SLOTS];   // global index bit handled by slot (round * R + register bit) or -1
 };
 
 struct LayerPlan {
-    int n, k, npasses;
+    int n, k, R, npasses;
     PassPlan pass[16];
 };
 
@@ -90,6 +90,9 @@ struct qr_ctx {
     // options
     long long opt_fusion = 1, opt_tile_bits = QR_MAX_TILE_BITS, opt_prefetch = 0;
     long long opt_ctas_fwd = 2, opt_ctas_bwd = 1, opt_final_ladder = 1, opt_ham_lut = 1;
+    long long opt_r_fwd = 3, opt_r_bwd = 3;
+    long long opt_async_fwd = 0, opt_async_bwd = 0;
+    long long opt_tile_bits_x = 0, opt_min_row_bits = 3;
     qr_perf perf;
 };
 
@@ -244,13 +247,19 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
     switch (key) {
         case QR_OPT_FUSION: c->opt_fusion = v ? 1 : 0; break;
         case QR_OPT_TILE_BITS:
-            if (v < QR_R || v > QR_MAX_TILE_BITS) return fail(QR_EINVAL, "tile bits must be in [%d, %d]", QR_R, QR_MAX_TILE_BITS);
+            if (v < 4 || v > QR_MAX_TILE_BITS) return fail(QR_EINVAL, "tile bits must be in [4, %d]", QR_MAX_TILE_BITS);
             c->opt_tile_bits = v; break;
         case QR_OPT_PREFETCH: c->opt_prefetch = v ? 1 : 0; break;
         case QR_OPT_CTAS_PER_SM_FWD: if (v < 1 || v > 8) return fail(QR_EINVAL, "bad CTAs/SM"); c->opt_ctas_fwd = v; break;
         case QR_OPT_CTAS_PER_SM_BWD: if (v < 1 || v > 8) return fail(QR_EINVAL, "bad CTAs/SM"); c->opt_ctas_bwd = v; break;
         case QR_OPT_FINAL_LADDER: c->opt_final_ladder = v ? 1 : 0; break;
         case QR_OPT_HAM_LUT: c->opt_ham_lut = v ? 1 : 0; break;
+        case QR_OPT_REG_BITS_FWD: if (v != 3 && v != 4) return fail(QR_EINVAL, "register bits must be 3 or 4"); c->opt_r_fwd = v; break;
+        case QR_OPT_REG_BITS_BWD: if (v != 3 && v != 4) return fail(QR_EINVAL, "register bits must be 3 or 4"); c->opt_r_bwd = v; break;
+        case QR_OPT_ASYNC_FWD: c->opt_async_fwd = v ? 1 : 0; break;
+        case QR_OPT_ASYNC_BWD: c->opt_async_bwd = v ? 1 : 0; break;
+        case QR_OPT_TILE_BITS_STRIDED: if (v != 0 && (v < 4 || v > QR_MAX_TILE_BITS)) return fail(QR_EINVAL, "bad strided tile bits"); c->opt_tile_bits_x = v; break;
+        case QR_OPT_MIN_ROW_BITS: if (v < 1 || v > 6) return fail(QR_EINVAL, "bad min row bits"); c->opt_min_row_bits = v; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -266,6 +275,12 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_CTAS_PER_SM_BWD: *v = c->opt_ctas_bwd; break;
         case QR_OPT_FINAL_LADDER: *v = c->opt_final_ladder; break;
         case QR_OPT_HAM_LUT: *v = c->opt_ham_lut; break;
+        case QR_OPT_REG_BITS_FWD: *v = c->opt_r_fwd; break;
+        case QR_OPT_REG_BITS_BWD: *v = c->opt_r_bwd; break;
+        case QR_OPT_ASYNC_FWD: *v = c->opt_async_fwd; break;
+        case QR_OPT_ASYNC_BWD: *v = c->opt_async_bwd; break;
+        case QR_OPT_TILE_BITS_STRIDED: *v = c->opt_tile_bits_x; break;
+        case QR_OPT_MIN_ROW_BITS: *v = c->opt_min_row_bits; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -669,50 +684,57 @@ extern "C" int qr_apply_ham(qr_ctx* c, int mode) {
 // Rounds of a pass whose gate bits are the local bits [first, k): the top group first (its
 // threads' lanes cover the lowest local bits -> coalesced global loads), then ascending groups;
 // every gate bit is assigned to the first group that covers it.
-static void plan_rounds(PassPlan& pp, int first) {
+static void plan_rounds(PassPlan& pp, int first, int R) {
     const int k = pp.k;
     int assigned[QR_MAX_TILE_BITS];
     for (int i = 0; i < QR_MAX_TILE_BITS; ++i) assigned[i] = -1;
     int nr = 0;
-    const int top = std::max(k - QR_R, 0);
+    const int top = std::max(k - R, 0);
     pp.g[nr++] = top;
-    for (int g = first; g < top; g += QR_R) pp.g[nr++] = g;
+    for (int g = first; g < top && nr < QR_MAXROUNDS + 4; g += R) {
+        if (nr < QR_MAXROUNDS) pp.g[nr] = g;
+        ++nr;
+    }
     pp.nrounds = nr;
-    for (int i = 0; i < QR_MAXROUNDS * QR_R; ++i) pp.gbit[i] = -1;
-    for (int r = 0; r < nr; ++r)
-        for (int b = 0; b < QR_R; ++b) {
+    for (int i = 0; i < QR_GATE_SLOTS; ++i) pp.gbit[i] = -1;
+    for (int r = 0; r < std::min(nr, QR_MAXROUNDS); ++r)
+        for (int b = 0; b < R; ++b) {
             const int lb = pp.g[r] + b;
             if (lb < first || lb >= k || assigned[lb] >= 0) continue;
             assigned[lb] = r;
-            pp.gbit[r * QR_R + b] = lb < pp.c ? lb : pp.h + (lb - pp.c);
+            pp.gbit[r * R + b] = lb < pp.c ? lb : pp.h + (lb - pp.c);
         }
 }
 
-static int make_plan(int n, int tile_bits, LayerPlan* lp) {
-    if (n < QR_R) return fail(QR_EINVAL, "fused path needs at least %d qubits", QR_R);
+static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x = 0, int min_row_bits = 3) {
+    if (n < 4) return fail(QR_EINVAL, "fused path needs at least 4 qubits");
     const int k = std::min(n, tile_bits);
     lp->n = n;
     lp->k = k;
+    lp->R = R;
     int np = 0;
     PassPlan& p0 = lp->pass[np++];
     p0.k = k; p0.c = k; p0.h = k;
-    plan_rounds(p0, 0);
+    plan_rounds(p0, 0, R);
     const int rem = n - k;
     if (rem > 0) {
-        const int umax = std::max(k - 3, 1);
+        // strided passes: tile of kx bits = c contiguous low bits (rows of 2^c amplitudes) + m gate bits
+        const int kx = std::min(k, tile_bits_x > 0 ? tile_bits_x : k);
+        const int umax = std::max(kx - std::min(min_row_bits, kx - 1), 1);
         const int nx = (rem + umax - 1) / umax;
         int h = k;
         for (int i = 0; i < nx; ++i) {
             const int m = rem / nx + (i < rem % nx ? 1 : 0);
             PassPlan& pp = lp->pass[np++];
-            pp.k = k; pp.c = k - m; pp.h = h;
-            plan_rounds(pp, pp.c);
+            pp.k = kx; pp.c = kx - m; pp.h = h;
+            plan_rounds(pp, pp.c, R);
             h += m;
         }
     }
     lp->npasses = np;
     for (int i = 0; i < np; ++i)
-        if (lp->pass[i].nrounds > QR_MAXROUNDS) return fail(QR_EINVAL, "internal: pass needs %d rounds", lp->pass[i].nrounds);
+        if (lp->pass[i].nrounds > QR_MAXROUNDS || lp->pass[i].nrounds * R > QR_GATE_SLOTS)
+            return fail(QR_EINVAL, "internal: pass needs %d rounds", lp->pass[i].nrounds);
     return 0;
 }
 
@@ -720,7 +742,7 @@ static int make_plan(int n, int tile_bits, LayerPlan* lp) {
 template <class F>
 static void fill_gates(const LayerPlan& lp, int pass, GateP* out, F gate_of_qubit) {
     const PassPlan& pp = lp.pass[pass];
-    for (int i = 0; i < QR_MAXROUNDS * QR_R; ++i) {
+    for (int i = 0; i < QR_GATE_SLOTS; ++i) {
         GateP g;
         g.c = 1.0; g.s = 0.0; g.axis = -1; g.pad = 0;
         if (pp.gbit[i] >= 0) g = gate_of_qubit(lp.n - 1 - pp.gbit[i]);
@@ -730,9 +752,13 @@ static void fill_gates(const LayerPlan& lp, int pass, GateP* out, F gate_of_qubi
 
 typedef void (*tile_fn)(const TilePass);
 
-static tile_fn tile_kernel(int nv, int nr) {
-    if (nv == 1) return nr == 1 ? k_tile_pass<1, 1> : nr == 2 ? k_tile_pass<1, 2> : k_tile_pass<1, 3>;
-    return nr == 1 ? k_tile_pass<2, 1> : nr == 2 ? k_tile_pass<2, 2> : k_tile_pass<2, 3>;
+static tile_fn tile_kernel(int nv, int R, int async) {
+    if (async) {
+        if (nv == 1) return R == 3 ? k_tile_pass<1, 3, true> : k_tile_pass<1, 4, true>;
+        return R == 3 ? k_tile_pass<2, 3, true> : k_tile_pass<2, 4, true>;
+    }
+    if (nv == 1) return R == 3 ? k_tile_pass<1, 3, false> : k_tile_pass<1, 4, false>;
+    return R == 3 ? k_tile_pass<2, 3, false> : k_tile_pass<2, 4, false>;
 }
 
 struct PassIO {
@@ -763,21 +789,26 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
     tp.angle_pre = angle_pre; tp.angle_post = angle_post;
     tp.flush_per_tile = flush_per_tile;
     tp.prefetch = (int)c->opt_prefetch;
-    const int threads = 1 << (pp.k - QR_R);
-    const long long per_sm = std::min<long long>(16, (nv == 1 ? c->opt_ctas_fwd : c->opt_ctas_bwd) * std::max(1, 256 / threads));
+    const int R = lp.R;
+    const int async = (nv == 1 ? c->opt_async_fwd : c->opt_async_bwd) ? 1 : 0;
+    const int threads = 1 << (pp.k - R);
+    const int full = 1 << (QR_MAX_TILE_BITS - R);
+    const long long ctas = async ? 1 : (nv == 1 ? c->opt_ctas_fwd : c->opt_ctas_bwd);
+    const long long per_sm = std::min<long long>(16, ctas * std::max(1, full / threads));
     const i64 grid = std::min<i64>(tp.num_tiles, (i64)c->sm_count * per_sm);
-    const size_t smem = pp.nrounds > 1 ? (size_t)nv * sizeof(double2) << pp.k : 0;
+    const size_t tile_bytes = sizeof(double2) << pp.k;
+    const size_t smem = async ? (size_t)(nv + 1) * tile_bytes : (pp.nrounds > 1 ? (size_t)nv * tile_bytes : 0);
     if (nv == 2) {
         const i64 nunits = flush_per_tile ? tp.num_tiles : grid;
         QR_TRY(ensure_scratch(c, (size_t)nunits * QR_SLOTS));
         *units = (int)nunits;
     }
     tp.partials = c->d_scratch;
-    tile_fn fn = tile_kernel(nv, pp.nrounds);
-    static bool attr_done[2][QR_MAXROUNDS + 1] = {{false}};
-    if (!attr_done[nv - 1][pp.nrounds]) {
-        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(double2) << QR_MAX_TILE_BITS));
-        attr_done[nv - 1][pp.nrounds] = true;
+    tile_fn fn = tile_kernel(nv, R, async);
+    static bool attr_done[2][5][2] = {{{false}}};
+    if (!attr_done[nv - 1][R][async]) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (int)sizeof(double2) << QR_MAX_TILE_BITS));
+        attr_done[nv - 1][R][async] = true;
     }
     QR_LAUNCH(fn, (unsigned)grid, threads, smem, c->stream, tp);
     KERNEL_CHECK();
@@ -882,10 +913,11 @@ struct GradLayout {   // where the per-(layer, pass) slot sums land in d_result
 static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const double* angles, const qr_obs* o,
                          int use_current, double* e_out, double* grad) {
     const int n = c->n;
-    LayerPlan lp;
-    QR_TRY(make_plan(n, (int)c->opt_tile_bits, &lp));
+    LayerPlan lpf, lp;   // forward / backward plans: same tile geometry, different register blocking
+    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits));
+    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits));
     const int P = lp.npasses;
-    const int GS = QR_MAXROUNDS * QR_R;           // gate entries per (layer, pass)
+    const int GS = QR_GATE_SLOTS;                 // gate entries per (layer, pass)
     const bool want_grad = grad != nullptr;
     const bool ry_layer = use_current != 0;       // ini_state given: apply the Ry(pi/4) layer as gates
     // ---- gate tables: [batch][ (ry layer) + L forward + L backward ][P][GS] ----
@@ -904,7 +936,7 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
             if (ry_layer) {
                 const double cs = std::cos(M_PI / 8.0), sn = std::sin(M_PI / 8.0);
                 for (int p = 0; p < P; ++p)
-                    fill_gates(lp, p, tb + ((size_t)lay * P + p) * GS, [&](int) { GateP g; g.c = cs; g.s = sn; g.axis = 1; g.pad = 0; return g; });
+                    fill_gates(lpf, p, tb + ((size_t)lay * P + p) * GS, [&](int) { GateP g; g.c = cs; g.s = sn; g.axis = 1; g.pad = 0; return g; });
                 ++lay;
             }
             for (int dir = 0; dir < (want_grad ? 2 : 1); ++dir)
@@ -913,7 +945,7 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
                     const double* an = angles + ((size_t)b * L + i) * n;
                     const double sgn = dir == 0 ? 1.0 : -1.0;
                     for (int p = 0; p < P; ++p)
-                        fill_gates(lp, p, tb + ((size_t)lay * P + p) * GS, [&](int q) {
+                        fill_gates(dir == 0 ? lpf : lp, p, tb + ((size_t)lay * P + p) * GS, [&](int q) {
                             GateP g; g.c = std::cos(0.5 * an[q]); g.s = sgn * std::sin(0.5 * an[q]); g.axis = ax[q]; g.pad = 0; return g; });
                 }
         }
@@ -944,7 +976,7 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     } else {
         for (int p = 0; p < P; ++p) {
             PassIO io = {c->buf[c->psi], nullptr, c->buf[c->psi], nullptr};
-            QR_TRY(launch_pass(c, lp, p, 1, io, d_tab + ((size_t)lay * P + p) * GS, gate_stride, -1, batch, stride, 0,
+            QR_TRY(launch_pass(c, lpf, p, 1, io, d_tab + ((size_t)lay * P + p) * GS, gate_stride, -1, batch, stride, 0,
                                nullptr, 0, 0, 0, 0, nullptr));
         }
         ++lay;
@@ -955,7 +987,7 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
             int lad = -1;
             if (p == 0 && n >= 2) { dst = other_buf(c, c->psi); QR_TRY(ensure_buf(c, dst)); lad = 0; }
             PassIO io = {c->buf[c->psi], nullptr, c->buf[dst], nullptr};
-            QR_TRY(launch_pass(c, lp, p, 1, io, d_tab + ((size_t)lay * P + p) * GS, gate_stride, lad, batch, stride, 0,
+            QR_TRY(launch_pass(c, lpf, p, 1, io, d_tab + ((size_t)lay * P + p) * GS, gate_stride, lad, batch, stride, 0,
                                nullptr, 0, 0, 0, 0, nullptr));
             c->psi = dst;
         }
@@ -1011,7 +1043,7 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
                     QR_LAUNCH(k_reduce_partials, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_scratch, units, QR_SLOTS,
                               d_slots + ((size_t)i * P + p) * QR_SLOTS);
                 } else {
-                    const int tiles_per_state = 1 << (n - lp.k);
+                    const int tiles_per_state = 1 << (n - lp.pass[p].k);
                     QR_LAUNCH(k_reduce_partials_grouped, (unsigned)batch, 32, 0, c->stream, (const double*)c->d_scratch,
                               tiles_per_state, QR_SLOTS, d_slots + ((size_t)i * P + p) * QR_SLOTS, slots_per_state);
                 }
@@ -1067,7 +1099,7 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     return 0;
 }
 
-static bool use_fused(qr_ctx* c) { return c->opt_fusion && c->n >= QR_R; }
+static bool use_fused(qr_ctx* c) { return c->opt_fusion && c->n >= 4; }
 
 extern "C" int qr_mcclean_expec(qr_ctx* c, int L, const int32_t* axes, const double* angles, const qr_obs* o,
                                 int use_current_state, double* e_out) {
@@ -1095,7 +1127,7 @@ extern "C" int qr_mcclean_grad_batch(qr_ctx* c, int batch, int L, const int32_t*
     QR_TRY(check_obs(c, o));
     if (batch < 1) return fail(QR_EINVAL, "batch must be >= 1");
     if (!axes || !angles || !e_out || !grad_out) return fail(QR_EINVAL, "null argument");
-    if (c->n < QR_R) return fail(QR_EINVAL, "batched path needs at least %d qubits", QR_R);
+    if (c->n < 4) return fail(QR_EINVAL, "batched path needs at least 4 qubits");
     for (i64 i = 0; i < (i64)batch * L * c->n; ++i)
         if (axes[i] < 0 || axes[i] > 2) return fail(QR_EINVAL, "Invalid axis %d", axes[i]);
     QR_TRY(use_device(c));
@@ -1192,10 +1224,11 @@ static int qaoa_unfused(qr_ctx* c, int p, const double* betas, const double* gam
 static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gammas, int use_current, double* e_out,
                       double* grad) {
     const int n = c->n;
-    LayerPlan lp;
-    QR_TRY(make_plan(n, (int)c->opt_tile_bits, &lp));
+    LayerPlan lpf, lp;
+    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits));
+    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits));
     const int P = lp.npasses;
-    const int GS = QR_MAXROUNDS * QR_R;
+    const int GS = QR_GATE_SLOTS;
     const bool want_grad = grad != nullptr;
     const int nlay_tab = p * (want_grad ? 2 : 1);
     const size_t tab_bytes = (size_t)nlay_tab * P * GS * sizeof(GateP);
@@ -1208,7 +1241,7 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
             for (int i = 0; i < p; ++i, ++lay) {
                 const double cs = std::cos(0.5 * betas[i]), sn = (dir == 0 ? 1.0 : -1.0) * std::sin(0.5 * betas[i]);
                 for (int q = 0; q < P; ++q)
-                    fill_gates(lp, q, tab + ((size_t)lay * P + q) * GS, [&](int) { GateP g; g.c = cs; g.s = sn; g.axis = 0; g.pad = 0; return g; });
+                    fill_gates(dir == 0 ? lpf : lp, q, tab + ((size_t)lay * P + q) * GS, [&](int) { GateP g; g.c = cs; g.s = sn; g.axis = 0; g.pad = 0; return g; });
             }
         CUDA_TRY(cudaMemcpyAsync(c->d_small, tab, tab_bytes, cudaMemcpyHostToDevice, c->stream));
     }
@@ -1223,7 +1256,7 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
     for (int i = 0; i < p; ++i)
         for (int q = 0; q < P; ++q) {
             PassIO io = {c->buf[c->psi], nullptr, c->buf[c->psi], nullptr};
-            QR_TRY(launch_pass(c, lp, q, 1, io, d_tab + ((size_t)i * P + q) * GS, 0, -1, 1, stride, 0, c->d_ham, q == 0 ? 1 : 0,
+            QR_TRY(launch_pass(c, lpf, q, 1, io, d_tab + ((size_t)i * P + q) * GS, 0, -1, 1, stride, 0, c->d_ham, q == 0 ? 1 : 0,
                                gammas[i], 0, 0.0, nullptr));
         }
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));

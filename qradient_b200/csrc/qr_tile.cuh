@@ -29,10 +29,9 @@
 #pragma once
 #include "qr_platform.cuh"
 
-#define QR_R 4                       // index bits held in registers per round
-#define QR_RA (1 << QR_R)            // amplitudes per thread per vector
-#define QR_MAXROUNDS 3
-#define QR_SLOTS (QR_MAXROUNDS * QR_R + 1)   // gradient accumulators per thread (+1: diagonal generator)
+#define QR_MAXROUNDS 4
+#define QR_GATE_SLOTS 12                      // gate bits per pass (= QR_MAX_TILE_BITS)
+#define QR_SLOTS (QR_GATE_SLOTS + 1)          // gradient accumulators per thread (+1: diagonal generator)
 #define QR_MAX_TILE_BITS 12
 
 struct GateP {
@@ -54,7 +53,7 @@ struct TilePass {
     const double2* src1;         // lambda in (NV == 2)
     double2* dst0;
     double2* dst1;
-    const GateP* gates;          // [batch][nrounds * QR_R]
+    const GateP* gates;          // [batch][nrounds * R]
     int gate_stride;
     const double* ham;           // diagonal Hamiltonian table (QAOA) or null
     int pre_phase, post_phase;   // multiply by exp(-i angle H) after load / before store
@@ -64,14 +63,16 @@ struct TilePass {
     int prefetch;
 };
 
-__device__ __forceinline__ int qr_swz(int l) { return l ^ ((l >> QR_R) & 7); }
+template <int R>
+__device__ __forceinline__ int qr_swz(int l) { return l ^ ((l >> R) & 7); }
 
-template <int NV, int BIT>
-__device__ __forceinline__ void qr_gate_on_bit(double2 (&a)[NV][QR_RA], const GateP gp, double& acc) {
+// one single-qubit rotation (and, for NV == 2, its gradient inner product) on register bit BIT
+template <int NV, int NA, int BIT>
+__device__ __forceinline__ void qr_gate_on_bit(double2 (&a)[NV][NA], const GateP gp, double& acc) {
     const double c = gp.c, s = gp.s;
     if (gp.axis == 0) {
 #pragma unroll
-        for (int r = 0; r < QR_RA; ++r) {
+        for (int r = 0; r < NA; ++r) {
             if (r & (1 << BIT)) continue;
             const int r1 = r | (1 << BIT);
             if (NV == 2) acc += im_conj_mul(a[NV - 1][r], a[0][r1]) + im_conj_mul(a[NV - 1][r1], a[0][r]);
@@ -84,7 +85,7 @@ __device__ __forceinline__ void qr_gate_on_bit(double2 (&a)[NV][QR_RA], const Ga
         }
     } else if (gp.axis == 1) {
 #pragma unroll
-        for (int r = 0; r < QR_RA; ++r) {
+        for (int r = 0; r < NA; ++r) {
             if (r & (1 << BIT)) continue;
             const int r1 = r | (1 << BIT);
             if (NV == 2) acc += re_conj_mul(a[NV - 1][r1], a[0][r]) - re_conj_mul(a[NV - 1][r], a[0][r1]);
@@ -97,7 +98,7 @@ __device__ __forceinline__ void qr_gate_on_bit(double2 (&a)[NV][QR_RA], const Ga
         }
     } else if (gp.axis == 2) {
 #pragma unroll
-        for (int r = 0; r < QR_RA; ++r) {
+        for (int r = 0; r < NA; ++r) {
             if (r & (1 << BIT)) continue;
             const int r1 = r | (1 << BIT);
             if (NV == 2) acc += im_conj_mul(a[NV - 1][r], a[0][r]) - im_conj_mul(a[NV - 1][r1], a[0][r1]);
@@ -111,70 +112,163 @@ __device__ __forceinline__ void qr_gate_on_bit(double2 (&a)[NV][QR_RA], const Ga
     }
 }
 
-template <int NV>
-__device__ __forceinline__ void qr_round_compute(double2 (&a)[NV][QR_RA], const GateP* __restrict__ gt, double* acc) {
-    qr_gate_on_bit<NV, 0>(a, gt[0], acc[0]);
-    qr_gate_on_bit<NV, 1>(a, gt[1], acc[1]);
-    qr_gate_on_bit<NV, 2>(a, gt[2], acc[2]);
-    qr_gate_on_bit<NV, 3>(a, gt[3], acc[3]);
+template <int NV, int R>
+__device__ __forceinline__ void qr_round_compute(double2 (&a)[NV][1 << R], const GateP* gt, double* acc) {
+    qr_gate_on_bit<NV, (1 << R), 0>(a, gt[0], acc[0]);
+    qr_gate_on_bit<NV, (1 << R), 1>(a, gt[1], acc[1]);
+    qr_gate_on_bit<NV, (1 << R), 2>(a, gt[2], acc[2]);
+    if (R > 3) qr_gate_on_bit<NV, (1 << R), (R > 3 ? 3 : 0)>(a, gt[R > 3 ? 3 : 0], acc[R > 3 ? 3 : 0]);
 }
 
-template <int NV, int NR>
-__global__ void __launch_bounds__(256, (NV == 1 ? 2 : 1)) k_tile_pass(const TilePass p) {
+// ---- async bulk-copy (TMA) + mbarrier helpers ------------------------------------------------
+// Product build: cp.async.bulk (UBLKCP in SASS) completing on an mbarrier.  Emulation build: the
+// copy is a synchronous memcpy, so a missing barrier shows up as wrong data rather than a hang.
+#ifndef QR_HOST_EMUL
+__device__ __forceinline__ unsigned qr_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void qr_mbar_init(u64* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(qr_smem_addr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void qr_mbar_expect_tx(u64* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(qr_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void qr_mbar_wait(u64* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(qr_smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void qr_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     qr_smem_addr(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(qr_smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void qr_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#else
+__device__ __forceinline__ void qr_mbar_init(u64*, int) {}
+__device__ __forceinline__ void qr_mbar_expect_tx(u64*, unsigned) {}
+__device__ __forceinline__ void qr_mbar_wait(u64*, unsigned) { __syncthreads(); }   // all issuing threads have copied
+__device__ __forceinline__ void qr_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, u64*) { memcpy(smem_dst, gsrc, bytes); }
+__device__ __forceinline__ void qr_fence_proxy_async() {}
+#endif
+
+// R = index bits per round held in registers (2^R amplitudes per thread per vector);
+// threads per tile = 2^(k-R).  The round loop is a run-time loop so the code stays inside the
+// instruction cache; per-round accumulators are folded into a small per-thread array.
+//
+// ASYNC = true: the tile is staged through shared memory by bulk async copies (one 64 KiB copy per
+// vector for contiguous tiles, one copy per >=128 B row otherwise) that complete on an mbarrier,
+// and the copies for the CTA's NEXT tile are issued as soon as the current tile has been read
+// into registers, so HBM reads overlap the gate arithmetic.  Shared memory: NV raw tiles + one
+// exchange tile (the vectors take turns in the exchange buffer) = 192 KiB for the backward pass.
+template <int NV, int R, bool ASYNC>
+__global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASYNC) ? 2 : 1)) k_tile_pass(const TilePass p) {
+    constexpr int RA = 1 << R;
     QR_DYN_SMEM(double2, smem);
+    __shared__ u64 full_bar;
+    __shared__ GateP sgt[QR_GATE_SLOTS];    // this pass's gate table (a dependent global load per gate
+                                            // would put an L2 round trip on every tile's critical path)
     const int tid = threadIdx.x;
     const int T = 1 << p.k;
-    double acc[QR_SLOTS];
+    double2* exch = ASYNC ? smem + NV * T : smem;   // ASYNC: [raw psi][raw lambda][exchange]
+    double acc_all[QR_SLOTS];
 #pragma unroll
-    for (int i = 0; i < QR_SLOTS; ++i) acc[i] = 0.0;
-    int tb[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        const int g = p.g[r];
-        tb[r] = (tid & ((1 << g) - 1)) | ((tid >> g) << (g + QR_R));
-    }
+    for (int i = 0; i < QR_SLOTS; ++i) acc_all[i] = 0.0;
     const int c = p.c, h = p.h;
     const int lomask = (1 << c) - 1;
     const int nlo = h - c;
     const u64 tmask = ((u64)1 << p.tiles_log2) - 1;
+    const int nrounds = p.nrounds;
+    const int g_first = p.g[0], g_last = p.g[nrounds - 1];
+    const int tb_first = (tid & ((1 << g_first) - 1)) | ((tid >> g_first) << (g_first + R));
+    const int tb_last = (tid & ((1 << g_last) - 1)) | ((tid >> g_last) << (g_last + R));
+    const int nrows = 1 << (p.k - c);            // rows of 2^c contiguous amplitudes per tile
+    const unsigned row_bytes = (unsigned)sizeof(double2) << c;
+
+    // issue the bulk copies of tile `tl` into the raw buffers
+    auto issue_tile = [&](i64 tl) {
+        const i64 nb = tl >> p.tiles_log2;
+        const u64 t2 = (u64)tl & tmask;
+        u64 nbase = ((t2 & (((u64)1 << nlo) - 1)) << c) | ((t2 >> nlo) << (h + p.k - c));
+        if (p.ladder) nbase = ladder_map(nbase, p.M1, p.M2) & ~(u64)(T - 1);
+        if (tid == 0) qr_mbar_expect_tx(&full_bar, (unsigned)(NV * T * sizeof(double2)));
+        for (int r = tid; r < nrows; r += blockDim.x) {
+            const u64 src = nbase | ((u64)r << h);
+            qr_bulk_load(smem + ((size_t)r << c), p.src0 + nb * p.state_stride + src, row_bytes, &full_bar);
+            if (NV == 2) qr_bulk_load(smem + T + ((size_t)r << c), p.src1 + nb * p.state_stride + src, row_bytes, &full_bar);
+        }
+    };
+    if (ASYNC) {
+        if (tid == 0) qr_mbar_init(&full_bar, 1);
+        __syncthreads();
+        if ((i64)blockIdx.x < p.num_tiles) issue_tile(blockIdx.x);
+    }
+    unsigned parity = 0;
+    i64 cur_b = -1;
 
     for (i64 tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const i64 b = tile >> p.tiles_log2;
         const u64 t = (u64)tile & tmask;
         const u64 tbase = ((t & (((u64)1 << nlo) - 1)) << c) | ((t >> nlo) << (h + p.k - c));
-        const GateP* __restrict__ gt = p.gates + b * p.gate_stride;
+        if (b != cur_b) {   // block-uniform: (re)load the gate table of this batch element
+            __syncthreads();
+            for (int i = tid; i < QR_GATE_SLOTS; i += blockDim.x) sgt[i] = p.gates[b * p.gate_stride + i];
+            __syncthreads();
+            cur_b = b;
+        }
+        const GateP* gt = sgt;
         const double2* __restrict__ s0 = p.src0 + b * p.state_stride;
         const double2* __restrict__ s1 = (NV == 2) ? p.src1 + b * p.state_stride : nullptr;
         double2* __restrict__ d0 = p.dst0 + b * p.state_stride;
         double2* __restrict__ d1 = (NV == 2) ? p.dst1 + b * p.state_stride : nullptr;
 
-        double2 a[NV][QR_RA];
-        // ---- round 0: global -> registers (ladder gather and QAOA phase folded in) ----
-        {
-            const int g = p.g[0];
+        double2 a[NV][RA];
+        if (ASYNC) {
+            // ---- raw shared tile -> registers (ladder permutation applied to the read index) ----
+            const int off = p.ladder ? (int)(ladder_map(tbase, p.M1, p.M2) & (u64)(T - 1)) : 0;
+            qr_mbar_wait(&full_bar, parity);
+            parity ^= 1u;
 #pragma unroll
-            for (int r = 0; r < QR_RA; ++r) {
-                const int l = tb[0] | (r << g);
+            for (int r = 0; r < RA; ++r) {
+                const int l = tb_first | (r << g_first);
+                const int sl = p.ladder ? (((int)ladder_map((u64)l, p.M1, p.M2) ^ off) & (T - 1)) : l;
+                a[0][r] = smem[sl];
+                if (NV == 2) a[NV - 1][r] = smem[T + sl];
+            }
+            __syncthreads();                       // every thread has consumed the raw tile
+            const i64 nt = tile + gridDim.x;
+            if (nt < p.num_tiles) issue_tile(nt);  // next tile streams in while this one is computed
+        } else {
+            // ---- global -> registers (ladder gather folded into the load addresses) ----
+#pragma unroll
+            for (int r = 0; r < RA; ++r) {
+                const int l = tb_first | (r << g_first);
                 const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
                 const u64 s = p.ladder ? ladder_map(d, p.M1, p.M2) : d;
                 a[0][r] = s0[s];
                 if (NV == 2) a[NV - 1][r] = s1[s];
             }
-            if (p.pre_phase) {
+        }
+        if (p.pre_phase) {
 #pragma unroll
-                for (int r = 0; r < QR_RA; ++r) {
-                    const int l = tb[0] | (r << g);
-                    const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
-                    double sn, cs;
-                    sincos(p.angle_pre * p.ham[d], &sn, &cs);
-                    const double2 ph = make_double2(cs, -sn);
+            for (int r = 0; r < RA; ++r) {
+                const int l = tb_first | (r << g_first);
+                const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
+                double sn, cs;
+                sincos(p.angle_pre * p.ham[d], &sn, &cs);
+                const double2 ph = make_double2(cs, -sn);
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) a[v][r] = cmul(a[v][r], ph);
-                }
+                for (int v = 0; v < NV; ++v) a[v][r] = cmul(a[v][r], ph);
             }
         }
 #ifndef QR_HOST_EMUL
-        if (p.prefetch) {   // pull the next tile of this CTA into L2 while this one is computed
+        if (!ASYNC && p.prefetch) {   // pull the next tile of this CTA into L2 while this one is computed
             const i64 nt = tile + gridDim.x;
             if (nt < p.num_tiles) {
                 const i64 nb = nt >> p.tiles_log2;
@@ -190,60 +284,82 @@ __global__ void __launch_bounds__(256, (NV == 1 ? 2 : 1)) k_tile_pass(const Tile
             }
         }
 #endif
-        qr_round_compute<NV>(a, gt, acc);
-        // ---- rounds 1..NR-1: exchange through swizzled shared memory ----
+        // ---- rounds: gates in registers, exchange through swizzled shared memory ----
+#pragma unroll 1
+        for (int rd = 0; rd < nrounds; ++rd) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            qr_round_compute<NV, R>(a, gt + rd * R, acc);
+            if (NV == 2) {   // static indices keep the accumulators in registers
 #pragma unroll
-        for (int rd = 1; rd < NR; ++rd) {
-            const int gp = p.g[rd - 1], gn = p.g[rd];
+                for (int rr = 0; rr < QR_MAXROUNDS; ++rr)
+                    if (rr == rd) {
 #pragma unroll
-            for (int r = 0; r < QR_RA; ++r) {
-                const int l = qr_swz(tb[rd - 1] | (r << gp));
-#pragma unroll
-                for (int v = 0; v < NV; ++v) smem[v * T + l] = a[v][r];
+                        for (int i = 0; i < R; ++i)
+                            if (rr * R + i < QR_GATE_SLOTS) acc_all[rr * R + i] += acc[i];
+                    }
             }
-            __syncthreads();
+            if (rd + 1 < nrounds) {
+                const int gp = p.g[rd], gn = p.g[rd + 1];
+                const int tbp = (tid & ((1 << gp) - 1)) | ((tid >> gp) << (gp + R));
+                const int tbn = (tid & ((1 << gn) - 1)) | ((tid >> gn) << (gn + R));
+                if (ASYNC) {   // one exchange tile: the vectors take turns
 #pragma unroll
-            for (int r = 0; r < QR_RA; ++r) {
-                const int l = qr_swz(tb[rd] | (r << gn));
+                    for (int v = 0; v < NV; ++v) {
 #pragma unroll
-                for (int v = 0; v < NV; ++v) a[v][r] = smem[v * T + l];
+                        for (int r = 0; r < RA; ++r) exch[qr_swz<R>(tbp | (r << gp))] = a[v][r];
+                        __syncthreads();
+#pragma unroll
+                        for (int r = 0; r < RA; ++r) a[v][r] = exch[qr_swz<R>(tbn | (r << gn))];
+                        __syncthreads();
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < RA; ++r) {
+                        const int l = qr_swz<R>(tbp | (r << gp));
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) exch[v * T + l] = a[v][r];
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int r = 0; r < RA; ++r) {
+                        const int l = qr_swz<R>(tbn | (r << gn));
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) a[v][r] = exch[v * T + l];
+                    }
+                    if (rd + 2 == nrounds) __syncthreads();   // smem is free for the next tile's first exchange
+                }
             }
-            if (rd == NR - 1) __syncthreads();   // smem is free for the next tile's first exchange
-            qr_round_compute<NV>(a, gt + rd * QR_R, acc + rd * QR_R);
         }
         // ---- registers -> global (QAOA: diagonal-generator inner product and un-phase) ----
-        {
-            const int g = p.g[NR - 1];
 #pragma unroll
-            for (int r = 0; r < QR_RA; ++r) {
-                const int l = tb[NR - 1] | (r << g);
-                const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
-                if (p.post_phase) {
-                    const double hv = p.ham[d];
-                    if (NV == 2) acc[QR_SLOTS - 1] += hv * im_conj_mul(a[NV - 1][r], a[0][r]);
-                    double sn, cs;
-                    sincos(p.angle_post * hv, &sn, &cs);
-                    const double2 ph = make_double2(cs, -sn);
+        for (int r = 0; r < RA; ++r) {
+            const int l = tb_last | (r << g_last);
+            const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
+            if (p.post_phase) {
+                const double hv = p.ham[d];
+                if (NV == 2) acc_all[QR_SLOTS - 1] += hv * im_conj_mul(a[NV - 1][r], a[0][r]);
+                double sn, cs;
+                sincos(p.angle_post * hv, &sn, &cs);
+                const double2 ph = make_double2(cs, -sn);
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) a[v][r] = cmul(a[v][r], ph);
-                }
-                d0[d] = a[0][r];
-                if (NV == 2) d1[d] = a[NV - 1][r];
+                for (int v = 0; v < NV; ++v) a[v][r] = cmul(a[v][r], ph);
             }
+            d0[d] = a[0][r];
+            if (NV == 2) d1[d] = a[NV - 1][r];
         }
         if (NV == 2 && p.flush_per_tile) {
 #pragma unroll
             for (int i = 0; i < QR_SLOTS; ++i) {
-                const double s = block_reduce_sum(acc[i]);
+                const double s = block_reduce_sum(acc_all[i]);
                 if (tid == 0) p.partials[(u64)tile * QR_SLOTS + i] = s;
-                acc[i] = 0.0;
+                acc_all[i] = 0.0;
             }
         }
     }
     if (NV == 2 && !p.flush_per_tile) {
 #pragma unroll
         for (int i = 0; i < QR_SLOTS; ++i) {
-            const double s = block_reduce_sum(acc[i]);
+            const double s = block_reduce_sum(acc_all[i]);
             if (tid == 0) p.partials[(u64)blockIdx.x * QR_SLOTS + i] = s;
         }
     }

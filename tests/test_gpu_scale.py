@@ -32,8 +32,9 @@ def test_config2_mcclean_20x20_golden():
     assert_parity(e, g, float(d["E"]), d["grad"], 1.0, 1e-10)
     assert abs(c.run_expec_val() - float(d["E"])) < 1e-10
     assert abs(c.state.norm_error()) < 1e-12
-    for opt in (("prefetch", 1), ("tile_bits", 10), ("ctas_per_sm_bwd", 2)):
-        c.state.set_option(*opt)
+    for opt in (("async_bwd", 0), ("async_fwd", 1), ("reg_bits_bwd", 4), ("reg_bits_fwd", 4), ("async_bwd", 1),
+                ("prefetch", 1), ("tile_bits", 10), ("ctas_per_sm_fwd", 1), ("async_fwd", 0), ("reg_bits_bwd", 3)):
+        c.state.set_option(*opt)       # options accumulate: every kernel variant is exercised
         e2, g2 = c.grad_run()
         assert_parity(e2, g2, float(d["E"]), d["grad"], 1.0, 1e-10)
 

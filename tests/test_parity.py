@@ -157,6 +157,34 @@ def test_mcclean_tile_geometries_vs_oracle(backend, n, L, tile_bits):
     assert abs(c.state.norm_error()) < 1e-12
 
 
+@pytest.mark.parametrize("opts", [dict(async_bwd=0, async_fwd=0, reg_bits_fwd=4, reg_bits_bwd=4),
+                                  dict(async_bwd=1, async_fwd=1, reg_bits_fwd=4, reg_bits_bwd=4),
+                                  dict(async_bwd=1, async_fwd=1, reg_bits_fwd=3, reg_bits_bwd=3),
+                                  dict(async_bwd=0, async_fwd=0, reg_bits_fwd=3, reg_bits_bwd=3, prefetch=1),
+                                  dict(tile_bits_strided=5, min_row_bits=2), dict(tile_bits_strided=4, min_row_bits=1, async_bwd=1)])
+@pytest.mark.parametrize("n,L,tile_bits", [(7, 2, 5), (10, 2, 12), (13, 1, 12), (9, 2, 4)])
+def test_kernel_variants_vs_oracle(backend, opts, n, L, tile_bits):
+    """Register blocking (3 or 4 bits per round) x staging (direct loads or bulk async copies)."""
+    rng = np.random.default_rng(7 * n + tile_bits)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    obs = mixed_obs(n)
+    e_ref, g_ref = orc.mcclean_grad_run(n, obs, axes, angles)
+    c = McClean(n, obs, L, axes=axes, angles=angles)
+    c.state.set_option("tile_bits", tile_bits)
+    for k, v in opts.items():
+        c.state.set_option(k, v)
+    e, g = c.grad_run()
+    assert_parity(e, g, e_ref, g_ref, obs_scale(obs), TOL)
+    q = Qaoa(n, MaxCut(n, edge_set=[(i, i + 1) for i in range(n - 1)]).to_observable(), 2)
+    q.state.set_option("tile_bits", tile_bits)
+    for k, v in opts.items():
+        q.state.set_option(k, v)
+    b, gm = rng.random(2), rng.random(2)
+    e_ref, g_ref = orc.qaoa_grad_run(n, orc.maxcut_observable(n, [(i, i + 1) for i in range(n - 1)]), b, gm)
+    e, g = q.grad_run(b, gm)
+    assert_parity(e, g, e_ref, g_ref, float(n - 1), TOL)
+
+
 def test_fused_equals_unfused(backend):
     n, L = 11, 3
     rng = np.random.default_rng(5)
