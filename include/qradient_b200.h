@@ -157,6 +157,25 @@ int qr_sample_bitstrings(qr_ctx* ctx, int n_shots, const double* uniforms, int64
 /* mean of H[idx] over the sampled indices, computed on the device from the loaded H table */
 int qr_ham_gather(qr_ctx* ctx, int n, const int64_t* idx, double* out_vals);
 
+/* ---- sharded state vector (no reference counterpart) ------------------------ */
+/* One context per rank holds 2^(n_total - log2_world) amplitudes: the top log2_world qubits are the
+ * rank bits.  All four ping-pong buffers are allocated so their IPC handles can be exchanged once. */
+int qr_shard_create(int n_total, int log2_world, int rank, int device, qr_ctx** out);
+int qr_shard_ipc_handle(qr_ctx* ctx, int buf, void* handle64);                    /* cudaIpcGetMemHandle  */
+int qr_shard_ipc_open(qr_ctx* ctx, int peer_rank, int buf, const void* handle64); /* cudaIpcOpenMemHandle */
+int qr_shard_set_peer_ptr(qr_ctx* ctx, int peer_rank, int buf, void* ptr, int peer_device); /* same process */
+int qr_shard_buffer_ptr(qr_ctx* ctx, int buf, void** out);
+int qr_shard_info(qr_ctx* ctx, int* n_total, int* log2_world, int* rank, int* logical_shard);
+/* McClean forward (+ adjoint backward) on the sharded register, as a sequence of steps; the caller
+ * must run a cross-rank barrier after every qr_shard_step (each step is stream-synchronised).
+ * Local qubits: fused tile passes; CNOT ladder: shard relabelling, no data movement; global qubits:
+ * one kernel per layer that exchanges and rotates over peer memory (NVLink P2P). */
+int qr_shard_mcclean_begin(qr_ctx* ctx, int n_layers, const int32_t* axes, const double* angles, const qr_obs* obs,
+                           int want_grad, int* n_steps);
+int qr_shard_step(qr_ctx* ctx, int step);
+/* this rank's partial sums of E and of dE/d angles[L * n_total]; sum over ranks (allreduce) */
+int qr_shard_mcclean_finish(qr_ctx* ctx, double* e_partial, double* grad_partial);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,15 @@ _SIGNATURES = {
     "qr_qaoa_grad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, P(c_double), c_void_p]),
     "qr_sample_bitstrings": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "qr_ham_gather": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "qr_shard_create": (c_int, [c_int, c_int, c_int, c_int, P(c_void_p)]),
+    "qr_shard_ipc_handle": (c_int, [c_void_p, c_int, c_void_p]),
+    "qr_shard_ipc_open": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "qr_shard_set_peer_ptr": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int]),
+    "qr_shard_buffer_ptr": (c_int, [c_void_p, c_int, P(c_void_p)]),
+    "qr_shard_info": (c_int, [c_void_p, P(c_int), P(c_int), P(c_int), P(c_int)]),
+    "qr_shard_mcclean_begin": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, P(c_int)]),
+    "qr_shard_step": (c_int, [c_void_p, c_int]),
+    "qr_shard_mcclean_finish": (c_int, [c_void_p, P(c_double), c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -150,18 +150,25 @@ __global__ void k_mul_ham(double2* __restrict__ v, const double* __restrict__ ha
 //   dst = O src ; partial[block] = sum_j Re(conj(src_j) dst_j)
 // dst may be null (expectation only).
 // ------------------------------------------------------------------------------------------
+struct PeerTable { const double2* p[16]; };   // shard base pointers by logical shard id (sharded states)
+
+// `jl` is the local index; j = idx_off | jl the full amplitude index (idx_off = shard id << nl).
+// X / Y terms on a rank bit (bit >= nl) read the partner amplitude from the peer shard.
 __global__ void k_apply_obs(const double2* __restrict__ src, double2* __restrict__ dst, u64 N,
-                            const ObsTerm* __restrict__ terms, int nterms, double* __restrict__ partial) {
+                            const ObsTerm* __restrict__ terms, int nterms, double* __restrict__ partial,
+                            u64 idx_off, int nl, PeerTable peers) {
     double acc = 0.0;
-    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (u64)gridDim.x * blockDim.x) {
-        const double2 a = src[j];
+    for (u64 jl = (u64)blockIdx.x * blockDim.x + threadIdx.x; jl < N; jl += (u64)gridDim.x * blockDim.x) {
+        const u64 j = idx_off | jl;
+        const double2 a = src[jl];
         double d = 0.0, ox = 0.0, oy = 0.0;
         for (int k = 0; k < nterms; ++k) {
             const ObsTerm t = terms[k];
             if (t.kind == 2) d += ((j >> t.bit_i) & 1) ? -t.w : t.w;
             else if (t.kind == 3) d += (((j >> t.bit_i) ^ (j >> t.bit_j)) & 1) ? -t.w : t.w;
             else {
-                const double2 p = src[j ^ ((u64)1 << t.bit_i)];
+                const double2 p = t.bit_i < nl ? src[jl ^ ((u64)1 << t.bit_i)]
+                                               : peers.p[(j >> nl) ^ ((u64)1 << (t.bit_i - nl))][jl];
                 if (t.kind == 0) { ox += t.w * p.x; oy += t.w * p.y; }
                 else {  // Y = [[0,-i],[i,0]]: bit 0 row gets -i p, bit 1 row gets +i p
                     const double sgn = ((j >> t.bit_i) & 1) ? 1.0 : -1.0;
@@ -171,7 +178,7 @@ __global__ void k_apply_obs(const double2* __restrict__ src, double2* __restrict
             }
         }
         const double2 o = make_double2(d * a.x + ox, d * a.y + oy);
-        if (dst) dst[j] = o;
+        if (dst) dst[jl] = o;
         acc += re_conj_mul(a, o);
     }
     acc = block_reduce_sum(acc);

@@ -94,6 +94,11 @@ struct qr_ctx {
     long long opt_async_fwd = 0, opt_async_bwd = 0;
     long long opt_tile_bits_x = 0, opt_min_row_bits = 3;
     qr_perf perf;
+    // ---- sharded states: this context holds one shard of an n_total-qubit register ----
+    int n_total = 0, g = 0, rank = 0;
+    double2* peer[QR_MAX_RANKS][QR_NBUF];
+    bool peer_mapped[QR_MAX_RANKS][QR_NBUF];
+    struct ShardRun* run = nullptr;
 };
 
 static inline int use_device(qr_ctx* c) {
@@ -211,6 +216,8 @@ extern "C" int qr_ctx_create(int n_qubits, int device, qr_ctx** out) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     memset(&c->perf, 0, sizeof(c->perf));
+    memset(c->peer, 0, sizeof(c->peer));
+    memset(c->peer_mapped, 0, sizeof(c->peer_mapped));
     int rc = 0;
     do {
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(QR_ECUDA, "stream creation failed"); break; }
@@ -226,10 +233,13 @@ extern "C" int qr_ctx_create(int n_qubits, int device, qr_ctx** out) {
     return qr_state_init(c, 0);
 }
 
+static void shard_release(qr_ctx* c);
+
 extern "C" int qr_ctx_destroy(qr_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    shard_release(c);
     for (int i = 0; i < QR_NBUF; ++i) if (c->buf[i]) cudaFree(c->buf[i]);
     if (c->d_ham) cudaFree(c->d_ham);
     if (c->d_scratch) cudaFree(c->d_scratch);
@@ -552,7 +562,8 @@ static int observable_pass(qr_ctx* c, const qr_obs* o, int src, int dst, double*
     const int grid = grid_for(c, c->N);
     QR_TRY(ensure_scratch(c, grid));
     QR_LAUNCH(k_apply_obs, grid, QR_BLOCK, 0, c->stream, (const double2*)c->buf[src],
-              dst >= 0 ? c->buf[dst] : (double2*)nullptr, c->N, d_terms, (int)o->terms.size(), c->d_scratch);
+              dst >= 0 ? c->buf[dst] : (double2*)nullptr, c->N, d_terms, (int)o->terms.size(), c->d_scratch, (u64)0, 64,
+              PeerTable());
     KERNEL_CHECK();
     return reduce_to_host(c, grid, 1, e_out);
 }
@@ -765,18 +776,23 @@ struct PassIO {
     const double2* src0; const double2* src1; double2* dst0; double2* dst1;
 };
 
+struct LadderSpec { u64 M1, M2, src_xor; };   // explicit gather map (sharded states)
+
 // launch one tile pass; returns the number of partial units written (backward) through *units
 static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const PassIO& io, const GateP* d_gates,
                        int gate_stride, int ladder_stacking /* -1 none, else gather of ladder(stacking) */,
                        i64 batch, i64 state_stride, int flush_per_tile, const double* ham, int pre_phase,
-                       double angle_pre, int post_phase, double angle_post, int* units) {
+                       double angle_pre, int post_phase, double angle_post, int* units, const LadderSpec* spec = nullptr) {
     const PassPlan& pp = lp.pass[pass];
     TilePass tp;
     memset(&tp, 0, sizeof(tp));
     tp.k = pp.k; tp.c = pp.c; tp.h = pp.h; tp.nrounds = pp.nrounds;
     for (int r = 0; r < QR_MAXROUNDS; ++r) tp.g[r] = r < pp.nrounds ? pp.g[r] : 0;
     tp.ladder = 0;
-    if (ladder_stacking >= 0) {
+    if (spec) {
+        tp.ladder = 1;
+        tp.M1 = spec->M1; tp.M2 = spec->M2; tp.src_xor = spec->src_xor;
+    } else if (ladder_stacking >= 0) {
         tp.ladder = 1;
         ladder_masks(lp.n, 1 - ladder_stacking, &tp.M1, &tp.M2);
     }
@@ -1005,7 +1021,7 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     for (i64 b = 0; b < batch; ++b) {
         QR_LAUNCH(k_apply_obs, ogrid, QR_BLOCK, 0, c->stream, (const double2*)(c->buf[c->psi] + b * stride),
                   want_grad ? c->buf[lam] + b * stride : (double2*)nullptr, c->N, d_terms, (int)o->terms.size(),
-                  c->d_scratch + (size_t)b * ogrid);
+                  c->d_scratch + (size_t)b * ogrid, (u64)0, 64, PeerTable());
         KERNEL_CHECK();
         c->perf.kernel_launches++;
     }
@@ -1398,5 +1414,352 @@ extern "C" int qr_ham_gather(qr_ctx* c, int n, const int64_t* idx, double* out) 
     CUDA_TRY(cudaMemcpyAsync(c->h_pin, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     memcpy(out, c->h_pin, (size_t)n * sizeof(double));
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Sharded state vector: one shard per rank, top log2(G) qubits = rank bits.
+//   * CNOT ladder: GF(2)-linear and banded towards more significant bits, so a whole destination
+//     shard reads exactly one source shard -> pure relabelling of shards (pi[rank] = logical shard
+//     id) plus the local gather with a rank-dependent XOR on the top local bits.  No data moves.
+//   * rotations on global qubits: k_global_gates (exchange + gates fused over peer memory).
+//   * the host sequences the steps; a cross-rank barrier is required after every step.
+// ------------------------------------------------------------------------------------------
+struct ShardRun {
+    int L = 0, P = 0;
+    bool want_grad = false;
+    std::vector<int32_t> axes;
+    std::vector<double> angles;
+    std::vector<ObsTerm> terms;
+    LayerPlan lpf, lpb;
+    std::vector<int> pi;          // pi[physical rank] = logical shard id
+    int lam = -1;
+    size_t tab_off = 0;
+    int n_steps = 0;
+    size_t res_local = 0, res_global = 0, res_total = 0;   // offsets (doubles) in d_result
+};
+
+static void shard_release(qr_ctx* c) {
+    for (int r = 0; r < QR_MAX_RANKS; ++r)
+        for (int b = 0; b < QR_NBUF; ++b)
+            if (c->peer_mapped[r][b] && c->peer[r][b]) { cudaIpcCloseMemHandle(c->peer[r][b]); c->peer[r][b] = nullptr; c->peer_mapped[r][b] = false; }
+    delete c->run;
+    c->run = nullptr;
+}
+
+extern "C" int qr_shard_create(int n_total, int log2_world, int rank, int device, qr_ctx** out) {
+    if (!out) return fail(QR_EINVAL, "null output");
+    if (log2_world < 1 || log2_world > 4) return fail(QR_EINVAL, "log2(world size) must be in [1, 4]");
+    if (rank < 0 || rank >= (1 << log2_world)) return fail(QR_EINVAL, "rank %d out of range", rank);
+    const int nl = n_total - log2_world;
+    if (nl < 4 || nl < log2_world) return fail(QR_EINVAL, "sharded registers need at least %d local qubits", std::max(4, log2_world));
+    QR_TRY(qr_ctx_create(nl, device, out));
+    qr_ctx* c = *out;
+    c->n_total = n_total;
+    c->g = log2_world;
+    c->rank = rank;
+    for (int b = 0; b < QR_NBUF; ++b) {
+        int rc = ensure_buf(c, b);
+        if (rc) { qr_ctx_destroy(c); *out = nullptr; return rc; }
+        c->peer[rank][b] = c->buf[b];
+    }
+    return 0;
+}
+
+static int need_shard(qr_ctx* c) {
+    if (!c) return fail(QR_EINVAL, "null context");
+    if (c->g == 0) return fail(QR_ESTATE, "context is not sharded (use qr_shard_create)");
+    return 0;
+}
+
+extern "C" int qr_shard_ipc_handle(qr_ctx* c, int buf, void* handle64) {
+    QR_TRY(need_shard(c));
+    if (buf < 0 || buf >= QR_NBUF || !handle64) return fail(QR_EINVAL, "bad buffer index");
+    QR_TRY(use_device(c));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, c->buf[buf]));
+    static_assert(sizeof(h) == 64, "IPC handle size");
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+extern "C" int qr_shard_ipc_open(qr_ctx* c, int peer_rank, int buf, const void* handle64) {
+    QR_TRY(need_shard(c));
+    if (peer_rank < 0 || peer_rank >= (1 << c->g) || buf < 0 || buf >= QR_NBUF || !handle64) return fail(QR_EINVAL, "bad peer/buffer");
+    if (peer_rank == c->rank) return 0;
+    QR_TRY(use_device(c));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer[peer_rank][buf] = (double2*)p;
+    c->peer_mapped[peer_rank][buf] = true;
+    return 0;
+}
+
+// same-process peers (one process driving several devices, or the CPU test tier)
+extern "C" int qr_shard_set_peer_ptr(qr_ctx* c, int peer_rank, int buf, void* ptr, int peer_device) {
+    QR_TRY(need_shard(c));
+    if (peer_rank < 0 || peer_rank >= (1 << c->g) || buf < 0 || buf >= QR_NBUF || !ptr) return fail(QR_EINVAL, "bad peer/buffer");
+    if (peer_rank == c->rank) return 0;
+    QR_TRY(use_device(c));
+    if (peer_device != c->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+        if (e != cudaSuccess) cudaGetLastError();   // already enabled is fine
+    }
+    c->peer[peer_rank][buf] = (double2*)ptr;
+    return 0;
+}
+
+extern "C" int qr_shard_buffer_ptr(qr_ctx* c, int buf, void** out) {
+    QR_TRY(need_shard(c));
+    if (buf < 0 || buf >= QR_NBUF || !out) return fail(QR_EINVAL, "bad buffer index");
+    *out = c->buf[buf];
+    return 0;
+}
+
+// full-register ladder map helpers
+static inline u64 full_map(u64 d, u64 m1, u64 m2) { return ladder_map(d, m1, m2); }
+
+// relabel after a ladder gather with masks (m1, m2): logical dest r reads logical source
+// sigma(r) = full_map(r << nl) >> nl; returns this rank's new logical id and the XOR carry.
+static void shard_relabel(qr_ctx* c, ShardRun* run, u64 m1, u64 m2, LadderSpec* spec) {
+    const int nl = c->n, G = 1 << c->g;
+    std::vector<int> inv_sigma(G);
+    std::vector<u64> carry(G);
+    for (int r = 0; r < G; ++r) {
+        const u64 img = full_map((u64)r << nl, m1, m2);
+        inv_sigma[(int)(img >> nl)] = r;
+        carry[r] = img & (((u64)1 << nl) - 1);
+    }
+    const int r_new = inv_sigma[run->pi[c->rank]];
+    spec->M1 = m1 & (((u64)1 << nl) - 1);
+    spec->M2 = m2 & (((u64)1 << nl) - 1);
+    spec->src_xor = carry[r_new];
+    for (int rho = 0; rho < G; ++rho) run->pi[rho] = inv_sigma[run->pi[rho]];
+}
+
+extern "C" int qr_shard_mcclean_begin(qr_ctx* c, int L, const int32_t* axes, const double* angles, const qr_obs* o,
+                                      int want_grad, int* n_steps) {
+    QR_TRY(need_shard(c));
+    if (!o || o->n != c->n_total) return fail(QR_EINVAL, "observable must be defined on all %d qubits", c->n_total);
+    if (L < 0 || (L > 0 && (!axes || !angles)) || !n_steps) return fail(QR_EINVAL, "bad arguments");
+    const int nt = c->n_total, nl = c->n, G = 1 << c->g;
+    for (i64 i = 0; i < (i64)L * nt; ++i)
+        if (axes[i] < 0 || axes[i] > 2) return fail(QR_EINVAL, "Invalid axis %d", axes[i]);
+    for (int r = 0; r < G; ++r)
+        for (int b = 0; b < QR_NBUF; ++b)
+            if (!c->peer[r][b]) return fail(QR_ESTATE, "peer buffers of rank %d are not mapped", r);
+    QR_TRY(use_device(c));
+    delete c->run;
+    ShardRun* run = c->run = new ShardRun();
+    run->L = L;
+    run->want_grad = want_grad != 0;
+    run->axes.assign(axes, axes + (size_t)L * nt);
+    run->angles.assign(angles, angles + (size_t)L * nt);
+    run->terms = o->terms;
+    QR_TRY(make_plan(nl, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &run->lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits));
+    QR_TRY(make_plan(nl, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &run->lpb, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits));
+    const int P = run->P = run->lpb.npasses;
+    run->pi.resize(G);
+    for (int r = 0; r < G; ++r) run->pi[r] = r;
+    c->psi = 0;
+    // gate tables of the local passes: [forward L][P][GS] then [backward L][P][GS]
+    const int GS = QR_GATE_SLOTS;
+    const size_t terms_bytes = (o->terms.size() + 1) * sizeof(ObsTerm);
+    run->tab_off = (terms_bytes + 255) & ~(size_t)255;
+    const size_t tab_entries = (size_t)(run->want_grad ? 2 : 1) * L * P * GS;
+    const size_t tab_bytes = tab_entries * sizeof(GateP);
+    run->res_local = 1;
+    run->res_global = 1 + (size_t)L * P * QR_SLOTS;
+    run->res_total = run->res_global + (size_t)L * 4;
+    QR_TRY(ensure_small(c, run->tab_off + tab_bytes + 1024));
+    QR_TRY(ensure_pin(c, std::max(run->tab_off + tab_bytes + 1024, run->res_total * sizeof(double))));
+    QR_TRY(ensure_result(c, run->res_total + 16));
+    QR_TRY(ensure_scratch(c, (size_t)c->sm_count * 16 * QR_SLOTS));
+    GateP* tab = (GateP*)(c->h_pin + run->tab_off);
+    int lay = 0;
+    for (int dir = 0; dir < (run->want_grad ? 2 : 1); ++dir)
+        for (int i = 0; i < L; ++i, ++lay) {
+            const int32_t* ax = axes + (size_t)i * nt;
+            const double* an = angles + (size_t)i * nt;
+            const double sgn = dir == 0 ? 1.0 : -1.0;
+            for (int p = 0; p < P; ++p)
+                fill_gates(dir == 0 ? run->lpf : run->lpb, p, tab + ((size_t)lay * P + p) * GS, [&](int qloc) {
+                    const int q = qloc + c->g;
+                    GateP g; g.c = std::cos(0.5 * an[q]); g.s = sgn * std::sin(0.5 * an[q]); g.axis = ax[q]; g.pad = 0; return g; });
+        }
+    CUDA_TRY(cudaMemcpyAsync((char*)c->d_small + run->tab_off, tab, tab_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (!o->terms.empty()) QR_TRY(upload_small(c, 0, o->terms.data(), o->terms.size() * sizeof(ObsTerm), 0));
+    CUDA_TRY(cudaMemsetAsync(c->d_result, 0, (run->res_total + 16) * sizeof(double), c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    perf_reset(c);
+    run->n_steps = run->want_grad ? 4 * L + 1 : 2 * L + 1;
+    *n_steps = run->n_steps;
+    return 0;
+}
+
+static int shard_global_step(qr_ctx* c, ShardRun* run, int layer, int nv) {
+    const int G = 1 << c->g, nt = c->n_total;
+    GlobalGates gg;
+    memset(&gg, 0, sizeof(gg));
+    gg.g = c->g;
+    gg.slice_len = c->N / G;
+    gg.slice_off = (u64)c->rank * gg.slice_len;
+    for (int rho = 0; rho < G; ++rho) {
+        gg.psi[run->pi[rho]] = c->peer[rho][c->psi];
+        if (nv == 2) gg.lam[run->pi[rho]] = c->peer[rho][run->lam];
+    }
+    const double sgn = nv == 2 ? -1.0 : 1.0;
+    for (int b = 0; b < c->g; ++b) {
+        const int q = c->g - 1 - b;
+        const double an = run->angles[(size_t)layer * nt + q];
+        gg.gate[b].c = std::cos(0.5 * an);
+        gg.gate[b].s = sgn * std::sin(0.5 * an);
+        gg.gate[b].axis = run->axes[(size_t)layer * nt + q];
+    }
+    const int grid = (int)std::min<u64>((gg.slice_len + 255) / 256, (u64)c->sm_count * 4);
+    gg.partials = c->d_scratch;
+    typedef void (*gfn)(const GlobalGates);
+    gfn fn = nullptr;
+    if (nv == 1) fn = c->g == 1 ? k_global_gates<1, 1> : c->g == 2 ? k_global_gates<1, 2> : c->g == 3 ? k_global_gates<1, 3> : k_global_gates<1, 4>;
+    else fn = c->g == 1 ? k_global_gates<2, 1> : c->g == 2 ? k_global_gates<2, 2> : c->g == 3 ? k_global_gates<2, 3> : k_global_gates<2, 4>;
+    QR_LAUNCH(fn, grid, 256, 0, c->stream, gg);
+    KERNEL_CHECK();
+    c->perf.kernel_launches++;
+    if (nv == 2) {
+        QR_LAUNCH(k_reduce_partials, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_scratch, grid, 4,
+                  c->d_result + run->res_global + (size_t)layer * 4);
+        KERNEL_CHECK();
+        c->perf.kernel_launches++;
+    }
+    return 0;
+}
+
+extern "C" int qr_shard_step(qr_ctx* c, int step) {
+    QR_TRY(need_shard(c));
+    ShardRun* run = c->run;
+    if (!run) return fail(QR_ESTATE, "no sharded run in progress");
+    if (step < 0 || step >= run->n_steps) return fail(QR_EINVAL, "step %d out of range", step);
+    QR_TRY(use_device(c));
+    const int L = run->L, P = run->P, nl = c->n, nt = c->n_total, GS = QR_GATE_SLOTS;
+    const GateP* d_tab = (const GateP*)((char*)c->d_small + run->tab_off);
+    const i64 stride = (i64)c->N;
+    if (step < 2 * L) {
+        const int i = step / 2;
+        if (step % 2 == 0) {   // ---- forward, local passes of layer i ----
+            if (i == 0) {
+                double table[48];
+                const double cs = std::cos(M_PI / 8.0), sn = std::sin(M_PI / 8.0);
+                for (int w = 0; w <= nt; ++w) { double v = 1.0; for (int q = 0; q < nt; ++q) v *= (q < nt - w) ? cs : sn; table[w] = v; }
+                const size_t off = c->small_cap - 512;
+                QR_TRY(upload_small(c, off, table, sizeof(double) * (nt + 1), c->pin_cap - 512));
+                const int pop = __builtin_popcount((unsigned)run->pi[c->rank]);
+                QR_LAUNCH(k_init_product, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[c->psi], c->N,
+                          (const double*)((char*)c->d_small + off) + pop, c->N - 1);
+                KERNEL_CHECK();
+            }
+            for (int p = 0; p < P; ++p) {
+                int dst = c->psi;
+                LadderSpec spec;
+                const LadderSpec* sp = nullptr;
+                if (p == 0) {
+                    u64 m1, m2;
+                    ladder_masks(nt, 1, &m1, &m2);   // gather of ladder(0) uses the masks of ladder(1)
+                    shard_relabel(c, run, m1, m2, &spec);
+                    sp = &spec;
+                    dst = other_buf(c, c->psi);
+                }
+                PassIO io = {c->buf[c->psi], nullptr, c->buf[dst], nullptr};
+                QR_TRY(launch_pass(c, run->lpf, p, 1, io, d_tab + ((size_t)i * P + p) * GS, 0, -1, 1, stride, 0, nullptr, 0, 0, 0, 0,
+                                   nullptr, sp));
+                c->psi = dst;
+            }
+        } else {
+            QR_TRY(shard_global_step(c, run, i, 1));
+        }
+    } else if (step == 2 * L) {   // ---- observable ----
+        PeerTable peers;
+        memset(&peers, 0, sizeof(peers));
+        const int G = 1 << c->g;
+        for (int rho = 0; rho < G; ++rho) peers.p[run->pi[rho]] = c->peer[rho][c->psi];
+        run->lam = other_buf(c, c->psi);
+        const int ogrid = grid_for(c, c->N);
+        QR_TRY(ensure_scratch(c, ogrid));
+        QR_LAUNCH(k_apply_obs, ogrid, QR_BLOCK, 0, c->stream, (const double2*)c->buf[c->psi],
+                  run->want_grad ? c->buf[run->lam] : (double2*)nullptr, c->N, (const ObsTerm*)c->d_small, (int)run->terms.size(),
+                  c->d_scratch, (u64)run->pi[c->rank] << nl, nl, peers);
+        KERNEL_CHECK();
+        QR_LAUNCH(k_reduce_partials, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_scratch, ogrid, 1, c->d_result);
+        KERNEL_CHECK();
+    } else {
+        const int t = step - (2 * L + 1);
+        const int i = L - 1 - t / 2;
+        if (t % 2 == 0) {   // ---- backward, local passes of layer i ----
+            for (int p = 0; p < P; ++p) {
+                int dpsi = c->psi, dlam = run->lam;
+                LadderSpec spec;
+                const LadderSpec* sp = nullptr;
+                if (p == 0 && i < L - 1) {
+                    u64 m1, m2;
+                    ladder_masks(nt, 0, &m1, &m2);   // inverse ladder of layer i+1 (mc_clean.py:77)
+                    shard_relabel(c, run, m1, m2, &spec);
+                    sp = &spec;
+                    dpsi = other_buf(c, c->psi, run->lam);
+                    dlam = other_buf(c, c->psi, run->lam, dpsi);
+                }
+                PassIO io = {c->buf[c->psi], c->buf[run->lam], c->buf[dpsi], c->buf[dlam]};
+                int units = 0;
+                QR_TRY(launch_pass(c, run->lpb, p, 2, io, d_tab + ((size_t)(L + i) * P + p) * GS, 0, -1, 1, stride, 0, nullptr, 0, 0, 0,
+                                   0, &units, sp));
+                c->psi = dpsi;
+                run->lam = dlam;
+                QR_LAUNCH(k_reduce_partials, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_scratch, units, QR_SLOTS,
+                          c->d_result + run->res_local + ((size_t)i * P + p) * QR_SLOTS);
+                KERNEL_CHECK();
+            }
+        } else {
+            QR_TRY(shard_global_step(c, run, i, 2));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// partial sums of this rank: E and dE/d angles[L * n_total]; the caller adds them over ranks
+extern "C" int qr_shard_mcclean_finish(qr_ctx* c, double* e_partial, double* grad_partial) {
+    QR_TRY(need_shard(c));
+    ShardRun* run = c->run;
+    if (!run || !e_partial) return fail(QR_ESTATE, "no sharded run in progress");
+    QR_TRY(use_device(c));
+    const int L = run->L, P = run->P, nt = c->n_total;
+    CUDA_TRY(cudaMemcpyAsync(c->h_pin, c->d_result, run->res_total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const double* res = (const double*)c->h_pin;
+    *e_partial = res[0];
+    if (run->want_grad && grad_partial) {
+        for (size_t i = 0; i < (size_t)L * nt; ++i) grad_partial[i] = 0.0;
+        for (int i = 0; i < L; ++i) {
+            for (int p = 0; p < P; ++p)
+                for (int s = 0; s < QR_GATE_SLOTS; ++s) {
+                    const int gb = run->lpb.pass[p].gbit[s];
+                    if (gb >= 0) grad_partial[(size_t)i * nt + (nt - 1 - gb)] = res[run->res_local + ((size_t)i * P + p) * QR_SLOTS + s];
+                }
+            for (int b = 0; b < c->g; ++b) grad_partial[(size_t)i * nt + (c->g - 1 - b)] = res[run->res_global + (size_t)i * 4 + b];
+        }
+        c->psi = run->lam;
+    }
+    delete c->run;
+    c->run = nullptr;
+    return 0;
+}
+
+extern "C" int qr_shard_info(qr_ctx* c, int* n_total, int* log2_world, int* rank, int* logical_shard) {
+    QR_TRY(need_shard(c));
+    if (n_total) *n_total = c->n_total;
+    if (log2_world) *log2_world = c->g;
+    if (rank) *rank = c->rank;
+    if (logical_shard) *logical_shard = c->run ? c->run->pi[c->rank] : c->rank;
     return 0;
 }

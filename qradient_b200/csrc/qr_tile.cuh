@@ -46,6 +46,7 @@ struct TilePass {
     int g[QR_MAXROUNDS];         // first local bit of the register group of each round
     int ladder;                  // 1: gather through the ladder map on load
     u64 M1, M2;
+    u64 src_xor;                 // sharded states: carry of the rank bits into the local source index
     int tiles_log2;              // log2(tiles per state) = n - k
     i64 num_tiles;               // batch * tiles per state
     i64 state_stride;            // amplitudes between consecutive states of a batch
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
         const i64 nb = tl >> p.tiles_log2;
         const u64 t2 = (u64)tl & tmask;
         u64 nbase = ((t2 & (((u64)1 << nlo) - 1)) << c) | ((t2 >> nlo) << (h + p.k - c));
-        if (p.ladder) nbase = ladder_map(nbase, p.M1, p.M2) & ~(u64)(T - 1);
+        if (p.ladder) nbase = (ladder_map(nbase, p.M1, p.M2) ^ p.src_xor) & ~(u64)(T - 1);
         if (tid == 0) qr_mbar_expect_tx(&full_bar, (unsigned)(NV * T * sizeof(double2)));
         for (int r = tid; r < nrows; r += blockDim.x) {
             const u64 src = nbase | ((u64)r << h);
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
         double2 a[NV][RA];
         if (ASYNC) {
             // ---- raw shared tile -> registers (ladder permutation applied to the read index) ----
-            const int off = p.ladder ? (int)(ladder_map(tbase, p.M1, p.M2) & (u64)(T - 1)) : 0;
+            const int off = p.ladder ? (int)((ladder_map(tbase, p.M1, p.M2) ^ p.src_xor) & (u64)(T - 1)) : 0;
             qr_mbar_wait(&full_bar, parity);
             parity ^= 1u;
 #pragma unroll
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
             for (int r = 0; r < RA; ++r) {
                 const int l = tb_first | (r << g_first);
                 const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
-                const u64 s = p.ladder ? ladder_map(d, p.M1, p.M2) : d;
+                const u64 s = p.ladder ? (ladder_map(d, p.M1, p.M2) ^ p.src_xor) : d;
                 a[0][r] = s0[s];
                 if (NV == 2) a[NV - 1][r] = s1[s];
             }
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
                 for (int line = tid; line < (T >> 3); line += blockDim.x) {
                     const int l = line << 3;
                     const u64 d = nbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
-                    const u64 s = p.ladder ? ladder_map(d, p.M1, p.M2) : d;
+                    const u64 s = p.ladder ? (ladder_map(d, p.M1, p.M2) ^ p.src_xor) : d;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src0 + nb * p.state_stride + s));
                     if (NV == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src1 + nb * p.state_stride + s));
                 }
@@ -361,6 +362,59 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
         for (int i = 0; i < QR_SLOTS; ++i) {
             const double s = block_reduce_sum(acc_all[i]);
             if (tid == 0) p.partials[(u64)blockIdx.x * QR_SLOTS + i] = s;
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Sharded states (top log2(G) qubits = rank bits): rotations on the GLOBAL qubits.
+//
+// One kernel does the exchange and the gates together over peer memory: rank r owns the slice
+// [r*N_loc/G, (r+1)*N_loc/G) of the local index range and, for every index in it, loads the G
+// amplitudes that differ only in the rank bits straight from the G peer shards (NVLink P2P
+// loads through CUDA-IPC mappings), applies the log2(G) single-qubit gates in registers
+// (backward: also the Im<lambda|P|psi> partials and both vectors), and stores them back to the
+// peers.  No staging buffer, no layout change; 7/8 of a shard crosses NVLink in each direction
+// per layer and vector, overlapped with the arithmetic by the usual load/store pipelining.
+// ------------------------------------------------------------------------------------------
+#define QR_MAX_RANKS 16
+struct GlobalGates {
+    int g;                        // log2(ranks)
+    u64 slice_off, slice_len;     // local index range handled by this rank
+    double2* psi[QR_MAX_RANKS];   // shard base pointers ordered by LOGICAL shard id
+    double2* lam[QR_MAX_RANKS];
+    GateP gate[4];                // gate on shard-id bit b (qubit g-1-b)
+    double* partials;             // [grid][4]
+};
+
+template <int NV, int GL>
+__global__ void __launch_bounds__(256) k_global_gates(const GlobalGates p) {
+    constexpr int NA = 1 << GL;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < p.slice_len; j += (u64)gridDim.x * blockDim.x) {
+        const u64 idx = p.slice_off + j;
+        double2 a[NV][NA];
+#pragma unroll
+        for (int s = 0; s < NA; ++s) {
+            a[0][s] = p.psi[s][idx];
+            if (NV == 2) a[NV - 1][s] = p.lam[s][idx];
+        }
+        qr_gate_on_bit<NV, NA, 0>(a, p.gate[0], acc[0]);
+        if (GL > 1) qr_gate_on_bit<NV, NA, (GL > 1 ? 1 : 0)>(a, p.gate[1], acc[1]);
+        if (GL > 2) qr_gate_on_bit<NV, NA, (GL > 2 ? 2 : 0)>(a, p.gate[2], acc[2]);
+        if (GL > 3) qr_gate_on_bit<NV, NA, (GL > 3 ? 3 : 0)>(a, p.gate[3], acc[3]);
+#pragma unroll
+        for (int s = 0; s < NA; ++s) {
+            p.psi[s][idx] = a[0][s];
+            if (NV == 2) p.lam[s][idx] = a[NV - 1][s];
+        }
+    }
+    if (NV == 2) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double s = block_reduce_sum(acc[i]);
+            if (threadIdx.x == 0) p.partials[(u64)blockIdx.x * 4 + i] = s;
         }
     }
 }

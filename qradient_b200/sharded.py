@@ -1,0 +1,192 @@
+"""State-vector sharding over several GPUs for registers that do not fit one device.
+
+The reference is single-process; this is the large-register extension named in BASELINE.json
+(McClean 33 qubits on 8 GPUs).  Rank r holds the amplitudes whose top log2(G) index bits equal r
+(qubits 0..log2(G)-1 are the "global" qubits, physical_components/state.py:84-88 bit order).
+
+    * local qubits  : the same fused tile passes as on one GPU;
+    * CNOT ladder   : a whole destination shard reads exactly one source shard, so the ladder is a
+                      relabelling of shards plus a local gather -- no data movement;
+    * global qubits : one kernel per layer and vector reads the G peer shards over NVLink (CUDA IPC
+                      mappings), applies the rotations in registers and writes them back;
+    * E and gradient: per-rank partial sums, one allreduce of L*n+1 doubles at the end.
+
+Two communicators: `TorchDistComm` (one process per GPU, torch.distributed: NCCL on GPUs, gloo in
+the CPU test tier) and `LocalComm` (all shards driven by one process; used by tests and by
+single-process multi-GPU runs).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .physical_components import Observable
+
+NBUF = 4
+
+
+class _Shard:
+    """One rank's shard context."""
+
+    def __init__(self, lib, n_total, log2_world, rank, device):
+        self.lib, self.rank, self.device = lib, rank, device
+        h = ctypes.c_void_p()
+        lib.call('qr_shard_create', int(n_total), int(log2_world), int(rank), int(device), ctypes.byref(h))
+        self.ctx = h
+
+    def handles(self):
+        out = []
+        for b in range(NBUF):
+            buf = ctypes.create_string_buffer(64)
+            self.lib.call('qr_shard_ipc_handle', self.ctx, b, buf)
+            out.append(buf.raw)
+        return out
+
+    def pointers(self):
+        out = []
+        for b in range(NBUF):
+            p = ctypes.c_void_p()
+            self.lib.call('qr_shard_buffer_ptr', self.ctx, b, ctypes.byref(p))
+            out.append(p.value)
+        return out
+
+    def set_option(self, name, value):
+        self.lib.call('qr_set_option', self.ctx, _lib.OPT[name], int(value))
+
+    def close(self):
+        if self.ctx is not None:
+            self.lib.cdll.qr_ctx_destroy(self.ctx)
+            self.ctx = None
+
+
+class TorchDistComm:
+    """One process per GPU; torch.distributed must be initialised by the caller."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def local_ranks(self):
+        return [self.rank]
+
+    def exchange_handles(self, shards):
+        gathered = [None] * self.world
+        self.dist.all_gather_object(gathered, shards[0].handles(), group=self.group)
+        for peer, hs in enumerate(gathered):
+            if peer == self.rank:
+                continue
+            for b, h in enumerate(hs):
+                shards[0].lib.call('qr_shard_ipc_open', shards[0].ctx, peer, b, h)
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+    def allreduce_sum(self, arrays):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(arrays[0]))
+        backend = self.dist.get_backend(self.group)
+        if backend == 'nccl':
+            tc = t.cuda()
+            self.dist.all_reduce(tc, group=self.group)
+            t = tc.cpu()
+        else:
+            self.dist.all_reduce(t, group=self.group)
+        return t.numpy()
+
+
+class LocalComm:
+    """All G shards live in this process (device d per shard, or one device for tests)."""
+
+    def __init__(self, world, devices=None):
+        self.world = world
+        self.devices = devices if devices is not None else [0] * world
+        self.rank = 0
+
+    def local_ranks(self):
+        return list(range(self.world))
+
+    def exchange_handles(self, shards):
+        ptrs = [s.pointers() for s in shards]
+        for s in shards:
+            for peer in range(self.world):
+                if peer == s.rank:
+                    continue
+                for b in range(NBUF):
+                    s.lib.call('qr_shard_set_peer_ptr', s.ctx, peer, b, ctypes.c_void_p(ptrs[peer][b]), self.devices[peer])
+
+    def barrier(self):
+        pass   # every step is stream-synchronised and the shards are stepped in lockstep
+
+    def allreduce_sum(self, arrays):
+        return np.sum(arrays, axis=0)
+
+
+class ShardedMcClean:
+    """McClean circuit (circuit_logic/mc_clean.py) on a register sharded over G = 2^g GPUs.
+
+    Same constructor arguments and return values as `McClean.grad_run` / `run_expec_val`; every
+    rank must call the methods collectively with identical arguments.
+    """
+
+    def __init__(self, qubit_number, observable, layer_number, comm, axes, angles, device=None):
+        self.qnum, self.lnum, self.comm = int(qubit_number), int(layer_number), comm
+        g = int(np.log2(comm.world))
+        if 2 ** g != comm.world or g < 1:
+            raise ValueError('world size must be a power of two >= 2')
+        self.log2_world = g
+        self._lib = _lib.lib()
+        self.observable = Observable(self.qnum, observable)
+        self.axes, self.angles = axes, angles
+        self.shards = []
+        for r in comm.local_ranks():
+            dev = device if device is not None else (comm.devices[r] if hasattr(comm, 'devices') else 0)
+            self.shards.append(_Shard(self._lib, self.qnum, g, r, dev))
+        comm.barrier()
+        comm.exchange_handles(self.shards)
+        comm.barrier()
+
+    def set_option(self, name, value):
+        for s in self.shards:
+            s.set_option(name, value)
+
+    def _params(self):
+        axes = np.asarray(self.axes)
+        angles = np.asarray(self.angles, dtype=np.float64)
+        if axes.shape != (self.lnum, self.qnum) or angles.shape != (self.lnum, self.qnum):
+            raise ValueError('axes and angles must have shape ({}, {})'.format(self.lnum, self.qnum))
+        if np.any((axes < 0) | (axes > 2)):
+            raise ValueError('Invalid axis')
+        return _lib.as_i32(axes), np.ascontiguousarray(angles)
+
+    def _run(self, want_grad):
+        axes, angles = self._params()
+        nsteps = ctypes.c_int()
+        for s in self.shards:
+            self._lib.call('qr_shard_mcclean_begin', s.ctx, self.lnum, _lib.ptr(axes), _lib.ptr(angles),
+                           self.observable._handle, int(want_grad), ctypes.byref(nsteps))
+        self.comm.barrier()
+        for step in range(nsteps.value):
+            for s in self.shards:
+                self._lib.call('qr_shard_step', s.ctx, step)
+            self.comm.barrier()
+        parts = []
+        for s in self.shards:
+            e = ctypes.c_double()
+            grad = np.zeros(self.lnum * self.qnum + 1, dtype=np.float64)
+            self._lib.call('qr_shard_mcclean_finish', s.ctx, ctypes.byref(e), _lib.ptr(grad[1:]) if want_grad else None)
+            grad[0] = e.value
+            parts.append(grad)
+        total = self.comm.allreduce_sum(parts)
+        return float(total[0]), np.array(total[1:]).reshape(self.lnum, self.qnum)
+
+    def run_expec_val(self):
+        return self._run(False)[0]
+
+    def grad_run(self):
+        return self._run(True)
+
+    def close(self):
+        for s in self.shards:
+            s.close()
+        self.shards = []

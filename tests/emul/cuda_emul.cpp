@@ -89,6 +89,62 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
 }
 }  // namespace emul
 
+// ---- shared-memory backed "device" allocations + IPC handles ------------------------------
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <map>
+#include <string>
+namespace {
+struct ShmBlock { std::string name; size_t bytes; bool owner; };
+std::map<void*, ShmBlock> g_blocks;
+int g_counter = 0;
+}
+cudaError_t emul_shm_malloc(void** p, size_t n) {
+    if (n == 0) n = 1;
+    char name[64];
+    snprintf(name, sizeof(name), "/qr_emul_%d_%d", (int)getpid(), g_counter++);
+    int fd = shm_open(name, O_CREAT | O_RDWR | O_EXCL, 0600);
+    if (fd < 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
+    if (ftruncate(fd, (off_t)n) != 0) { close(fd); shm_unlink(name); *p = nullptr; return cudaErrorMemoryAllocation; }
+    void* q = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (q == MAP_FAILED) { shm_unlink(name); *p = nullptr; return cudaErrorMemoryAllocation; }
+    g_blocks[q] = ShmBlock{name, n, true};
+    *p = q;
+    return cudaSuccess;
+}
+cudaError_t emul_shm_free(void* p) {
+    if (!p) return cudaSuccess;
+    auto it = g_blocks.find(p);
+    if (it == g_blocks.end()) return cudaErrorInvalidValue;
+    munmap(p, it->second.bytes);
+    if (it->second.owner) shm_unlink(it->second.name.c_str());
+    g_blocks.erase(it);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+    auto it = g_blocks.find(p);
+    if (it == g_blocks.end()) return cudaErrorInvalidValue;
+    memset(h->reserved, 0, sizeof(h->reserved));
+    strncpy(h->reserved, it->second.name.c_str(), sizeof(h->reserved) - 1);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+    int fd = shm_open(h.reserved, O_RDWR, 0600);
+    if (fd < 0) return cudaErrorInvalidValue;
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return cudaErrorInvalidValue; }
+    void* q = mmap(nullptr, (size_t)st.st_size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (q == MAP_FAILED) return cudaErrorInvalidValue;
+    g_blocks[q] = ShmBlock{h.reserved, (size_t)st.st_size, false};
+    *p = q;
+    return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void* p) { return emul_shm_free(p); }
+
 double emul_now_ms() {
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();

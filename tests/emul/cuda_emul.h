@@ -83,11 +83,22 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     memset(p, 0, sizeof(*p)); p->multiProcessorCount = 4; p->totalGlobalMem = (size_t)8 << 30;
     p->sharedMemPerBlockOptin = 227 * 1024; p->major = 10; p->minor = 0; strcpy(p->name, "host-emulation");
     p->l2CacheSize = 1 << 20; return cudaSuccess; }
-static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
-static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
-static inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
-template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMalloc((void**)p, n); }
+// "device" allocations are POSIX shared memory so that the IPC entry points work across the
+// processes of a gloo world_size-2 test (emulates cudaIpcGetMemHandle / cudaIpcOpenMemHandle)
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+cudaError_t emul_shm_malloc(void** p, size_t n);
+cudaError_t emul_shm_free(void* p);
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p);
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned flags);
+cudaError_t cudaIpcCloseMemHandle(void* p);
+static inline cudaError_t cudaMalloc(void** p, size_t n) { return emul_shm_malloc(p, n); }
+template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return emul_shm_malloc((void**)p, n); }
+static inline cudaError_t cudaFree(void* p) { return emul_shm_free(p); }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaSuccess; }
+static inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMallocHost((void**)p, n); }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }

@@ -1,0 +1,67 @@
+"""State sharding over ranks (qradient_b200/sharded.py): virtual shards in one process on both
+backends, and a real world_size-2 `gloo` run on CPU (two processes, IPC-mapped shard buffers)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from backends import backend  # noqa: F401
+from conftest import assert_parity, obs_scale
+from oracle import qr_oracle as orc
+from qradient_b200.sharded import ShardedMcClean, LocalComm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def mixed_obs(n):
+    m = np.full((n, n), None)
+    m[0, 1] = 1.0
+    m[1, n - 1] = 0.5
+    return {"zz": m, "x": np.array([0.3] + [None] * (n - 1), dtype=object),
+            "y": np.array([None, 0.2] + [None] * (n - 3) + [0.7], dtype=object),
+            "z": np.array([None, -0.4] + [None] * (n - 2), dtype=object)}
+
+
+@pytest.mark.parametrize("n,L,G,tile_bits", [(7, 2, 2, 12), (8, 3, 4, 12), (9, 2, 8, 12), (10, 2, 4, 5), (9, 3, 2, 4),
+                                             (12, 2, 16, 6)])
+def test_virtual_shards_vs_oracle(backend, n, L, G, tile_bits):
+    rng = np.random.default_rng(n * 10 + G)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    obs = mixed_obs(n)
+    e_ref, g_ref = orc.mcclean_grad_run(n, obs, axes, angles)
+    c = ShardedMcClean(n, obs, L, LocalComm(G), axes, angles)
+    try:
+        c.set_option("tile_bits", tile_bits)
+        e, g = c.grad_run()
+        assert_parity(e, g, e_ref, g_ref, obs_scale(obs), 1e-10)
+        assert abs(c.run_expec_val() - e_ref) <= 1e-10 * obs_scale(obs)
+        c.angles = angles + 0.1          # parameters can be re-assigned between calls
+        e2, g2 = c.grad_run()
+        e_ref2, g_ref2 = orc.mcclean_grad_run(n, obs, axes, angles + 0.1)
+        assert_parity(e2, g2, e_ref2, g_ref2, obs_scale(obs), 1e-10)
+    finally:
+        c.close()
+
+
+def test_sharded_argument_checks(backend):
+    with pytest.raises(ValueError):
+        ShardedMcClean(6, mixed_obs(6), 1, LocalComm(3), np.zeros((1, 6), int), np.zeros((1, 6)))
+    with pytest.raises(ValueError):
+        ShardedMcClean(5, mixed_obs(5), 1, LocalComm(4), np.zeros((1, 5), int), np.zeros((1, 5)))   # < 4 local qubits
+    c = ShardedMcClean(8, mixed_obs(8), 1, LocalComm(2), np.full((1, 8), 3), np.zeros((1, 8)))
+    with pytest.raises(ValueError):
+        c.grad_run()
+    c.close()
+
+
+def test_gloo_world_size_2_on_cpu():
+    """Two processes, torch.distributed gloo, shard buffers mapped across processes."""
+    script = os.path.join(ROOT, "scripts", "shard_run.py")
+    env = dict(os.environ, QR_SHARD_BACKEND="emul", MASTER_ADDR="127.0.0.1", MASTER_PORT="29741")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29741", script, "--qubits", "9", "--layers", "3", "--check"]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "PARITY OK" in res.stdout, res.stdout + res.stderr
