@@ -54,6 +54,7 @@ WORKLOADS = {
     "mcclean3": dict(kind="mcclean", n=3, L=3, seed=1234, name="McClean 3 qubits x 3 layers grad_run, ZZ(0,1)"),
     "qaoa26": dict(kind="qaoa", n=26, L=10, seed=10, name="QAOA MaxCut 3-regular 26 qubits p=10 grad_run"),
     "batch14": dict(kind="batch", n=14, L=14, seed=4, B=8192, name="McClean 14x14, 8192 parameter sets, grad_run_batch"),
+    "shard": dict(kind="shard", n=30, L=20, seed=5, name="McClean (30+log2 G) qubits x 20 layers, state sharded over G GPUs"),
 }
 
 
@@ -214,6 +215,43 @@ def main():
 
     n, L = w["n"], w["L"]
     units_per_step = 1
+    if w["kind"] == "shard" and world > 1:
+        # BASELINE config 5: one register sharded over all ranks (NVLink P2P for the global qubits)
+        from qradient_b200.sharded import ShardedMcClean, TorchDistComm
+        n = w["n"] + int(np.log2(world))
+        axes, angles = mcclean_inputs(dict(w, n=n))
+        sh = ShardedMcClean(n, zz01(n), L, TorchDistComm(), axes, angles, device=local_rank)
+        for _ in range(max(args.warmup - 2, 1)):
+            sh.grad_run()
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e_sh, _ = sh.grad_run()
+        dist.barrier(); torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            sec = dt.item() / args.steps
+            P = 3
+            bsched = 16.0 * 2.0 ** n / world * (1 + 2 * P * L + 2 + 4 * P * L)
+            nvl = 16.0 * 2.0 ** n / world * (world - 1) / world * 3 * L     # bytes per direction per GPU
+            peak, peak_src = measured_peak()
+            print(json.dumps({"metric": "McClean grad_run full gradients/sec", "value": 1.0 / sec, "unit": "gradients/s",
+                              "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec,
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)",
+                              "data": "synthetic", "E": e_sh,
+                              "config": {"workload": "McClean %d qubits x %d layers, state sharded over %d GPUs" % (n, L, world),
+                                         "n_qubits": n, "layers": L, "parallelism": "state sharded on the top %d qubits" % int(np.log2(world))},
+                              "e2e": {"value": 1.0 / sec, "unit": "gradients/s", "h2d_bytes_per_step": int(axes.size * 12),
+                                      "d2h_bytes_per_step": int((L * n + 1) * 8)},
+                              "roofline": {"bound": "hbm", "achieved": bsched / sec / 1e9, "peak": peak, "unit": "GB/s",
+                                           "frac": bsched / sec / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                                           "note": "whole-gradient B_sched per GPU; NVLink bytes/direction/GPU = %.3g" % nvl}}))
+        sh.close()
+        dist.destroy_process_group()
+        return
+    if w["kind"] == "shard":
+        w = dict(w, kind="mcclean")
     if w["kind"] == "mcclean":
         axes, angles = mcclean_inputs(w, rank)
         circ = McClean(n, zz01(n), L, axes=axes, angles=angles, device=local_rank)
