@@ -310,6 +310,9 @@ def main():
         dist.all_reduce(lt)
         launches = int(lt.item())
     total_units = units_per_step * args.steps * world
+    if t_dev <= 0.0:          # gate-at-a-time path (n < 4) records no device events: use the wall clock
+        t_dev = t_wall
+        perf = dict(perf, ms_total=t_wall / args.steps)
     value = total_units / (t_dev / 1e3)
     e2e = total_units / (t_wall / 1e3)
     peak, peak_src = measured_peak()
@@ -335,8 +338,8 @@ def main():
                      "note": "state vector is L2-resident at n<=21 (2 x %.0f MiB): fraction of the HBM peak is reported "
                              "but launch latency / L2 bound; see hbm_target for the HBM-bound size" % (16 * 2.0 ** n / 2 ** 20)
                      if n <= 21 else "HBM-bound size"},
-        "sched": {"B_sched_bytes": perf["algorithmic_bytes"], "achieved_GBps": perf["algorithmic_bytes"] / (perf["ms_total"] * 1e-3) / 1e9,
-                  "frac_of_peak": perf["algorithmic_bytes"] / (perf["ms_total"] * 1e-3) / 1e9 / peak,
+        "sched": {"B_sched_bytes": perf["algorithmic_bytes"], "achieved_GBps": perf["algorithmic_bytes"] / (max(perf["ms_total"], 1e-9) * 1e-3) / 1e9,
+                  "frac_of_peak": perf["algorithmic_bytes"] / (max(perf["ms_total"], 1e-9) * 1e-3) / 1e9 / peak,
                   "ms_forward": perf["ms_forward"], "ms_observable": perf["ms_observable"], "ms_backward": perf["ms_backward"]},
     }
     # ---- the HBM-bound north-star size, measured in the same run (N = 1, default workload only) ----

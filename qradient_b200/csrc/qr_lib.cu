@@ -80,6 +80,7 @@ struct qr_ctx {
     bool ham_loaded = false;
     double* d_scratch = nullptr; // reduction partials
     size_t scratch_cap = 0;      // in doubles
+    unsigned* d_counter = nullptr;   // arrival counter of the fused final reduction (kept at zero between launches)
     double* d_result = nullptr;  // small results
     size_t result_cap = 0;
     void* d_small = nullptr;     // gate tables / observable terms / tables
@@ -225,6 +226,8 @@ extern "C" int qr_ctx_create(int n_qubits, int device, qr_ctx** out) {
         if ((rc = ensure_buf(c, 0))) break;
         if ((rc = ensure_scratch(c, (size_t)c->sm_count * 8 * 16))) break;
         if ((rc = ensure_result(c, 64))) break;
+        if (cudaMalloc((void**)&c->d_counter, 64) != cudaSuccess) { rc = fail(QR_ENOMEM, "counter allocation failed"); break; }
+        cudaMemsetAsync(c->d_counter, 0, 64, c->stream);
         if ((rc = ensure_small(c, 1 << 16))) break;
         if ((rc = ensure_pin(c, 1 << 16))) break;
     } while (0);
@@ -244,6 +247,7 @@ extern "C" int qr_ctx_destroy(qr_ctx* c) {
     if (c->d_ham) cudaFree(c->d_ham);
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_result) cudaFree(c->d_result);
+    if (c->d_counter) cudaFree(c->d_counter);
     if (c->d_small) cudaFree(c->d_small);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -730,7 +734,7 @@ static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x
     const int rem = n - k;
     if (rem > 0) {
         // strided passes: tile of kx bits = c contiguous low bits (rows of 2^c amplitudes) + m gate bits
-        const int kx = std::min(k, tile_bits_x > 0 ? tile_bits_x : k);
+        const int kx = tile_bits_x > 0 ? std::min(n, tile_bits_x) : k;
         const int umax = std::max(kx - std::min(min_row_bits, kx - 1), 1);
         const int nx = (rem + umax - 1) / umax;
         int h = k;
@@ -782,7 +786,8 @@ struct LadderSpec { u64 M1, M2, src_xor; };   // explicit gather map (sharded st
 static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const PassIO& io, const GateP* d_gates,
                        int gate_stride, int ladder_stacking /* -1 none, else gather of ladder(stacking) */,
                        i64 batch, i64 state_stride, int flush_per_tile, const double* ham, int pre_phase,
-                       double angle_pre, int post_phase, double angle_post, int* units, const LadderSpec* spec = nullptr) {
+                       double angle_pre, int post_phase, double angle_post, int* units, const LadderSpec* spec = nullptr,
+                       double* final_out = nullptr) {
     const PassPlan& pp = lp.pass[pass];
     TilePass tp;
     memset(&tp, 0, sizeof(tp));
@@ -813,13 +818,16 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
     const long long per_sm = std::min<long long>(16, ctas * std::max(1, full / threads));
     const i64 grid = std::min<i64>(tp.num_tiles, (i64)c->sm_count * per_sm);
     const size_t tile_bytes = sizeof(double2) << pp.k;
-    const size_t smem = async ? (size_t)(nv + 1) * tile_bytes : (pp.nrounds > 1 ? (size_t)nv * tile_bytes : 0);
+    size_t smem = async ? (size_t)(nv + 1) * tile_bytes : (pp.nrounds > 1 ? (size_t)nv * tile_bytes : 0);
+    if (nv == 2 && !async) smem = (size_t)nv * tile_bytes + (size_t)QR_SLOTS * threads * sizeof(double);   // + accumulators
     if (nv == 2) {
         const i64 nunits = flush_per_tile ? tp.num_tiles : grid;
         QR_TRY(ensure_scratch(c, (size_t)nunits * QR_SLOTS));
         *units = (int)nunits;
     }
     tp.partials = c->d_scratch;
+    tp.final_out = (nv == 2 && !flush_per_tile) ? final_out : nullptr;
+    tp.done_counter = c->d_counter;
     tile_fn fn = tile_kernel(nv, R, async);
     static bool attr_done[2][5][2] = {{{false}}};
     if (!attr_done[nv - 1][R][async]) {
@@ -1051,14 +1059,13 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
                 PassIO io = {c->buf[c->psi], c->buf[lam], c->buf[dpsi], c->buf[dlam]};
                 int units = 0;
                 QR_TRY(launch_pass(c, lp, p, 2, io, d_tab + ((size_t)tlay * P + p) * GS, gate_stride, lad, batch, stride,
-                                   flush, nullptr, 0, 0, 0, 0, &units));
+                                   flush, nullptr, 0, 0, 0, 0, &units, nullptr,
+                                   batch == 1 ? d_slots + ((size_t)i * P + p) * QR_SLOTS : nullptr));
                 c->psi = dpsi;
                 lam = dlam;
                 ++n_bwd_pass;
-                if (batch == 1) {
-                    QR_LAUNCH(k_reduce_partials, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_scratch, units, QR_SLOTS,
-                              d_slots + ((size_t)i * P + p) * QR_SLOTS);
-                } else {
+                if (batch == 1) continue;   // second-stage reduction is fused into the pass (last CTA)
+                {
                     const int tiles_per_state = 1 << (n - lp.pass[p].k);
                     QR_LAUNCH(k_reduce_partials_grouped, (unsigned)batch, 32, 0, c->stream, (const double*)c->d_scratch,
                               tiles_per_state, QR_SLOTS, d_slots + ((size_t)i * P + p) * QR_SLOTS, slots_per_state);
@@ -1296,11 +1303,7 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
                 PassIO io = {c->buf[c->psi], c->buf[lam], c->buf[c->psi], c->buf[lam]};
                 int units = 0;
                 QR_TRY(launch_pass(c, lp, q, 2, io, d_tab + ((size_t)(p + i) * P + q) * GS, 0, -1, 1, stride, 0, c->d_ham, 0, 0.0,
-                                   q == P - 1 ? 1 : 0, -gammas[i], &units));
-                QR_LAUNCH(k_reduce_partials, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_scratch, units, QR_SLOTS,
-                          d_slots + ((size_t)i * P + q) * QR_SLOTS);
-                KERNEL_CHECK();
-                c->perf.kernel_launches++;
+                                   q == P - 1 ? 1 : 0, -gammas[i], &units, nullptr, d_slots + ((size_t)i * P + q) * QR_SLOTS));
                 ++n_bwd_pass;
             }
     }
@@ -1712,12 +1715,9 @@ extern "C" int qr_shard_step(qr_ctx* c, int step) {
                 PassIO io = {c->buf[c->psi], c->buf[run->lam], c->buf[dpsi], c->buf[dlam]};
                 int units = 0;
                 QR_TRY(launch_pass(c, run->lpb, p, 2, io, d_tab + ((size_t)(L + i) * P + p) * GS, 0, -1, 1, stride, 0, nullptr, 0, 0, 0,
-                                   0, &units, sp));
+                                   0, &units, sp, c->d_result + run->res_local + ((size_t)i * P + p) * QR_SLOTS));
                 c->psi = dpsi;
                 run->lam = dlam;
-                QR_LAUNCH(k_reduce_partials, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_scratch, units, QR_SLOTS,
-                          c->d_result + run->res_local + ((size_t)i * P + p) * QR_SLOTS);
-                KERNEL_CHECK();
             }
         } else {
             QR_TRY(shard_global_step(c, run, i, 2));

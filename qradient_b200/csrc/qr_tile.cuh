@@ -60,12 +60,49 @@ struct TilePass {
     int pre_phase, post_phase;   // multiply by exp(-i angle H) after load / before store
     double angle_pre, angle_post;
     double* partials;            // [units][QR_SLOTS]; unit = CTA, or tile when flush_per_tile
+    double* final_out;           // if set: the last CTA writes the QR_SLOTS sums over all CTAs here
+    unsigned* done_counter;      // zero-initialised arrival counter for final_out
     int flush_per_tile;
     int prefetch;
 };
 
 template <int R>
 __device__ __forceinline__ int qr_swz(int l) { return l ^ ((l >> R) & 7); }
+
+// Block-wide sums of QR_SLOTS accumulators with ONE barrier pair: warp shuffles, per-warp rows in
+// shared memory, then thread i < QR_SLOTS adds the rows in warp order and writes out[i].
+__device__ __forceinline__ void qr_block_reduce_slots(const double (&acc)[QR_SLOTS], double* out) {
+    __shared__ double rows[32][QR_SLOTS + 1];
+    const int tid = threadIdx.x;
+    if (blockDim.x >= 32) {
+        const int lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+        for (int i = 0; i < QR_SLOTS; ++i) {
+            double v = acc[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) rows[w][i] = v;
+        }
+        __syncthreads();
+        if (tid < QR_SLOTS) {
+            double v = 0.0;
+            for (int r = 0; r < nw; ++r) v += rows[r][tid];
+            out[tid] = v;
+        }
+        __syncthreads();
+    } else {
+#pragma unroll
+        for (int i = 0; i < QR_SLOTS; ++i) rows[tid][i] = acc[i];
+        __syncthreads();
+        if (tid == 0)
+            for (int i = 0; i < QR_SLOTS; ++i) {
+                double v = 0.0;
+                for (unsigned r = 0; r < blockDim.x; ++r) v += rows[r][i];
+                out[i] = v;
+            }
+        __syncthreads();
+    }
+}
 
 // one single-qubit rotation (and, for NV == 2, its gradient inner product) on register bit BIT
 template <int NV, int NA, int BIT>
@@ -178,9 +215,17 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
     const int tid = threadIdx.x;
     const int T = 1 << p.k;
     double2* exch = ASYNC ? smem + NV * T : smem;   // ASYNC: [raw psi][raw lambda][exchange]
+    // Backward pass: the 13 per-thread gradient accumulators live in shared memory ([slot][thread],
+    // conflict free) so that the 64 data registers + addressing fit 128 registers without spills.
+    constexpr bool ACC_SMEM = (NV == 2 && !ASYNC);
+    double* acc_sm = reinterpret_cast<double*>(smem + NV * T);
     double acc_all[QR_SLOTS];
 #pragma unroll
     for (int i = 0; i < QR_SLOTS; ++i) acc_all[i] = 0.0;
+    if (ACC_SMEM) {
+#pragma unroll
+        for (int i = 0; i < QR_SLOTS; ++i) acc_sm[i * blockDim.x + tid] = 0.0;
+    }
     const int c = p.c, h = p.h;
     const int lomask = (1 << c) - 1;
     const int nlo = h - c;
@@ -290,7 +335,10 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
         for (int rd = 0; rd < nrounds; ++rd) {
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
             qr_round_compute<NV, R>(a, gt + rd * R, acc);
-            if (NV == 2) {   // static indices keep the accumulators in registers
+            if (ACC_SMEM) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) acc_sm[(rd * R + i) * blockDim.x + tid] += acc[i];
+            } else if (NV == 2) {   // static indices keep the accumulators in registers
 #pragma unroll
                 for (int rr = 0; rr < QR_MAXROUNDS; ++rr)
                     if (rr == rd) {
@@ -338,7 +386,7 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
             const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
             if (p.post_phase) {
                 const double hv = p.ham[d];
-                if (NV == 2) acc_all[QR_SLOTS - 1] += hv * im_conj_mul(a[NV - 1][r], a[0][r]);
+                if (NV == 2) acc_all[QR_SLOTS - 1] += hv * im_conj_mul(a[NV - 1][r], a[0][r]);   // (register slot; folded below)
                 double sn, cs;
                 sincos(p.angle_post * hv, &sn, &cs);
                 const double2 ph = make_double2(cs, -sn);
@@ -349,23 +397,43 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
             if (NV == 2) d1[d] = a[NV - 1][r];
         }
         if (NV == 2 && p.flush_per_tile) {
+            if (ACC_SMEM) {
 #pragma unroll
-            for (int i = 0; i < QR_SLOTS; ++i) {
-                const double s = block_reduce_sum(acc_all[i]);
-                if (tid == 0) p.partials[(u64)tile * QR_SLOTS + i] = s;
-                acc_all[i] = 0.0;
+                for (int i = 0; i < QR_GATE_SLOTS; ++i) { acc_all[i] = acc_sm[i * blockDim.x + tid]; acc_sm[i * blockDim.x + tid] = 0.0; }
             }
+            qr_block_reduce_slots(acc_all, p.partials + (u64)tile * QR_SLOTS);
+#pragma unroll
+            for (int i = 0; i < QR_SLOTS; ++i) acc_all[i] = 0.0;
         }
     }
     if (NV == 2 && !p.flush_per_tile) {
+        if (ACC_SMEM) {
 #pragma unroll
-        for (int i = 0; i < QR_SLOTS; ++i) {
-            const double s = block_reduce_sum(acc_all[i]);
-            if (tid == 0) p.partials[(u64)blockIdx.x * QR_SLOTS + i] = s;
+            for (int i = 0; i < QR_GATE_SLOTS; ++i) acc_all[i] = acc_sm[i * blockDim.x + tid];
+        }
+        qr_block_reduce_slots(acc_all, p.partials + (u64)blockIdx.x * QR_SLOTS);
+        // second stage fused in: the last CTA to arrive adds the per-CTA partials in CTA order
+        // (fixed order => run-to-run deterministic) and writes the QR_SLOTS sums of this pass.
+        if (p.final_out) {
+            __shared__ int is_last;
+            __threadfence();
+            if (tid == 0) {
+                const unsigned prev = atomicAdd(p.done_counter, 1u);
+                is_last = (prev + 1 == gridDim.x);
+            }
+            __syncthreads();
+            if (is_last) {
+                __threadfence();
+                for (int i = tid; i < QR_SLOTS; i += blockDim.x) {
+                    double v = 0.0;
+                    for (unsigned b = 0; b < gridDim.x; ++b) v += ((volatile double*)p.partials)[(u64)b * QR_SLOTS + i];
+                    p.final_out[i] = v;
+                }
+                if (tid == 0) *p.done_counter = 0u;   // re-arm for the next launch on this stream
+            }
         }
     }
 }
-
 
 // ------------------------------------------------------------------------------------------
 // Sharded states (top log2(G) qubits = rank bits): rotations on the GLOBAL qubits.

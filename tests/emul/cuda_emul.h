@@ -50,6 +50,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
 #define blockDim (emul::g_blockDim)
 #define gridDim (emul::g_gridDim)
 static inline void __syncthreads() { emul::sync(); }
+static inline void __syncwarp() { emul::sync(); }   // fibers of a warp run one after another: a warp barrier must yield too
 static inline double __shfl_xor_sync(unsigned, double v, int m) { return emul::shfl_xor(v, m); }
 static inline double __shfl_down_sync(unsigned, double v, int d) {
     // only used in full-warp tree reductions where lane 0's result matters: xor gives the same sum
@@ -62,6 +63,7 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline double atomicAdd(double* p, double v) { double o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { auto o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 static inline void __threadfence() {}
 
 // ---- runtime subset -------------------------------------------------------------------
