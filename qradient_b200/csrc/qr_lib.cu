@@ -819,7 +819,6 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
     const i64 grid = std::min<i64>(tp.num_tiles, (i64)c->sm_count * per_sm);
     const size_t tile_bytes = sizeof(double2) << pp.k;
     size_t smem = async ? (size_t)(nv + 1) * tile_bytes : (pp.nrounds > 1 ? (size_t)nv * tile_bytes : 0);
-    if (nv == 2 && !async) smem = (size_t)nv * tile_bytes + (size_t)QR_SLOTS * threads * sizeof(double);   // + accumulators
     if (nv == 2) {
         const i64 nunits = flush_per_tile ? tp.num_tiles : grid;
         QR_TRY(ensure_scratch(c, (size_t)nunits * QR_SLOTS));

@@ -1,5 +1,6 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:k_tile_passILi2ELi3ELb0 -s 0 -c 2 -o gpurun_out/prof_bwd_r1e \
-    python scripts/prof_run.py --n 28 --L 3 > gpurun_out/ncu_full.log 2>&1
-tail -2 gpurun_out/ncu_full.log
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+timeout 300 python scripts/prof_run.py --n 20 --L 20 --reps 5 2>&1 | tail -1
+timeout 300 python scripts/prof_run.py --n 30 --L 3 --reps 2 2>&1 | tail -1
+timeout 300 python scripts/prof_run.py --n 30 --L 3 --reps 2 --tile-bits 11 2>&1 | tail -1
+timeout 300 python scripts/prof_run.py --n 26 --L 5 --reps 2 2>&1 | tail -1
