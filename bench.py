@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--tile-bits", type=int, default=None)
     ap.add_argument("--ctas-bwd", type=int, default=None)
     ap.add_argument("--ctas-fwd", type=int, default=None)
+    ap.add_argument("--batch-chunk-mb", type=int, default=None)
     ap.add_argument("--hbm-target", type=int, default=1, help="also measure the 30x30 HBM-bound target (N=1 only)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -272,7 +273,7 @@ def main():
         units_per_step = B
         h2d, d2h = axes.size * 4 + angles.size * 8, B * (L * n + 1) * 8
     for name, val in (("prefetch", args.prefetch), ("tile_bits", args.tile_bits), ("ctas_per_sm_bwd", args.ctas_bwd),
-                      ("ctas_per_sm_fwd", args.ctas_fwd)):
+                      ("ctas_per_sm_fwd", args.ctas_fwd), ("batch_chunk_mb", args.batch_chunk_mb)):
         if val is not None:
             circ.state.set_option(name, val)
 

@@ -157,6 +157,10 @@ struct PeerTable { const double2* p[16]; };   // shard base pointers by logical 
 __global__ void k_apply_obs(const double2* __restrict__ src, double2* __restrict__ dst, u64 N,
                             const ObsTerm* __restrict__ terms, int nterms, double* __restrict__ partial,
                             u64 idx_off, int nl, PeerTable peers) {
+    // gridDim.y = number of independent states laid out back to back (batched circuits)
+    src += (u64)blockIdx.y * N;
+    if (dst) dst += (u64)blockIdx.y * N;
+    partial += (u64)blockIdx.y * gridDim.x;
     double acc = 0.0;
     for (u64 jl = (u64)blockIdx.x * blockDim.x + threadIdx.x; jl < N; jl += (u64)gridDim.x * blockDim.x) {
         const u64 j = idx_off | jl;
@@ -388,4 +392,39 @@ __global__ void k_sample_search(const double2* __restrict__ v, u64 N, const doub
 
 __global__ void k_gather_f64(const double* __restrict__ table, const i64* __restrict__ idx, int n, double* __restrict__ out) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = table[idx[i]];
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Batched circuits: build the per-(circuit, layer, pass) gate tables on the device from the raw
+// axes / angles arrays (the host loop over 8192 x 28 x 2 x 12 entries dominated the e2e time).
+//   tab[b][lay][p][s], lay = dir * L + i;  qmap[dir][p][s] = qubit handled by slot s, or -1.
+// ------------------------------------------------------------------------------------------
+struct GatePOut { double c, s; int axis; int pad; };   // same layout as GateP (qr_tile.cuh)
+
+__global__ void k_build_gates(const int* __restrict__ axes, const double* __restrict__ angles,
+                              const int* __restrict__ qmap, GatePOut* __restrict__ tab, i64 batch, int L, int n,
+                              int P, int GS, int ndir) {
+    const i64 per_batch = (i64)ndir * L * P * GS;
+    const i64 total = batch * per_batch;
+    for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+        const i64 b = idx / per_batch;
+        i64 r = idx - b * per_batch;
+        const int s = (int)(r % GS); r /= GS;
+        const int p = (int)(r % P); r /= P;
+        const int lay = (int)r;
+        const int dir = lay / L, i = lay - dir * L;
+        const int q = qmap[((size_t)dir * P + p) * GS + s];
+        GatePOut g;
+        g.c = 1.0; g.s = 0.0; g.axis = -1; g.pad = 0;
+        if (q >= 0) {
+            const double th = 0.5 * angles[((size_t)b * L + i) * n + q];
+            double sn, cs;
+            sincos(th, &sn, &cs);
+            g.c = cs;
+            g.s = dir == 0 ? sn : -sn;
+            g.axis = axes[((size_t)b * L + i) * n + q];
+        }
+        tab[idx] = g;
+    }
 }

@@ -93,7 +93,7 @@ struct qr_ctx {
     long long opt_ctas_fwd = 2, opt_ctas_bwd = 1, opt_final_ladder = 1, opt_ham_lut = 1;
     long long opt_r_fwd = 3, opt_r_bwd = 3;
     long long opt_async_fwd = 0, opt_async_bwd = 0;
-    long long opt_tile_bits_x = 0, opt_min_row_bits = 3;
+    long long opt_tile_bits_x = 0, opt_min_row_bits = 3, opt_batch_chunk_mb = 0;
     qr_perf perf;
     // ---- sharded states: this context holds one shard of an n_total-qubit register ----
     int n_total = 0, g = 0, rank = 0;
@@ -274,6 +274,7 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
         case QR_OPT_ASYNC_BWD: c->opt_async_bwd = v ? 1 : 0; break;
         case QR_OPT_TILE_BITS_STRIDED: if (v != 0 && (v < 4 || v > QR_MAX_TILE_BITS)) return fail(QR_EINVAL, "bad strided tile bits"); c->opt_tile_bits_x = v; break;
         case QR_OPT_MIN_ROW_BITS: if (v < 1 || v > 6) return fail(QR_EINVAL, "bad min row bits"); c->opt_min_row_bits = v; break;
+        case QR_OPT_BATCH_CHUNK_MB: if (v < 0 || v > 65536) return fail(QR_EINVAL, "bad batch chunk"); c->opt_batch_chunk_mb = v; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -295,6 +296,7 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_ASYNC_BWD: *v = c->opt_async_bwd; break;
         case QR_OPT_TILE_BITS_STRIDED: *v = c->opt_tile_bits_x; break;
         case QR_OPT_MIN_ROW_BITS: *v = c->opt_min_row_bits; break;
+        case QR_OPT_BATCH_CHUNK_MB: *v = c->opt_batch_chunk_mb; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -949,9 +951,33 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     const size_t tab_bytes = (size_t)batch * per_batch * sizeof(GateP);
     const size_t terms_bytes = (o->terms.size() + 1) * sizeof(ObsTerm);
     const size_t tab_off = (terms_bytes + 255) & ~(size_t)255;
-    QR_TRY(ensure_small(c, tab_off + tab_bytes + 1024));
-    QR_TRY(ensure_pin(c, tab_off + tab_bytes + 1024));
-    {
+    const size_t raw_off = (tab_off + tab_bytes + 1024 + 255) & ~(size_t)255;   // batched: raw axes/angles/qmap staging
+    const size_t raw_bytes = batch > 1 ? (size_t)batch * L * n * (sizeof(double) + sizeof(int32_t)) + 2 * (size_t)P * GS * sizeof(int) + 1024 : 0;
+    QR_TRY(ensure_small(c, raw_off + raw_bytes + 1024));
+    QR_TRY(ensure_pin(c, batch > 1 ? std::max((size_t)1 << 16, (size_t)batch * (1 + (size_t)L * P * QR_SLOTS) * sizeof(double) + 8192)
+                                   : tab_off + tab_bytes + 1024));
+    if (batch > 1) {
+        // device-side table build: upload raw parameters + the slot->qubit maps of both directions
+        char* d_raw = (char*)c->d_small + raw_off;
+        double* d_angles = (double*)d_raw;
+        int* d_axes = (int*)(d_raw + (size_t)batch * L * n * sizeof(double));
+        int* d_qmap = d_axes + (size_t)batch * L * n;
+        int* qmap = (int*)c->h_pin;
+        for (int dir = 0; dir < 2; ++dir)
+            for (int p = 0; p < P; ++p)
+                for (int s2 = 0; s2 < GS; ++s2) {
+                    const int gb = (dir == 0 ? lpf : lp).pass[p].gbit[s2];
+                    qmap[((size_t)dir * P + p) * GS + s2] = gb < 0 ? -1 : n - 1 - gb;
+                }
+        CUDA_TRY(cudaMemcpyAsync(d_qmap, qmap, 2 * (size_t)P * GS * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_angles, angles, (size_t)batch * L * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_axes, axes, (size_t)batch * L * n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        const i64 total = (i64)batch * per_batch;
+        QR_LAUNCH(k_build_gates, grid_for(c, (u64)total), QR_BLOCK, 0, c->stream, (const int*)d_axes, (const double*)d_angles,
+                  (const int*)d_qmap, (GatePOut*)((char*)c->d_small + tab_off), batch, L, n, P, GS, want_grad ? 2 : 1);
+        KERNEL_CHECK();
+        c->perf.kernel_launches++;
+    } else {
         GateP* tab = (GateP*)(c->h_pin + tab_off);
         for (i64 b = 0; b < batch; ++b) {
             GateP* tb = tab + b * per_batch;
@@ -1025,10 +1051,10 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     const int ogrid = grid_for(c, c->N);
     QR_TRY(ensure_scratch(c, (size_t)ogrid * std::max<i64>(batch, 1)));
     QR_TRY(ensure_result(c, (size_t)batch * (1 + (want_grad ? (size_t)L * P * QR_SLOTS : 0)) + 16));
-    for (i64 b = 0; b < batch; ++b) {
-        QR_LAUNCH(k_apply_obs, ogrid, QR_BLOCK, 0, c->stream, (const double2*)(c->buf[c->psi] + b * stride),
-                  want_grad ? c->buf[lam] + b * stride : (double2*)nullptr, c->N, d_terms, (int)o->terms.size(),
-                  c->d_scratch + (size_t)b * ogrid, (u64)0, 64, PeerTable());
+    {
+        QR_LAUNCH(k_apply_obs, dim3((unsigned)ogrid, (unsigned)batch), QR_BLOCK, 0, c->stream, (const double2*)c->buf[c->psi],
+                  want_grad ? c->buf[lam] : (double2*)nullptr, c->N, d_terms, (int)o->terms.size(), c->d_scratch, (u64)0, 64,
+                  PeerTable());
         KERNEL_CHECK();
         c->perf.kernel_launches++;
     }
@@ -1158,7 +1184,8 @@ extern "C" int qr_mcclean_grad_batch(qr_ctx* c, int batch, int L, const int32_t*
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     const u64 per_state = c->N * sizeof(double2) * QR_NBUF;
-    u64 chunk = std::max<u64>(1, std::min<u64>((u64)batch, ((u64)1 << 28) / std::max<u64>(per_state / QR_NBUF, 1)));
+    const u64 chunk_bytes = c->opt_batch_chunk_mb > 0 ? (u64)c->opt_batch_chunk_mb << 20 : (u64)1 << 28;   // per buffer
+    u64 chunk = std::max<u64>(1, std::min<u64>((u64)batch, chunk_bytes / std::max<u64>(per_state / QR_NBUF, 1)));
     // (re)allocate the buffers for `chunk` states
     if (c->buf_amps < c->N * chunk) {
         CUDA_TRY(cudaStreamSynchronize(c->stream));
