@@ -428,3 +428,10 @@ __global__ void k_build_gates(const int* __restrict__ axes, const double* __rest
         tab[idx] = g;
     }
 }
+
+
+// integer-valued diagonal Hamiltonian -> 16-bit index table: hidx[j] = H[j] - hmin
+__global__ void k_ham_index(const double* __restrict__ ham, short* __restrict__ hidx, u64 N, double hmin) {
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (u64)gridDim.x * blockDim.x)
+        hidx[j] = (short)__double2int_rn(ham[j] - hmin);
+}

@@ -78,6 +78,10 @@ struct qr_ctx {
     int psi = 0;                 // buffer holding the state vector
     double* d_ham = nullptr;     // diagonal Hamiltonian table [N]
     bool ham_loaded = false;
+    short* d_hidx = nullptr;     // integer-valued H: H = hmin + hidx (phase look-up table path)
+    bool ham_integer = false;
+    double ham_min = 0.0;
+    int ham_range = 0;
     double* d_scratch = nullptr; // reduction partials
     size_t scratch_cap = 0;      // in doubles
     unsigned* d_counter = nullptr;   // arrival counter of the fused final reduction (kept at zero between launches)
@@ -245,6 +249,7 @@ extern "C" int qr_ctx_destroy(qr_ctx* c) {
     shard_release(c);
     for (int i = 0; i < QR_NBUF; ++i) if (c->buf[i]) cudaFree(c->buf[i]);
     if (c->d_ham) cudaFree(c->d_ham);
+    if (c->d_hidx) cudaFree(c->d_hidx);
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_result) cudaFree(c->d_result);
     if (c->d_counter) cudaFree(c->d_counter);
@@ -627,6 +632,25 @@ extern "C" int qr_ham_load(qr_ctx* c, const qr_obs* o) {
     QR_TRY(upload_terms(c, o->terms, &d_terms));
     QR_LAUNCH(k_ham_build, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->d_ham, c->N, d_terms, (int)o->terms.size());
     KERNEL_CHECK();
+    // integer weights => H takes at most 2 sum|w| + 1 integer values: phases come from a small table
+    double wsum = 0.0;
+    bool integral = true;
+    for (const ObsTerm& t : o->terms)
+        if (t.kind >= 2) { wsum += std::fabs(t.w); if (t.w != std::floor(t.w)) integral = false; }
+    c->ham_integer = false;
+    if (integral && 2.0 * wsum + 1.0 <= (double)QR_LUT_MAX) {
+        if (!c->d_hidx) {
+            cudaError_t e = cudaMalloc((void**)&c->d_hidx, c->N * sizeof(short));
+            if (e != cudaSuccess) { c->d_hidx = nullptr; cudaGetLastError(); }
+        }
+        if (c->d_hidx) {
+            c->ham_min = -wsum;
+            c->ham_range = (int)(2.0 * wsum + 1.0);
+            QR_LAUNCH(k_ham_index, grid_for(c, c->N), QR_BLOCK, 0, c->stream, (const double*)c->d_ham, c->d_hidx, c->N, c->ham_min);
+            KERNEL_CHECK();
+            c->ham_integer = true;
+        }
+    }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->ham_loaded = true;
     return 0;
@@ -789,7 +813,7 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
                        int gate_stride, int ladder_stacking /* -1 none, else gather of ladder(stacking) */,
                        i64 batch, i64 state_stride, int flush_per_tile, const double* ham, int pre_phase,
                        double angle_pre, int post_phase, double angle_post, int* units, const LadderSpec* spec = nullptr,
-                       double* final_out = nullptr) {
+                       double* final_out = nullptr, const double2* lut = nullptr) {
     const PassPlan& pp = lp.pass[pass];
     TilePass tp;
     memset(&tp, 0, sizeof(tp));
@@ -809,6 +833,7 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
     tp.src0 = io.src0; tp.src1 = io.src1; tp.dst0 = io.dst0; tp.dst1 = io.dst1;
     tp.gates = d_gates; tp.gate_stride = gate_stride;
     tp.ham = ham; tp.pre_phase = pre_phase; tp.post_phase = post_phase;
+    if (lut && c->ham_integer) { tp.hidx = c->d_hidx; tp.lut = lut; tp.lut_size = c->ham_range; tp.hmin = c->ham_min; }
     tp.angle_pre = angle_pre; tp.angle_post = angle_post;
     tp.flush_per_tile = flush_per_tile;
     tp.prefetch = (int)c->opt_prefetch;
@@ -1281,8 +1306,9 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
     const bool want_grad = grad != nullptr;
     const int nlay_tab = p * (want_grad ? 2 : 1);
     const size_t tab_bytes = (size_t)nlay_tab * P * GS * sizeof(GateP);
-    QR_TRY(ensure_small(c, tab_bytes + 1024));
-    QR_TRY(ensure_pin(c, tab_bytes + 1024));
+    const size_t lut_space = (size_t)2 * p * QR_LUT_MAX * sizeof(double2) + 2048;   // reserved up front: no realloc mid-stream
+    QR_TRY(ensure_small(c, tab_bytes + 1024 + lut_space));
+    QR_TRY(ensure_pin(c, std::max(tab_bytes + 1024 + lut_space, (size_t)(1 + (size_t)p * P * QR_SLOTS) * sizeof(double) + 1024)));
     {
         GateP* tab = (GateP*)c->h_pin;
         int lay = 0;
@@ -1296,6 +1322,22 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
     }
     const GateP* d_tab = (const GateP*)c->d_small;
     const i64 stride = (i64)c->N;
+    // phase look-up tables exp(-i gamma_i h) (forward) and exp(+i gamma_i h) (backward), host libm values
+    const bool lut_on = c->ham_integer && c->opt_ham_lut;
+    const double2* d_lut = nullptr;
+    if (lut_on) {
+        const size_t lut_off = (tab_bytes + 1024 + 255) & ~(size_t)255;
+        const size_t lut_bytes = (size_t)2 * p * c->ham_range * sizeof(double2);
+        double2* lut = (double2*)(c->h_pin + lut_off);
+        for (int dir = 0; dir < 2; ++dir)
+            for (int i = 0; i < p; ++i)
+                for (int v = 0; v < c->ham_range; ++v) {
+                    const double ang = (dir == 0 ? gammas[i] : -gammas[i]) * (c->ham_min + v);
+                    lut[((size_t)dir * p + i) * c->ham_range + v] = make_double2(std::cos(ang), -std::sin(ang));
+                }
+        CUDA_TRY(cudaMemcpyAsync((char*)c->d_small + lut_off, lut, lut_bytes, cudaMemcpyHostToDevice, c->stream));
+        d_lut = (const double2*)((char*)c->d_small + lut_off);
+    }
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     if (!use_current) {
         QR_LAUNCH(k_init_basis, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[c->psi], c->N, 1, std::pow(2.0, -0.5 * n));
@@ -1306,7 +1348,7 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
         for (int q = 0; q < P; ++q) {
             PassIO io = {c->buf[c->psi], nullptr, c->buf[c->psi], nullptr};
             QR_TRY(launch_pass(c, lpf, q, 1, io, d_tab + ((size_t)i * P + q) * GS, 0, -1, 1, stride, 0, c->d_ham, q == 0 ? 1 : 0,
-                               gammas[i], 0, 0.0, nullptr));
+                               gammas[i], 0, 0.0, nullptr, nullptr, nullptr, d_lut ? d_lut + (size_t)i * c->ham_range : nullptr));
         }
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     const int g = grid_for(c, c->N);
@@ -1329,7 +1371,8 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
                 PassIO io = {c->buf[c->psi], c->buf[lam], c->buf[c->psi], c->buf[lam]};
                 int units = 0;
                 QR_TRY(launch_pass(c, lp, q, 2, io, d_tab + ((size_t)(p + i) * P + q) * GS, 0, -1, 1, stride, 0, c->d_ham, 0, 0.0,
-                                   q == P - 1 ? 1 : 0, -gammas[i], &units, nullptr, d_slots + ((size_t)i * P + q) * QR_SLOTS));
+                                   q == P - 1 ? 1 : 0, -gammas[i], &units, nullptr, d_slots + ((size_t)i * P + q) * QR_SLOTS,
+                                   d_lut ? d_lut + (size_t)(p + i) * c->ham_range : nullptr));
                 ++n_bwd_pass;
             }
     }

@@ -33,6 +33,7 @@
 #define QR_GATE_SLOTS 12                      // gate bits per pass (= QR_MAX_TILE_BITS)
 #define QR_SLOTS (QR_GATE_SLOTS + 1)          // gradient accumulators per thread (+1: diagonal generator)
 #define QR_MAX_TILE_BITS 12
+#define QR_LUT_MAX 256                        // phase look-up table entries (integer-valued Hamiltonians)
 
 struct GateP {
     double c, s;    // cos(theta/2), sin(theta/2) (sign already folded in for un-rotation)
@@ -57,6 +58,10 @@ struct TilePass {
     const GateP* gates;          // [batch][nrounds * R]
     int gate_stride;
     const double* ham;           // diagonal Hamiltonian table (QAOA) or null
+    const short* hidx;           // integer-valued H: H[j] = hmin + hidx[j] (2 B/amp instead of 8) or null
+    const double2* lut;          // exp(-i angle (hmin + v)) for v in [0, lut_size): replaces sincos per amplitude
+    int lut_size;
+    double hmin;
     int pre_phase, post_phase;   // multiply by exp(-i angle H) after load / before store
     double angle_pre, angle_post;
     double* partials;            // [units][QR_SLOTS]; unit = CTA, or tile when flush_per_tile
@@ -212,6 +217,7 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
     __shared__ u64 full_bar;
     __shared__ GateP sgt[QR_GATE_SLOTS];    // this pass's gate table (a dependent global load per gate
                                             // would put an L2 round trip on every tile's critical path)
+    __shared__ double2 lut_sm[QR_LUT_MAX];  // QAOA phase factors by integer Hamiltonian value
     const int tid = threadIdx.x;
     const int T = 1 << p.k;
     double2* exch = ASYNC ? smem + NV * T : smem;   // ASYNC: [raw psi][raw lambda][exchange]
@@ -257,6 +263,11 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
     }
     unsigned parity = 0;
     i64 cur_b = -1;
+    const bool use_lut = p.hidx != nullptr && (p.pre_phase || p.post_phase);
+    if (use_lut) {
+        for (int i = threadIdx.x; i < p.lut_size; i += blockDim.x) lut_sm[i] = p.lut[i];
+        __syncthreads();
+    }
 
     for (i64 tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const i64 b = tile >> p.tiles_log2;
@@ -306,9 +317,13 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
             for (int r = 0; r < RA; ++r) {
                 const int l = tb_first | (r << g_first);
                 const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
-                double sn, cs;
-                sincos(p.angle_pre * p.ham[d], &sn, &cs);
-                const double2 ph = make_double2(cs, -sn);
+                double2 ph;
+                if (use_lut) ph = lut_sm[p.hidx[d]];
+                else {
+                    double sn, cs;
+                    sincos(p.angle_pre * p.ham[d], &sn, &cs);
+                    ph = make_double2(cs, -sn);
+                }
 #pragma unroll
                 for (int v = 0; v < NV; ++v) a[v][r] = cmul(a[v][r], ph);
             }
@@ -385,11 +400,19 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
             const int l = tb_last | (r << g_last);
             const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
             if (p.post_phase) {
-                const double hv = p.ham[d];
-                if (NV == 2) acc_all[QR_SLOTS - 1] += hv * im_conj_mul(a[NV - 1][r], a[0][r]);   // (register slot; folded below)
-                double sn, cs;
-                sincos(p.angle_post * hv, &sn, &cs);
-                const double2 ph = make_double2(cs, -sn);
+                double hv;
+                double2 ph;
+                if (use_lut) {
+                    const int hi = p.hidx[d];
+                    hv = p.hmin + (double)hi;
+                    ph = lut_sm[hi];
+                } else {
+                    hv = p.ham[d];
+                    double sn, cs;
+                    sincos(p.angle_post * hv, &sn, &cs);
+                    ph = make_double2(cs, -sn);
+                }
+                if (NV == 2) acc_all[QR_SLOTS - 1] += hv * im_conj_mul(a[NV - 1][r], a[0][r]);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) a[v][r] = cmul(a[v][r], ph);
             }
