@@ -91,6 +91,11 @@ int qr_state_init(qr_ctx* ctx, int which);
 /* State.vec setter / getter: n_amps must equal 2^n */
 int qr_state_upload(qr_ctx* ctx, const double* re_im, size_t n_amps);
 int qr_state_download(qr_ctx* ctx, double* re_im, size_t n_amps);
+/* device-side copies of the state vector; replace the reference's `state_history[i] = state.vec`
+ * snapshots (mc_clean.py:132, qaoa.py:118-120) without a host round trip */
+int qr_state_save(qr_ctx* ctx, int slot);
+int qr_state_load(qr_ctx* ctx, int slot);
+int qr_state_free_snapshots(qr_ctx* ctx);
 /* device address of the current state vector (for torch / NCCL plumbing; complex128[2^n]) */
 int qr_state_device_ptr(qr_ctx* ctx, void** out);
 /* xrot / yrot / zrot (state.py:90-92,142-144,168-170): axis 0,1,2 = X,Y,Z; exp(-i angle P/2) */

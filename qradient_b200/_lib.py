@@ -46,6 +46,9 @@ _SIGNATURES = {
     "qr_state_upload": (c_int, [c_void_p, c_void_p, c_size_t]),
     "qr_state_download": (c_int, [c_void_p, c_void_p, c_size_t]),
     "qr_state_device_ptr": (c_int, [c_void_p, P(c_void_p)]),
+    "qr_state_save": (c_int, [c_void_p, c_int]),
+    "qr_state_load": (c_int, [c_void_p, c_int]),
+    "qr_state_free_snapshots": (c_int, [c_void_p]),
     "qr_apply_rot": (c_int, [c_void_p, c_int, c_double, c_int]),
     "qr_apply_drot": (c_int, [c_void_p, c_int, c_double, c_int]),
     "qr_apply_cnot": (c_int, [c_void_p, c_int, c_int]),

@@ -69,6 +69,25 @@ class McClean(ParametrizedCircuit):
                        self.observable._handle, use_current, ctypes.byref(e), _lib.ptr(grad))
         return e.value, grad
 
+    # -- mc_clean.py:80-115 ----------------------------------------------------------------------
+    def grad_run_with_component_sampling(self, hide_progbar=True, ini_state=None):
+        """Exact E under the full observable, gradient under ONE observable component drawn with
+        np.random.choice(p=weight_distribution) (mc_clean.py:101-103).  Needs
+        use_observable_components=True at construction, like the reference."""
+        if not getattr(self.observable, 'store_components', False):
+            raise AttributeError('construct the circuit with use_observable_components=True')
+        ini = None if ini_state is None else np.array(ini_state, dtype=complex)
+        expec_val = self.run_expec_val(ini_state=None if ini is None else ini.copy())
+        component = np.random.choice(np.arange(self.observable.num_components), p=self.observable.weight_distribution)
+        axes, angles = self._params()
+        use_current = self._adopt(None if ini is None else ini.copy())
+        e = ctypes.c_double()
+        grad = np.empty([self.lnum, self.qnum], dtype='double')
+        comp_obs = self.observable.component(component)
+        self._lib.call('qr_mcclean_grad', self.state._ctx, self.lnum, _lib.ptr(axes), _lib.ptr(angles),
+                       comp_obs._handle, use_current, ctypes.byref(e), _lib.ptr(grad))
+        return expec_val, grad
+
     # -- extension: many parameter sets at once (timing-test.ipynb cell 6 host loop) -------------
     def grad_run_batch(self, angles, axes=None):
         """angles: [B, L, n]; axes: [B, L, n] or [L, n] (default: self.axes).

@@ -6,6 +6,7 @@ the diagonal Hamiltonian of the observable ('z' / 'zz' terms).  grad_run returns
 the two-vector adjoint recurrence in fused CUDA tile passes.
 """
 import ctypes
+import warnings
 
 import numpy as np
 
@@ -59,6 +60,61 @@ class Qaoa(ParametrizedCircuit):
         self._lib.call('qr_qaoa_grad', self.state._ctx, self.lnum, _lib.ptr(betas), _lib.ptr(gammas), use_current,
                        ctypes.byref(e), _lib.ptr(grad))
         return e.value, grad
+
+    # -- qaoa.py:72-81 ------------------------------------------------------------------------
+    def sample_grad(self, betas, gammas, shot_num=1, hide_progbar=True, exact_expec_val=True, ini_state=None):
+        warnings.warn('Not implemented yet.')
+
+    # -- qaoa.py:83-158, matrix free ------------------------------------------------------------
+    def sample_grad_dense(self, betas, gammas, shot_num=1, hide_progbar=True, exact_expec_val=True, ini_state=None):
+        """Finite-shot parameter-shift gradient where every shifted circuit is measured in the
+        computational basis (the eigenbasis of H).  The reference propagates dense 2^n x 2^n
+        left-hand-side matrices (qaoa.py:95-134); here each shifted state is pushed through the
+        remaining layers on the device and `shot_num` bitstrings are drawn from |psi|^2 by the
+        prefix-sum sampler.  Same RNG consumption as the reference: one uniform(size=shot_num) per
+        `__sample` call, in the same order (component +, component -, ..., qubit +, qubit -)."""
+        st, n, p = self.state, self.qnum, self.lnum
+        use_current = self._adopt(ini_state)
+        betas, gammas = self._check_parameters(betas, gammas)
+        if not use_current:
+            st.reset()
+        for i in range(p):                                   # qaoa.py:116-120
+            st.exp_ham_classical(gammas[i])
+            st.save(2 * i)
+            for q in range(n):
+                st.xrot(betas[i], q)
+            st.save(2 * i + 1)
+        expec_val = self.expec_val() if exact_expec_val else self.sample_expec_val(shot_num)   # :122-126
+        grad = np.ndarray([p, 2], dtype='double')
+        ncomp = st.gates.num_ham_components()
+
+        def finish_and_sample(first_layer):
+            """run layers first_layer..p-1 on the current state, then sample the cost"""
+            if first_layer < p:
+                e = ctypes.c_double()
+                b, g = np.ascontiguousarray(betas[first_layer:]), np.ascontiguousarray(gammas[first_layer:])
+                self._lib.call('qr_qaoa_expec', st._ctx, p - first_layer, _lib.ptr(b), _lib.ptr(g), 1, ctypes.byref(e))
+            return self.sample_cost(shot_num)
+
+        for i in range(p):
+            plus, minus = np.empty(ncomp), np.empty(ncomp)
+            for j in range(ncomp):                           # gamma_i : qaoa.py:139-147
+                for sign, out in ((1., plus), (-1., minus)):
+                    st.load(2 * i)
+                    st.exp_ham_classical_component(sign * np.pi / 4, j)
+                    for q in range(n):
+                        st.xrot(betas[i], q)
+                    out[j] = finish_and_sample(i + 1)
+            grad[i, 1] = (plus - minus).sum()
+            plus, minus = np.empty(n), np.empty(n)
+            for q in range(n):                               # beta_i : qaoa.py:149-157
+                for sign, out in ((1., plus), (-1., minus)):
+                    st.load(2 * i + 1)
+                    st.xrot(sign * np.pi / 2, q)
+                    out[q] = finish_and_sample(i + 1)
+            grad[i, 0] = .5 * (plus - minus).sum()
+        st.free_snapshots()
+        return expec_val, grad
 
     # -- qaoa.py:196-198 applied to the current state --------------------------------------------
     def sample_cost(self, shot_num, uniforms=None):

@@ -104,6 +104,7 @@ struct qr_ctx {
     double2* peer[QR_MAX_RANKS][QR_NBUF];
     bool peer_mapped[QR_MAX_RANKS][QR_NBUF];
     struct ShardRun* run = nullptr;
+    std::vector<double2*> snapshots;   // device copies of the state vector (qr_state_save / qr_state_load)
 };
 
 static inline int use_device(qr_ctx* c) {
@@ -250,6 +251,7 @@ extern "C" int qr_ctx_destroy(qr_ctx* c) {
     for (int i = 0; i < QR_NBUF; ++i) if (c->buf[i]) cudaFree(c->buf[i]);
     if (c->d_ham) cudaFree(c->d_ham);
     if (c->d_hidx) cudaFree(c->d_hidx);
+    for (double2* sp : c->snapshots) if (sp) cudaFree(sp);
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_result) cudaFree(c->d_result);
     if (c->d_counter) cudaFree(c->d_counter);
@@ -355,6 +357,38 @@ extern "C" int qr_state_download(qr_ctx* c, double* re_im, size_t n_amps) {
 extern "C" int qr_state_device_ptr(qr_ctx* c, void** out) {
     if (!c || !out) return fail(QR_EINVAL, "null argument");
     *out = c->buf[c->psi];
+    return 0;
+}
+
+// device-side snapshots of the state vector (the reference keeps numpy copies: state_history)
+extern "C" int qr_state_save(qr_ctx* c, int slot) {
+    if (!c) return fail(QR_EINVAL, "null context");
+    if (slot < 0 || slot > 4096) return fail(QR_EINVAL, "bad snapshot slot %d", slot);
+    QR_TRY(use_device(c));
+    if ((size_t)slot >= c->snapshots.size()) c->snapshots.resize(slot + 1, nullptr);
+    if (!c->snapshots[slot]) {
+        cudaError_t e = cudaMalloc((void**)&c->snapshots[slot], c->N * sizeof(double2));
+        if (e != cudaSuccess) { c->snapshots[slot] = nullptr; return fail(QR_ENOMEM, "cannot allocate snapshot %d: %s", slot, cudaGetErrorString(e)); }
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->snapshots[slot], c->buf[c->psi], c->N * sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int qr_state_load(qr_ctx* c, int slot) {
+    if (!c) return fail(QR_EINVAL, "null context");
+    if (slot < 0 || (size_t)slot >= c->snapshots.size() || !c->snapshots[slot]) return fail(QR_EINVAL, "snapshot %d does not exist", slot);
+    QR_TRY(use_device(c));
+    CUDA_TRY(cudaMemcpyAsync(c->buf[c->psi], c->snapshots[slot], c->N * sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int qr_state_free_snapshots(qr_ctx* c) {
+    if (!c) return fail(QR_EINVAL, "null context");
+    QR_TRY(use_device(c));
+    for (double2*& sp : c->snapshots) { if (sp) cudaFree(sp); sp = nullptr; }
+    c->snapshots.clear();
     return 0;
 }
 

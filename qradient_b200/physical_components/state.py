@@ -83,6 +83,16 @@ class State:
             raise ValueError('state vector must have shape ({},), got {}'.format(self._N, arr.shape))
         self._lib.call('qr_state_upload', self._ctx, _lib.ptr(arr), self._N)
 
+    def save(self, slot):
+        """Device-side snapshot of the vector (stands in for `state_history[i] = state.vec`)."""
+        self._lib.call('qr_state_save', self._ctx, int(slot))
+
+    def load(self, slot):
+        self._lib.call('qr_state_load', self._ctx, int(slot))
+
+    def free_snapshots(self):
+        self._lib.call('qr_state_free_snapshots', self._ctx)
+
     def device_ptr(self):
         p = ctypes.c_void_p()
         self._lib.call('qr_state_device_ptr', self._ctx, ctypes.byref(p))

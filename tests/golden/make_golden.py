@@ -354,3 +354,29 @@ if __name__ == "__main__":
         c = McClean(20, zz01(20), 20, axes=axes, angles=angles)
         e, grad = c.grad_run()
         save("gv10_mcclean_20x20", n=20, L=20, axes=axes, angles=angles, E=e, grad=grad, **obs_to_arrays(20, zz01(20)))
+
+
+def extra_goldens():
+    """GV11: Qaoa.sample_grad_dense (qaoa.py:83-158); GV12: McClean.grad_run_with_component_sampling."""
+    n, p = 4, 2
+    edges = [[0, 1], [1, 2], [0, 2], [2, 3]]
+    c = Qaoa(n, MaxCut(n, edge_set=np.array(edges)).to_observable(), p)
+    betas, gammas = np.array([0.3, 0.7]), np.array([0.2, 0.9])
+    np.random.seed(5)
+    e, grad = c.sample_grad_dense(betas, gammas, shot_num=25)
+    save("gv11_qaoa_sample_grad_dense", n=n, p=p, edges=np.array(edges), betas=betas, gammas=gammas, E=e, grad=grad, shot_num=25, seed=5)
+    n, L = 5, 3
+    rng = np.random.default_rng(12)
+    obs = {"x": np.array([0.5, None, None, None, None], dtype=object), "z": np.array([None, 0.8, None, None, 0.3], dtype=object),
+           "zz": np.full((5, 5), None)}
+    obs["zz"][0, 1] = 1.0
+    obs["zz"][2, 4] = 0.6
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    c = McClean(n, obs, L, use_observable_components=True, axes=axes, angles=angles)
+    np.random.seed(2)
+    e, grad = c.grad_run_with_component_sampling()
+    save("gv12_mcclean_component_sampling", n=n, L=L, axes=axes, angles=angles, E=e, grad=grad, seed=2, **obs_to_arrays(n, obs))
+
+
+if __name__ == "__main__" and os.environ.get("QR_GOLDEN_EXTRA", "1") == "1":
+    extra_goldens()

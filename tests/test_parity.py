@@ -387,3 +387,50 @@ def test_sampling_edge_cases(backend):
             lo, hi = min(a, b), max(a, b)
             assert abs(cdf[lo] - uu) < 1e-13 and abs(cdf[hi - 1] - uu) < 1e-13, (a, b, uu)
     assert np.mean(idx == ref) > 0.99
+
+
+def test_qaoa_sample_grad_dense_golden(backend):
+    """qaoa.py:83-158 through the matrix-free device path; same global-RNG draw order."""
+    d = load_golden("gv11_qaoa_sample_grad_dense")
+    n, p = int(d["n"]), int(d["p"])
+    q = Qaoa(n, MaxCut(n, edge_set=d["edges"]).to_observable(), p)
+    np.random.seed(int(d["seed"]))
+    e, g = q.sample_grad_dense(d["betas"], d["gammas"], shot_num=int(d["shot_num"]))
+    assert abs(e - float(d["E"])) < 1e-10 * len(d["edges"])
+    np.testing.assert_allclose(g, d["grad"], atol=1e-12)
+    with pytest.warns(UserWarning, match="Not implemented"):
+        q.sample_grad(d["betas"], d["gammas"])
+
+
+def test_mcclean_component_sampling_golden(backend):
+    """mc_clean.py:80-115: np.random.choice over observable components, then the adjoint sweep."""
+    d = load_golden("gv12_mcclean_component_sampling")
+    n, L, obs = int(d["n"]), int(d["L"]), obs_from_golden(d)
+    c = McClean(n, obs, L, use_observable_components=True, axes=d["axes"], angles=d["angles"])
+    np.random.seed(int(d["seed"]))
+    e, g = c.grad_run_with_component_sampling()
+    assert_parity(e, g, float(d["E"]), d["grad"], obs_scale(obs), TOL)
+    c2 = McClean(n, obs, L, axes=d["axes"], angles=d["angles"])
+    with pytest.raises(AttributeError):
+        c2.grad_run_with_component_sampling()
+
+
+def test_state_snapshots(backend):
+    n = 6
+    rng = np.random.default_rng(1)
+    v = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    st = State(n)
+    st.vec = v
+    st.save(3)
+    st.xrot(0.3, 2)
+    st.save(0)
+    w = np.array(st.vec)
+    st.load(3)
+    np.testing.assert_array_equal(st.vec, v)
+    st.load(0)
+    np.testing.assert_array_equal(st.vec, w)
+    with pytest.raises(ValueError):
+        st.load(2)
+    st.free_snapshots()
+    with pytest.raises(ValueError):
+        st.load(0)
