@@ -43,7 +43,7 @@ enum { QR_TERM_X = 0, QR_TERM_Y = 1, QR_TERM_Z = 2, QR_TERM_ZZ = 3 };
 enum {
     QR_OPT_FUSION = 0,        /* 1 (default): fused tile passes; 0: one kernel per gate          */
     QR_OPT_TILE_BITS = 1,     /* log2 amplitudes per shared-memory tile (default 12)            */
-    QR_OPT_PREFETCH = 2,      /* L2-prefetch the CTA's next tile: bit0 backward (default on), bit1 forward */
+    QR_OPT_PREFETCH = 2,      /* L2 prefetch distance in tiles: bits 0-1 backward (default 1), bits 2-3 forward (default 0) */
     QR_OPT_CTAS_PER_SM_FWD = 3,
     QR_OPT_CTAS_PER_SM_BWD = 4,
     QR_OPT_FINAL_LADDER = 5,  /* 1 (default): leave state.vec exactly as mc_clean.py:77 does     */

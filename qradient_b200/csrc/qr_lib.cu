@@ -270,7 +270,7 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
         case QR_OPT_TILE_BITS:
             if (v < 4 || v > QR_MAX_TILE_BITS) return fail(QR_EINVAL, "tile bits must be in [4, %d]", QR_MAX_TILE_BITS);
             c->opt_tile_bits = v; break;
-        case QR_OPT_PREFETCH: if (v < 0 || v > 3) return fail(QR_EINVAL, "prefetch must be in [0, 3]"); c->opt_prefetch = v; break;
+        case QR_OPT_PREFETCH: if (v < 0 || v > 15) return fail(QR_EINVAL, "prefetch must be in [0, 15]"); c->opt_prefetch = v; break;
         case QR_OPT_CTAS_PER_SM_FWD: if (v < 1 || v > 8) return fail(QR_EINVAL, "bad CTAs/SM"); c->opt_ctas_fwd = v; break;
         case QR_OPT_CTAS_PER_SM_BWD: if (v < 1 || v > 8) return fail(QR_EINVAL, "bad CTAs/SM"); c->opt_ctas_bwd = v; break;
         case QR_OPT_FINAL_LADDER: c->opt_final_ladder = v ? 1 : 0; break;
@@ -870,7 +870,7 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
     if (lut && c->ham_integer) { tp.hidx = c->d_hidx; tp.lut = lut; tp.lut_size = c->ham_range; tp.hmin = c->ham_min; }
     tp.angle_pre = angle_pre; tp.angle_post = angle_post;
     tp.flush_per_tile = flush_per_tile;
-    tp.prefetch = nv == 2 ? (int)(c->opt_prefetch & 1) : (int)((c->opt_prefetch >> 1) & 1);   // bit0: backward, bit1: forward
+    tp.prefetch = nv == 2 ? (int)(c->opt_prefetch & 3) : (int)((c->opt_prefetch >> 2) & 3);   // tiles ahead: bits 0-1 backward, bits 2-3 forward
     const int R = lp.R;
     const int async = (nv == 1 ? c->opt_async_fwd : c->opt_async_bwd) ? 1 : 0;
     const int threads = 1 << (pp.k - R);

@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
         }
 #ifndef QR_HOST_EMUL
         if (!ASYNC && p.prefetch) {   // pull the next tile of this CTA into L2 while this one is computed
-            const i64 nt = tile + gridDim.x;
+            const i64 nt = tile + (i64)gridDim.x * p.prefetch;   // p.prefetch = distance in tiles
             if (nt < p.num_tiles) {
                 const i64 nb = nt >> p.tiles_log2;
                 const u64 t2 = (u64)nt & tmask;
