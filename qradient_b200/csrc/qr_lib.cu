@@ -58,6 +58,8 @@ struct PassPlan {
     int k, c, h, nrounds;
     int g[QR_MAXROUNDS];
     int gbit[QR_GATE_SLOTS];   // global index bit handled by slot (round * R + register bit) or -1
+    bool dc;                   // decoupled-exchange kernel (k == 12, R == 3)
+    DcPlan dcp;
 };
 
 struct LayerPlan {
@@ -98,6 +100,7 @@ struct qr_ctx {
     long long opt_r_fwd = 3, opt_r_bwd = 3;
     long long opt_async_fwd = 0, opt_async_bwd = 0;
     long long opt_tile_bits_x = 0, opt_min_row_bits = 3, opt_batch_chunk_mb = 0;
+    long long opt_decoupled = 0;   // bit0: backward, bit1: forward use the decoupled-exchange kernel
     qr_perf perf;
     // ---- sharded states: this context holds one shard of an n_total-qubit register ----
     int n_total = 0, g = 0, rank = 0;
@@ -282,6 +285,7 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
         case QR_OPT_TILE_BITS_STRIDED: if (v != 0 && (v < 4 || v > QR_MAX_TILE_BITS)) return fail(QR_EINVAL, "bad strided tile bits"); c->opt_tile_bits_x = v; break;
         case QR_OPT_MIN_ROW_BITS: if (v < 1 || v > 6) return fail(QR_EINVAL, "bad min row bits"); c->opt_min_row_bits = v; break;
         case QR_OPT_BATCH_CHUNK_MB: if (v < 0 || v > 65536) return fail(QR_EINVAL, "bad batch chunk"); c->opt_batch_chunk_mb = v; break;
+        case QR_OPT_DECOUPLED: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad decoupled mode"); c->opt_decoupled = v; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -304,6 +308,7 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_TILE_BITS_STRIDED: *v = c->opt_tile_bits_x; break;
         case QR_OPT_MIN_ROW_BITS: *v = c->opt_min_row_bits; break;
         case QR_OPT_BATCH_CHUNK_MB: *v = c->opt_batch_chunk_mb; break;
+        case QR_OPT_DECOUPLED: *v = c->opt_decoupled; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -781,7 +786,38 @@ static void plan_rounds(PassPlan& pp, int first, int R) {
         }
 }
 
-static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x = 0, int min_row_bits = 3) {
+// Decoupled-exchange plan of a k = 12 pass whose gate bits are the local bits [first, 12): groups
+// A,B,C,D of 3 bits; D is in the registers at load time (natural, coalesced layout), the other
+// groups that carry gates are swapped in through the slot that currently holds them.
+static void plan_dc(PassPlan& pp, int first) {
+    int cont[3] = {0, 1, 2}, reg = 3;   // group held by S0, S1, S2 and by the registers
+    DcPlan& d = pp.dcp;
+    int nr = 0;
+    auto record = [&]() {
+        for (int s = 0; s < 3; ++s) d.gp[nr][s] = 3 * cont[s];
+        d.gp[nr][3] = 3 * reg;
+        for (int b = 0; b < 3; ++b) {
+            const int lb = 3 * reg + b;
+            pp.gbit[nr * 3 + b] = lb < first ? -1 : (lb < pp.c ? lb : pp.h + (lb - pp.c));
+        }
+        ++nr;
+    };
+    for (int i = 0; i < QR_GATE_SLOTS; ++i) pp.gbit[i] = -1;
+    record();
+    for (int grp = 0; grp < 3; ++grp) {
+        if (3 * grp + 2 < first) continue;   // no gate bit in this group
+        int s = 0;
+        while (cont[s] != grp) ++s;
+        d.swap_slot[nr - 1] = s;
+        std::swap(cont[s], reg);
+        record();
+    }
+    d.nrounds = nr;
+    pp.nrounds = nr;
+    pp.dc = true;
+}
+
+static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x = 0, int min_row_bits = 3, bool allow_dc = false) {
     if (n < 4) return fail(QR_EINVAL, "fused path needs at least 4 qubits");
     const int k = std::min(n, tile_bits);
     lp->n = n;
@@ -789,8 +825,8 @@ static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x
     lp->R = R;
     int np = 0;
     PassPlan& p0 = lp->pass[np++];
-    p0.k = k; p0.c = k; p0.h = k;
-    plan_rounds(p0, 0, R);
+    p0.k = k; p0.c = k; p0.h = k; p0.dc = false;
+    if (allow_dc && k == 12 && R == 3) plan_dc(p0, 0); else plan_rounds(p0, 0, R);
     const int rem = n - k;
     if (rem > 0) {
         // strided passes: tile of kx bits = c contiguous low bits (rows of 2^c amplitudes) + m gate bits
@@ -801,8 +837,8 @@ static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x
         for (int i = 0; i < nx; ++i) {
             const int m = rem / nx + (i < rem % nx ? 1 : 0);
             PassPlan& pp = lp->pass[np++];
-            pp.k = kx; pp.c = kx - m; pp.h = h;
-            plan_rounds(pp, pp.c, R);
+            pp.k = kx; pp.c = kx - m; pp.h = h; pp.dc = false;
+            if (allow_dc && kx == 12 && R == 3) plan_dc(pp, pp.c); else plan_rounds(pp, pp.c, R);
             h += m;
         }
     }
@@ -888,6 +924,19 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
     tp.partials = c->d_scratch;
     tp.final_out = (nv == 2 && !flush_per_tile) ? final_out : nullptr;
     tp.done_counter = c->d_counter;
+    if (pp.dc) {   // decoupled-exchange kernel (single state, k = 12, R = 3)
+        typedef void (*dc_fn)(const TilePass, const DcPlan);
+        dc_fn dfn = nv == 1 ? k_tile_pass_dc<1> : k_tile_pass_dc<2>;
+        static bool dc_attr[2] = {false, false};
+        if (!dc_attr[nv - 1]) {
+            CUDA_TRY(cudaFuncSetAttribute(dfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(double2) << QR_MAX_TILE_BITS));
+            dc_attr[nv - 1] = true;
+        }
+        QR_LAUNCH(dfn, (unsigned)grid, threads, (size_t)nv * tile_bytes, c->stream, tp, pp.dcp);
+        KERNEL_CHECK();
+        c->perf.kernel_launches++;
+        return 0;
+    }
     tile_fn fn = tile_kernel(nv, R, async);
     static bool attr_done[2][5][2] = {{{false}}};
     if (!attr_done[nv - 1][R][async]) {
@@ -998,8 +1047,10 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
                          int use_current, double* e_out, double* grad) {
     const int n = c->n;
     LayerPlan lpf, lp;   // forward / backward plans: same tile geometry, different register blocking
-    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits));
-    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits));
+    const bool dc_f = batch == 1 && !c->opt_async_fwd && (c->opt_decoupled & 2);
+    const bool dc_b = batch == 1 && !c->opt_async_bwd && (c->opt_decoupled & 1);
+    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits, dc_f));
+    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits, dc_b));
     const int P = lp.npasses;
     const int GS = QR_GATE_SLOTS;                 // gate entries per (layer, pass)
     const bool want_grad = grad != nullptr;
@@ -1333,8 +1384,10 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
                       double* grad) {
     const int n = c->n;
     LayerPlan lpf, lp;
-    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits));
-    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits));
+    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
+                     !c->opt_async_fwd && (c->opt_decoupled & 2)));
+    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
+                     !c->opt_async_bwd && (c->opt_decoupled & 1)));
     const int P = lp.npasses;
     const int GS = QR_GATE_SLOTS;
     const bool want_grad = grad != nullptr;
@@ -1665,8 +1718,10 @@ extern "C" int qr_shard_mcclean_begin(qr_ctx* c, int L, const int32_t* axes, con
     run->axes.assign(axes, axes + (size_t)L * nt);
     run->angles.assign(angles, angles + (size_t)L * nt);
     run->terms = o->terms;
-    QR_TRY(make_plan(nl, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &run->lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits));
-    QR_TRY(make_plan(nl, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &run->lpb, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits));
+    QR_TRY(make_plan(nl, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &run->lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
+                     !c->opt_async_fwd && (c->opt_decoupled & 2)));
+    QR_TRY(make_plan(nl, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &run->lpb, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
+                     !c->opt_async_bwd && (c->opt_decoupled & 1)));
     const int P = run->P = run->lpb.npasses;
     run->pi.resize(G);
     for (int r = 0; r < G; ++r) run->pi[r] = r;

@@ -459,6 +459,203 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
 }
 
 // ------------------------------------------------------------------------------------------
+// Decoupled-exchange tile pass (k = 12, 512 threads, 3 bits per round).
+//
+// Same arithmetic as k_tile_pass, different thread <-> index-bit bookkeeping.  The 12 local bits
+// are four groups A=(0,1,2) B=(3,4,5) C=(6,7,8) D=(9,10,11); a thread id has three 3-bit slots
+// S0=(t0..t2) S1=(t3..t5) S2=(t6..t8) and the registers hold a fourth group.  An exchange swaps the
+// register group with ONE slot, so only the 8 threads that differ in that slot trade data:
+//     S0: 8 neighbouring lanes  -> __syncwarp
+//     S1: a pair of warps       -> named barrier, 64 threads
+//     S2: every other warp      -> named barrier, 256 threads
+// No block-wide barrier is left in the gate loop, so the 16 warps of the single resident CTA drift
+// apart and their FP64, shared-memory and global-memory phases overlap.  Every thread writes an
+// amplitude back to the address it read it from (address = swizzled local index), which removes
+// all write-after-read hazards inside a tile; the one hazard between consecutive tiles is covered
+// by an arrive-early / wait-late mbarrier.
+// ------------------------------------------------------------------------------------------
+struct DcPlan {
+    int nrounds;
+    int gp[QR_MAXROUNDS][4];   // bit position of the group held by S0, S1, S2, REG in each round
+    int swap_slot[QR_MAXROUNDS];   // slot exchanged with the registers after round r (r < nrounds-1)
+};
+
+#ifndef QR_HOST_EMUL
+__device__ __forceinline__ void qr_named_barrier(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void qr_mbar_arrive(u64* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(qr_smem_addr(bar)) : "memory");
+}
+#else
+__device__ __forceinline__ void qr_named_barrier(int, int) { __syncthreads(); }   // over-synchronises: fine
+__device__ __forceinline__ void qr_mbar_arrive(u64*) {}
+#endif
+
+// bank swizzle for the decoupled kernel: the 8 lanes of a quarter warp always differ in exactly one
+// 3-bit group, whichever it is, so the 16-byte column is the XOR of all four groups
+__device__ __forceinline__ int qr_swz_dc(int l) { return l ^ (((l >> 3) ^ (l >> 6) ^ (l >> 9)) & 7); }
+
+template <int NV>
+__global__ void __launch_bounds__(512, (NV == 1 ? 2 : 1)) k_tile_pass_dc(const TilePass p, const DcPlan dc) {
+    constexpr int R = 3, RA = 8, K = 12, T = 1 << K;
+    QR_DYN_SMEM(double2, smem);
+    __shared__ u64 tile_bar;
+    __shared__ GateP sgt[QR_GATE_SLOTS];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int s0 = tid & 7, s1 = (tid >> 3) & 7, s2 = tid >> 6;
+    double acc_all[QR_SLOTS];
+#pragma unroll
+    for (int i = 0; i < QR_SLOTS; ++i) acc_all[i] = 0.0;
+    const int c = p.c, h = p.h;
+    const int lomask = (1 << c) - 1;
+    const int nlo = h - c;
+    const u64 tmask = ((u64)1 << p.tiles_log2) - 1;
+    const int nrounds = dc.nrounds;
+    __shared__ double2 lut_sm[QR_LUT_MAX];
+    const bool use_lut = p.hidx != nullptr && (p.pre_phase || p.post_phase);
+    if (tid == 0) qr_mbar_init(&tile_bar, 512);
+    for (int i = tid; i < QR_GATE_SLOTS; i += blockDim.x) sgt[i] = p.gates[i];
+    if (use_lut)
+        for (int i = tid; i < p.lut_size; i += blockDim.x) lut_sm[i] = p.lut[i];
+    __syncthreads();
+    const int lb_first = (s0 << dc.gp[0][0]) | (s1 << dc.gp[0][1]) | (s2 << dc.gp[0][2]);
+    const int gr_first = dc.gp[0][3];
+    const int lb_last = (s0 << dc.gp[nrounds - 1][0]) | (s1 << dc.gp[nrounds - 1][1]) | (s2 << dc.gp[nrounds - 1][2]);
+    const int gr_last = dc.gp[nrounds - 1][3];
+    unsigned iter = 0;
+
+    for (i64 tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+        const u64 t = (u64)tile & tmask;
+        const u64 tbase = ((t & (((u64)1 << nlo) - 1)) << c) | ((t >> nlo) << (h + K - c));
+        double2 a[NV][RA];
+#pragma unroll
+        for (int r = 0; r < RA; ++r) {
+            const int l = lb_first | (r << gr_first);
+            const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
+            const u64 s = p.ladder ? (ladder_map(d, p.M1, p.M2) ^ p.src_xor) : d;
+            a[0][r] = p.src0[s];
+            if (NV == 2) a[NV - 1][r] = p.src1[s];
+        }
+        if (p.pre_phase) {
+#pragma unroll
+            for (int r = 0; r < RA; ++r) {
+                const int l = lb_first | (r << gr_first);
+                const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
+                double2 ph;
+                if (use_lut) ph = lut_sm[p.hidx[d]];
+                else {
+                    double sn, cs;
+                    sincos(p.angle_pre * p.ham[d], &sn, &cs);
+                    ph = make_double2(cs, -sn);
+                }
+#pragma unroll
+                for (int v = 0; v < NV; ++v) a[v][r] = cmul(a[v][r], ph);
+            }
+        }
+#ifndef QR_HOST_EMUL
+        if (p.prefetch) {
+            const i64 nt = tile + (i64)gridDim.x * p.prefetch;
+            if (nt < p.num_tiles) {
+                const u64 t2 = (u64)nt & tmask;
+                const u64 nbase = ((t2 & (((u64)1 << nlo) - 1)) << c) | ((t2 >> nlo) << (h + K - c));
+                for (int line = tid; line < (T >> 3); line += blockDim.x) {
+                    const int l = line << 3;
+                    const u64 d = nbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
+                    const u64 s = p.ladder ? (ladder_map(d, p.M1, p.M2) ^ p.src_xor) : d;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src0 + s));
+                    if (NV == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src1 + s));
+                }
+            }
+        }
+#endif
+#pragma unroll 1
+        for (int rd = 0; rd < nrounds; ++rd) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            qr_round_compute<NV, R>(a, sgt + rd * R, acc);
+            if (NV == 2) {
+#pragma unroll
+                for (int rr = 0; rr < QR_MAXROUNDS; ++rr)
+                    if (rr == rd) {
+#pragma unroll
+                        for (int i = 0; i < R; ++i) acc_all[rr * R + i] += acc[i];
+                    }
+            }
+            if (rd + 1 < nrounds) {
+                const int lbp = (s0 << dc.gp[rd][0]) | (s1 << dc.gp[rd][1]) | (s2 << dc.gp[rd][2]);
+                const int grp = dc.gp[rd][3];
+                const int lbn = (s0 << dc.gp[rd + 1][0]) | (s1 << dc.gp[rd + 1][1]) | (s2 << dc.gp[rd + 1][2]);
+                const int grn = dc.gp[rd + 1][3];
+                if (rd == 0 && iter > 0) qr_mbar_wait(&tile_bar, (iter - 1) & 1u);   // previous tile fully read
+#pragma unroll
+                for (int r = 0; r < RA; ++r) {
+                    const int l = qr_swz_dc(lbp | (r << grp));
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) smem[v * T + l] = a[v][r];
+                }
+                const int slot = dc.swap_slot[rd];
+                if (slot == 0) __syncwarp();
+                else if (slot == 1) qr_named_barrier(1 + (warp >> 1), 64);
+                else qr_named_barrier(9 + (warp & 1), 256);
+#pragma unroll
+                for (int r = 0; r < RA; ++r) {
+                    const int l = qr_swz_dc(lbn | (r << grn));
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) a[v][r] = smem[v * T + l];
+                }
+                if (rd + 2 == nrounds) qr_mbar_arrive(&tile_bar);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RA; ++r) {
+            const int l = lb_last | (r << gr_last);
+            const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
+            if (p.post_phase) {
+                double hv;
+                double2 ph;
+                if (use_lut) {
+                    const int hi = p.hidx[d];
+                    hv = p.hmin + (double)hi;
+                    ph = lut_sm[hi];
+                } else {
+                    hv = p.ham[d];
+                    double sn, cs;
+                    sincos(p.angle_post * hv, &sn, &cs);
+                    ph = make_double2(cs, -sn);
+                }
+                if (NV == 2) acc_all[QR_SLOTS - 1] += hv * im_conj_mul(a[NV - 1][r], a[0][r]);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) a[v][r] = cmul(a[v][r], ph);
+            }
+            p.dst0[d] = a[0][r];
+            if (NV == 2) p.dst1[d] = a[NV - 1][r];
+        }
+    }
+    if (NV == 2) {
+        __syncthreads();
+        qr_block_reduce_slots(acc_all, p.partials + (u64)blockIdx.x * QR_SLOTS);
+        if (p.final_out) {
+            __shared__ int is_last;
+            __threadfence();
+            if (tid == 0) {
+                const unsigned prev = atomicAdd(p.done_counter, 1u);
+                is_last = (prev + 1 == gridDim.x);
+            }
+            __syncthreads();
+            if (is_last) {
+                __threadfence();
+                for (int i = tid; i < QR_SLOTS; i += blockDim.x) {
+                    double v = 0.0;
+                    for (unsigned b = 0; b < gridDim.x; ++b) v += ((volatile double*)p.partials)[(u64)b * QR_SLOTS + i];
+                    p.final_out[i] = v;
+                }
+                if (tid == 0) *p.done_counter = 0u;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Sharded states (top log2(G) qubits = rank bits): rotations on the GLOBAL qubits.
 //
 // One kernel does the exchange and the gates together over peer memory: rank r owns the slice

@@ -1,6 +1,5 @@
 #!/bin/bash
-for cfg in "--prefetch 1" "--prefetch 2" "--prefetch 3" "--prefetch 5"; do
-timeout 300 python scripts/prof_run.py --n 30 --L 3 --reps 2 $cfg 2>&1 | tail -1
-done
-timeout 300 python scripts/prof_run.py --n 20 --L 20 --reps 5 --prefetch 0 2>&1 | tail -1
-timeout 300 python scripts/prof_run.py --n 20 --L 20 --reps 5 --prefetch 1 2>&1 | tail -1
+mkdir -p gpurun_out
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:k_tile_pass_dcILi2 -s 0 -c 2 -o gpurun_out/prof_bwd_dc \
+    python scripts/prof_run.py --n 28 --L 3 --decoupled 1 > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log

@@ -20,6 +20,7 @@ ap.add_argument("--r-bwd", type=int, default=3)
 ap.add_argument("--tile-bits", type=int, default=12)
 ap.add_argument("--async-fwd", type=int, default=0)
 ap.add_argument("--tile-bits-x", type=int, default=0)
+ap.add_argument("--decoupled", type=int, default=0)
 ap.add_argument("--min-row-bits", type=int, default=3)
 ap.add_argument("--async-bwd", type=int, default=0)
 args = ap.parse_args()
@@ -36,6 +37,7 @@ c.state.set_option("reg_bits_bwd", args.r_bwd)
 c.state.set_option("tile_bits", args.tile_bits)
 c.state.set_option("async_fwd", args.async_fwd)
 c.state.set_option("tile_bits_strided", args.tile_bits_x)
+c.state.set_option("decoupled", args.decoupled)
 c.state.set_option("min_row_bits", args.min_row_bits)
 c.state.set_option("async_bwd", args.async_bwd)
 for _ in range(args.reps):

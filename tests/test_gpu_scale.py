@@ -33,10 +33,33 @@ def test_config2_mcclean_20x20_golden():
     assert abs(c.run_expec_val() - float(d["E"])) < 1e-10
     assert abs(c.state.norm_error()) < 1e-12
     for opt in (("async_bwd", 0), ("async_fwd", 1), ("reg_bits_bwd", 4), ("reg_bits_fwd", 4), ("async_bwd", 1),
-                ("prefetch", 1), ("tile_bits", 10), ("ctas_per_sm_fwd", 1), ("async_fwd", 0), ("reg_bits_bwd", 3)):
+                ("prefetch", 1), ("tile_bits", 10), ("ctas_per_sm_fwd", 1), ("async_fwd", 0), ("reg_bits_bwd", 3),
+                ("tile_bits", 12), ("reg_bits_fwd", 3), ("async_bwd", 0), ("decoupled", 1), ("decoupled", 3), ("decoupled", 2)):
         c.state.set_option(*opt)       # options accumulate: every kernel variant is exercised
         e2, g2 = c.grad_run()
         assert_parity(e2, g2, float(d["E"]), d["grad"], 1.0, 1e-10)
+
+
+def test_decoupled_kernel_24_qubits_matches_default():
+    """Decoupled-exchange kernel (named barriers, warp-local exchanges) vs the default kernel."""
+    from qradient_b200.circuit_logic import McClean, Qaoa
+    from qradient_b200.optimization_problems import MaxCut
+    n, L = 25, 4
+    rng = np.random.default_rng(25)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    c = McClean(n, zz01(n), L, axes=axes, angles=angles)
+    e0, g0 = c.grad_run()
+    for mode in (1, 2, 3):
+        c.state.set_option("decoupled", mode)
+        for _ in range(3):     # races would show up as run-to-run differences
+            e1, g1 = c.grad_run()
+            assert_parity(e1, g1, e0, g0, 1.0, 1e-12)
+    q = Qaoa(22, MaxCut(22, edge_set=MaxCut.random_regular(22, 3, seed=3)).to_observable(), 3)
+    b, gm = rng.random(3), rng.random(3)
+    e0, g0 = q.grad_run(b, gm)
+    q.state.set_option("decoupled", 3)
+    e1, g1 = q.grad_run(b, gm)
+    assert_parity(e1, g1, e0, g0, 33.0, 1e-12)
 
 
 def test_mcclean_16x8_mixed_vs_oracle():

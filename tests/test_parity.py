@@ -161,8 +161,9 @@ def test_mcclean_tile_geometries_vs_oracle(backend, n, L, tile_bits):
                                   dict(async_bwd=1, async_fwd=1, reg_bits_fwd=4, reg_bits_bwd=4),
                                   dict(async_bwd=1, async_fwd=1, reg_bits_fwd=3, reg_bits_bwd=3),
                                   dict(async_bwd=0, async_fwd=0, reg_bits_fwd=3, reg_bits_bwd=3, prefetch=1),
-                                  dict(tile_bits_strided=5, min_row_bits=2), dict(tile_bits_strided=4, min_row_bits=1, async_bwd=1)])
-@pytest.mark.parametrize("n,L,tile_bits", [(7, 2, 5), (10, 2, 12), (13, 1, 12), (9, 2, 4)])
+                                  dict(tile_bits_strided=5, min_row_bits=2), dict(tile_bits_strided=4, min_row_bits=1, async_bwd=1),
+                                  dict(decoupled=3)])
+@pytest.mark.parametrize("n,L,tile_bits", [(7, 2, 5), (10, 2, 12), (13, 1, 12), (9, 2, 4), (12, 2, 12)])
 def test_kernel_variants_vs_oracle(backend, opts, n, L, tile_bits):
     """Register blocking (3 or 4 bits per round) x staging (direct loads or bulk async copies)."""
     rng = np.random.default_rng(7 * n + tile_bits)
