@@ -7,6 +7,7 @@
 #include "../../include/qradient_b200.h"
 #include "qr_kernels.cuh"
 #include "qr_tile.cuh"
+#include "qr_tile12.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -60,6 +61,8 @@ struct PassPlan {
     int gbit[QR_GATE_SLOTS];   // global index bit handled by slot (round * R + register bit) or -1
     bool dc;                   // decoupled-exchange kernel (k == 12, R == 3)
     DcPlan dcp;
+    bool lean;                 // lean static kernel k_tile12 (k == 12): slot = local bit
+    int ngroups;               // lean: active register groups (1..4)
 };
 
 struct LayerPlan {
@@ -101,6 +104,7 @@ struct qr_ctx {
     long long opt_async_fwd = 0, opt_async_bwd = 0;
     long long opt_tile_bits_x = 0, opt_min_row_bits = 3, opt_batch_chunk_mb = 0;
     long long opt_decoupled = 0;   // bit0: backward, bit1: forward use the decoupled-exchange kernel
+    long long opt_lean = 3;        // bit0: backward, bit1: forward use the lean static 12-bit tile kernel
     qr_perf perf;
     // ---- sharded states: this context holds one shard of an n_total-qubit register ----
     int n_total = 0, g = 0, rank = 0;
@@ -286,6 +290,7 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
         case QR_OPT_MIN_ROW_BITS: if (v < 1 || v > 6) return fail(QR_EINVAL, "bad min row bits"); c->opt_min_row_bits = v; break;
         case QR_OPT_BATCH_CHUNK_MB: if (v < 0 || v > 65536) return fail(QR_EINVAL, "bad batch chunk"); c->opt_batch_chunk_mb = v; break;
         case QR_OPT_DECOUPLED: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad decoupled mode"); c->opt_decoupled = v; break;
+        case QR_OPT_LEAN: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad lean mode"); c->opt_lean = v; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -309,6 +314,7 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_MIN_ROW_BITS: *v = c->opt_min_row_bits; break;
         case QR_OPT_BATCH_CHUNK_MB: *v = c->opt_batch_chunk_mb; break;
         case QR_OPT_DECOUPLED: *v = c->opt_decoupled; break;
+        case QR_OPT_LEAN: *v = c->opt_lean; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -817,7 +823,19 @@ static void plan_dc(PassPlan& pp, int first) {
     pp.dc = true;
 }
 
-static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x = 0, int min_row_bits = 3, bool allow_dc = false) {
+// Lean plan of a k = 12 pass whose gate bits are the local bits [first, 12): fixed groups
+// G0..G3 = local bits 0-2, 3-5, 6-8, 9-11, visited G3 [G0] [G1] [G2]; gradient slot = local bit.
+static void plan_lean(PassPlan& pp, int first) {
+    for (int i = 0; i < QR_GATE_SLOTS; ++i) pp.gbit[i] = -1;
+    for (int lb = first; lb < QR_MAX_TILE_BITS; ++lb) pp.gbit[lb] = lb < pp.c ? lb : pp.h + (lb - pp.c);
+    pp.ngroups = first < 3 ? 4 : (first < 6 ? 3 : (first < 9 ? 2 : 1));
+    pp.nrounds = pp.ngroups;
+    pp.g[0] = 9;
+    pp.lean = true;
+}
+
+static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x = 0, int min_row_bits = 3, bool allow_dc = false,
+                     bool allow_lean = false) {
     if (n < 4) return fail(QR_EINVAL, "fused path needs at least 4 qubits");
     const int k = std::min(n, tile_bits);
     lp->n = n;
@@ -825,8 +843,9 @@ static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x
     lp->R = R;
     int np = 0;
     PassPlan& p0 = lp->pass[np++];
-    p0.k = k; p0.c = k; p0.h = k; p0.dc = false;
-    if (allow_dc && k == 12 && R == 3) plan_dc(p0, 0); else plan_rounds(p0, 0, R);
+    p0.k = k; p0.c = k; p0.h = k; p0.dc = false; p0.lean = false; p0.ngroups = 0;
+    if (allow_lean && k == 12) plan_lean(p0, 0);
+    else if (allow_dc && k == 12 && R == 3) plan_dc(p0, 0); else plan_rounds(p0, 0, R);
     const int rem = n - k;
     if (rem > 0) {
         // strided passes: tile of kx bits = c contiguous low bits (rows of 2^c amplitudes) + m gate bits
@@ -837,14 +856,15 @@ static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x
         for (int i = 0; i < nx; ++i) {
             const int m = rem / nx + (i < rem % nx ? 1 : 0);
             PassPlan& pp = lp->pass[np++];
-            pp.k = kx; pp.c = kx - m; pp.h = h; pp.dc = false;
-            if (allow_dc && kx == 12 && R == 3) plan_dc(pp, pp.c); else plan_rounds(pp, pp.c, R);
+            pp.k = kx; pp.c = kx - m; pp.h = h; pp.dc = false; pp.lean = false; pp.ngroups = 0;
+            if (allow_lean && kx == 12) plan_lean(pp, pp.c);
+            else if (allow_dc && kx == 12 && R == 3) plan_dc(pp, pp.c); else plan_rounds(pp, pp.c, R);
             h += m;
         }
     }
     lp->npasses = np;
     for (int i = 0; i < np; ++i)
-        if (lp->pass[i].nrounds > QR_MAXROUNDS || lp->pass[i].nrounds * R > QR_GATE_SLOTS)
+        if (!lp->pass[i].lean && (lp->pass[i].nrounds > QR_MAXROUNDS || lp->pass[i].nrounds * R > QR_GATE_SLOTS))
             return fail(QR_EINVAL, "internal: pass needs %d rounds", lp->pass[i].nrounds);
     return 0;
 }
@@ -924,6 +944,38 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
     tp.partials = c->d_scratch;
     tp.final_out = (nv == 2 && !flush_per_tile) ? final_out : nullptr;
     tp.done_counter = c->d_counter;
+    if (pp.lean) {   // lean static kernel (k = 12, 512 threads)
+        typedef void (*lean_fn)(const TilePass, const Tile12X);
+        const int ph = (pre_phase || post_phase) ? 1 : 0;
+        lean_fn lfn = nv == 1 ? (ph ? k_tile12<1, true> : k_tile12<1, false>) : (ph ? k_tile12<2, true> : k_tile12<2, false>);
+        static bool lean_attr[2][2] = {{false, false}, {false, false}};
+        if (!lean_attr[nv - 1][ph]) {
+            CUDA_TRY(cudaFuncSetAttribute(lfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(double2) << QR_MAX_TILE_BITS));
+            lean_attr[nv - 1][ph] = true;
+        }
+        Tile12X x;
+        memset(&x, 0, sizeof(x));
+        x.ngroups = pp.ngroups;
+        const u64 lom = ((u64)1 << pp.c) - 1;
+        for (int r = 0; r < 8; ++r) {
+            const u64 lf = (u64)r << 9, ll = (u64)r << (pp.ngroups > 1 ? 6 : 9);
+            x.droff_first[r] = (lf & lom) | ((lf >> pp.c) << pp.h);
+            x.roff_first[r] = tp.ladder ? ladder_map(x.droff_first[r], tp.M1, tp.M2) : x.droff_first[r];
+            x.roff_last[r] = (ll & lom) | ((ll >> pp.c) << pp.h);
+        }
+        const long long lctas = nv == 1 ? std::min<long long>(2, c->opt_ctas_fwd) : 1;
+        const i64 lgrid = std::min<i64>(tp.num_tiles, (i64)c->sm_count * lctas);
+        if (nv == 2) {
+            const i64 nunits = flush_per_tile ? tp.num_tiles : lgrid;
+            QR_TRY(ensure_scratch(c, (size_t)nunits * QR_SLOTS));
+            *units = (int)nunits;
+            tp.partials = c->d_scratch;
+        }
+        QR_LAUNCH(lfn, (unsigned)lgrid, QR_T12_THREADS, pp.ngroups > 1 ? (size_t)nv * tile_bytes : 0, c->stream, tp, x);
+        KERNEL_CHECK();
+        c->perf.kernel_launches++;
+        return 0;
+    }
     if (pp.dc) {   // decoupled-exchange kernel (single state, k = 12, R = 3)
         typedef void (*dc_fn)(const TilePass, const DcPlan);
         dc_fn dfn = nv == 1 ? k_tile_pass_dc<1> : k_tile_pass_dc<2>;
@@ -1049,8 +1101,10 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     LayerPlan lpf, lp;   // forward / backward plans: same tile geometry, different register blocking
     const bool dc_f = batch == 1 && !c->opt_async_fwd && (c->opt_decoupled & 2);
     const bool dc_b = batch == 1 && !c->opt_async_bwd && (c->opt_decoupled & 1);
-    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits, dc_f));
-    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits, dc_b));
+    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits, dc_f,
+                     !dc_f && !c->opt_async_fwd && (c->opt_lean & 2)));
+    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits, dc_b,
+                     !dc_b && !c->opt_async_bwd && (c->opt_lean & 1)));
     const int P = lp.npasses;
     const int GS = QR_GATE_SLOTS;                 // gate entries per (layer, pass)
     const bool want_grad = grad != nullptr;
@@ -1385,9 +1439,11 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
     const int n = c->n;
     LayerPlan lpf, lp;
     QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
-                     !c->opt_async_fwd && (c->opt_decoupled & 2)));
+                     !c->opt_async_fwd && (c->opt_decoupled & 2),
+                     !c->opt_async_fwd && !(c->opt_decoupled & 2) && (c->opt_lean & 2)));
     QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
-                     !c->opt_async_bwd && (c->opt_decoupled & 1)));
+                     !c->opt_async_bwd && (c->opt_decoupled & 1),
+                     !c->opt_async_bwd && !(c->opt_decoupled & 1) && (c->opt_lean & 1)));
     const int P = lp.npasses;
     const int GS = QR_GATE_SLOTS;
     const bool want_grad = grad != nullptr;
@@ -1719,9 +1775,11 @@ extern "C" int qr_shard_mcclean_begin(qr_ctx* c, int L, const int32_t* axes, con
     run->angles.assign(angles, angles + (size_t)L * nt);
     run->terms = o->terms;
     QR_TRY(make_plan(nl, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &run->lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
-                     !c->opt_async_fwd && (c->opt_decoupled & 2)));
+                     !c->opt_async_fwd && (c->opt_decoupled & 2),
+                     !c->opt_async_fwd && !(c->opt_decoupled & 2) && (c->opt_lean & 2)));
     QR_TRY(make_plan(nl, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &run->lpb, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
-                     !c->opt_async_bwd && (c->opt_decoupled & 1)));
+                     !c->opt_async_bwd && (c->opt_decoupled & 1),
+                     !c->opt_async_bwd && !(c->opt_decoupled & 1) && (c->opt_lean & 1)));
     const int P = run->P = run->lpb.npasses;
     run->pi.resize(G);
     for (int r = 0; r < G; ++r) run->pi[r] = r;

@@ -157,10 +157,11 @@ def test_mcclean_tile_geometries_vs_oracle(backend, n, L, tile_bits):
     assert abs(c.state.norm_error()) < 1e-12
 
 
-@pytest.mark.parametrize("opts", [dict(async_bwd=0, async_fwd=0, reg_bits_fwd=4, reg_bits_bwd=4),
+@pytest.mark.parametrize("opts", [dict(lean=0, async_bwd=0, async_fwd=0, reg_bits_fwd=4, reg_bits_bwd=4),
                                   dict(async_bwd=1, async_fwd=1, reg_bits_fwd=4, reg_bits_bwd=4),
                                   dict(async_bwd=1, async_fwd=1, reg_bits_fwd=3, reg_bits_bwd=3),
-                                  dict(async_bwd=0, async_fwd=0, reg_bits_fwd=3, reg_bits_bwd=3, prefetch=1),
+                                  dict(lean=0, async_bwd=0, async_fwd=0, reg_bits_fwd=3, reg_bits_bwd=3, prefetch=1),
+                                  dict(lean=3, prefetch=1), dict(lean=1), dict(lean=2),
                                   dict(tile_bits_strided=5, min_row_bits=2), dict(tile_bits_strided=4, min_row_bits=1, async_bwd=1),
                                   dict(decoupled=3)])
 @pytest.mark.parametrize("n,L,tile_bits", [(7, 2, 5), (10, 2, 12), (13, 1, 12), (9, 2, 4), (12, 2, 12)])
@@ -184,6 +185,51 @@ def test_kernel_variants_vs_oracle(backend, opts, n, L, tile_bits):
     e_ref, g_ref = orc.qaoa_grad_run(n, orc.maxcut_observable(n, [(i, i + 1) for i in range(n - 1)]), b, gm)
     e, g = q.grad_run(b, gm)
     assert_parity(e, g, e_ref, g_ref, float(n - 1), TOL)
+
+
+@pytest.mark.parametrize("n,L", [(12, 3), (14, 2), (16, 2), (17, 1), (19, 1)])
+def test_lean_tile_kernel_group_counts(backend, n, L):
+    """k_tile12 (qr_tile12.cuh): strided passes with 1, 2 and 3 register groups next to the 4-group first
+    pass, against the generic tile kernel (lean=0) and, where it finishes in seconds, the oracle."""
+    rng = np.random.default_rng(1200 + n)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    obs = mixed_obs(n)
+    c = McClean(n, obs, L, axes=axes, angles=angles)
+    e1, g1 = c.grad_run()
+    v1 = np.array(c.state.vec)
+    c.state.set_option("lean", 0)
+    e0, g0 = c.grad_run()
+    assert_parity(e1, g1, e0, g0, obs_scale(obs), 1e-12)
+    np.testing.assert_allclose(v1, c.state.vec, atol=1e-13)
+    if n <= 14:
+        e_ref, g_ref = orc.mcclean_grad_run(n, obs, axes, angles)
+        assert_parity(e1, g1, e_ref, g_ref, obs_scale(obs), TOL)
+    c.state.set_option("lean", 3)
+    np.testing.assert_allclose(c.run_expec_val(), e0, atol=1e-12 * obs_scale(obs))
+
+
+@pytest.mark.parametrize("case", ["all_x", "all_y", "all_z", "special_angles"])
+def test_lean_tile_kernel_special_gates(backend, case):
+    """tan-form edge cases: cos = 0 or sin = 0 exactly, |cos| = |sin|, negative factors, passes without / with only Rz."""
+    n, L = 13, 2
+    rng = np.random.default_rng(77)
+    angles = rng.uniform(0, 2 * np.pi, (L, n))
+    axes = rng.integers(0, 3, (L, n))
+    if case == "all_x":
+        axes[:] = 0
+    elif case == "all_y":
+        axes[:] = 1
+    elif case == "all_z":
+        axes[:] = 2
+    else:
+        special = np.array([0.0, np.pi, 2 * np.pi, np.pi / 2, 3 * np.pi / 2, -np.pi / 2, 4 * np.pi, 1e-9, np.pi - 1e-9])
+        angles = special[rng.integers(0, len(special), (L, n))]
+    obs = mixed_obs(n)
+    e_ref, g_ref = orc.mcclean_grad_run(n, obs, axes, angles)
+    c = McClean(n, obs, L, axes=axes, angles=angles)
+    e, g = c.grad_run()
+    assert_parity(e, g, e_ref, g_ref, obs_scale(obs), TOL)
+    np.testing.assert_allclose(c.run_expec_val(), e_ref, atol=TOL * obs_scale(obs))
 
 
 def test_fused_equals_unfused(backend):
