@@ -43,7 +43,7 @@ enum { QR_TERM_X = 0, QR_TERM_Y = 1, QR_TERM_Z = 2, QR_TERM_ZZ = 3 };
 enum {
     QR_OPT_FUSION = 0,        /* 1 (default): fused tile passes; 0: one kernel per gate          */
     QR_OPT_TILE_BITS = 1,     /* log2 amplitudes per shared-memory tile (default 12)            */
-    QR_OPT_PREFETCH = 2,      /* L2 prefetch distance in tiles: bits 0-1 backward (default 1), bits 2-3 forward (default 0) */
+    QR_OPT_PREFETCH = 2,      /* L2 prefetch distance in tiles: bits 0-1 backward (default 1), bits 2-3 forward (default 0), bit 4: contiguous passes only */
     QR_OPT_CTAS_PER_SM_FWD = 3,
     QR_OPT_CTAS_PER_SM_BWD = 4,
     QR_OPT_FINAL_LADDER = 5,  /* 1 (default): leave state.vec exactly as mc_clean.py:77 does     */
@@ -56,7 +56,11 @@ enum {
     QR_OPT_MIN_ROW_BITS = 12, /* log2 of the minimum contiguous run (amplitudes) in strided passes */
     QR_OPT_BATCH_CHUNK_MB = 13, /* batched circuits: MiB of state per buffer processed per chunk (0 = 256) */
     QR_OPT_DECOUPLED = 14,    /* decoupled-exchange tile kernel: bit0 backward, bit1 forward           */
-    QR_OPT_LEAN = 15          /* lean static 12-bit tile kernel (default 3): bit0 backward, bit1 forward */
+    QR_OPT_LEAN = 15,         /* lean static 12-bit tile kernel (default 3): bit0 backward, bit1 forward */
+    QR_OPT_BUF_SKEW = 16,     /* bytes between the start offsets of consecutive state buffers (multiple of 256) */
+    QR_OPT_CLUSTER = 18,      /* CTA pairs (thread-block clusters of 2) on adjacent tiles: bits 0-1 backward, 2-3 forward; 0 none, 1 strided passes, 2 all */
+    QR_OPT_STAGED = 19,       /* k_tile12: next tile staged in shared memory by asynchronous copies: bit0 backward, bit1 forward */
+    QR_OPT_PAGE_BITS = 17     /* log2 amplitudes per memory page (default 17 = 2 MiB); strided passes share the index bits above it; 0 = off */
 };
 
 typedef struct qr_perf {

@@ -63,6 +63,7 @@ struct PassPlan {
     DcPlan dcp;
     bool lean;                 // lean static kernel k_tile12 (k == 12): slot = local bit
     int ngroups;               // lean: active register groups (1..4)
+    int m1, h2;                // lean: two-segment geometry (Geo12); single segment: m1 = k - c, h2 = h + m1
 };
 
 struct LayerPlan {
@@ -79,6 +80,7 @@ struct qr_ctx {
     int sm_count = 1;
     cudaStream_t stream = nullptr;
     double2* buf[QR_NBUF] = {nullptr, nullptr, nullptr, nullptr};
+    void* buf_base[QR_NBUF] = {nullptr, nullptr, nullptr, nullptr};   // raw allocations (buf[i] = base + i * skew)
     u64 buf_amps = 0;            // capacity of each buffer in amplitudes (>= N; batch paths grow it)
     int psi = 0;                 // buffer holding the state vector
     double* d_ham = nullptr;     // diagonal Hamiltonian table [N]
@@ -105,6 +107,10 @@ struct qr_ctx {
     long long opt_tile_bits_x = 0, opt_min_row_bits = 3, opt_batch_chunk_mb = 0;
     long long opt_decoupled = 0;   // bit0: backward, bit1: forward use the decoupled-exchange kernel
     long long opt_lean = 3;        // bit0: backward, bit1: forward use the lean static 12-bit tile kernel
+    long long opt_page_bits = 17;  // log2 amplitudes per memory page (2 MiB): strided passes share the index bits above it; 0 = off
+    long long opt_staged = 0;      // bit0 backward, bit1 forward: next tile staged in shared memory by asynchronous copies
+    long long opt_cluster = 1;     // bits 0-1 backward, bits 2-3 forward: 0 none, 1 CTA pairs in the strided passes, 2 in every pass
+    long long opt_buf_skew = 0;    // bytes between the start offsets of consecutive state buffers (multiple of 256)
     qr_perf perf;
     // ---- sharded states: this context holds one shard of an n_total-qubit register ----
     int n_total = 0, g = 0, rank = 0;
@@ -157,9 +163,15 @@ static int ensure_pin(qr_ctx* c, size_t bytes) {
 
 static int ensure_buf(qr_ctx* c, int i) {
     if (c->buf[i]) return 0;
-    cudaError_t e = cudaMalloc((void**)&c->buf[i], c->buf_amps * sizeof(double2));
+    // Buffer i starts i * skew bytes into its allocation, so that the same amplitude index of psi,
+    // lambda and their ping-pong partners does not land on the same DRAM channel / bank (the
+    // allocations themselves are a power of two apart).
+    const size_t skew = (size_t)c->opt_buf_skew * (size_t)i;
+    cudaError_t e = cudaMalloc(&c->buf_base[i], c->buf_amps * sizeof(double2) + skew);
+    if (e == cudaSuccess) c->buf[i] = (double2*)((char*)c->buf_base[i] + skew);
     if (e != cudaSuccess) {
         c->buf[i] = nullptr;
+        c->buf_base[i] = nullptr;
         return fail(QR_ENOMEM, "cannot allocate state buffer %d of %.2f GiB for %d qubits: %s", i,
                     (double)(c->buf_amps * sizeof(double2)) / (double)(1ull << 30), c->n, cudaGetErrorString(e));
     }
@@ -255,7 +267,7 @@ extern "C" int qr_ctx_destroy(qr_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     shard_release(c);
-    for (int i = 0; i < QR_NBUF; ++i) if (c->buf[i]) cudaFree(c->buf[i]);
+    for (int i = 0; i < QR_NBUF; ++i) if (c->buf_base[i]) cudaFree(c->buf_base[i]);
     if (c->d_ham) cudaFree(c->d_ham);
     if (c->d_hidx) cudaFree(c->d_hidx);
     for (double2* sp : c->snapshots) if (sp) cudaFree(sp);
@@ -277,7 +289,9 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
         case QR_OPT_TILE_BITS:
             if (v < 4 || v > QR_MAX_TILE_BITS) return fail(QR_EINVAL, "tile bits must be in [4, %d]", QR_MAX_TILE_BITS);
             c->opt_tile_bits = v; break;
-        case QR_OPT_PREFETCH: if (v < 0 || v > 15) return fail(QR_EINVAL, "prefetch must be in [0, 15]"); c->opt_prefetch = v; break;
+        case QR_OPT_PREFETCH: if (v < 0 || v > 31) return fail(QR_EINVAL, "prefetch must be in [0, 31]"); c->opt_prefetch = v; break;
+        case QR_OPT_STAGED: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad staged mode"); c->opt_staged = v; break;
+        case QR_OPT_CLUSTER: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad cluster mode"); c->opt_cluster = v; break;
         case QR_OPT_CTAS_PER_SM_FWD: if (v < 1 || v > 8) return fail(QR_EINVAL, "bad CTAs/SM"); c->opt_ctas_fwd = v; break;
         case QR_OPT_CTAS_PER_SM_BWD: if (v < 1 || v > 8) return fail(QR_EINVAL, "bad CTAs/SM"); c->opt_ctas_bwd = v; break;
         case QR_OPT_FINAL_LADDER: c->opt_final_ladder = v ? 1 : 0; break;
@@ -287,10 +301,20 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
         case QR_OPT_ASYNC_FWD: c->opt_async_fwd = v ? 1 : 0; break;
         case QR_OPT_ASYNC_BWD: c->opt_async_bwd = v ? 1 : 0; break;
         case QR_OPT_TILE_BITS_STRIDED: if (v != 0 && (v < 4 || v > QR_MAX_TILE_BITS)) return fail(QR_EINVAL, "bad strided tile bits"); c->opt_tile_bits_x = v; break;
-        case QR_OPT_MIN_ROW_BITS: if (v < 1 || v > 6) return fail(QR_EINVAL, "bad min row bits"); c->opt_min_row_bits = v; break;
+        case QR_OPT_MIN_ROW_BITS: if (v < 1 || v > 11) return fail(QR_EINVAL, "bad min row bits"); c->opt_min_row_bits = v; break;
         case QR_OPT_BATCH_CHUNK_MB: if (v < 0 || v > 65536) return fail(QR_EINVAL, "bad batch chunk"); c->opt_batch_chunk_mb = v; break;
         case QR_OPT_DECOUPLED: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad decoupled mode"); c->opt_decoupled = v; break;
         case QR_OPT_LEAN: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad lean mode"); c->opt_lean = v; break;
+        case QR_OPT_PAGE_BITS: if (v != 0 && (v < 13 || v > 40)) return fail(QR_EINVAL, "bad page bits"); c->opt_page_bits = v; break;
+        case QR_OPT_BUF_SKEW:
+            if (v < 0 || v > (1ll << 30) || (v & 255)) return fail(QR_EINVAL, "buffer skew must be a multiple of 256 bytes");
+            if (v != c->opt_buf_skew) {   // takes effect for buffers allocated from now on: drop all but the state
+                CUDA_TRY(cudaStreamSynchronize(c->stream));
+                for (int i = 0; i < QR_NBUF; ++i)
+                    if (i != c->psi && c->buf_base[i]) { cudaFree(c->buf_base[i]); c->buf[i] = nullptr; c->buf_base[i] = nullptr; }
+            }
+            c->opt_buf_skew = v;
+            break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -315,6 +339,10 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_BATCH_CHUNK_MB: *v = c->opt_batch_chunk_mb; break;
         case QR_OPT_DECOUPLED: *v = c->opt_decoupled; break;
         case QR_OPT_LEAN: *v = c->opt_lean; break;
+        case QR_OPT_BUF_SKEW: *v = c->opt_buf_skew; break;
+        case QR_OPT_PAGE_BITS: *v = c->opt_page_bits; break;
+        case QR_OPT_CLUSTER: *v = c->opt_cluster; break;
+        case QR_OPT_STAGED: *v = c->opt_staged; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -827,7 +855,13 @@ static void plan_dc(PassPlan& pp, int first) {
 // G0..G3 = local bits 0-2, 3-5, 6-8, 9-11, visited G3 [G0] [G1] [G2]; gradient slot = local bit.
 static void plan_lean(PassPlan& pp, int first) {
     for (int i = 0; i < QR_GATE_SLOTS; ++i) pp.gbit[i] = -1;
-    for (int lb = first; lb < QR_MAX_TILE_BITS; ++lb) pp.gbit[lb] = lb < pp.c ? lb : pp.h + (lb - pp.c);
+    const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2};
+    for (int lb = first; lb < QR_MAX_TILE_BITS; ++lb) {
+        u64 gidx = geo12_local(geo, (u64)1 << lb);
+        int gb = 0;
+        while (!((gidx >> gb) & 1)) ++gb;
+        pp.gbit[lb] = gb;
+    }
     pp.ngroups = first < 3 ? 4 : (first < 6 ? 3 : (first < 9 ? 2 : 1));
     pp.nrounds = pp.ngroups;
     pp.g[0] = 9;
@@ -835,7 +869,7 @@ static void plan_lean(PassPlan& pp, int first) {
 }
 
 static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x = 0, int min_row_bits = 3, bool allow_dc = false,
-                     bool allow_lean = false) {
+                     bool allow_lean = false, int page_bits = 17) {
     if (n < 4) return fail(QR_EINVAL, "fused path needs at least 4 qubits");
     const int k = std::min(n, tile_bits);
     lp->n = n;
@@ -843,7 +877,7 @@ static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x
     lp->R = R;
     int np = 0;
     PassPlan& p0 = lp->pass[np++];
-    p0.k = k; p0.c = k; p0.h = k; p0.dc = false; p0.lean = false; p0.ngroups = 0;
+    p0.k = k; p0.c = k; p0.h = k; p0.dc = false; p0.lean = false; p0.ngroups = 0; p0.m1 = 0; p0.h2 = k;
     if (allow_lean && k == 12) plan_lean(p0, 0);
     else if (allow_dc && k == 12 && R == 3) plan_dc(p0, 0); else plan_rounds(p0, 0, R);
     const int rem = n - k;
@@ -853,14 +887,35 @@ static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x
         const int umax = std::max(kx - std::min(min_row_bits, kx - 1), 1);
         const int nx = (rem + umax - 1) / umax;
         int h = k;
+        // lean kernel: the index bits >= page_bit select the 2 MiB page; share them evenly between the
+        // strided passes (each pass = a run of the remaining low bits + a run of the page bits)
+        const int page_bit = page_bits;
+        const bool split = allow_lean && kx == 12 && nx > 1 && page_bit > k && n > page_bit;
+        const int hi_total = split ? n - page_bit : 0;
+        int lo_next = k, hi_next = page_bit;
         for (int i = 0; i < nx; ++i) {
             const int m = rem / nx + (i < rem % nx ? 1 : 0);
             PassPlan& pp = lp->pass[np++];
             pp.k = kx; pp.c = kx - m; pp.h = h; pp.dc = false; pp.lean = false; pp.ngroups = 0;
+            pp.m1 = m; pp.h2 = h + m;
+            if (split) {
+                int mh = hi_total / nx + (i < hi_total % nx ? 1 : 0);          // page bits of this pass
+                int ml = m - mh;                                                // low bits of this pass
+                const int lo_left = page_bit - lo_next;
+                if (ml > lo_left) { ml = lo_left; mh = m - ml; }
+                if (ml < 0) { ml = 0; mh = m; }
+                if (i == nx - 1) { ml = page_bit - lo_next; mh = m - ml; }      // last pass takes what is left
+                pp.h = ml > 0 ? lo_next : hi_next;
+                pp.m1 = ml > 0 ? ml : mh;
+                pp.h2 = ml > 0 ? hi_next : pp.h + pp.m1;
+                lo_next += ml;
+                hi_next += mh;
+            }
             if (allow_lean && kx == 12) plan_lean(pp, pp.c);
             else if (allow_dc && kx == 12 && R == 3) plan_dc(pp, pp.c); else plan_rounds(pp, pp.c, R);
             h += m;
         }
+        if (split && (lo_next != page_bit || hi_next != n)) return fail(QR_EINVAL, "internal: page-bit split does not cover the register");
     }
     lp->npasses = np;
     for (int i = 0; i < np; ++i)
@@ -908,6 +963,7 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
     TilePass tp;
     memset(&tp, 0, sizeof(tp));
     tp.k = pp.k; tp.c = pp.c; tp.h = pp.h; tp.nrounds = pp.nrounds;
+    tp.m1 = pp.m1; tp.h2 = pp.h2;
     for (int r = 0; r < QR_MAXROUNDS; ++r) tp.g[r] = r < pp.nrounds ? pp.g[r] : 0;
     tp.ladder = 0;
     if (spec) {
@@ -947,23 +1003,27 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
     if (pp.lean) {   // lean static kernel (k = 12, 512 threads)
         typedef void (*lean_fn)(const TilePass, const Tile12X);
         const int ph = (pre_phase || post_phase) ? 1 : 0;
-        lean_fn lfn = nv == 1 ? (ph ? k_tile12<1, true> : k_tile12<1, false>) : (ph ? k_tile12<2, true> : k_tile12<2, false>);
-        static bool lean_attr[2][2] = {{false, false}, {false, false}};
-        if (!lean_attr[nv - 1][ph]) {
-            CUDA_TRY(cudaFuncSetAttribute(lfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(double2) << QR_MAX_TILE_BITS));
-            lean_attr[nv - 1][ph] = true;
+        const int staged = (nv == 2 ? (c->opt_staged & 1) : (c->opt_staged & 2)) ? 1 : 0;
+        lean_fn lfn;
+        if (staged) lfn = nv == 1 ? (ph ? k_tile12<1, true, true> : k_tile12<1, false, true>) : (ph ? k_tile12<2, true, true> : k_tile12<2, false, true>);
+        else lfn = nv == 1 ? (ph ? k_tile12<1, true, false> : k_tile12<1, false, false>) : (ph ? k_tile12<2, true, false> : k_tile12<2, false, false>);
+        static bool lean_attr[2][2][2] = {{{false, false}, {false, false}}, {{false, false}, {false, false}}};
+        if (!lean_attr[nv - 1][ph][staged]) {
+            CUDA_TRY(cudaFuncSetAttribute(lfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (int)sizeof(double2) << QR_MAX_TILE_BITS));
+            lean_attr[nv - 1][ph][staged] = true;
         }
+        if (staged) tp.prefetch = 0;
         Tile12X x;
         memset(&x, 0, sizeof(x));
         x.ngroups = pp.ngroups;
-        const u64 lom = ((u64)1 << pp.c) - 1;
+        const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2};
         for (int r = 0; r < 8; ++r) {
             const u64 lf = (u64)r << 9, ll = (u64)r << (pp.ngroups > 1 ? 6 : 9);
-            x.droff_first[r] = (lf & lom) | ((lf >> pp.c) << pp.h);
+            x.droff_first[r] = geo12_local(geo, lf);
             x.roff_first[r] = tp.ladder ? ladder_map(x.droff_first[r], tp.M1, tp.M2) : x.droff_first[r];
-            x.roff_last[r] = (ll & lom) | ((ll >> pp.c) << pp.h);
+            x.roff_last[r] = geo12_local(geo, ll);
         }
-        const long long lctas = nv == 1 ? std::min<long long>(2, c->opt_ctas_fwd) : 1;
+        const long long lctas = (nv == 1 && !staged) ? std::min<long long>(2, c->opt_ctas_fwd) : 1;
         const i64 lgrid = std::min<i64>(tp.num_tiles, (i64)c->sm_count * lctas);
         if (nv == 2) {
             const i64 nunits = flush_per_tile ? tp.num_tiles : lgrid;
@@ -971,7 +1031,18 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
             *units = (int)nunits;
             tp.partials = c->d_scratch;
         }
-        QR_LAUNCH(lfn, (unsigned)lgrid, QR_T12_THREADS, pp.ngroups > 1 ? (size_t)nv * tile_bytes : 0, c->stream, tp, x);
+        // backward passes: clusters of 2 CTAs take adjacent tiles and align their loads (see k_tile12)
+        const int want_cluster = (nv == 2 ? (int)(c->opt_cluster & 3) : (int)((c->opt_cluster >> 2) & 3));
+        const bool strided_pass = pp.c < QR_MAX_TILE_BITS;
+        x.cluster = (want_cluster == 2 || (want_cluster == 1 && strided_pass)) && lgrid % 2 == 0 ? 2 : 1;
+        // L2 prefetch of the next tile: opt_prefetch bit 4 = contiguous passes only
+        if ((c->opt_prefetch & 16) && strided_pass) tp.prefetch = 0;
+        const size_t lsmem = staged ? (size_t)(nv + 1) * tile_bytes : (pp.ngroups > 1 ? (size_t)nv * tile_bytes : 0);
+        if (x.cluster > 1) {
+            CUDA_TRY(QR_LAUNCH_CLUSTER(lfn, (unsigned)lgrid, QR_T12_THREADS, lsmem, c->stream, 2u, tp, x));
+        } else {
+            QR_LAUNCH(lfn, (unsigned)lgrid, QR_T12_THREADS, lsmem, c->stream, tp, x);
+        }
         KERNEL_CHECK();
         c->perf.kernel_launches++;
         return 0;
@@ -1102,9 +1173,9 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     const bool dc_f = batch == 1 && !c->opt_async_fwd && (c->opt_decoupled & 2);
     const bool dc_b = batch == 1 && !c->opt_async_bwd && (c->opt_decoupled & 1);
     QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits, dc_f,
-                     !dc_f && !c->opt_async_fwd && (c->opt_lean & 2)));
+                     !dc_f && !c->opt_async_fwd && (c->opt_lean & 2), (int)c->opt_page_bits));
     QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits, dc_b,
-                     !dc_b && !c->opt_async_bwd && (c->opt_lean & 1)));
+                     !dc_b && !c->opt_async_bwd && (c->opt_lean & 1), (int)c->opt_page_bits));
     const int P = lp.npasses;
     const int GS = QR_GATE_SLOTS;                 // gate entries per (layer, pass)
     const bool want_grad = grad != nullptr;
@@ -1353,7 +1424,7 @@ extern "C" int qr_mcclean_grad_batch(qr_ctx* c, int batch, int L, const int32_t*
     // (re)allocate the buffers for `chunk` states
     if (c->buf_amps < c->N * chunk) {
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        for (int i = 0; i < QR_NBUF; ++i) if (c->buf[i]) { cudaFree(c->buf[i]); c->buf[i] = nullptr; }
+        for (int i = 0; i < QR_NBUF; ++i) if (c->buf_base[i]) { cudaFree(c->buf_base[i]); c->buf[i] = nullptr; c->buf_base[i] = nullptr; }
         c->buf_amps = c->N * chunk;
         c->psi = 0;
         QR_TRY(ensure_buf(c, 0));
@@ -1440,10 +1511,10 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
     LayerPlan lpf, lp;
     QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
                      !c->opt_async_fwd && (c->opt_decoupled & 2),
-                     !c->opt_async_fwd && !(c->opt_decoupled & 2) && (c->opt_lean & 2)));
+                     !c->opt_async_fwd && !(c->opt_decoupled & 2) && (c->opt_lean & 2), (int)c->opt_page_bits));
     QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
                      !c->opt_async_bwd && (c->opt_decoupled & 1),
-                     !c->opt_async_bwd && !(c->opt_decoupled & 1) && (c->opt_lean & 1)));
+                     !c->opt_async_bwd && !(c->opt_decoupled & 1) && (c->opt_lean & 1), (int)c->opt_page_bits));
     const int P = lp.npasses;
     const int GS = QR_GATE_SLOTS;
     const bool want_grad = grad != nullptr;
@@ -1693,7 +1764,7 @@ extern "C" int qr_shard_ipc_handle(qr_ctx* c, int buf, void* handle64) {
     if (buf < 0 || buf >= QR_NBUF || !handle64) return fail(QR_EINVAL, "bad buffer index");
     QR_TRY(use_device(c));
     cudaIpcMemHandle_t h;
-    CUDA_TRY(cudaIpcGetMemHandle(&h, c->buf[buf]));
+    CUDA_TRY(cudaIpcGetMemHandle(&h, c->buf_base[buf]));
     static_assert(sizeof(h) == 64, "IPC handle size");
     memcpy(handle64, &h, 64);
     return 0;
@@ -1708,7 +1779,7 @@ extern "C" int qr_shard_ipc_open(qr_ctx* c, int peer_rank, int buf, const void* 
     memcpy(&h, handle64, 64);
     void* p = nullptr;
     CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-    c->peer[peer_rank][buf] = (double2*)p;
+    c->peer[peer_rank][buf] = (double2*)((char*)p + (size_t)c->opt_buf_skew * (size_t)buf);   // every rank uses the same skew
     c->peer_mapped[peer_rank][buf] = true;
     return 0;
 }
@@ -1776,10 +1847,10 @@ extern "C" int qr_shard_mcclean_begin(qr_ctx* c, int L, const int32_t* axes, con
     run->terms = o->terms;
     QR_TRY(make_plan(nl, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &run->lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
                      !c->opt_async_fwd && (c->opt_decoupled & 2),
-                     !c->opt_async_fwd && !(c->opt_decoupled & 2) && (c->opt_lean & 2)));
+                     !c->opt_async_fwd && !(c->opt_decoupled & 2) && (c->opt_lean & 2), (int)c->opt_page_bits));
     QR_TRY(make_plan(nl, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &run->lpb, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
                      !c->opt_async_bwd && (c->opt_decoupled & 1),
-                     !c->opt_async_bwd && !(c->opt_decoupled & 1) && (c->opt_lean & 1)));
+                     !c->opt_async_bwd && !(c->opt_decoupled & 1) && (c->opt_lean & 1), (int)c->opt_page_bits));
     const int P = run->P = run->lpb.npasses;
     run->pi.resize(G);
     for (int r = 0; r < G; ++r) run->pi[r] = r;

@@ -43,6 +43,7 @@ struct GateP {
 
 struct TilePass {
     int k, c, h;                 // tile geometry (see header comment)
+    int m1, h2;                  // k_tile12 only: second segment of gate bits (qr_tile12.cuh, Geo12)
     int nrounds;
     int g[QR_MAXROUNDS];         // first local bit of the register group of each round
     int ladder;                  // 1: gather through the ladder map on load

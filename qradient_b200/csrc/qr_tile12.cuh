@@ -13,11 +13,13 @@
 //    access).  All shared-memory addresses are a per-thread base XOR a compile-time constant, all
 //    global addresses a per-thread base XOR a per-register constant held in the constant bank,
 //    and the four rounds are unrolled, so no register shuffling or shift/mask chains remain.
-//  * tan-form rotations.  Rx/Ry with (c, s) are applied as f * [[1, -t], [t, 1]]-type updates with
-//    f = the larger of |c|, |s| and t = the ratio: ONE fma per real component instead of mul+fma.
-//    The scalar F = prod f of the pass is applied once per amplitude (folded into the Z phase
-//    below when there is one).  Gradient partials taken on the not-yet-rescaled registers are
-//    corrected by a per-gate constant (1 / remaining scale^2) when the CTA flushes them.
+//  * Rotations as three in-place shears (lifting steps).  [[c, -s], [s, c]] with c >= 0 is
+//    a -= tau b;  b += s a;  a -= tau b   with tau = s / (1 + c) = tan(phi/2), |tau| <= 1
+//    (c < 0: the same for (-c, -s) and a sign that is folded into the pass's diagonal).  Three fma
+//    per real component pair instead of two mul + two fma, exactly unitary, and -- the point --
+//    every step overwrites one operand with a function of the other, so no temporaries: the
+//    two-output form (new a and new b both from old a and old b) cost 32 live temporaries per gate,
+//    one MOV per FMA after branch joins and local-memory spills on every tile's critical path.
 //  * Merged Z rotations.  All Rz of the pass are one diagonal: amplitude (thread t, register r)
 //    is multiplied by zt(t) * zr[r]; zt is computed once per CTA, zr is an 8-entry table.
 //  * Z gradients from one product.  Im<lambda|Z_q|psi> = sum_j (+-) w_j with
@@ -26,7 +28,7 @@
 //    bit the sign is a per-thread constant, so the per-thread total of w is kept in one register
 //    for the whole kernel and signed at the end.
 //
-// FP64 instructions per amplitude of a 12-gate backward pass: ~65 (was 133).
+// FP64 instructions per amplitude of a 12-gate backward pass: ~80 (was 133), no register moves.
 //
 // Roofline: HBM.  Algorithmic bytes per launch = NV * 32 B * 2^n.
 #pragma once
@@ -34,8 +36,24 @@
 
 #define QR_T12_THREADS 512
 
+// Two-segment tile geometry (k = 12): local bits [0,c) are global bits [0,c); local bits [c,c+m1) are
+// global bits [h,h+m1); local bits [c+m1,12) are global bits [h2,h2+m2).  The planner uses the
+// second segment to spread the page-selecting index bits (>= 2 MiB) over the strided passes, so
+// no pass touches more than ~128 distinct pages per tile and vector (a pass whose 512 rows lie
+// in 512 different pages runs 1.7x slower in the two-vector backward sweep: TLB reach).
+struct Geo12 { int c, h, m1, h2; };
+__host__ __device__ __forceinline__ u64 geo12_local(const Geo12 g, u64 l) {
+    return (l & (((u64)1 << g.c) - 1)) | (((l >> g.c) & (((u64)1 << g.m1) - 1)) << g.h) | ((l >> (g.c + g.m1)) << g.h2);
+}
+__host__ __device__ __forceinline__ u64 geo12_tile(const Geo12 g, u64 t) {
+    const int nlo = g.h - g.c, nmid = g.h2 - g.h - g.m1, m2 = QR_MAX_TILE_BITS - g.c - g.m1;
+    return ((t & (((u64)1 << nlo) - 1)) << g.c) | (((t >> nlo) & (((u64)1 << nmid) - 1)) << (g.h + g.m1)) |
+           ((t >> (nlo + nmid)) << (g.h2 + m2));
+}
+
 struct Tile12X {
     int ngroups;            // active register groups: 1 = G3; 2 = G3,G2; 3 = G3,G1,G2; 4 = G3,G0,G1,G2
+    int cluster;            // thread-block cluster size of the launch (1 or 2)
     u64 roff_first[8];      // global offset of register r at load time (group G3), gather map applied
     u64 roff_last[8];       // global offset of register r at store time (G2, or G3 when ngroups == 1)
     u64 droff_first[8];     // same as roff_first without the gather map (destination index: phase tables)
@@ -43,18 +61,18 @@ struct Tile12X {
 
 // converted gate of local bit b (shared memory, rebuilt per batch element)
 struct Gate12 {
-    double t;      // ratio (tan-form)
-    double corr;   // gradient correction 1 / (scale still to come)^2
-    int mode;      // -1 none; 0 X |c|>=|s|; 1 X |c|<|s|; 2 Y lo; 3 Y hi; 4 Z
-    int pad;
+    double tau;    // tan(phi/2) of the reduced rotation
+    double sig;    // sin(phi) of the reduced rotation
+    int mode;      // -1 none; 0 X; 1 Y; 4 Z
+    int neg;       // reduced rotation = -(rotation): sign folded into the diagonal of the pass
 };
 
 template <int NV, int BIT>
 __device__ __forceinline__ void qr12_gate(double2 (&a)[NV][8], const Gate12& g, double& acc) {
     const int m = g.mode;
-    if (m < 0 || m > 3) return;
-    const double t = g.t;
-    if (m < 2) {   // X  (state.py:90-92)
+    if (m != 0 && m != 1) return;
+    const double tau = g.tau, sig = g.sig;
+    if (m == 0) {   // X (state.py:90-92): a' = c a - i s b, b' = -i s a + c b
         if (NV == 2) {
             double s = 0.0;
 #pragma unroll
@@ -65,32 +83,21 @@ __device__ __forceinline__ void qr12_gate(double2 (&a)[NV][8], const Gate12& g, 
             }
             acc += s;
         }
-        if (m == 0) {   // f (a - i t b), f (b - i t a)
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                if (r & (1 << BIT)) continue;
-                const int r1 = r | (1 << BIT);
+        for (int r = 0; r < 8; ++r) {
+            if (r & (1 << BIT)) continue;
+            const int r1 = r | (1 << BIT);
 #pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    const double2 x = a[v][r], y = a[v][r1];
-                    a[v][r] = make_double2(x.x + t * y.y, x.y - t * y.x);
-                    a[v][r1] = make_double2(y.x + t * x.y, y.y - t * x.x);
-                }
-            }
-        } else {        // f (t a - i b), f (t b - i a)
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                if (r & (1 << BIT)) continue;
-                const int r1 = r | (1 << BIT);
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    const double2 x = a[v][r], y = a[v][r1];
-                    a[v][r] = make_double2(t * x.x + y.y, t * x.y - y.x);
-                    a[v][r1] = make_double2(t * y.x + x.y, t * y.y - x.x);
-                }
+            for (int v = 0; v < NV; ++v) {   // a -= i tau b ; b -= i sig a ; a -= i tau b
+                a[v][r].x += tau * a[v][r1].y;
+                a[v][r].y -= tau * a[v][r1].x;
+                a[v][r1].x += sig * a[v][r].y;
+                a[v][r1].y -= sig * a[v][r].x;
+                a[v][r].x += tau * a[v][r1].y;
+                a[v][r].y -= tau * a[v][r1].x;
             }
         }
-    } else {       // Y  (state.py:142-144)
+    } else {        // Y (state.py:142-144): a' = c a - s b, b' = s a + c b
         if (NV == 2) {
             double s = 0.0;
 #pragma unroll
@@ -101,29 +108,18 @@ __device__ __forceinline__ void qr12_gate(double2 (&a)[NV][8], const Gate12& g, 
             }
             acc += s;
         }
-        if (m == 2) {   // f (a - t b), f (b + t a)
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                if (r & (1 << BIT)) continue;
-                const int r1 = r | (1 << BIT);
+        for (int r = 0; r < 8; ++r) {
+            if (r & (1 << BIT)) continue;
+            const int r1 = r | (1 << BIT);
 #pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    const double2 x = a[v][r], y = a[v][r1];
-                    a[v][r] = make_double2(x.x - t * y.x, x.y - t * y.y);
-                    a[v][r1] = make_double2(y.x + t * x.x, y.y + t * x.y);
-                }
-            }
-        } else {        // f (t a - b), f (a + t b)
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                if (r & (1 << BIT)) continue;
-                const int r1 = r | (1 << BIT);
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    const double2 x = a[v][r], y = a[v][r1];
-                    a[v][r] = make_double2(t * x.x - y.x, t * x.y - y.y);
-                    a[v][r1] = make_double2(x.x + t * y.x, x.y + t * y.y);
-                }
+            for (int v = 0; v < NV; ++v) {   // a -= tau b ; b += sig a ; a -= tau b
+                a[v][r].x -= tau * a[v][r1].x;
+                a[v][r].y -= tau * a[v][r1].y;
+                a[v][r1].x += sig * a[v][r].x;
+                a[v][r1].y += sig * a[v][r].y;
+                a[v][r].x -= tau * a[v][r1].x;
+                a[v][r].y -= tau * a[v][r1].y;
             }
         }
     }
@@ -171,6 +167,37 @@ __device__ __forceinline__ void qr12_exchange(double2 (&a)[NV][8], double2* smem
     }
 }
 
+// same exchange through ONE tile-sized buffer: the vectors take turns (staged kernel: the other
+// 128 KiB of shared memory hold the next tile).  The buffer holds vector NV-1 when it returns.
+template <int NV, int GP, int GN>
+__device__ __forceinline__ void qr12_exchange_1buf(double2 (&a)[NV][8], double2* xbuf, int tid) {
+    const int bp = qr12_sbase<GP>(tid), bn = qr12_sbase<GN>(tid);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        // safe without a barrier: this thread overwrites only the slots it read itself last time
+        // (v == 0: its GP slots of the previous exchange's last vector; v > 0: needs the barrier below)
+        if (v > 0) __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) xbuf[bp ^ (r * qr12_smul<GP>())] = a[v][r];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) a[v][r] = xbuf[bn ^ (r * qr12_smul<GN>())];
+    }
+}
+
+// ---- per-thread asynchronous copies (LDGSTS): 16 B global -> shared, no register staging ----
+#ifndef QR_HOST_EMUL
+__device__ __forceinline__ void qr_cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void qr_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void qr_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#else
+__device__ __forceinline__ void qr_cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
+__device__ __forceinline__ void qr_cp_async_commit() {}
+__device__ __forceinline__ void qr_cp_async_wait_all() {}
+#endif
+
 // diagonal phase exp(-i angle H[d]) from the integer look-up table or, for general H, sincos
 __device__ __noinline__ double2 qr12_phase_slow(const double* __restrict__ ham, u64 d, double angle, double* hv) {
     const double v = ham[d];
@@ -182,19 +209,26 @@ __device__ __noinline__ double2 qr12_phase_slow(const double* __restrict__ ham, 
 
 // PHASE: QAOA diagonal phase before the gates (forward) / generator inner product + un-phase after them
 // (backward); compiled out of the McClean instantiations.
-template <int NV, bool PHASE>
-__global__ void __launch_bounds__(QR_T12_THREADS, (NV == 1 ? 2 : 1)) k_tile12(const TilePass p, const Tile12X x) {
+//
+// STAGED: the CTA's NEXT tile is copied global -> shared memory by per-thread asynchronous copies
+// (LDGSTS) while the current tile is computed.  Every thread copies exactly the 8 amplitudes per
+// vector it will hold itself at load time into slots nobody else touches, so the stage needs no
+// barrier at all: wait for the own copy group, read the slots into registers, re-issue the copies
+// of the tile after that.  Shared memory: NV tile-sized stages + ONE exchange buffer (the vectors
+// take turns) = 192 KiB for the backward pass; HBM reads overlap the whole gate/exchange phase
+// instead of only reaching L2 (prefetch) or being waited for (direct loads).
+template <int NV, bool PHASE, bool STAGED>
+__global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)) k_tile12(const TilePass p, const Tile12X x) {
     constexpr int T = 1 << QR_MAX_TILE_BITS;
     QR_DYN_SMEM(double2, smem);
+    double2* const stage = smem + (STAGED ? T : 0);   // STAGED: [exchange][stage psi][stage lambda]
     __shared__ Gate12 sg[QR_GATE_SLOTS];
     __shared__ double2 szr[8];                  // Z phases of the G3 register bits (times nothing else)
     __shared__ double2 szb[QR_GATE_SLOTS][2];   // per gate bit: Z phase for bit value 0 / 1 (identity if not Z)
-    __shared__ double s_scale[2];               // F = product of the tan-form factors; has_z flag
+    __shared__ int s_flags[2];                  // [0]: the pass needs its diagonal (an Rz, or an odd number of sign flips)
     __shared__ double2 lut_sm[QR_LUT_MAX];
     const int tid = threadIdx.x;
-    const int c = p.c, h = p.h;
-    const int lomask = (1 << c) - 1;
-    const int nlo = h - c;
+    const Geo12 geo = {p.c, p.h, p.m1, p.h2};
     const u64 tmask = ((u64)1 << p.tiles_log2) - 1;
     const int ng = x.ngroups;
 
@@ -204,10 +238,10 @@ __global__ void __launch_bounds__(QR_T12_THREADS, (NV == 1 ? 2 : 1)) k_tile12(co
     double wtot = 0.0;   // running sum of Im(conj(lambda) psi) over this thread's amplitudes
 
     // per-thread global offsets (local bits 0-8 at load time; the last group's thread bits at store time)
-    const u64 toff_d = (u64)(tid & lomask) | ((u64)(tid >> c) << h);                     // destination index bits
+    const u64 toff_d = geo12_local(geo, (u64)tid);                                       // destination index bits
     const u64 toff_s = p.ladder ? ladder_map(toff_d, p.M1, p.M2) : toff_d;               // gathered source bits
     const int tbl = ng > 1 ? qr12_tb(tid, 6) : tid;
-    const u64 toff_l = (u64)(tbl & lomask) | ((u64)(tbl >> c) << h);
+    const u64 toff_l = geo12_local(geo, (u64)tbl);
 
     const bool use_lut = PHASE && p.hidx != nullptr && (p.pre_phase || p.post_phase);
     if (use_lut) {
@@ -215,8 +249,8 @@ __global__ void __launch_bounds__(QR_T12_THREADS, (NV == 1 ? 2 : 1)) k_tile12(co
     }
     i64 cur_b = -1;
     double2 zt = make_double2(1.0, 0.0);   // thread factor of the merged diagonal (includes F)
-    double fscale = 1.0;
-    bool has_z = false;
+    bool has_z = false;       // apply the diagonal zt * zr after the load
+    bool has_zgate = false;   // the pass has an Rz: take the Z-gradient product w
 
     // flush helper state: sign pattern of the thread-bit Z gates is applied when partials leave the thread
     auto finalize = [&]() {
@@ -225,52 +259,74 @@ __global__ void __launch_bounds__(QR_T12_THREADS, (NV == 1 ? 2 : 1)) k_tile12(co
             const int m = sg[b].mode;
             double v = acc_all[b];
             if (b < 9 && m == 4) v = ((tid >> b) & 1) ? -wtot : wtot;
-            acc_all[b] = v * sg[b].corr;
+            acc_all[b] = v;
         }
     };
 
-    for (i64 tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    // issue the asynchronous copies of this thread's amplitudes of tile `tl` into its stage slots
+    auto issue_stage = [&](i64 tl) {
+        const i64 nb = tl >> p.tiles_log2;
+        const u64 nbase = geo12_tile(geo, (u64)tl & tmask);
+        const u64 sb = (p.ladder ? (ladder_map(nbase, p.M1, p.M2) ^ p.src_xor) : nbase) ^ toff_s;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const u64 sidx = sb ^ x.roff_first[r];
+            qr_cp_async16(stage + tid + (r << 9), p.src0 + nb * p.state_stride + sidx);
+            if (NV == 2) qr_cp_async16(stage + T + tid + (r << 9), p.src1 + nb * p.state_stride + sidx);
+        }
+        qr_cp_async_commit();
+    };
+    if (STAGED && (i64)blockIdx.x < p.num_tiles) {
+#ifndef QR_HOST_EMUL
+        if (x.cluster > 1) asm volatile("barrier.cluster.arrive.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory");
+#endif
+        issue_stage(blockIdx.x);
+    }
+
+    // Uniform trip count over the grid: with x.cluster > 1 every CTA of a cluster must reach the
+    // per-tile cluster barrier the same number of times (a CTA without a tile just arrives).
+    const i64 iters = (p.num_tiles + gridDim.x - 1) / gridDim.x;
+    for (i64 it = 0; it < iters; ++it) {
+        const i64 tile = (i64)blockIdx.x + it * gridDim.x;
+#ifndef QR_HOST_EMUL
+        // CTAs of a cluster own ADJACENT tiles (rows 128 B apart in the strided passes).  Aligning their
+        // loads in time lets the DRAM controller serve both halves of a 256 B chunk from one row
+        // activation: measured 4.8 -> 5.8 TB/s on the bare two-vector access pattern (scripts/membench.cu).
+        if (x.cluster > 1 && (!STAGED || it + 1 < iters)) asm volatile("barrier.cluster.arrive.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory");
+#endif
+        if (tile >= p.num_tiles) continue;
         const i64 b = tile >> p.tiles_log2;
         const u64 t = (u64)tile & tmask;
-        const u64 tbase = ((t & (((u64)1 << nlo) - 1)) << c) | ((t >> nlo) << (h + QR_MAX_TILE_BITS - c));
+        const u64 tbase = geo12_tile(geo, t);
         if (b != cur_b) {   // block-uniform: convert the gate table of this batch element
             __syncthreads();
             if (tid < QR_GATE_SLOTS) {
                 const GateP g = p.gates[b * p.gate_stride + tid];
                 Gate12 o;
-                o.t = 0.0; o.corr = 1.0; o.mode = -1; o.pad = 0;
+                o.tau = 0.0; o.sig = 0.0; o.mode = -1; o.neg = 0;
                 double2 z0 = make_double2(1.0, 0.0), z1 = z0;
-                double f = 1.0;
                 if (g.axis == 0 || g.axis == 1) {
-                    const bool lo = fabs(g.c) >= fabs(g.s);
-                    f = lo ? g.c : g.s;
-                    o.t = lo ? g.s / g.c : g.c / g.s;
-                    o.mode = g.axis * 2 + (lo ? 0 : 1);
+                    // reduce to |phi| <= pi/2 (c >= 0): R(c, s) = -R(-c, -s)
+                    const double cc = g.c < 0.0 ? -g.c : g.c, ss = g.c < 0.0 ? -g.s : g.s;
+                    o.neg = g.c < 0.0 ? 1 : 0;
+                    o.tau = ss / (1.0 + cc);
+                    o.sig = ss;
+                    o.mode = g.axis;
                 } else if (g.axis == 2) {   // Rz: (c - i s) on bit value 0, (c + i s) on bit value 1 (state.py:168-170)
                     o.mode = 4;
                     z0 = make_double2(g.c, -g.s);
                     z1 = make_double2(g.c, g.s);
                 }
-                o.corr = f;   // temporarily: this gate's factor
                 sg[tid] = o;
                 szb[tid][0] = z0;
                 szb[tid][1] = z1;
             }
             __syncthreads();
             if (tid == 0) {
-                // application order G3, G0, G1, G2: a gate's partial sees the factors of the gates after it
-                const int ord[12] = {9, 10, 11, 0, 1, 2, 3, 4, 5, 6, 7, 8};
-                double rem = 1.0;   // product of the factors not yet applied
-                bool z = false;
-                for (int i = 11; i >= 0; --i) {
-                    const int bb = ord[i];
-                    rem *= sg[bb].corr;   // a partial is taken before its own gate: its factor is still to come too
-                    const bool isz = sg[bb].mode == 4;
-                    sg[bb].corr = isz ? 1.0 : 1.0 / (rem * rem);   // Z partials come from the raw (unscaled) load
-                    z = z || isz;
-                }
-                s_scale[0] = rem;
-                s_scale[1] = z ? 1.0 : 0.0;
+                int z = 0, neg = 0;
+                for (int i = 0; i < QR_GATE_SLOTS; ++i) { z |= (sg[i].mode == 4); neg ^= sg[i].neg; }
+                s_flags[0] = z | neg;
+                s_flags[1] = neg;
             }
             if (tid < 8) {
                 double2 z = make_double2(1.0, 0.0);
@@ -279,26 +335,36 @@ __global__ void __launch_bounds__(QR_T12_THREADS, (NV == 1 ? 2 : 1)) k_tile12(co
                 szr[tid] = z;
             }
             __syncthreads();
-            fscale = s_scale[0];
-            has_z = s_scale[1] != 0.0;
-            zt = make_double2(fscale, 0.0);
+            has_z = s_flags[0] != 0;
+            has_zgate = false;
+#pragma unroll
+            for (int j = 0; j < QR_GATE_SLOTS; ++j) has_zgate = has_zgate || sg[j].mode == 4;
+            zt = make_double2(s_flags[1] ? -1.0 : 1.0, 0.0);
 #pragma unroll
             for (int j = 0; j < 9; ++j) zt = cmul(zt, szb[j][(tid >> j) & 1]);
             cur_b = b;
         }
-        const double2* __restrict__ s0 = p.src0 + b * p.state_stride;
-        const double2* __restrict__ s1 = (NV == 2) ? p.src1 + b * p.state_stride : nullptr;
-        double2* __restrict__ d0 = p.dst0 + b * p.state_stride;
-        double2* __restrict__ d1 = (NV == 2) ? p.dst1 + b * p.state_stride : nullptr;
+        // batch element offset: state_stride is a multiple of 2^n, so it can be OR-ed into the index bits
+        const u64 boff = (u64)b * (u64)p.state_stride;
 
         // ---- global -> registers (group G3; ladder gather folded into the load addresses) ----
-        const u64 sbt = (p.ladder ? (ladder_map(tbase, p.M1, p.M2) ^ p.src_xor) : tbase) ^ toff_s;
+        const u64 sbt = ((p.ladder ? (ladder_map(tbase, p.M1, p.M2) ^ p.src_xor) : tbase) ^ toff_s) | boff;
         double2 a[NV][8];
+        if (STAGED) {
+            qr_cp_async_wait_all();
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const u64 s = sbt ^ x.roff_first[r];
-            a[0][r] = s0[s];
-            if (NV == 2) a[NV - 1][r] = s1[s];
+            for (int r = 0; r < 8; ++r) {
+                a[0][r] = stage[tid + (r << 9)];
+                if (NV == 2) a[NV - 1][r] = stage[T + tid + (r << 9)];
+            }
+            if (tile + gridDim.x < p.num_tiles) issue_stage(tile + gridDim.x);   // lands while this tile is computed
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const u64 s = sbt ^ x.roff_first[r];
+                a[0][r] = p.src0[s];
+                if (NV == 2) a[NV - 1][r] = p.src1[s];
+            }
         }
 #ifndef QR_HOST_EMUL
         if (p.prefetch) {   // pull the next tile of this CTA into L2 while this one is computed
@@ -306,9 +372,9 @@ __global__ void __launch_bounds__(QR_T12_THREADS, (NV == 1 ? 2 : 1)) k_tile12(co
             if (nt < p.num_tiles) {
                 const i64 nb = nt >> p.tiles_log2;
                 const u64 t2 = (u64)nt & tmask;
-                const u64 nbase = ((t2 & (((u64)1 << nlo) - 1)) << c) | ((t2 >> nlo) << (h + QR_MAX_TILE_BITS - c));
+                const u64 nbase = geo12_tile(geo, t2);
                 const int l = tid << 3;   // one 128 B line per thread
-                const u64 d = nbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
+                const u64 d = nbase | geo12_local(geo, (u64)l);
                 const u64 s = p.ladder ? (ladder_map(d, p.M1, p.M2) ^ p.src_xor) : d;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src0 + nb * p.state_stride + s));
                 if (NV == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src1 + nb * p.state_stride + s));
@@ -316,7 +382,7 @@ __global__ void __launch_bounds__(QR_T12_THREADS, (NV == 1 ? 2 : 1)) k_tile12(co
         }
 #endif
         // ---- Z gradients: w = Im(conj(lambda) psi), signed sums over the register bits, total for the thread bits ----
-        if (NV == 2 && has_z) {
+        if (NV == 2 && has_zgate) {
             double w[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) w[r] = im_conj_mul(a[NV - 1][r], a[0][r]);
@@ -350,34 +416,28 @@ __global__ void __launch_bounds__(QR_T12_THREADS, (NV == 1 ? 2 : 1)) k_tile12(co
 #pragma unroll
                 for (int v = 0; v < NV; ++v) a[v][r] = cmul(a[v][r], ph);
             }
-        } else if (fscale != 1.0) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-#pragma unroll
-                for (int v = 0; v < NV; ++v) a[v][r] = make_double2(a[v][r].x * fscale, a[v][r].y * fscale);
-            }
         }
         // ---- rounds ----
         qr12_round<NV, 9>(a, sg, acc_all);
         if (ng == 4) {
-            qr12_exchange<NV, 9, 0>(a, smem, tid);
+            if (STAGED) qr12_exchange_1buf<NV, 9, 0>(a, smem, tid); else qr12_exchange<NV, 9, 0>(a, smem, tid);
             qr12_round<NV, 0>(a, sg, acc_all);
-            qr12_exchange<NV, 0, 3>(a, smem, tid);
+            if (STAGED) qr12_exchange_1buf<NV, 0, 3>(a, smem, tid); else qr12_exchange<NV, 0, 3>(a, smem, tid);
         } else if (ng == 3) {
-            qr12_exchange<NV, 9, 3>(a, smem, tid);
+            if (STAGED) qr12_exchange_1buf<NV, 9, 3>(a, smem, tid); else qr12_exchange<NV, 9, 3>(a, smem, tid);
         }
         if (ng >= 3) {
             qr12_round<NV, 3>(a, sg, acc_all);
-            qr12_exchange<NV, 3, 6>(a, smem, tid);
+            if (STAGED) qr12_exchange_1buf<NV, 3, 6>(a, smem, tid); else qr12_exchange<NV, 3, 6>(a, smem, tid);
         } else if (ng == 2) {
-            qr12_exchange<NV, 9, 6>(a, smem, tid);
+            if (STAGED) qr12_exchange_1buf<NV, 9, 6>(a, smem, tid); else qr12_exchange<NV, 9, 6>(a, smem, tid);
         }
         if (ng >= 2) {
             qr12_round<NV, 6>(a, sg, acc_all);
             __syncthreads();   // every thread has read its last exchange: smem is free for the next tile
         }
         // ---- registers -> global (QAOA backward: diagonal-generator inner product and un-phase) ----
-        const u64 dlt = tbase | toff_l;
+        const u64 dlt = tbase | toff_l | boff;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const u64 d = dlt | x.roff_last[r];
@@ -385,16 +445,16 @@ __global__ void __launch_bounds__(QR_T12_THREADS, (NV == 1 ? 2 : 1)) k_tile12(co
                 double hv;
                 double2 ph;
                 if (use_lut) {
-                    const int hi = p.hidx[d];
+                    const int hi = p.hidx[d ^ boff];
                     hv = p.hmin + (double)hi;
                     ph = lut_sm[hi];
-                } else ph = qr12_phase_slow(p.ham, d, p.angle_post, &hv);
+                } else ph = qr12_phase_slow(p.ham, d ^ boff, p.angle_post, &hv);
                 if (NV == 2) acc_all[QR_SLOTS - 1] += hv * im_conj_mul(a[NV - 1][r], a[0][r]);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) a[v][r] = cmul(a[v][r], ph);
             }
-            d0[d] = a[0][r];
-            if (NV == 2) d1[d] = a[NV - 1][r];
+            p.dst0[d] = a[0][r];
+            if (NV == 2) p.dst1[d] = a[NV - 1][r];
         }
         if (NV == 2 && p.flush_per_tile) {
             finalize();

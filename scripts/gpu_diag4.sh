@@ -1,0 +1,25 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+rm -f gpurun_out/diag_cluster.log
+run() { timeout 120 python scripts/diag_clocks.py --n 30 --L 3 "$@" 2>&1 | grep "^n=" | tail -1 >> gpurun_out/diag_cluster.log; }
+run --opt cluster=0 --opt prefetch=1 --opt page_bits=0
+run --opt cluster=1 --opt prefetch=1 --opt page_bits=0
+run --opt cluster=1 --opt prefetch=17 --opt page_bits=0
+run --opt cluster=2 --opt prefetch=17 --opt page_bits=0
+run --opt cluster=2 --opt prefetch=0 --opt page_bits=0
+run --opt cluster=0 --opt prefetch=0 --opt page_bits=0
+run --opt cluster=1 --opt prefetch=17 --opt page_bits=17
+run --opt cluster=1 --opt prefetch=17 --opt page_bits=19
+cat gpurun_out/diag_cluster.log
+for cfg in "1 17"; do
+set -- $cfg
+cat > /tmp/prof_cfg.py <<PY
+import sys, runpy
+PY
+done
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_n30_c1p17.csv \
+    python scripts/prof_run.py --n 30 --L 3 --opt cluster=1 --opt prefetch=17 --opt page_bits=0 > gpurun_out/ncu_list.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_n30_c2p0.csv \
+    python scripts/prof_run.py --n 30 --L 3 --opt cluster=2 --opt prefetch=0 --opt page_bits=0 > gpurun_out/ncu_list.log 2>&1

@@ -24,6 +24,7 @@ ap.add_argument("--decoupled", type=int, default=0)
 ap.add_argument("--min-row-bits", type=int, default=3)
 ap.add_argument("--async-bwd", type=int, default=0)
 ap.add_argument("--lean", type=int, default=3)
+ap.add_argument("--opt", action="append", default=[], help="name=value library option")
 args = ap.parse_args()
 rng = np.random.default_rng(args.n)
 zz = np.full((args.n, args.n), None)
@@ -42,6 +43,9 @@ c.state.set_option("decoupled", args.decoupled)
 c.state.set_option("min_row_bits", args.min_row_bits)
 c.state.set_option("async_bwd", args.async_bwd)
 c.state.set_option("lean", args.lean)
+for o in args.opt:
+    k, v = o.split("=")
+    c.state.set_option(k, int(v))
 for _ in range(args.reps):
     e, g = c.grad_run()
 p = c.perf()

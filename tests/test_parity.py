@@ -161,7 +161,7 @@ def test_mcclean_tile_geometries_vs_oracle(backend, n, L, tile_bits):
                                   dict(async_bwd=1, async_fwd=1, reg_bits_fwd=4, reg_bits_bwd=4),
                                   dict(async_bwd=1, async_fwd=1, reg_bits_fwd=3, reg_bits_bwd=3),
                                   dict(lean=0, async_bwd=0, async_fwd=0, reg_bits_fwd=3, reg_bits_bwd=3, prefetch=1),
-                                  dict(lean=3, prefetch=1), dict(lean=1), dict(lean=2),
+                                  dict(lean=3, prefetch=1), dict(lean=1), dict(lean=2), dict(staged=3), dict(staged=1, cluster=2),
                                   dict(tile_bits_strided=5, min_row_bits=2), dict(tile_bits_strided=4, min_row_bits=1, async_bwd=1),
                                   dict(decoupled=3)])
 @pytest.mark.parametrize("n,L,tile_bits", [(7, 2, 5), (10, 2, 12), (13, 1, 12), (9, 2, 4), (12, 2, 12)])
@@ -206,6 +206,34 @@ def test_lean_tile_kernel_group_counts(backend, n, L):
         assert_parity(e1, g1, e_ref, g_ref, obs_scale(obs), TOL)
     c.state.set_option("lean", 3)
     np.testing.assert_allclose(c.run_expec_val(), e0, atol=1e-12 * obs_scale(obs))
+
+
+@pytest.mark.parametrize("n,min_row_bits,page_bits", [(17, 9, 13), (19, 8, 13), (18, 9, 14), (16, 10, 13)])
+def test_lean_tile_kernel_two_segment_geometry(backend, n, min_row_bits, page_bits):
+    """Strided passes whose gate bits are two runs of index bits (the planner shares the page-selecting bits between
+    the passes): forced at small n by a small page size and wide rows; against the single-run generic kernel."""
+    L = 2
+    rng = np.random.default_rng(50 + n)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    obs = mixed_obs(n)
+    c = McClean(n, obs, L, axes=axes, angles=angles)
+    c.state.set_option("min_row_bits", min_row_bits)
+    c.state.set_option("page_bits", page_bits)
+    e1, g1 = c.grad_run()
+    v1 = np.array(c.state.vec)
+    c.state.set_option("lean", 0)
+    e0, g0 = c.grad_run()
+    assert_parity(e1, g1, e0, g0, obs_scale(obs), 1e-12)
+    np.testing.assert_allclose(v1, c.state.vec, atol=1e-13)
+    c.state.set_option("lean", 3)
+    q = Qaoa(n, MaxCut(n, edge_set=[(i, i + 1) for i in range(n - 1)]).to_observable(), 2)
+    q.state.set_option("min_row_bits", min_row_bits)
+    q.state.set_option("page_bits", page_bits)
+    b, gm = rng.random(2), rng.random(2)
+    e1, g1 = q.grad_run(b, gm)
+    q.state.set_option("lean", 0)
+    e0, g0 = q.grad_run(b, gm)
+    assert_parity(e1, g1, e0, g0, float(n - 1), 1e-12)
 
 
 @pytest.mark.parametrize("case", ["all_x", "all_y", "all_z", "special_angles"])
