@@ -59,8 +59,9 @@ enum {
     QR_OPT_LEAN = 15,         /* lean static 12-bit tile kernel (default 3): bit0 backward, bit1 forward */
     QR_OPT_BUF_SKEW = 16,     /* bytes between the start offsets of consecutive state buffers (multiple of 256) */
     QR_OPT_CLUSTER = 18,      /* CTA pairs (thread-block clusters of 2) on adjacent tiles: bits 0-1 backward, 2-3 forward; 0 none, 1 strided passes, 2 all */
-    QR_OPT_STAGED = 19,       /* k_tile12: next tile staged in shared memory by asynchronous copies: bit0 backward, bit1 forward */
-    QR_OPT_PAGE_BITS = 17     /* log2 amplitudes per memory page (default 17 = 2 MiB); strided passes share the index bits above it; 0 = off */
+    QR_OPT_STAGED = 19,       /* k_tile12: next tile staged in shared memory by asynchronous copies: bit0 backward, bit1 forward, bit2 (default) auto */
+    QR_OPT_STAGED_MIN_BIT = 20, /* auto mode: strided backward passes whose lowest gate bit is >= this (default 21) are staged */
+    QR_OPT_PAGE_BITS = 17     /* log2 amplitudes per memory page (17 = 2 MiB): strided passes share the index bits above it; 0 (default) = off */
 };
 
 typedef struct qr_perf {

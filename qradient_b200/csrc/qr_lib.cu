@@ -107,9 +107,10 @@ struct qr_ctx {
     long long opt_tile_bits_x = 0, opt_min_row_bits = 3, opt_batch_chunk_mb = 0;
     long long opt_decoupled = 0;   // bit0: backward, bit1: forward use the decoupled-exchange kernel
     long long opt_lean = 3;        // bit0: backward, bit1: forward use the lean static 12-bit tile kernel
-    long long opt_page_bits = 17;  // log2 amplitudes per memory page (2 MiB): strided passes share the index bits above it; 0 = off
-    long long opt_staged = 0;      // bit0 backward, bit1 forward: next tile staged in shared memory by asynchronous copies
-    long long opt_cluster = 1;     // bits 0-1 backward, bits 2-3 forward: 0 none, 1 CTA pairs in the strided passes, 2 in every pass
+    long long opt_page_bits = 0;   // log2 amplitudes per memory page (2 MiB): strided passes share the index bits above it; 0 = off
+    long long opt_staged = 4;      // bit0 backward, bit1 forward: next tile staged in shared memory by asynchronous copies; bit2: auto (backward)
+    long long opt_staged_min_bit = 21;   // auto mode: strided backward passes whose lowest gate bit is >= this are staged
+    long long opt_cluster = 0;     // bits 0-1 backward, bits 2-3 forward: 0 none, 1 CTA pairs in the strided passes, 2 in every pass
     long long opt_buf_skew = 0;    // bytes between the start offsets of consecutive state buffers (multiple of 256)
     qr_perf perf;
     // ---- sharded states: this context holds one shard of an n_total-qubit register ----
@@ -290,7 +291,8 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
             if (v < 4 || v > QR_MAX_TILE_BITS) return fail(QR_EINVAL, "tile bits must be in [4, %d]", QR_MAX_TILE_BITS);
             c->opt_tile_bits = v; break;
         case QR_OPT_PREFETCH: if (v < 0 || v > 31) return fail(QR_EINVAL, "prefetch must be in [0, 31]"); c->opt_prefetch = v; break;
-        case QR_OPT_STAGED: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad staged mode"); c->opt_staged = v; break;
+        case QR_OPT_STAGED: if (v < 0 || v > 7) return fail(QR_EINVAL, "bad staged mode"); c->opt_staged = v; break;
+        case QR_OPT_STAGED_MIN_BIT: if (v < 0 || v > 64) return fail(QR_EINVAL, "bad staged min bit"); c->opt_staged_min_bit = v; break;
         case QR_OPT_CLUSTER: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad cluster mode"); c->opt_cluster = v; break;
         case QR_OPT_CTAS_PER_SM_FWD: if (v < 1 || v > 8) return fail(QR_EINVAL, "bad CTAs/SM"); c->opt_ctas_fwd = v; break;
         case QR_OPT_CTAS_PER_SM_BWD: if (v < 1 || v > 8) return fail(QR_EINVAL, "bad CTAs/SM"); c->opt_ctas_bwd = v; break;
@@ -343,6 +345,7 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_PAGE_BITS: *v = c->opt_page_bits; break;
         case QR_OPT_CLUSTER: *v = c->opt_cluster; break;
         case QR_OPT_STAGED: *v = c->opt_staged; break;
+        case QR_OPT_STAGED_MIN_BIT: *v = c->opt_staged_min_bit; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -1003,7 +1006,11 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
     if (pp.lean) {   // lean static kernel (k = 12, 512 threads)
         typedef void (*lean_fn)(const TilePass, const Tile12X);
         const int ph = (pre_phase || post_phase) ? 1 : 0;
-        const int staged = (nv == 2 ? (c->opt_staged & 1) : (c->opt_staged & 2)) ? 1 : 0;
+        // staged (asynchronous shared-memory copies of the next tile) vs direct loads + L2 prefetch, per pass:
+        // measured at n = 30 (profiles/README.md) the L2 prefetch wins for the contiguous pass and for strides
+        // below 32 MiB, and loses badly (22 vs 17 ms) when all gate bits are >= 21 -> auto mode (bit 2).
+        int staged = (nv == 2 ? (c->opt_staged & 1) : (c->opt_staged & 2)) ? 1 : 0;
+        if (nv == 2 && (c->opt_staged & 4) && pp.c < QR_MAX_TILE_BITS && pp.h >= c->opt_staged_min_bit) staged = 1;
         lean_fn lfn;
         if (staged) lfn = nv == 1 ? (ph ? k_tile12<1, true, true> : k_tile12<1, false, true>) : (ph ? k_tile12<2, true, true> : k_tile12<2, false, true>);
         else lfn = nv == 1 ? (ph ? k_tile12<1, true, false> : k_tile12<1, false, false>) : (ph ? k_tile12<2, true, false> : k_tile12<2, false, false>);

@@ -20,7 +20,7 @@ __device__ __forceinline__ u64 local_to_global(const Map& m, int l) {
 }
 
 template <int NV, int MODE>
-__global__ void __launch_bounds__(512, 1) k_touch(double2* v0, double2* v1, Map m, u64 tile_mask_bits, long long num_tiles, const u64* tile_base) {
+__global__ void __launch_bounds__(512, 1) k_touch(double2* v0, double2* v1, double2* w0, double2* w1, Map m, u64 tile_mask_bits, long long num_tiles, const u64* tile_base) {
     const int tid = threadIdx.x;
     const u64 toff = local_to_global(m, tid);
     u64 roff[8];
@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(512, 1) k_touch(double2* v0, double2* v1, Map 
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             a[0][r].x += 1.0;
-            v0[tb | roff[r]] = a[0][r];
-            if (NV == 2) { a[NV - 1][r].y += 1.0; v1[tb | roff[r]] = a[NV - 1][r]; }
+            w0[tb | roff[r]] = a[0][r];
+            if (NV == 2) { a[NV - 1][r].y += 1.0; w1[tb | roff[r]] = a[NV - 1][r]; }
         }
     }
 }
@@ -61,6 +61,7 @@ int main(int argc, char** argv) {
     const int mode = argc > 12 ? atoi(argv[12]) : 0;   // 0 plain, 1 L2 prefetch, 2 cluster barrier per tile, 3 one CTA takes adjacent tile pairs
     const int cs = argc > 13 ? atoi(argv[13]) : 1;     // cluster size
     const int grid = argc > 14 ? atoi(argv[14]) : 148;
+    const int oop = argc > 15 ? atoi(argv[15]) : 0;    // 1: out of place (separate destination buffers)
     const u64 N = (u64)1 << n;
     const long long num_tiles = (long long)(N >> 12);
     // tile t -> base index: deposit t's bits into the unused global bits, ascending
@@ -75,6 +76,8 @@ int main(int argc, char** argv) {
     double2 *v0, *v1 = nullptr;
     if (cudaMalloc(&v0, N * 16) != cudaSuccess) { fprintf(stderr, "alloc failed\n"); return 1; }
     if (nv == 2 && cudaMalloc(&v1, N * 16) != cudaSuccess) { fprintf(stderr, "alloc failed\n"); return 1; }
+    double2 *w0 = nullptr, *w1 = nullptr;
+    if (oop) { if (cudaMalloc(&w0, N * 16) != cudaSuccess) return 1; if (nv == 2 && cudaMalloc(&w1, N * 16) != cudaSuccess) return 1; }
     cudaMemset(v0, 0, N * 16);
     if (v1) cudaMemset(v1, 0, N * 16);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -86,17 +89,17 @@ int main(int argc, char** argv) {
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        void (*fn)(double2*, double2*, Map, u64, long long, const u64*) = nullptr;
+        void (*fn)(double2*, double2*, double2*, double2*, Map, u64, long long, const u64*) = nullptr;
         if (nv == 1) fn = mode == 0 ? k_touch<1, 0> : mode == 1 ? k_touch<1, 1> : mode == 2 ? k_touch<1, 2> : k_touch<1, 3>;
         else fn = mode == 0 ? k_touch<2, 0> : mode == 1 ? k_touch<2, 1> : mode == 2 ? k_touch<2, 2> : k_touch<2, 3>;
-        cudaLaunchKernelEx(&cfg, fn, v0, v1, m, (u64)0, num_tiles, (const u64*)d_base);
+        cudaLaunchKernelEx(&cfg, fn, v0, v1, oop ? w0 : v0, oop ? w1 : v1, m, (u64)0, num_tiles, (const u64*)d_base);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (rep > 0 && ms < best) best = ms;
     }
     cudaError_t err = cudaGetLastError();
-    printf("n=%d nv=%d mode=%d cs=%d grid=%d bits=", n, nv, mode, cs, grid);
+    printf("n=%d nv=%d mode=%d cs=%d grid=%d oop=%d bits=", n, nv, mode, cs, grid, oop);
     for (int j = 0; j < 9; ++j) printf("%d,", (int)m.bitpos[j]);
     printf(" ms=%.3f GB/s=%.0f %s\n", best, nv * 32.0 * N / best / 1e6, err == cudaSuccess ? "" : cudaGetErrorString(err));
     return 0;
