@@ -108,6 +108,13 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# per-launch DRAM traffic of the backward tile pass at n = 30 (ncu dram__bytes_read.sum + dram__bytes_write.sum,
+# averaged over the 9 backward launches of profiles/r1_launches_mcclean30_L3_tile12_default.csv; algorithmic: 68.72e9)
+TRAFFIC30_BWD = 69.9e9
+TRAFFIC30_SRC = ("ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 9 backward launches in "
+                 "profiles/r1_launches_mcclean30_L3_tile12_default.csv (reads 35.5 GB incl. ~3 % L2-prefetch over-fetch, writes 34.4 GB)")
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -192,6 +199,7 @@ def main():
     ap.add_argument("--ctas-bwd", type=int, default=None)
     ap.add_argument("--ctas-fwd", type=int, default=None)
     ap.add_argument("--batch-chunk-mb", type=int, default=None)
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (see include/qradient_b200.h QR_OPT_*)")
     ap.add_argument("--hbm-target", type=int, default=1, help="also measure the 30x30 HBM-bound target (N=1 only)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -278,6 +286,9 @@ def main():
                       ("ctas_per_sm_fwd", args.ctas_fwd), ("batch_chunk_mb", args.batch_chunk_mb)):
         if val is not None:
             circ.state.set_option(name, val)
+    for o in args.opt:
+        k_, v_ = o.split("=")
+        circ.state.set_option(k_, int(v_))
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -334,7 +345,7 @@ def main():
                 "ms_per_step": t_wall / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_tile_pass<2,*> (backward tile pass: psi and lambda)",
+        "roofline": {"bound": "hbm", "kernel": "k_tile12<2,*> (backward tile pass: psi and lambda, qr_tile12.cuh)",
                      "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak, "peak_source": peak_src,
                      "bytes_per_launch": perf["bwd_pass_bytes"], "ms_per_launch": perf["bwd_pass_ms_avg"],
                      "traffic": None,
@@ -355,6 +366,9 @@ def main():
             for name, val in (("prefetch", args.prefetch), ("ctas_per_sm_bwd", args.ctas_bwd), ("ctas_per_sm_fwd", args.ctas_fwd)):
                 if val is not None:
                     c30.state.set_option(name, val)
+            for o in args.opt:
+                k_, v_ = o.split("=")
+                c30.state.set_option(k_, int(v_))
             c30.grad_run()
             t0 = time.perf_counter()
             e30, _ = c30.grad_run()
@@ -365,10 +379,9 @@ def main():
             line["hbm_target"] = {
                 "workload": w30["name"], "gradients_per_s": 1e3 / p30["ms_total"], "e2e_gradients_per_s": 1.0 / wall30,
                 "ms_per_gradient": p30["ms_total"], "E": e30, "passes_per_layer": p30["passes_per_layer"],
-                "roofline": {"bound": "hbm", "kernel": "k_tile_pass<2,3,false> backward", "achieved": b30, "peak": peak, "unit": "GB/s",
+                "roofline": {"bound": "hbm", "kernel": "k_tile12<2,false,*> backward (qr_tile12.cuh)", "achieved": b30, "peak": peak, "unit": "GB/s",
                              "frac": b30 / peak, "bytes_per_launch": p30["bwd_pass_bytes"], "ms_per_launch": p30["bwd_pass_ms_avg"],
-                             "traffic": 68.77e9, "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                                                                   "(profiles/r1_launches_mcclean30_L3_sync.csv: 34.39 + 34.38 GB)"},
+                             "traffic": TRAFFIC30_BWD, "traffic_source": TRAFFIC30_SRC},
                 "forward_pass": {"achieved": f30, "frac": f30 / peak, "ms_per_launch": p30["fwd_pass_ms_avg"]},
                 "sched": {"B_sched_bytes": p30["algorithmic_bytes"], "achieved_GBps": p30["algorithmic_bytes"] / (p30["ms_total"] * 1e-3) / 1e9,
                           "frac_of_peak": p30["algorithmic_bytes"] / (p30["ms_total"] * 1e-3) / 1e9 / peak}}

@@ -111,6 +111,8 @@ struct qr_ctx {
     long long opt_staged = 4;      // bit0 backward, bit1 forward: next tile staged in shared memory by asynchronous copies; bit2: auto (backward)
     long long opt_staged_min_bit = 21;   // auto mode: strided backward passes whose lowest gate bit is >= this are staged
     long long opt_cluster = 0;     // bits 0-1 backward, bits 2-3 forward: 0 none, 1 CTA pairs in the strided passes, 2 in every pass
+    long long opt_cache_hints = 0; // k_tile12: bit0 streaming stores, bit1 streaming loads (all passes); bits 2-3: same, out-of-place passes only
+    long long opt_debug = 0;       // timing diagnostics (results are wrong): bit0 no ladder gather map, bit1 ladder passes in place
     long long opt_buf_skew = 0;    // bytes between the start offsets of consecutive state buffers (multiple of 256)
     qr_perf perf;
     // ---- sharded states: this context holds one shard of an n_total-qubit register ----
@@ -292,6 +294,8 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
             c->opt_tile_bits = v; break;
         case QR_OPT_PREFETCH: if (v < 0 || v > 31) return fail(QR_EINVAL, "prefetch must be in [0, 31]"); c->opt_prefetch = v; break;
         case QR_OPT_STAGED: if (v < 0 || v > 7) return fail(QR_EINVAL, "bad staged mode"); c->opt_staged = v; break;
+        case QR_OPT_DEBUG: c->opt_debug = v; break;
+        case QR_OPT_CACHE_HINTS: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad cache hints"); c->opt_cache_hints = v; break;
         case QR_OPT_STAGED_MIN_BIT: if (v < 0 || v > 64) return fail(QR_EINVAL, "bad staged min bit"); c->opt_staged_min_bit = v; break;
         case QR_OPT_CLUSTER: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad cluster mode"); c->opt_cluster = v; break;
         case QR_OPT_CTAS_PER_SM_FWD: if (v < 1 || v > 8) return fail(QR_EINVAL, "bad CTAs/SM"); c->opt_ctas_fwd = v; break;
@@ -346,6 +350,8 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_CLUSTER: *v = c->opt_cluster; break;
         case QR_OPT_STAGED: *v = c->opt_staged; break;
         case QR_OPT_STAGED_MIN_BIT: *v = c->opt_staged_min_bit; break;
+        case QR_OPT_DEBUG: *v = c->opt_debug; break;
+        case QR_OPT_CACHE_HINTS: *v = c->opt_cache_hints; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -976,10 +982,12 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         tp.ladder = 1;
         ladder_masks(lp.n, 1 - ladder_stacking, &tp.M1, &tp.M2);
     }
+    if (c->opt_debug & 1) tp.ladder = 0;          // timing diagnostics only (wrong results): no gather map
     tp.tiles_log2 = lp.n - pp.k;
     tp.num_tiles = batch << tp.tiles_log2;
     tp.state_stride = state_stride;
     tp.src0 = io.src0; tp.src1 = io.src1; tp.dst0 = io.dst0; tp.dst1 = io.dst1;
+    if (c->opt_debug & 2) { tp.dst0 = (double2*)io.src0; tp.dst1 = (double2*)io.src1; }   // timing diagnostics only: in place
     tp.gates = d_gates; tp.gate_stride = gate_stride;
     tp.ham = ham; tp.pre_phase = pre_phase; tp.post_phase = post_phase;
     if (lut && c->ham_integer) { tp.hidx = c->d_hidx; tp.lut = lut; tp.lut_size = c->ham_range; tp.hmin = c->ham_min; }
@@ -1023,6 +1031,10 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         Tile12X x;
         memset(&x, 0, sizeof(x));
         x.ngroups = pp.ngroups;
+        {   // cache hints: opt bits 0-1 = all passes, bits 2-3 = out-of-place (ladder) passes only
+            const bool oop = io.src0 != io.dst0;
+            x.cache_hints = (int)(c->opt_cache_hints & 3) | (oop ? (int)((c->opt_cache_hints >> 2) & 3) : 0);
+        }
         const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2};
         for (int r = 0; r < 8; ++r) {
             const u64 lf = (u64)r << 9, ll = (u64)r << (pp.ngroups > 1 ? 6 : 9);

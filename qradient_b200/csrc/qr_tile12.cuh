@@ -54,6 +54,7 @@ __host__ __device__ __forceinline__ u64 geo12_tile(const Geo12 g, u64 t) {
 struct Tile12X {
     int ngroups;            // active register groups: 1 = G3; 2 = G3,G2; 3 = G3,G1,G2; 4 = G3,G0,G1,G2
     int cluster;            // thread-block cluster size of the launch (1 or 2)
+    int cache_hints;        // bit0: streaming (evict-first) stores, bit1: streaming loads
     u64 roff_first[8];      // global offset of register r at load time (group G3), gather map applied
     u64 roff_last[8];       // global offset of register r at store time (G2, or G3 when ngroups == 1)
     u64 droff_first[8];     // same as roff_first without the gather map (destination index: phase tables)
@@ -184,6 +185,15 @@ __device__ __forceinline__ void qr12_exchange_1buf(double2 (&a)[NV][8], double2*
         for (int r = 0; r < 8; ++r) a[v][r] = xbuf[bn ^ (r * qr12_smul<GN>())];
     }
 }
+
+// streaming (evict-first) accesses: every amplitude is read once and written once per pass
+#ifndef QR_HOST_EMUL
+__device__ __forceinline__ double2 qr_ldcs(const double2* p) { return __ldcs(p); }
+__device__ __forceinline__ void qr_stcs(double2* p, double2 v) { __stcs(p, v); }
+#else
+__device__ __forceinline__ double2 qr_ldcs(const double2* p) { return *p; }
+__device__ __forceinline__ void qr_stcs(double2* p, double2 v) { *p = v; }
+#endif
 
 // ---- per-thread asynchronous copies (LDGSTS): 16 B global -> shared, no register staging ----
 #ifndef QR_HOST_EMUL
@@ -362,8 +372,8 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const u64 s = sbt ^ x.roff_first[r];
-                a[0][r] = p.src0[s];
-                if (NV == 2) a[NV - 1][r] = p.src1[s];
+                a[0][r] = (x.cache_hints & 2) ? qr_ldcs(p.src0 + s) : p.src0[s];
+                if (NV == 2) a[NV - 1][r] = (x.cache_hints & 2) ? qr_ldcs(p.src1 + s) : p.src1[s];
             }
         }
 #ifndef QR_HOST_EMUL
@@ -453,8 +463,13 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
 #pragma unroll
                 for (int v = 0; v < NV; ++v) a[v][r] = cmul(a[v][r], ph);
             }
-            p.dst0[d] = a[0][r];
-            if (NV == 2) p.dst1[d] = a[NV - 1][r];
+            if (x.cache_hints & 1) {
+                qr_stcs(p.dst0 + d, a[0][r]);
+                if (NV == 2) qr_stcs(p.dst1 + d, a[NV - 1][r]);
+            } else {
+                p.dst0[d] = a[0][r];
+                if (NV == 2) p.dst1[d] = a[NV - 1][r];
+            }
         }
         if (NV == 2 && p.flush_per_tile) {
             finalize();

@@ -12,7 +12,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=28)
 ap.add_argument("--L", type=int, default=2)
 ap.add_argument("--reps", type=int, default=1)
-ap.add_argument("--prefetch", type=int, default=0)
+ap.add_argument("--prefetch", type=int, default=1)
 ap.add_argument("--ctas-bwd", type=int, default=1)
 ap.add_argument("--ctas-fwd", type=int, default=2)
 ap.add_argument("--r-fwd", type=int, default=3)
