@@ -110,9 +110,9 @@ class ClockSampler:
 
 # per-launch DRAM traffic of the backward tile pass at n = 30 (ncu dram__bytes_read.sum + dram__bytes_write.sum,
 # averaged over the 9 backward launches of profiles/r1_launches_mcclean30_L3_tile12_default.csv; algorithmic: 68.72e9)
-TRAFFIC30_BWD = 69.9e9
+TRAFFIC30_BWD = 69.3e9
 TRAFFIC30_SRC = ("ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 9 backward launches in "
-                 "profiles/r1_launches_mcclean30_L3_tile12_default.csv (reads 35.5 GB incl. ~3 % L2-prefetch over-fetch, writes 34.4 GB)")
+                 "profiles/r1_launches_mcclean30_L3_tile12_default.csv (reads 35.0 GB incl. ~2 % L2-prefetch over-fetch, writes 34.3 GB)")
 
 
 def measured_peak():
