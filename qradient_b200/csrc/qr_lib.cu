@@ -111,6 +111,7 @@ struct qr_ctx {
     long long opt_staged = 4;      // bit0 backward, bit1 forward: next tile staged in shared memory by asynchronous copies; bit2: auto (backward)
     long long opt_staged_min_bit = 21;   // auto mode: strided backward passes whose lowest gate bit is >= this are staged
     long long opt_cluster = 0;     // bits 0-1 backward, bits 2-3 forward: 0 none, 1 CTA pairs in the strided passes, 2 in every pass
+    long long opt_low_bits_pass = 0;   // k_tile12: pass that applies the gates on index bits 0-2 (0 = contiguous pass, -1 = last strided pass)
     long long opt_cache_hints = 0; // k_tile12: bit0 streaming stores, bit1 streaming loads (all passes); bits 2-3: same, out-of-place passes only
     long long opt_debug = 0;       // timing diagnostics (results are wrong): bit0 no ladder gather map, bit1 ladder passes in place
     long long opt_buf_skew = 0;    // bytes between the start offsets of consecutive state buffers (multiple of 256)
@@ -293,8 +294,9 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
             if (v < 4 || v > QR_MAX_TILE_BITS) return fail(QR_EINVAL, "tile bits must be in [4, %d]", QR_MAX_TILE_BITS);
             c->opt_tile_bits = v; break;
         case QR_OPT_PREFETCH: if (v < 0 || v > 31) return fail(QR_EINVAL, "prefetch must be in [0, 31]"); c->opt_prefetch = v; break;
-        case QR_OPT_STAGED: if (v < 0 || v > 7) return fail(QR_EINVAL, "bad staged mode"); c->opt_staged = v; break;
+        case QR_OPT_STAGED: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad staged mode"); c->opt_staged = v; break;
         case QR_OPT_DEBUG: c->opt_debug = v; break;
+        case QR_OPT_LOW_BITS_PASS: if (v < -1 || v > 15) return fail(QR_EINVAL, "bad low-bits pass"); c->opt_low_bits_pass = v; break;
         case QR_OPT_CACHE_HINTS: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad cache hints"); c->opt_cache_hints = v; break;
         case QR_OPT_STAGED_MIN_BIT: if (v < 0 || v > 64) return fail(QR_EINVAL, "bad staged min bit"); c->opt_staged_min_bit = v; break;
         case QR_OPT_CLUSTER: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad cluster mode"); c->opt_cluster = v; break;
@@ -352,6 +354,7 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_STAGED_MIN_BIT: *v = c->opt_staged_min_bit; break;
         case QR_OPT_DEBUG: *v = c->opt_debug; break;
         case QR_OPT_CACHE_HINTS: *v = c->opt_cache_hints; break;
+        case QR_OPT_LOW_BITS_PASS: *v = c->opt_low_bits_pass; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -862,7 +865,7 @@ static void plan_dc(PassPlan& pp, int first) {
 
 // Lean plan of a k = 12 pass whose gate bits are the local bits [first, 12): fixed groups
 // G0..G3 = local bits 0-2, 3-5, 6-8, 9-11, visited G3 [G0] [G1] [G2]; gradient slot = local bit.
-static void plan_lean(PassPlan& pp, int first) {
+static void plan_lean(PassPlan& pp, int first, bool with_low = false) {
     for (int i = 0; i < QR_GATE_SLOTS; ++i) pp.gbit[i] = -1;
     const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2};
     for (int lb = first; lb < QR_MAX_TILE_BITS; ++lb) {
@@ -872,13 +875,17 @@ static void plan_lean(PassPlan& pp, int first) {
         pp.gbit[lb] = gb;
     }
     pp.ngroups = first < 3 ? 4 : (first < 6 ? 3 : (first < 9 ? 2 : 1));
+    if (with_low) {   // the gates of index bits 0-2 (inside every tile's 128 B rows) are applied in this strided pass
+        for (int lb = 0; lb < 3; ++lb) pp.gbit[lb] = lb;
+        pp.ngroups = 4;
+    }
     pp.nrounds = pp.ngroups;
     pp.g[0] = 9;
     pp.lean = true;
 }
 
 static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x = 0, int min_row_bits = 3, bool allow_dc = false,
-                     bool allow_lean = false, int page_bits = 17) {
+                     bool allow_lean = false, int page_bits = 17, int low_bits_pass = 0) {
     if (n < 4) return fail(QR_EINVAL, "fused path needs at least 4 qubits");
     const int k = std::min(n, tile_bits);
     lp->n = n;
@@ -887,7 +894,18 @@ static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x
     int np = 0;
     PassPlan& p0 = lp->pass[np++];
     p0.k = k; p0.c = k; p0.h = k; p0.dc = false; p0.lean = false; p0.ngroups = 0; p0.m1 = 0; p0.h2 = k;
-    if (allow_lean && k == 12) plan_lean(p0, 0);
+    // lean kernel: the gates on index bits 0-2 may be moved from the (on-chip bound) contiguous pass to a
+    // (memory bound) strided pass, whose tiles contain those bits as well
+    const int rem0 = n - k;
+    int low_pass = 0;
+    if (allow_lean && k == 12 && low_bits_pass != 0 && rem0 > 0) {
+        const int kx0 = tile_bits_x > 0 ? std::min(n, tile_bits_x) : k;
+        const int umax0 = std::max(kx0 - std::min(min_row_bits, kx0 - 1), 1);
+        const int nx0 = (rem0 + umax0 - 1) / umax0;
+        low_pass = low_bits_pass < 0 ? nx0 : std::min(low_bits_pass, nx0);
+        if (kx0 != 12 || rem0 / nx0 < 7) low_pass = 0;   // only into a pass with >= 7 strided gate bits (3 other groups are active anyway)
+    }
+    if (allow_lean && k == 12) plan_lean(p0, low_pass ? 3 : 0);
     else if (allow_dc && k == 12 && R == 3) plan_dc(p0, 0); else plan_rounds(p0, 0, R);
     const int rem = n - k;
     if (rem > 0) {
@@ -920,7 +938,7 @@ static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x
                 lo_next += ml;
                 hi_next += mh;
             }
-            if (allow_lean && kx == 12) plan_lean(pp, pp.c);
+            if (allow_lean && kx == 12) plan_lean(pp, pp.c, low_pass == i + 1);
             else if (allow_dc && kx == 12 && R == 3) plan_dc(pp, pp.c); else plan_rounds(pp, pp.c, R);
             h += m;
         }
@@ -1019,15 +1037,17 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         // below 32 MiB, and loses badly (22 vs 17 ms) when all gate bits are >= 21 -> auto mode (bit 2).
         int staged = (nv == 2 ? (c->opt_staged & 1) : (c->opt_staged & 2)) ? 1 : 0;
         if (nv == 2 && (c->opt_staged & 4) && pp.c < QR_MAX_TILE_BITS && pp.h >= c->opt_staged_min_bit) staged = 1;
+        if (nv == 2 && !staged && (c->opt_staged & 8)) staged = 2;   // bit 3: psi-only staging for the other backward passes
         lean_fn lfn;
-        if (staged) lfn = nv == 1 ? (ph ? k_tile12<1, true, true> : k_tile12<1, false, true>) : (ph ? k_tile12<2, true, true> : k_tile12<2, false, true>);
-        else lfn = nv == 1 ? (ph ? k_tile12<1, true, false> : k_tile12<1, false, false>) : (ph ? k_tile12<2, true, false> : k_tile12<2, false, false>);
-        static bool lean_attr[2][2][2] = {{{false, false}, {false, false}}, {{false, false}, {false, false}}};
+        if (staged == 2 && nv == 2) lfn = ph ? k_tile12<2, true, 2> : k_tile12<2, false, 2>;
+        else if (staged) lfn = nv == 1 ? (ph ? k_tile12<1, true, 1> : k_tile12<1, false, 1>) : (ph ? k_tile12<2, true, 1> : k_tile12<2, false, 1>);
+        else lfn = nv == 1 ? (ph ? k_tile12<1, true, 0> : k_tile12<1, false, 0>) : (ph ? k_tile12<2, true, 0> : k_tile12<2, false, 0>);
+        static bool lean_attr[2][2][3] = {{{false, false, false}, {false, false, false}}, {{false, false, false}, {false, false, false}}};
         if (!lean_attr[nv - 1][ph][staged]) {
             CUDA_TRY(cudaFuncSetAttribute(lfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (int)sizeof(double2) << QR_MAX_TILE_BITS));
             lean_attr[nv - 1][ph][staged] = true;
         }
-        if (staged) tp.prefetch = 0;
+        if (staged == 1) tp.prefetch = 0;
         Tile12X x;
         memset(&x, 0, sizeof(x));
         x.ngroups = pp.ngroups;
@@ -1192,9 +1212,9 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     const bool dc_f = batch == 1 && !c->opt_async_fwd && (c->opt_decoupled & 2);
     const bool dc_b = batch == 1 && !c->opt_async_bwd && (c->opt_decoupled & 1);
     QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits, dc_f,
-                     !dc_f && !c->opt_async_fwd && (c->opt_lean & 2), (int)c->opt_page_bits));
+                     !dc_f && !c->opt_async_fwd && (c->opt_lean & 2), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
     QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits, dc_b,
-                     !dc_b && !c->opt_async_bwd && (c->opt_lean & 1), (int)c->opt_page_bits));
+                     !dc_b && !c->opt_async_bwd && (c->opt_lean & 1), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
     const int P = lp.npasses;
     const int GS = QR_GATE_SLOTS;                 // gate entries per (layer, pass)
     const bool want_grad = grad != nullptr;
@@ -1530,10 +1550,10 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
     LayerPlan lpf, lp;
     QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
                      !c->opt_async_fwd && (c->opt_decoupled & 2),
-                     !c->opt_async_fwd && !(c->opt_decoupled & 2) && (c->opt_lean & 2), (int)c->opt_page_bits));
+                     !c->opt_async_fwd && !(c->opt_decoupled & 2) && (c->opt_lean & 2), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
     QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
                      !c->opt_async_bwd && (c->opt_decoupled & 1),
-                     !c->opt_async_bwd && !(c->opt_decoupled & 1) && (c->opt_lean & 1), (int)c->opt_page_bits));
+                     !c->opt_async_bwd && !(c->opt_decoupled & 1) && (c->opt_lean & 1), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
     const int P = lp.npasses;
     const int GS = QR_GATE_SLOTS;
     const bool want_grad = grad != nullptr;
@@ -1866,10 +1886,10 @@ extern "C" int qr_shard_mcclean_begin(qr_ctx* c, int L, const int32_t* axes, con
     run->terms = o->terms;
     QR_TRY(make_plan(nl, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &run->lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
                      !c->opt_async_fwd && (c->opt_decoupled & 2),
-                     !c->opt_async_fwd && !(c->opt_decoupled & 2) && (c->opt_lean & 2), (int)c->opt_page_bits));
+                     !c->opt_async_fwd && !(c->opt_decoupled & 2) && (c->opt_lean & 2), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
     QR_TRY(make_plan(nl, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &run->lpb, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
                      !c->opt_async_bwd && (c->opt_decoupled & 1),
-                     !c->opt_async_bwd && !(c->opt_decoupled & 1) && (c->opt_lean & 1), (int)c->opt_page_bits));
+                     !c->opt_async_bwd && !(c->opt_decoupled & 1) && (c->opt_lean & 1), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
     const int P = run->P = run->lpb.npasses;
     run->pi.resize(G);
     for (int r = 0; r < G; ++r) run->pi[r] = r;

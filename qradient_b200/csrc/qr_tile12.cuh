@@ -227,11 +227,14 @@ __device__ __noinline__ double2 qr12_phase_slow(const double* __restrict__ ham, 
 // of the tile after that.  Shared memory: NV tile-sized stages + ONE exchange buffer (the vectors
 // take turns) = 192 KiB for the backward pass; HBM reads overlap the whole gate/exchange phase
 // instead of only reaching L2 (prefetch) or being waited for (direct loads).
-template <int NV, bool PHASE, bool STAGED>
+// STAGED == 2 (backward only): only psi is staged, lambda is loaded directly (L2 prefetch) and the
+// exchange keeps its two buffers and single barrier: [exchange psi][exchange lambda][stage psi].
+template <int NV, bool PHASE, int STAGED>
 __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)) k_tile12(const TilePass p, const Tile12X x) {
+    constexpr int NSV = STAGED == 1 ? NV : (STAGED == 2 ? 1 : 0);   // staged vectors
     constexpr int T = 1 << QR_MAX_TILE_BITS;
     QR_DYN_SMEM(double2, smem);
-    double2* const stage = smem + (STAGED ? T : 0);   // STAGED: [exchange][stage psi][stage lambda]
+    double2* const stage = smem + (STAGED == 1 ? T : (STAGED == 2 ? NV * T : 0));   // STAGED 1: [exchange][stage psi][stage lambda]
     __shared__ Gate12 sg[QR_GATE_SLOTS];
     __shared__ double2 szr[8];                  // Z phases of the G3 register bits (times nothing else)
     __shared__ double2 szb[QR_GATE_SLOTS][2];   // per gate bit: Z phase for bit value 0 / 1 (identity if not Z)
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
         for (int r = 0; r < 8; ++r) {
             const u64 sidx = sb ^ x.roff_first[r];
             qr_cp_async16(stage + tid + (r << 9), p.src0 + nb * p.state_stride + sidx);
-            if (NV == 2) qr_cp_async16(stage + T + tid + (r << 9), p.src1 + nb * p.state_stride + sidx);
+            if (NSV == 2) qr_cp_async16(stage + T + tid + (r << 9), p.src1 + nb * p.state_stride + sidx);
         }
         qr_cp_async_commit();
     };
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
         // CTAs of a cluster own ADJACENT tiles (rows 128 B apart in the strided passes).  Aligning their
         // loads in time lets the DRAM controller serve both halves of a 256 B chunk from one row
         // activation: measured 4.8 -> 5.8 TB/s on the bare two-vector access pattern (scripts/membench.cu).
-        if (x.cluster > 1 && (!STAGED || it + 1 < iters)) asm volatile("barrier.cluster.arrive.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory");
+        if (x.cluster > 1 && (STAGED == 0 || it + 1 < iters)) asm volatile("barrier.cluster.arrive.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory");
 #endif
         if (tile >= p.num_tiles) continue;
         const i64 b = tile >> p.tiles_log2;
@@ -365,7 +368,8 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 a[0][r] = stage[tid + (r << 9)];
-                if (NV == 2) a[NV - 1][r] = stage[T + tid + (r << 9)];
+                if (NSV == 2) a[NV - 1][r] = stage[T + tid + (r << 9)];
+                else if (NV == 2) a[NV - 1][r] = p.src1[sbt ^ x.roff_first[r]];
             }
             if (tile + gridDim.x < p.num_tiles) issue_stage(tile + gridDim.x);   // lands while this tile is computed
         } else {
@@ -386,7 +390,7 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
                 const int l = tid << 3;   // one 128 B line per thread
                 const u64 d = nbase | geo12_local(geo, (u64)l);
                 const u64 s = p.ladder ? (ladder_map(d, p.M1, p.M2) ^ p.src_xor) : d;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src0 + nb * p.state_stride + s));
+                if (STAGED != 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src0 + nb * p.state_stride + s));
                 if (NV == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src1 + nb * p.state_stride + s));
             }
         }
@@ -430,17 +434,17 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
         // ---- rounds ----
         qr12_round<NV, 9>(a, sg, acc_all);
         if (ng == 4) {
-            if (STAGED) qr12_exchange_1buf<NV, 9, 0>(a, smem, tid); else qr12_exchange<NV, 9, 0>(a, smem, tid);
+            if (STAGED == 1) qr12_exchange_1buf<NV, 9, 0>(a, smem, tid); else qr12_exchange<NV, 9, 0>(a, smem, tid);
             qr12_round<NV, 0>(a, sg, acc_all);
-            if (STAGED) qr12_exchange_1buf<NV, 0, 3>(a, smem, tid); else qr12_exchange<NV, 0, 3>(a, smem, tid);
+            if (STAGED == 1) qr12_exchange_1buf<NV, 0, 3>(a, smem, tid); else qr12_exchange<NV, 0, 3>(a, smem, tid);
         } else if (ng == 3) {
-            if (STAGED) qr12_exchange_1buf<NV, 9, 3>(a, smem, tid); else qr12_exchange<NV, 9, 3>(a, smem, tid);
+            if (STAGED == 1) qr12_exchange_1buf<NV, 9, 3>(a, smem, tid); else qr12_exchange<NV, 9, 3>(a, smem, tid);
         }
         if (ng >= 3) {
             qr12_round<NV, 3>(a, sg, acc_all);
-            if (STAGED) qr12_exchange_1buf<NV, 3, 6>(a, smem, tid); else qr12_exchange<NV, 3, 6>(a, smem, tid);
+            if (STAGED == 1) qr12_exchange_1buf<NV, 3, 6>(a, smem, tid); else qr12_exchange<NV, 3, 6>(a, smem, tid);
         } else if (ng == 2) {
-            if (STAGED) qr12_exchange_1buf<NV, 9, 6>(a, smem, tid); else qr12_exchange<NV, 9, 6>(a, smem, tid);
+            if (STAGED == 1) qr12_exchange_1buf<NV, 9, 6>(a, smem, tid); else qr12_exchange<NV, 9, 6>(a, smem, tid);
         }
         if (ng >= 2) {
             qr12_round<NV, 6>(a, sg, acc_all);

@@ -161,7 +161,7 @@ def test_mcclean_tile_geometries_vs_oracle(backend, n, L, tile_bits):
                                   dict(async_bwd=1, async_fwd=1, reg_bits_fwd=4, reg_bits_bwd=4),
                                   dict(async_bwd=1, async_fwd=1, reg_bits_fwd=3, reg_bits_bwd=3),
                                   dict(lean=0, async_bwd=0, async_fwd=0, reg_bits_fwd=3, reg_bits_bwd=3, prefetch=1),
-                                  dict(lean=3, prefetch=1), dict(lean=1), dict(lean=2), dict(staged=3), dict(staged=1, cluster=2),
+                                  dict(lean=3, prefetch=1), dict(lean=1), dict(lean=2), dict(staged=3), dict(staged=1, cluster=2), dict(staged=8), dict(staged=12, prefetch=1),
                                   dict(tile_bits_strided=5, min_row_bits=2), dict(tile_bits_strided=4, min_row_bits=1, async_bwd=1),
                                   dict(decoupled=3)])
 @pytest.mark.parametrize("n,L,tile_bits", [(7, 2, 5), (10, 2, 12), (13, 1, 12), (9, 2, 4), (12, 2, 12)])
@@ -233,6 +233,30 @@ def test_lean_tile_kernel_two_segment_geometry(backend, n, min_row_bits, page_bi
     e1, g1 = q.grad_run(b, gm)
     q.state.set_option("lean", 0)
     e0, g0 = q.grad_run(b, gm)
+    assert_parity(e1, g1, e0, g0, float(n - 1), 1e-12)
+
+
+def test_lean_tile_kernel_low_bits_in_strided_pass(backend):
+    """The gates on index bits 0-2 applied by the strided pass (4 register groups there, 3 in the contiguous pass)."""
+    n, L = 19, 2
+    rng = np.random.default_rng(19)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    obs = mixed_obs(n)
+    c = McClean(n, obs, L, axes=axes, angles=angles)
+    e0, g0 = c.grad_run()
+    v0 = np.array(c.state.vec)
+    c.state.set_option("low_bits_pass", -1)
+    e1, g1 = c.grad_run()
+    assert_parity(e1, g1, e0, g0, obs_scale(obs), 1e-12)
+    np.testing.assert_allclose(v0, c.state.vec, atol=1e-13)
+    c.state.set_option("staged", 3)
+    e2, g2 = c.grad_run()
+    assert_parity(e2, g2, e0, g0, obs_scale(obs), 1e-12)
+    q = Qaoa(n, MaxCut(n, edge_set=[(i, i + 1) for i in range(n - 1)]).to_observable(), 2)
+    b, gm = rng.random(2), rng.random(2)
+    e0, g0 = q.grad_run(b, gm)
+    q.state.set_option("low_bits_pass", 1)
+    e1, g1 = q.grad_run(b, gm)
     assert_parity(e1, g1, e0, g0, float(n - 1), 1e-12)
 
 
