@@ -166,10 +166,21 @@ class ShardedMcClean:
             self._lib.call('qr_shard_mcclean_begin', s.ctx, self.lnum, _lib.ptr(axes), _lib.ptr(angles),
                            self.observable._handle, int(want_grad), ctypes.byref(nsteps))
         self.comm.barrier()
+        import time
+        L = self.lnum
+        self.step_seconds = {'fwd_local': 0.0, 'fwd_global': 0.0, 'observable': 0.0, 'bwd_local': 0.0, 'bwd_global': 0.0}
         for step in range(nsteps.value):
+            t0 = time.perf_counter()
             for s in self.shards:
                 self._lib.call('qr_shard_step', s.ctx, step)
             self.comm.barrier()
+            if step < 2 * L:
+                kind = 'fwd_local' if step % 2 == 0 else 'fwd_global'
+            elif step == 2 * L:
+                kind = 'observable'
+            else:
+                kind = 'bwd_local' if (step - 2 * L - 1) % 2 == 0 else 'bwd_global'
+            self.step_seconds[kind] += time.perf_counter() - t0   # wall time of this rank incl. the barrier
         parts = []
         for s in self.shards:
             e = ctypes.c_double()
