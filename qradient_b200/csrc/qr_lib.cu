@@ -867,20 +867,23 @@ static void plan_dc(PassPlan& pp, int first) {
 // G0..G3 = local bits 0-2, 3-5, 6-8, 9-11, visited G3 [G0] [G1] [G2]; gradient slot = local bit.
 static void plan_lean(PassPlan& pp, int first, bool with_low = false) {
     for (int i = 0; i < QR_GATE_SLOTS; ++i) pp.gbit[i] = -1;
-    const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2};
-    for (int lb = first; lb < QR_MAX_TILE_BITS; ++lb) {
+    const int K = pp.k;
+    const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2, K};
+    for (int lb = first; lb < K; ++lb) {
         u64 gidx = geo12_local(geo, (u64)1 << lb);
         int gb = 0;
         while (!((gidx >> gb) & 1)) ++gb;
         pp.gbit[lb] = gb;
     }
-    pp.ngroups = first < 3 ? 4 : (first < 6 ? 3 : (first < 9 ? 2 : 1));
+    // chain of register groups (Tile12X::ngroups): L = K-3 | [0] | [3] | [6], or L | 2 | 5 for K = 11 with 64 B rows
+    if (K == 11 && first == 2) pp.ngroups = 5;
+    else pp.ngroups = first < 3 ? 4 : (first < 6 ? 3 : (first < K - 3 ? 2 : 1));
     if (with_low) {   // the gates of index bits 0-2 (inside every tile's 128 B rows) are applied in this strided pass
         for (int lb = 0; lb < 3; ++lb) pp.gbit[lb] = lb;
         pp.ngroups = 4;
     }
     pp.nrounds = pp.ngroups;
-    pp.g[0] = 9;
+    pp.g[0] = K - 3;
     pp.lean = true;
 }
 
@@ -898,14 +901,15 @@ static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x
     // (memory bound) strided pass, whose tiles contain those bits as well
     const int rem0 = n - k;
     int low_pass = 0;
-    if (allow_lean && k == 12 && low_bits_pass != 0 && rem0 > 0) {
+    if (allow_lean && k == 12 && low_bits_pass != 0 && rem0 > 0) {   // (12-bit tiles only)
         const int kx0 = tile_bits_x > 0 ? std::min(n, tile_bits_x) : k;
         const int umax0 = std::max(kx0 - std::min(min_row_bits, kx0 - 1), 1);
         const int nx0 = (rem0 + umax0 - 1) / umax0;
         low_pass = low_bits_pass < 0 ? nx0 : std::min(low_bits_pass, nx0);
         if (kx0 != 12 || rem0 / nx0 < 7) low_pass = 0;   // only into a pass with >= 7 strided gate bits (3 other groups are active anyway)
     }
-    if (allow_lean && k == 12) plan_lean(p0, low_pass ? 3 : 0);
+    const bool lean_k = allow_lean && (k == 12 || k == 11) && (tile_bits_x == 0 || tile_bits_x == k) && (k == 12 || min_row_bits >= 2);
+    if (lean_k) plan_lean(p0, low_pass ? 3 : 0);
     else if (allow_dc && k == 12 && R == 3) plan_dc(p0, 0); else plan_rounds(p0, 0, R);
     const int rem = n - k;
     if (rem > 0) {
@@ -917,7 +921,7 @@ static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x
         // lean kernel: the index bits >= page_bit select the 2 MiB page; share them evenly between the
         // strided passes (each pass = a run of the remaining low bits + a run of the page bits)
         const int page_bit = page_bits;
-        const bool split = allow_lean && kx == 12 && nx > 1 && page_bit > k && n > page_bit;
+        const bool split = lean_k && kx == 12 && nx > 1 && page_bit > k && n > page_bit;
         const int hi_total = split ? n - page_bit : 0;
         int lo_next = k, hi_next = page_bit;
         for (int i = 0; i < nx; ++i) {
@@ -938,7 +942,7 @@ static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x
                 lo_next += ml;
                 hi_next += mh;
             }
-            if (allow_lean && kx == 12) plan_lean(pp, pp.c, low_pass == i + 1);
+            if (lean_k) plan_lean(pp, pp.c, low_pass == i + 1);
             else if (allow_dc && kx == 12 && R == 3) plan_dc(pp, pp.c); else plan_rounds(pp, pp.c, R);
             h += m;
         }
@@ -1036,16 +1040,19 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         // measured at n = 30 (profiles/README.md) the L2 prefetch wins for the contiguous pass and for strides
         // below 32 MiB, and loses badly (22 vs 17 ms) when all gate bits are >= 21 -> auto mode (bit 2).
         int staged = (nv == 2 ? (c->opt_staged & 1) : (c->opt_staged & 2)) ? 1 : 0;
-        if (nv == 2 && (c->opt_staged & 4) && pp.c < QR_MAX_TILE_BITS && pp.h >= c->opt_staged_min_bit) staged = 1;
+        if (nv == 2 && (c->opt_staged & 4) && pp.c < pp.k && pp.h >= c->opt_staged_min_bit) staged = 1;
         if (nv == 2 && !staged && (c->opt_staged & 8)) staged = 2;   // bit 3: psi-only staging for the other backward passes
+        const int K = pp.k;   // 12, or 11 (half-size tiles, direct loads only)
+        if (K == 11) staged = 0;
         lean_fn lfn;
-        if (staged == 2 && nv == 2) lfn = ph ? k_tile12<2, true, 2> : k_tile12<2, false, 2>;
+        if (K == 11) lfn = nv == 1 ? (ph ? k_tile12<1, true, 0, 11> : k_tile12<1, false, 0, 11>) : (ph ? k_tile12<2, true, 0, 11> : k_tile12<2, false, 0, 11>);
+        else if (staged == 2 && nv == 2) lfn = ph ? k_tile12<2, true, 2> : k_tile12<2, false, 2>;
         else if (staged) lfn = nv == 1 ? (ph ? k_tile12<1, true, 1> : k_tile12<1, false, 1>) : (ph ? k_tile12<2, true, 1> : k_tile12<2, false, 1>);
         else lfn = nv == 1 ? (ph ? k_tile12<1, true, 0> : k_tile12<1, false, 0>) : (ph ? k_tile12<2, true, 0> : k_tile12<2, false, 0>);
-        static bool lean_attr[2][2][3] = {{{false, false, false}, {false, false, false}}, {{false, false, false}, {false, false, false}}};
-        if (!lean_attr[nv - 1][ph][staged]) {
+        static bool lean_attr[2][2][2][3] = {};
+        if (!lean_attr[K - 11][nv - 1][ph][staged]) {
             CUDA_TRY(cudaFuncSetAttribute(lfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (int)sizeof(double2) << QR_MAX_TILE_BITS));
-            lean_attr[nv - 1][ph][staged] = true;
+            lean_attr[K - 11][nv - 1][ph][staged] = true;
         }
         if (staged == 1) tp.prefetch = 0;
         Tile12X x;
@@ -1055,14 +1062,15 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
             const bool oop = io.src0 != io.dst0;
             x.cache_hints = (int)(c->opt_cache_hints & 3) | (oop ? (int)((c->opt_cache_hints >> 2) & 3) : 0);
         }
-        const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2};
+        const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2, K};
+        x.last_group = pp.ngroups == 1 ? K - 3 : (pp.ngroups == 5 ? 5 : 6);
         for (int r = 0; r < 8; ++r) {
-            const u64 lf = (u64)r << 9, ll = (u64)r << (pp.ngroups > 1 ? 6 : 9);
+            const u64 lf = (u64)r << (K - 3), ll = (u64)r << x.last_group;
             x.droff_first[r] = geo12_local(geo, lf);
             x.roff_first[r] = tp.ladder ? ladder_map(x.droff_first[r], tp.M1, tp.M2) : x.droff_first[r];
             x.roff_last[r] = geo12_local(geo, ll);
         }
-        const long long lctas = (nv == 1 && !staged) ? std::min<long long>(2, c->opt_ctas_fwd) : 1;
+        const long long lctas = K == 11 ? (nv == 1 ? 4 : 2) : ((nv == 1 && !staged) ? std::min<long long>(2, c->opt_ctas_fwd) : 1);
         const i64 lgrid = std::min<i64>(tp.num_tiles, (i64)c->sm_count * lctas);
         if (nv == 2) {
             const i64 nunits = flush_per_tile ? tp.num_tiles : lgrid;
@@ -1072,15 +1080,15 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         }
         // backward passes: clusters of 2 CTAs take adjacent tiles and align their loads (see k_tile12)
         const int want_cluster = (nv == 2 ? (int)(c->opt_cluster & 3) : (int)((c->opt_cluster >> 2) & 3));
-        const bool strided_pass = pp.c < QR_MAX_TILE_BITS;
+        const bool strided_pass = pp.c < K;
         x.cluster = (want_cluster == 2 || (want_cluster == 1 && strided_pass)) && lgrid % 2 == 0 ? 2 : 1;
         // L2 prefetch of the next tile: opt_prefetch bit 4 = contiguous passes only
         if ((c->opt_prefetch & 16) && strided_pass) tp.prefetch = 0;
         const size_t lsmem = staged ? (size_t)(nv + 1) * tile_bytes : (pp.ngroups > 1 ? (size_t)nv * tile_bytes : 0);
         if (x.cluster > 1) {
-            CUDA_TRY(QR_LAUNCH_CLUSTER(lfn, (unsigned)lgrid, QR_T12_THREADS, lsmem, c->stream, 2u, tp, x));
+            CUDA_TRY(QR_LAUNCH_CLUSTER(lfn, (unsigned)lgrid, 1u << (K - 3), lsmem, c->stream, 2u, tp, x));
         } else {
-            QR_LAUNCH(lfn, (unsigned)lgrid, QR_T12_THREADS, lsmem, c->stream, tp, x);
+            QR_LAUNCH(lfn, (unsigned)lgrid, 1 << (K - 3), lsmem, c->stream, tp, x);
         }
         KERNEL_CHECK();
         c->perf.kernel_launches++;

@@ -41,18 +41,20 @@
 // second segment to spread the page-selecting index bits (>= 2 MiB) over the strided passes, so
 // no pass touches more than ~128 distinct pages per tile and vector (a pass whose 512 rows lie
 // in 512 different pages runs 1.7x slower in the two-vector backward sweep: TLB reach).
-struct Geo12 { int c, h, m1, h2; };
+struct Geo12 { int c, h, m1, h2, k; };   // k = tile bits (12, or 11 for the half-size tiles)
 __host__ __device__ __forceinline__ u64 geo12_local(const Geo12 g, u64 l) {
     return (l & (((u64)1 << g.c) - 1)) | (((l >> g.c) & (((u64)1 << g.m1) - 1)) << g.h) | ((l >> (g.c + g.m1)) << g.h2);
 }
 __host__ __device__ __forceinline__ u64 geo12_tile(const Geo12 g, u64 t) {
-    const int nlo = g.h - g.c, nmid = g.h2 - g.h - g.m1, m2 = QR_MAX_TILE_BITS - g.c - g.m1;
+    const int nlo = g.h - g.c, nmid = g.h2 - g.h - g.m1, m2 = g.k - g.c - g.m1;
     return ((t & (((u64)1 << nlo) - 1)) << g.c) | (((t >> nlo) & (((u64)1 << nmid) - 1)) << (g.h + g.m1)) |
            ((t >> (nlo + nmid)) << (g.h2 + m2));
 }
 
 struct Tile12X {
-    int ngroups;            // active register groups: 1 = G3; 2 = G3,G2; 3 = G3,G1,G2; 4 = G3,G0,G1,G2
+    int ngroups;            // chain of register groups (first local bit of each; K = tile bits, L = K-3):
+                            // 1 = L; 2 = L,6; 3 = L,3,6; 4 = L,0,3,6; 5 (K = 11, 64 B rows) = L,2,5
+    int last_group;         // first local bit of the register group held at store time
     int cluster;            // thread-block cluster size of the launch (1 or 2)
     int cache_hints;        // bit0: streaming (evict-first) stores, bit1: streaming loads
     u64 roff_first[8];      // global offset of register r at load time (group G3), gather map applied
@@ -127,42 +129,41 @@ __device__ __forceinline__ void qr12_gate(double2 (&a)[NV][8], const Gate12& g, 
 }
 
 // gates of the register group whose first local bit is G (slots G, G+1, G+2)
-template <int NV, int G>
+template <int NV, int G, int NB = 3>
 __device__ __forceinline__ void qr12_round(double2 (&a)[NV][8], const Gate12* sg, double (&acc)[QR_SLOTS]) {
     qr12_gate<NV, 0>(a, sg[G + 0], acc[G + 0]);
-    qr12_gate<NV, 1>(a, sg[G + 1], acc[G + 1]);
-    qr12_gate<NV, 2>(a, sg[G + 2], acc[G + 2]);
+    if (NB > 1) qr12_gate<NV, 1>(a, sg[G + (NB > 1 ? 1 : 0)], acc[G + (NB > 1 ? 1 : 0)]);
+    if (NB > 2) qr12_gate<NV, 2>(a, sg[G + (NB > 2 ? 2 : 0)], acc[G + (NB > 2 ? 2 : 0)]);
 }
 
 // thread's local-index base when the register group starts at local bit g (3 zero bits inserted)
 __device__ __forceinline__ int qr12_tb(int tid, int g) { return (tid & ((1 << g) - 1)) | ((tid >> g) << (g + 3)); }
 
-// swizzled shared-memory index of register r for register group G: base ^ (r * MUL)
+// swizzled shared-memory index sw(l) = l ^ ((l >> 3) & 7) of register r for register group G
+// (l = tb | r << G): a per-thread base XOR a compile-time constant per register.
 template <int G>
 __device__ __forceinline__ int qr12_sbase(int tid) {
     const int tb = qr12_tb(tid, G);
-    if (G == 0) return tb ^ ((tb >> 3) & 7);   // low bits: r ^ (bits 3-5)
-    if (G == 3) return tb;                      // low bits ^ r, bits 3-5 = r
-    return tb ^ ((tb >> 3) & 7);                // G >= 6: swizzle does not involve r
+    return tb ^ ((tb >> 3) & 7);
 }
 template <int G>
-__device__ __forceinline__ constexpr int qr12_smul() { return G == 0 ? 1 : (G == 3 ? 9 : (1 << G)); }
+__device__ __forceinline__ constexpr int qr12_cr(int r) { return (r << G) ^ (((r << G) >> 3) & 7); }
 
 // registers of group GP -> shared memory -> registers of group GN (one block barrier)
-template <int NV, int GP, int GN>
+template <int NV, int GP, int GN, int K = QR_MAX_TILE_BITS>
 __device__ __forceinline__ void qr12_exchange(double2 (&a)[NV][8], double2* smem, int tid) {
-    constexpr int T = 1 << QR_MAX_TILE_BITS;
+    constexpr int T = 1 << K;
     const int bp = qr12_sbase<GP>(tid), bn = qr12_sbase<GN>(tid);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        const int l = bp ^ (r * qr12_smul<GP>());
+        const int l = bp ^ qr12_cr<GP>(r);
 #pragma unroll
         for (int v = 0; v < NV; ++v) smem[v * T + l] = a[v][r];
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        const int l = bn ^ (r * qr12_smul<GN>());
+        const int l = bn ^ qr12_cr<GN>(r);
 #pragma unroll
         for (int v = 0; v < NV; ++v) a[v][r] = smem[v * T + l];
     }
@@ -179,10 +180,10 @@ __device__ __forceinline__ void qr12_exchange_1buf(double2 (&a)[NV][8], double2*
         // (v == 0: its GP slots of the previous exchange's last vector; v > 0: needs the barrier below)
         if (v > 0) __syncthreads();
 #pragma unroll
-        for (int r = 0; r < 8; ++r) xbuf[bp ^ (r * qr12_smul<GP>())] = a[v][r];
+        for (int r = 0; r < 8; ++r) xbuf[bp ^ qr12_cr<GP>(r)] = a[v][r];
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < 8; ++r) a[v][r] = xbuf[bn ^ (r * qr12_smul<GN>())];
+        for (int r = 0; r < 8; ++r) a[v][r] = xbuf[bn ^ qr12_cr<GN>(r)];
     }
 }
 
@@ -229,10 +230,14 @@ __device__ __noinline__ double2 qr12_phase_slow(const double* __restrict__ ham, 
 // instead of only reaching L2 (prefetch) or being waited for (direct loads).
 // STAGED == 2 (backward only): only psi is staged, lambda is loaded directly (L2 prefetch) and the
 // exchange keeps its two buffers and single barrier: [exchange psi][exchange lambda][stage psi].
-template <int NV, bool PHASE, int STAGED>
-__global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)) k_tile12(const TilePass p, const Tile12X x) {
+// K = 11: half-size tiles (2048 amplitudes, 256 threads, 64 KiB of shared memory for the backward pass): two
+// backward CTAs per SM, whose load / FP64 / exchange phases overlap; used where it does not cost a pass.
+template <int NV, bool PHASE, int STAGED, int K = QR_MAX_TILE_BITS>
+__global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 1 ? 4 : 2)) : ((NV == 1 && !STAGED) ? 2 : 1)))
+    k_tile12(const TilePass p, const Tile12X x) {
     constexpr int NSV = STAGED == 1 ? NV : (STAGED == 2 ? 1 : 0);   // staged vectors
-    constexpr int T = 1 << QR_MAX_TILE_BITS;
+    constexpr int T = 1 << K;
+    constexpr int LG = K - 3;   // first local bit of the register group held at load time
     QR_DYN_SMEM(double2, smem);
     double2* const stage = smem + (STAGED == 1 ? T : (STAGED == 2 ? NV * T : 0));   // STAGED 1: [exchange][stage psi][stage lambda]
     __shared__ Gate12 sg[QR_GATE_SLOTS];
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
     __shared__ int s_flags[2];                  // [0]: the pass needs its diagonal (an Rz, or an odd number of sign flips)
     __shared__ double2 lut_sm[QR_LUT_MAX];
     const int tid = threadIdx.x;
-    const Geo12 geo = {p.c, p.h, p.m1, p.h2};
+    const Geo12 geo = {p.c, p.h, p.m1, p.h2, K};
     const u64 tmask = ((u64)1 << p.tiles_log2) - 1;
     const int ng = x.ngroups;
 
@@ -253,7 +258,7 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
     // per-thread global offsets (local bits 0-8 at load time; the last group's thread bits at store time)
     const u64 toff_d = geo12_local(geo, (u64)tid);                                       // destination index bits
     const u64 toff_s = p.ladder ? ladder_map(toff_d, p.M1, p.M2) : toff_d;               // gathered source bits
-    const int tbl = ng > 1 ? qr12_tb(tid, 6) : tid;
+    const int tbl = ng > 1 ? qr12_tb(tid, x.last_group) : tid;
     const u64 toff_l = geo12_local(geo, (u64)tbl);
 
     const bool use_lut = PHASE && p.hidx != nullptr && (p.pre_phase || p.post_phase);
@@ -271,7 +276,7 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
         for (int b = 0; b < QR_GATE_SLOTS; ++b) {
             const int m = sg[b].mode;
             double v = acc_all[b];
-            if (b < 9 && m == 4) v = ((tid >> b) & 1) ? -wtot : wtot;
+            if (b < LG && m == 4) v = ((tid >> b) & 1) ? -wtot : wtot;
             acc_all[b] = v;
         }
     };
@@ -284,8 +289,8 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const u64 sidx = sb ^ x.roff_first[r];
-            qr_cp_async16(stage + tid + (r << 9), p.src0 + nb * p.state_stride + sidx);
-            if (NSV == 2) qr_cp_async16(stage + T + tid + (r << 9), p.src1 + nb * p.state_stride + sidx);
+            qr_cp_async16(stage + tid + (r << LG), p.src0 + nb * p.state_stride + sidx);
+            if (NSV == 2) qr_cp_async16(stage + T + tid + (r << LG), p.src1 + nb * p.state_stride + sidx);
         }
         qr_cp_async_commit();
     };
@@ -314,7 +319,8 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
         if (b != cur_b) {   // block-uniform: convert the gate table of this batch element
             __syncthreads();
             if (tid < QR_GATE_SLOTS) {
-                const GateP g = p.gates[b * p.gate_stride + tid];
+                GateP g = p.gates[b * p.gate_stride + tid];
+                if (tid >= K) g.axis = -1;
                 Gate12 o;
                 o.tau = 0.0; o.sig = 0.0; o.mode = -1; o.neg = 0;
                 double2 z0 = make_double2(1.0, 0.0), z1 = z0;
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
             if (tid < 8) {
                 double2 z = make_double2(1.0, 0.0);
 #pragma unroll
-                for (int j = 0; j < 3; ++j) z = cmul(z, szb[9 + j][(tid >> j) & 1]);
+                for (int j = 0; j < 3; ++j) z = cmul(z, szb[LG + j][(tid >> j) & 1]);
                 szr[tid] = z;
             }
             __syncthreads();
@@ -354,7 +360,7 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
             for (int j = 0; j < QR_GATE_SLOTS; ++j) has_zgate = has_zgate || sg[j].mode == 4;
             zt = make_double2(s_flags[1] ? -1.0 : 1.0, 0.0);
 #pragma unroll
-            for (int j = 0; j < 9; ++j) zt = cmul(zt, szb[j][(tid >> j) & 1]);
+            for (int j = 0; j < LG; ++j) zt = cmul(zt, szb[j][(tid >> j) & 1]);
             cur_b = b;
         }
         // batch element offset: state_stride is a multiple of 2^n, so it can be OR-ed into the index bits
@@ -367,8 +373,8 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
             qr_cp_async_wait_all();
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                a[0][r] = stage[tid + (r << 9)];
-                if (NSV == 2) a[NV - 1][r] = stage[T + tid + (r << 9)];
+                a[0][r] = stage[tid + (r << LG)];
+                if (NSV == 2) a[NV - 1][r] = stage[T + tid + (r << LG)];
                 else if (NV == 2) a[NV - 1][r] = p.src1[sbt ^ x.roff_first[r]];
             }
             if (tile + gridDim.x < p.num_tiles) issue_stage(tile + gridDim.x);   // lands while this tile is computed
@@ -404,9 +410,9 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
             const double e2 = w[4] + w[5], o2 = w[4] - w[5], e3 = w[6] + w[7], o3 = w[6] - w[7];
             const double ee0 = e0 + e1, eo0 = e0 - e1, ee1 = e2 + e3, eo1 = e2 - e3;
             wtot += ee0 + ee1;
-            if (sg[9].mode == 4) acc_all[9] += (o0 + o1) + (o2 + o3);
-            if (sg[10].mode == 4) acc_all[10] += eo0 + eo1;
-            if (sg[11].mode == 4) acc_all[11] += ee0 - ee1;
+            if (sg[LG].mode == 4) acc_all[LG] += (o0 + o1) + (o2 + o3);
+            if (sg[LG + 1].mode == 4) acc_all[LG + 1] += eo0 + eo1;
+            if (sg[LG + 2].mode == 4) acc_all[LG + 2] += ee0 - ee1;
         }
         // ---- QAOA forward: exp(-i gamma H) before the mixer ----
         if (PHASE && p.pre_phase) {
@@ -432,24 +438,33 @@ __global__ void __launch_bounds__(QR_T12_THREADS, ((NV == 1 && !STAGED) ? 2 : 1)
             }
         }
         // ---- rounds ----
-        qr12_round<NV, 9>(a, sg, acc_all);
+#define QR12_X(GP, GN) do { if (STAGED == 1) qr12_exchange_1buf<NV, GP, GN>(a, smem, tid); else qr12_exchange<NV, GP, GN, K>(a, smem, tid); } while (0)
+        qr12_round<NV, LG>(a, sg, acc_all);
         if (ng == 4) {
-            if (STAGED == 1) qr12_exchange_1buf<NV, 9, 0>(a, smem, tid); else qr12_exchange<NV, 9, 0>(a, smem, tid);
+            QR12_X(LG, 0);
             qr12_round<NV, 0>(a, sg, acc_all);
-            if (STAGED == 1) qr12_exchange_1buf<NV, 0, 3>(a, smem, tid); else qr12_exchange<NV, 0, 3>(a, smem, tid);
+            QR12_X(0, 3);
         } else if (ng == 3) {
-            if (STAGED == 1) qr12_exchange_1buf<NV, 9, 3>(a, smem, tid); else qr12_exchange<NV, 9, 3>(a, smem, tid);
+            QR12_X(LG, 3);
         }
-        if (ng >= 3) {
+        if (ng == 3 || ng == 4) {
             qr12_round<NV, 3>(a, sg, acc_all);
-            if (STAGED == 1) qr12_exchange_1buf<NV, 3, 6>(a, smem, tid); else qr12_exchange<NV, 3, 6>(a, smem, tid);
+            QR12_X(3, 6);
         } else if (ng == 2) {
-            if (STAGED == 1) qr12_exchange_1buf<NV, 9, 6>(a, smem, tid); else qr12_exchange<NV, 9, 6>(a, smem, tid);
+            QR12_X(LG, 6);
         }
-        if (ng >= 2) {
-            qr12_round<NV, 6>(a, sg, acc_all);
+        if (ng >= 2 && ng <= 4) {
+            qr12_round<NV, 6, (K == 12 ? 3 : 2)>(a, sg, acc_all);   // K = 11: bit 8 belongs to the load group
             __syncthreads();   // every thread has read its last exchange: smem is free for the next tile
         }
+        if (K == 11 && ng == 5) {   // 64 B rows: gate bits 2-10 = groups 8 | 2 | 5
+            QR12_X(LG, 2);
+            qr12_round<NV, 2>(a, sg, acc_all);
+            QR12_X(2, 5);
+            qr12_round<NV, 5>(a, sg, acc_all);
+            __syncthreads();
+        }
+#undef QR12_X
         // ---- registers -> global (QAOA backward: diagonal-generator inner product and un-phase) ----
         const u64 dlt = tbase | toff_l | boff;
 #pragma unroll

@@ -236,6 +236,35 @@ def test_lean_tile_kernel_two_segment_geometry(backend, n, min_row_bits, page_bi
     assert_parity(e1, g1, e0, g0, float(n - 1), 1e-12)
 
 
+@pytest.mark.parametrize("n,L,min_row_bits", [(11, 3, 3), (12, 2, 3), (14, 2, 3), (17, 2, 3), (19, 1, 3), (13, 2, 2), (20, 1, 2)])
+def test_lean_tile_kernel_half_size_tiles(backend, n, L, min_row_bits):
+    """k_tile12 with K = 11 (2048-amplitude tiles, 256 threads): every chain of register groups, incl. the
+    64 B-row chain 8 | 2 | 5, against the 12-bit tiles (and the oracle where it finishes in seconds)."""
+    rng = np.random.default_rng(1100 + n)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    obs = mixed_obs(n)
+    c = McClean(n, obs, L, axes=axes, angles=angles)
+    e0, g0 = c.grad_run()
+    v0 = np.array(c.state.vec)
+    c.state.set_option("tile_bits", 11)
+    c.state.set_option("min_row_bits", min_row_bits)
+    e1, g1 = c.grad_run()
+    assert_parity(e1, g1, e0, g0, obs_scale(obs), 1e-12)
+    np.testing.assert_allclose(v0, c.state.vec, atol=1e-13)
+    np.testing.assert_allclose(c.run_expec_val(), e0, atol=1e-12 * obs_scale(obs))
+    if n <= 14:
+        e_ref, g_ref = orc.mcclean_grad_run(n, obs, axes, angles)
+        assert_parity(e1, g1, e_ref, g_ref, obs_scale(obs), TOL)
+    if n <= 17:
+        q = Qaoa(n, MaxCut(n, edge_set=[(i, i + 1) for i in range(n - 1)]).to_observable(), 2)
+        b, gm = rng.random(2), rng.random(2)
+        e0, g0 = q.grad_run(b, gm)
+        q.state.set_option("tile_bits", 11)
+        q.state.set_option("min_row_bits", min_row_bits)
+        e1, g1 = q.grad_run(b, gm)
+        assert_parity(e1, g1, e0, g0, float(n - 1), 1e-12)
+
+
 def test_lean_tile_kernel_low_bits_in_strided_pass(backend):
     """The gates on index bits 0-2 applied by the strided pass (4 register groups there, 3 in the contiguous pass)."""
     n, L = 19, 2
