@@ -42,7 +42,7 @@ enum { QR_TERM_X = 0, QR_TERM_Y = 1, QR_TERM_Z = 2, QR_TERM_ZZ = 3 };
 /* qr_set_option keys */
 enum {
     QR_OPT_FUSION = 0,        /* 1 (default): fused tile passes; 0: one kernel per gate          */
-    QR_OPT_TILE_BITS = 1,     /* log2 amplitudes per shared-memory tile (default 12)            */
+    QR_OPT_TILE_BITS = 1,     /* log2 amplitudes per shared-memory tile; 0 (default) = auto: 11 or 12 */
     QR_OPT_PREFETCH = 2,      /* L2 prefetch distance in tiles: bits 0-1 backward (default 1), bits 2-3 forward (default 0), bit 4: contiguous passes only */
     QR_OPT_CTAS_PER_SM_FWD = 3,
     QR_OPT_CTAS_PER_SM_BWD = 4,

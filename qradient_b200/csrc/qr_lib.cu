@@ -100,7 +100,7 @@ struct qr_ctx {
     size_t pin_cap = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // options
-    long long opt_fusion = 1, opt_tile_bits = QR_MAX_TILE_BITS, opt_prefetch = 1;
+    long long opt_fusion = 1, opt_tile_bits = 0 /* auto */, opt_prefetch = 1;
     long long opt_ctas_fwd = 2, opt_ctas_bwd = 1, opt_final_ladder = 1, opt_ham_lut = 1;
     long long opt_r_fwd = 3, opt_r_bwd = 3;
     long long opt_async_fwd = 0, opt_async_bwd = 0;
@@ -291,7 +291,7 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
     switch (key) {
         case QR_OPT_FUSION: c->opt_fusion = v ? 1 : 0; break;
         case QR_OPT_TILE_BITS:
-            if (v < 4 || v > QR_MAX_TILE_BITS) return fail(QR_EINVAL, "tile bits must be in [4, %d]", QR_MAX_TILE_BITS);
+            if (v != 0 && (v < 4 || v > QR_MAX_TILE_BITS)) return fail(QR_EINVAL, "tile bits must be 0 (auto) or in [4, %d]", QR_MAX_TILE_BITS);
             c->opt_tile_bits = v; break;
         case QR_OPT_PREFETCH: if (v < 0 || v > 31) return fail(QR_EINVAL, "prefetch must be in [0, 31]"); c->opt_prefetch = v; break;
         case QR_OPT_STAGED: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad staged mode"); c->opt_staged = v; break;
@@ -887,6 +887,17 @@ static void plan_lean(PassPlan& pp, int first, bool with_low = false) {
     pp.lean = true;
 }
 
+// QR_OPT_TILE_BITS = 0 (auto): half-size tiles (two backward CTAs per SM) where they cost neither a pass nor row
+// width against 12-bit tiles -- n = 13..19 and 22..26 (measured: +14 % batched 14x14, +3..5 % at n = 22..26,
+// neutral at 20, -10 % at 27: profiles/README.md); 12-bit tiles otherwise.
+static int pick_tile_bits(const qr_ctx* c, int n) {
+    if (c->opt_tile_bits != 0) return (int)c->opt_tile_bits;
+    const bool lean_on = (c->opt_lean & 3) == 3 && !c->opt_async_fwd && !c->opt_async_bwd && !c->opt_decoupled &&
+                         c->opt_tile_bits_x == 0 && c->opt_min_row_bits == 3 && c->opt_low_bits_pass == 0;
+    if (lean_on && ((n >= 13 && n <= 19) || (n >= 22 && n <= 26))) return 11;
+    return QR_MAX_TILE_BITS;
+}
+
 static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x = 0, int min_row_bits = 3, bool allow_dc = false,
                      bool allow_lean = false, int page_bits = 17, int low_bits_pass = 0) {
     if (n < 4) return fail(QR_EINVAL, "fused path needs at least 4 qubits");
@@ -1219,9 +1230,9 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     LayerPlan lpf, lp;   // forward / backward plans: same tile geometry, different register blocking
     const bool dc_f = batch == 1 && !c->opt_async_fwd && (c->opt_decoupled & 2);
     const bool dc_b = batch == 1 && !c->opt_async_bwd && (c->opt_decoupled & 1);
-    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits, dc_f,
+    QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits, dc_f,
                      !dc_f && !c->opt_async_fwd && (c->opt_lean & 2), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
-    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits, dc_b,
+    QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits, dc_b,
                      !dc_b && !c->opt_async_bwd && (c->opt_lean & 1), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
     const int P = lp.npasses;
     const int GS = QR_GATE_SLOTS;                 // gate entries per (layer, pass)
@@ -1556,10 +1567,10 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
                       double* grad) {
     const int n = c->n;
     LayerPlan lpf, lp;
-    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
+    QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
                      !c->opt_async_fwd && (c->opt_decoupled & 2),
                      !c->opt_async_fwd && !(c->opt_decoupled & 2) && (c->opt_lean & 2), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
-    QR_TRY(make_plan(n, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
+    QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
                      !c->opt_async_bwd && (c->opt_decoupled & 1),
                      !c->opt_async_bwd && !(c->opt_decoupled & 1) && (c->opt_lean & 1), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
     const int P = lp.npasses;
@@ -1892,10 +1903,10 @@ extern "C" int qr_shard_mcclean_begin(qr_ctx* c, int L, const int32_t* axes, con
     run->axes.assign(axes, axes + (size_t)L * nt);
     run->angles.assign(angles, angles + (size_t)L * nt);
     run->terms = o->terms;
-    QR_TRY(make_plan(nl, (int)c->opt_tile_bits, (int)c->opt_r_fwd, &run->lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
+    QR_TRY(make_plan(nl, pick_tile_bits(c, nl), (int)c->opt_r_fwd, &run->lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
                      !c->opt_async_fwd && (c->opt_decoupled & 2),
                      !c->opt_async_fwd && !(c->opt_decoupled & 2) && (c->opt_lean & 2), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
-    QR_TRY(make_plan(nl, (int)c->opt_tile_bits, (int)c->opt_r_bwd, &run->lpb, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
+    QR_TRY(make_plan(nl, pick_tile_bits(c, nl), (int)c->opt_r_bwd, &run->lpb, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
                      !c->opt_async_bwd && (c->opt_decoupled & 1),
                      !c->opt_async_bwd && !(c->opt_decoupled & 1) && (c->opt_lean & 1), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
     const int P = run->P = run->lpb.npasses;

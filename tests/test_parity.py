@@ -195,6 +195,7 @@ def test_lean_tile_kernel_group_counts(backend, n, L):
     axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
     obs = mixed_obs(n)
     c = McClean(n, obs, L, axes=axes, angles=angles)
+    c.state.set_option("tile_bits", 12)
     e1, g1 = c.grad_run()
     v1 = np.array(c.state.vec)
     c.state.set_option("lean", 0)
@@ -244,6 +245,7 @@ def test_lean_tile_kernel_half_size_tiles(backend, n, L, min_row_bits):
     axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
     obs = mixed_obs(n)
     c = McClean(n, obs, L, axes=axes, angles=angles)
+    c.state.set_option("tile_bits", 12)
     e0, g0 = c.grad_run()
     v0 = np.array(c.state.vec)
     c.state.set_option("tile_bits", 11)
@@ -258,6 +260,7 @@ def test_lean_tile_kernel_half_size_tiles(backend, n, L, min_row_bits):
     if n <= 17:
         q = Qaoa(n, MaxCut(n, edge_set=[(i, i + 1) for i in range(n - 1)]).to_observable(), 2)
         b, gm = rng.random(2), rng.random(2)
+        q.state.set_option("tile_bits", 12)
         e0, g0 = q.grad_run(b, gm)
         q.state.set_option("tile_bits", 11)
         q.state.set_option("min_row_bits", min_row_bits)
