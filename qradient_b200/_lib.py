@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqradient_b200.so")
+LIB_PATH = os.environ.get("QRADIENT_B200_LIB", os.path.join(_HERE, "libqradient_b200.so"))   # override: A/B timing of library builds
 
 QR_OK, QR_EINVAL, QR_ECUDA, QR_ENOMEM, QR_ESTATE = 0, 1, 2, 3, 4
 TERM_KIND = {"x": 0, "y": 1, "z": 2, "zz": 3}

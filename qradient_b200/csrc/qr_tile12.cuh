@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
     // per-thread global offsets (local bits 0-8 at load time; the last group's thread bits at store time)
     const u64 toff_d = geo12_local(geo, (u64)tid);                                       // destination index bits
     const u64 toff_s = p.ladder ? ladder_map(toff_d, p.M1, p.M2) : toff_d;               // gathered source bits
-    const int tbl = ng > 1 ? qr12_tb(tid, x.last_group) : tid;
+    const int tbl = ng > 1 ? qr12_tb(tid, K == 12 ? 6 : x.last_group) : tid;   // K = 12: the last group is always 6
     const u64 toff_l = geo12_local(geo, (u64)tbl);
 
     const bool use_lut = PHASE && p.hidx != nullptr && (p.pre_phase || p.post_phase);
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
             __syncthreads();
             if (tid < QR_GATE_SLOTS) {
                 GateP g = p.gates[b * p.gate_stride + tid];
-                if (tid >= K) g.axis = -1;
+                if (K < QR_GATE_SLOTS && tid >= K) g.axis = -1;
                 Gate12 o;
                 o.tau = 0.0; o.sig = 0.0; o.mode = -1; o.neg = 0;
                 double2 z0 = make_double2(1.0, 0.0), z1 = z0;
@@ -447,13 +447,13 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
         } else if (ng == 3) {
             QR12_X(LG, 3);
         }
-        if (ng == 3 || ng == 4) {
+        if (K == 12 ? ng >= 3 : (ng == 3 || ng == 4)) {
             qr12_round<NV, 3>(a, sg, acc_all);
             QR12_X(3, 6);
         } else if (ng == 2) {
             QR12_X(LG, 6);
         }
-        if (ng >= 2 && ng <= 4) {
+        if (K == 12 ? ng >= 2 : (ng >= 2 && ng <= 4)) {
             qr12_round<NV, 6, (K == 12 ? 3 : 2)>(a, sg, acc_all);   // K = 11: bit 8 belongs to the load group
             __syncthreads();   // every thread has read its last exchange: smem is free for the next tile
         }
