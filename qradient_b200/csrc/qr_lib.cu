@@ -894,8 +894,13 @@ static int pick_tile_bits(const qr_ctx* c, int n) {
     if (c->opt_tile_bits != 0) return (int)c->opt_tile_bits;
     const bool lean_on = (c->opt_lean & 3) == 3 && !c->opt_async_fwd && !c->opt_async_bwd && !c->opt_decoupled &&
                          c->opt_tile_bits_x == 0 && c->opt_min_row_bits == 3 && c->opt_low_bits_pass == 0;
-    if (lean_on && ((n >= 13 && n <= 19) || (n >= 22 && n <= 26))) return 11;
+    if (lean_on && ((n >= 13 && n <= 20) || (n >= 22 && n <= 26))) return 11;
     return QR_MAX_TILE_BITS;
+}
+// n = 20 in auto mode: 11 | 9 with 64 B rows (the 16 MiB state is L2 resident, where narrow rows cost nothing): +5 %
+static int pick_min_row_bits(const qr_ctx* c, int n) {
+    if (c->opt_tile_bits == 0 && n == 20 && pick_tile_bits(c, n) == 11) return 2;
+    return (int)c->opt_min_row_bits;
 }
 
 static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x = 0, int min_row_bits = 3, bool allow_dc = false,
@@ -1230,9 +1235,9 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     LayerPlan lpf, lp;   // forward / backward plans: same tile geometry, different register blocking
     const bool dc_f = batch == 1 && !c->opt_async_fwd && (c->opt_decoupled & 2);
     const bool dc_b = batch == 1 && !c->opt_async_bwd && (c->opt_decoupled & 1);
-    QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits, dc_f,
+    QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, pick_min_row_bits(c, n), dc_f,
                      !dc_f && !c->opt_async_fwd && (c->opt_lean & 2), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
-    QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits, dc_b,
+    QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, pick_min_row_bits(c, n), dc_b,
                      !dc_b && !c->opt_async_bwd && (c->opt_lean & 1), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
     const int P = lp.npasses;
     const int GS = QR_GATE_SLOTS;                 // gate entries per (layer, pass)
@@ -1567,10 +1572,10 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
                       double* grad) {
     const int n = c->n;
     LayerPlan lpf, lp;
-    QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
+    QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, pick_min_row_bits(c, n),
                      !c->opt_async_fwd && (c->opt_decoupled & 2),
                      !c->opt_async_fwd && !(c->opt_decoupled & 2) && (c->opt_lean & 2), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
-    QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
+    QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, pick_min_row_bits(c, n),
                      !c->opt_async_bwd && (c->opt_decoupled & 1),
                      !c->opt_async_bwd && !(c->opt_decoupled & 1) && (c->opt_lean & 1), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
     const int P = lp.npasses;
@@ -1903,10 +1908,10 @@ extern "C" int qr_shard_mcclean_begin(qr_ctx* c, int L, const int32_t* axes, con
     run->axes.assign(axes, axes + (size_t)L * nt);
     run->angles.assign(angles, angles + (size_t)L * nt);
     run->terms = o->terms;
-    QR_TRY(make_plan(nl, pick_tile_bits(c, nl), (int)c->opt_r_fwd, &run->lpf, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
+    QR_TRY(make_plan(nl, pick_tile_bits(c, nl), (int)c->opt_r_fwd, &run->lpf, (int)c->opt_tile_bits_x, pick_min_row_bits(c, nl),
                      !c->opt_async_fwd && (c->opt_decoupled & 2),
                      !c->opt_async_fwd && !(c->opt_decoupled & 2) && (c->opt_lean & 2), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
-    QR_TRY(make_plan(nl, pick_tile_bits(c, nl), (int)c->opt_r_bwd, &run->lpb, (int)c->opt_tile_bits_x, (int)c->opt_min_row_bits,
+    QR_TRY(make_plan(nl, pick_tile_bits(c, nl), (int)c->opt_r_bwd, &run->lpb, (int)c->opt_tile_bits_x, pick_min_row_bits(c, nl),
                      !c->opt_async_bwd && (c->opt_decoupled & 1),
                      !c->opt_async_bwd && !(c->opt_decoupled & 1) && (c->opt_lean & 1), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
     const int P = run->P = run->lpb.npasses;
