@@ -1,0 +1,49 @@
+"""GV13: the reference's optimiser loops (optimization.py: McCleanOpt / QaoaOpt with Adam, GradientDescent,
+RateDecayOnPlateau) run UNMODIFIED on the reference's circuit classes (same shim as make_golden.py).
+
+    python tests/golden/make_golden_opt.py        (build container only: needs /root/reference)
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import make_golden as mg  # noqa: E402  (loads the reference modules; writes nothing on import)
+
+opt = mg._load("_ref_optimization", os.path.join(mg.REF, "qradient/optimization.py"))
+
+
+def run_mcclean(name, optimizer, steps, n=5, L=3, seed=13):
+    rng = np.random.default_rng(seed)
+    obs = {"x": np.array([0.5] + [None] * (n - 1), dtype=object), "zz": np.full((n, n), None)}
+    obs["zz"][0, 1] = 1.0
+    obs["zz"][2, 4] = -0.6
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    c = mg.McClean(n, obs, L, axes=axes, angles=angles.copy())
+    o = opt.McCleanOpt(c, dict(optimizer), max_iter=steps + 1, ini_parameters=angles.copy())
+    for _ in range(steps):
+        o.step()
+    return {name + "_cost": o.cost_history[:steps].copy(), name + "_params": o.param_history[:steps + 1].copy(),
+            "mc_axes": axes, "mc_angles": angles, **{"mc_" + k: v for k, v in mg.obs_to_arrays(n, obs).items()}}
+
+
+def run_qaoa(name, optimizer, steps, n=6, p=2):
+    edges = np.array([[0, 1], [1, 2], [2, 3], [3, 4], [4, 5], [0, 5], [1, 4]])
+    c = mg.Qaoa(n, mg.MaxCut(n, edge_set=edges).to_observable(), p)
+    betas, gammas = np.array([0.3, 0.7]), np.array([0.2, 0.9])
+    o = opt.QaoaOpt(c, dict(optimizer), betas.copy(), gammas.copy(), max_iter=steps + 1)
+    for _ in range(steps):
+        o.step()
+    return {name + "_cost": o.cost_history[:steps].copy(), name + "_params": o.param_history[:steps + 1].copy(),
+            "qa_edges": edges, "qa_betas": betas, "qa_gammas": gammas}
+
+
+if __name__ == "__main__":
+    d = {"steps": 6}
+    d.update(run_mcclean("mc_adam", {"name": "Adam", "step_size": 0.05}, 6))
+    d.update(run_mcclean("mc_gd", {"name": "GradientDescent", "step_size": 0.1}, 6))
+    d.update(run_mcclean("mc_plateau", {"name": "RateDecayOnPlateau", "step_size": 0.8, "plateau_length": 1, "decay_rate": 0.5}, 6))
+    d.update(run_qaoa("qa_adam", {"name": "Adam", "step_size": 0.05, "beta1": 0.8}, 6))
+    d.update(run_qaoa("qa_gd", {"name": "GradientDescent", "step_size": 0.02}, 6))
+    mg.save("gv13_optimizers", **d)
