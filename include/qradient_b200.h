@@ -170,6 +170,10 @@ int qr_qaoa_grad(qr_ctx* ctx, int n_layers, const double* betas, const double* g
 /* index = first k with cumsum(|vec|^2)[k] >= u  (scipy rv_discrete inverse CDF); uniforms are
  * supplied by the caller from the numpy stream so the draw order matches the reference. */
 int qr_sample_bitstrings(qr_ctx* ctx, int n_shots, const double* uniforms, int64_t* out_idx);
+/* vec[k] <- vec[perm[k]] with a permutation kept on the device: measurement in the order of the sorted
+ * eigenvalues of a diagonal observable (McClean.sample_grad_dense, mc_clean.py:207-268, matrix-free) */
+int qr_perm_load(qr_ctx* ctx, const int64_t* perm, size_t n_amps);
+int qr_state_permute(qr_ctx* ctx);
 /* mean of H[idx] over the sampled indices, computed on the device from the loaded H table */
 int qr_ham_gather(qr_ctx* ctx, int n, const int64_t* idx, double* out_vals);
 

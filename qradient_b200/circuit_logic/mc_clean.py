@@ -143,6 +143,67 @@ class McClean(ParametrizedCircuit):
                 grad[i, dq] = .5 * (shifted[0] - shifted[1])
         return expec_val, grad
 
+    # -- mc_clean.py:207-268: finite-shot gradient, observable measured in its eigenbasis ---------
+    def sample_grad_dense(self, shot_num=1, hide_progbar=True, exact_expec_val=True, ini_state=None):
+        """Parameter-shift gradient where every shifted circuit is measured `shot_num` times in the eigenbasis
+        of the observable (returns the exact expectation value, like the reference).
+
+        The reference diagonalises the dense 2^n x 2^n observable and propagates dense left-hand-side
+        matrices (mc_clean.py:221-244).  Matrix-free here, for observables made of z / zz terms: their
+        eigenbasis is the computational basis and the eigenvalues are the diagonal H, so each shifted
+        state is pushed through the remaining layers on the device, re-ordered by the ascending
+        eigenvalues (`numpy.linalg.eigh` order; ties do not change which eigenvalue a draw selects) and
+        sampled by the prefix-sum sampler with the uniforms scipy's `rvs` would draw.  Observables with
+        x / y terms need the dense eigensystem and are not supported."""
+        obs = self.observable
+        if np.any(obs.term_kinds < 2):
+            raise NotImplementedError('sample_grad_dense: only observables made of z / zz terms can be measured matrix-free; '
+                                      'x / y terms need the dense 2^n x 2^n eigensystem of the reference (mc_clean.py:221)')
+        axes, angles = self._params()
+        n, L = self.qnum, self.lnum
+        st = self.state
+        if getattr(self, '_eig_order', None) is None:          # the reference's has_loaded_eigensystem
+            st._load_ham(obs)
+            ham = st._download_ham()
+            self._eig_order = np.argsort(ham, kind='stable')
+            self.eigenvalues = ham[self._eig_order]
+            st.load_permutation(self._eig_order)
+        if ini_state is None:
+            st.reset()
+        else:
+            st.vec = ini_state
+        grad = np.ndarray([L, n], dtype='double')
+        for q in range(n):
+            st.yrot(np.pi / 4., q)
+        for i in range(L):
+            st.cnot_ladder(0)
+            for q in range(n):
+                self._rot(i, q)
+            st.save(i)                                          # mc_clean.py:238 state_history[i]
+        expec_val = self.expec_val() if exact_expec_val else self.sample_expec_val(shot_num)
+
+        def measure(i):
+            """layers i+1 .. L-1 on the current state, then shot_num draws of the eigenvalue"""
+            for j in range(i + 1, L):
+                st.cnot_ladder(0)
+                for q in range(n):
+                    self._rot(j, q)
+            st.permute()
+            return self.eigenvalues[self.sample_bitstrings(shot_num)].mean()
+
+        for i in range(L):
+            for q in range(n):
+                st.load(i)
+                self._manual_rot(i, q, np.pi / 2)
+                sample1 = measure(i)
+                st.load(i)                                      # the reference shifts the same vector on by -pi (mc_clean.py:262)
+                self._manual_rot(i, q, np.pi / 2)
+                self._manual_rot(i, q, -np.pi)
+                sample2 = measure(i)
+                grad[i, q] = (sample1 - sample2) / 2.
+        st.free_snapshots()
+        return expec_val, grad
+
     def _rot(self, i, q, angle_sign=1.):
         self._manual_rot(i, q, angle_sign * self.angles[i, q])
 

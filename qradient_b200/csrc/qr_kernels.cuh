@@ -390,6 +390,12 @@ __global__ void k_sample_search(const double2* __restrict__ v, u64 N, const doub
     }
 }
 
+// psi'[k] = psi[perm[k]]: measurement-basis ordering for the inverse-CDF sampler (mc_clean.py:255-261 samples
+// in the order of the sorted eigenvalues of the observable, not in index order)
+__global__ void k_permute_gather(const double2* __restrict__ src, const i64* __restrict__ perm, double2* __restrict__ dst, u64 N) {
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (u64)gridDim.x * blockDim.x) dst[k] = src[perm[k]];
+}
+
 __global__ void k_gather_f64(const double* __restrict__ table, const i64* __restrict__ idx, int n, double* __restrict__ out) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = table[idx[i]];
 }

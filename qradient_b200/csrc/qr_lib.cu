@@ -84,6 +84,7 @@ struct qr_ctx {
     u64 buf_amps = 0;            // capacity of each buffer in amplitudes (>= N; batch paths grow it)
     int psi = 0;                 // buffer holding the state vector
     double* d_ham = nullptr;     // diagonal Hamiltonian table [N]
+    i64* d_perm = nullptr;       // index permutation for qr_state_permute [N]
     bool ham_loaded = false;
     short* d_hidx = nullptr;     // integer-valued H: H = hmin + hidx (phase look-up table path)
     bool ham_integer = false;
@@ -273,6 +274,7 @@ extern "C" int qr_ctx_destroy(qr_ctx* c) {
     shard_release(c);
     for (int i = 0; i < QR_NBUF; ++i) if (c->buf_base[i]) cudaFree(c->buf_base[i]);
     if (c->d_ham) cudaFree(c->d_ham);
+    if (c->d_perm) cudaFree(c->d_perm);
     if (c->d_hidx) cudaFree(c->d_hidx);
     for (double2* sp : c->snapshots) if (sp) cudaFree(sp);
     if (c->d_scratch) cudaFree(c->d_scratch);
@@ -1742,6 +1744,38 @@ extern "C" int qr_sample_bitstrings(qr_ctx* c, int S, const double* uniforms, in
     CUDA_TRY(cudaMemcpyAsync(c->h_pin, d_idx, (size_t)S * sizeof(i64), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     memcpy(out_idx, c->h_pin, (size_t)S * sizeof(i64));
+    return 0;
+}
+
+// ---- state permutation (sampling in the order of the sorted eigenvalues of a diagonal observable) ----
+extern "C" int qr_perm_load(qr_ctx* c, const int64_t* perm, size_t n_amps) {
+    if (!c || !perm) return fail(QR_EINVAL, "null argument");
+    if (n_amps != c->N) return fail(QR_EINVAL, "permutation must have 2^n = %llu entries", (unsigned long long)c->N);
+    std::vector<bool> seen(c->N, false);
+    for (u64 k = 0; k < c->N; ++k) {
+        if (perm[k] < 0 || (u64)perm[k] >= c->N || seen[(size_t)perm[k]]) return fail(QR_EINVAL, "not a permutation of 0..2^n-1 (entry %llu)", (unsigned long long)k);
+        seen[(size_t)perm[k]] = true;
+    }
+    QR_TRY(use_device(c));
+    if (!c->d_perm) {
+        cudaError_t e = cudaMalloc((void**)&c->d_perm, c->N * sizeof(i64));
+        if (e != cudaSuccess) { c->d_perm = nullptr; return fail(QR_ENOMEM, "cannot allocate the permutation table: %s", cudaGetErrorString(e)); }
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_perm, perm, c->N * sizeof(i64), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int qr_state_permute(qr_ctx* c) {
+    if (!c) return fail(QR_EINVAL, "null context");
+    if (!c->d_perm) return fail(QR_ESTATE, "no permutation loaded (qr_perm_load)");
+    QR_TRY(use_device(c));
+    const int dst = other_buf(c, c->psi);
+    QR_TRY(ensure_buf(c, dst));
+    QR_LAUNCH(k_permute_gather, grid_for(c, c->N), QR_BLOCK, 0, c->stream, (const double2*)c->buf[c->psi], (const i64*)c->d_perm, c->buf[dst], c->N);
+    KERNEL_CHECK();
+    c->psi = dst;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

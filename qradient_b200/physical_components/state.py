@@ -163,6 +163,15 @@ class State:
     def x_summed(self):                            # state.py:121-123
         self._lib.call('qr_apply_x_summed', self._ctx)
 
+    def load_permutation(self, perm):
+        """Keep an index permutation on the device for `permute()` (measurement orderings)."""
+        perm = np.ascontiguousarray(perm, dtype=np.int64)
+        self._lib.call('qr_perm_load', self._ctx, _lib.ptr(perm), int(perm.size))
+
+    def permute(self):
+        """vec[k] <- vec[perm[k]] on the device."""
+        self._lib.call('qr_state_permute', self._ctx)
+
     def norm_error(self):                          # state.py:331-332
         out = ctypes.c_double()
         self._lib.call('qr_norm2', self._ctx, ctypes.byref(out))

@@ -47,3 +47,28 @@ if __name__ == "__main__":
     d.update(run_qaoa("qa_adam", {"name": "Adam", "step_size": 0.05, "beta1": 0.8}, 6))
     d.update(run_qaoa("qa_gd", {"name": "GradientDescent", "step_size": 0.02}, 6))
     mg.save("gv13_optimizers", **d)
+
+
+def gv14_mcclean_sample_grad_dense():
+    """GV14: McClean.sample_grad_dense (mc_clean.py:207-268) for diagonal observables: a non-degenerate one and
+    ZZ(0,1) (two 8-fold degenerate eigenvalues)."""
+    out = {}
+    for tag, n, L, shots, seed in (("a", 4, 3, 20, 3), ("b", 4, 2, 15, 8)):
+        rng = np.random.default_rng(21 + seed)
+        obs = {"zz": np.full((n, n), None)}
+        obs["zz"][0, 1] = 1.0
+        if tag == "a":
+            obs["z"] = np.array([0.4, None, -0.7, None], dtype=object)
+            obs["zz"][1, 3] = 0.5
+        axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+        c = mg.McClean(n, obs, L, axes=axes, angles=angles)
+        np.random.seed(seed)
+        e, g = c.sample_grad_dense(shot_num=shots)
+        out.update({tag + "_n": n, tag + "_L": L, tag + "_shots": shots, tag + "_seed": seed, tag + "_axes": axes, tag + "_angles": angles,
+                    tag + "_E": e, tag + "_grad": g, tag + "_eigenvalues": c.eigenvalues,
+                    **{tag + "_" + k: v for k, v in mg.obs_to_arrays(n, obs).items()}})
+    mg.save("gv14_mcclean_sample_grad_dense", **out)
+
+
+if __name__ == "__main__":
+    gv14_mcclean_sample_grad_dense()
