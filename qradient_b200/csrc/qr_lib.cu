@@ -112,6 +112,7 @@ struct qr_ctx {
     long long opt_staged = 4;      // bit0 backward, bit1 forward: next tile staged in shared memory by asynchronous copies; bit2: auto (backward)
     long long opt_staged_min_bit = 21;   // auto mode: strided backward passes whose lowest gate bit is >= this are staged
     long long opt_cluster = 0;     // bits 0-1 backward, bits 2-3 forward: 0 none, 1 CTA pairs in the strided passes, 2 in every pass
+    long long opt_src_order = 0;   // k_tile12 ladder passes enumerate tiles in source order: bit0 backward, bit1 forward
     long long opt_low_bits_pass = 0;   // k_tile12: pass that applies the gates on index bits 0-2 (0 = contiguous pass, -1 = last strided pass)
     long long opt_cache_hints = 0; // k_tile12: bit0 streaming stores, bit1 streaming loads (all passes); bits 2-3: same, out-of-place passes only
     long long opt_debug = 0;       // timing diagnostics (results are wrong): bit0 no ladder gather map, bit1 ladder passes in place
@@ -298,6 +299,7 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
         case QR_OPT_PREFETCH: if (v < 0 || v > 31) return fail(QR_EINVAL, "prefetch must be in [0, 31]"); c->opt_prefetch = v; break;
         case QR_OPT_STAGED: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad staged mode"); c->opt_staged = v; break;
         case QR_OPT_DEBUG: c->opt_debug = v; break;
+        case QR_OPT_SRC_ORDER: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad source-order mode"); c->opt_src_order = v; break;
         case QR_OPT_LOW_BITS_PASS: if (v < -1 || v > 15) return fail(QR_EINVAL, "bad low-bits pass"); c->opt_low_bits_pass = v; break;
         case QR_OPT_CACHE_HINTS: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad cache hints"); c->opt_cache_hints = v; break;
         case QR_OPT_STAGED_MIN_BIT: if (v < 0 || v > 64) return fail(QR_EINVAL, "bad staged min bit"); c->opt_staged_min_bit = v; break;
@@ -356,6 +358,7 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_STAGED_MIN_BIT: *v = c->opt_staged_min_bit; break;
         case QR_OPT_DEBUG: *v = c->opt_debug; break;
         case QR_OPT_CACHE_HINTS: *v = c->opt_cache_hints; break;
+        case QR_OPT_SRC_ORDER: *v = c->opt_src_order; break;
         case QR_OPT_LOW_BITS_PASS: *v = c->opt_low_bits_pass; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
@@ -1021,6 +1024,10 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
     } else if (ladder_stacking >= 0) {
         tp.ladder = 1;
         ladder_masks(lp.n, 1 - ladder_stacking, &tp.M1, &tp.M2);
+        if (pp.lean && (c->opt_src_order & (nv == 2 ? 1 : 2))) {   // k_tile12: enumerate the tiles in source order
+            tp.src_order = 1;
+            ladder_masks(lp.n, ladder_stacking, &tp.iM1, &tp.iM2);
+        }
     }
     if (c->opt_debug & 1) tp.ladder = 0;          // timing diagnostics only (wrong results): no gather map
     tp.tiles_log2 = lp.n - pp.k;

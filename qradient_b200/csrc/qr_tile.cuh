@@ -49,6 +49,8 @@ struct TilePass {
     int ladder;                  // 1: gather through the ladder map on load
     u64 M1, M2;
     u64 src_xor;                 // sharded states: carry of the rank bits into the local source index
+    int src_order;               // k_tile12 ladder passes: tiles are enumerated in SOURCE order (sequential reads, scattered writes)
+    u64 iM1, iM2;                // masks of the inverse gather map (destination tile of a source tile)
     int tiles_log2;              // log2(tiles per state) = n - k
     i64 num_tiles;               // batch * tiles per state
     i64 state_stride;            // amplitudes between consecutive states of a batch

@@ -251,6 +251,15 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
     const Geo12 geo = {p.c, p.h, p.m1, p.h2, K};
     const u64 tmask = ((u64)1 << p.tiles_log2) - 1;
     const int ng = x.ngroups;
+    // destination base index of tile t.  Ladder passes may enumerate the tiles in SOURCE order: the gather map
+    // scatters consecutive destination tiles over the whole source vector (a new 2 MiB page per tile and CTA, on
+    // which the L2 prefetch is far less effective); enumerating source tiles keeps the reads (and the prefetch)
+    // sequential and scatters the fire-and-forget writes instead.  The map is banded towards the less significant
+    // bits, so the tile bits of the inverse map depend on the tile bits of the source only.
+    auto dest_base = [&](u64 t) -> u64 {
+        const u64 g0 = geo12_tile(geo, t);
+        return p.src_order ? (ladder_map(g0, p.iM1, p.iM2) & ~(u64)(T - 1)) : g0;
+    };
 
     double acc_all[QR_SLOTS];
 #pragma unroll
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
     // issue the asynchronous copies of this thread's amplitudes of tile `tl` into its stage slots
     auto issue_stage = [&](i64 tl) {
         const i64 nb = tl >> p.tiles_log2;
-        const u64 nbase = geo12_tile(geo, (u64)tl & tmask);
+        const u64 nbase = dest_base((u64)tl & tmask);
         const u64 sb = (p.ladder ? (ladder_map(nbase, p.M1, p.M2) ^ p.src_xor) : nbase) ^ toff_s;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -317,7 +326,7 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
         if (tile >= p.num_tiles) continue;
         const i64 b = tile >> p.tiles_log2;
         const u64 t = (u64)tile & tmask;
-        const u64 tbase = geo12_tile(geo, t);
+        const u64 tbase = dest_base(t);
         if (b != cur_b) {   // block-uniform: convert the gate table of this batch element
             __syncthreads();
             if (tid < QR_GATE_SLOTS) {
@@ -394,7 +403,7 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
             if (nt < p.num_tiles) {
                 const i64 nb = nt >> p.tiles_log2;
                 const u64 t2 = (u64)nt & tmask;
-                const u64 nbase = geo12_tile(geo, t2);
+                const u64 nbase = dest_base(t2);
                 const int l = tid << 3;   // one 128 B line per thread
                 const u64 d = nbase | geo12_local(geo, (u64)l);
                 const u64 s = p.ladder ? (ladder_map(d, p.M1, p.M2) ^ p.src_xor) : d;

@@ -161,7 +161,7 @@ def test_mcclean_tile_geometries_vs_oracle(backend, n, L, tile_bits):
                                   dict(async_bwd=1, async_fwd=1, reg_bits_fwd=4, reg_bits_bwd=4),
                                   dict(async_bwd=1, async_fwd=1, reg_bits_fwd=3, reg_bits_bwd=3),
                                   dict(lean=0, async_bwd=0, async_fwd=0, reg_bits_fwd=3, reg_bits_bwd=3, prefetch=1),
-                                  dict(lean=3, prefetch=1), dict(lean=1), dict(lean=2), dict(staged=3), dict(staged=1, cluster=2), dict(staged=8), dict(staged=12, prefetch=1),
+                                  dict(lean=3, prefetch=1), dict(lean=1), dict(lean=2), dict(staged=3), dict(staged=1, cluster=2), dict(staged=8), dict(staged=12, prefetch=1), dict(src_order=3), dict(src_order=1, tile_bits=12),
                                   dict(tile_bits_strided=5, min_row_bits=2), dict(tile_bits_strided=4, min_row_bits=1, async_bwd=1),
                                   dict(decoupled=3)])
 @pytest.mark.parametrize("n,L,tile_bits", [(7, 2, 5), (10, 2, 12), (13, 1, 12), (9, 2, 4), (12, 2, 12)])
