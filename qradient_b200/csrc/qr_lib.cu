@@ -112,6 +112,7 @@ struct qr_ctx {
     long long opt_staged = 4;      // bit0 backward, bit1 forward: next tile staged in shared memory by asynchronous copies; bit2: auto (backward)
     long long opt_staged_min_bit = 21;   // auto mode: strided backward passes whose lowest gate bit is >= this are staged
     long long opt_cluster = 0;     // bits 0-1 backward, bits 2-3 forward: 0 none, 1 CTA pairs in the strided passes, 2 in every pass
+    long long opt_pair = 0;        // k_tile12 pair kernel (cluster of two half-size CTAs per 12-bit tile): bit0 backward, bit1 forward
     long long opt_src_order = 0;   // k_tile12 ladder passes enumerate tiles in source order: bit0 backward, bit1 forward
     long long opt_low_bits_pass = 0;   // k_tile12: pass that applies the gates on index bits 0-2 (0 = contiguous pass, -1 = last strided pass)
     long long opt_cache_hints = 0; // k_tile12: bit0 streaming stores, bit1 streaming loads (all passes); bits 2-3: same, out-of-place passes only
@@ -299,6 +300,7 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
         case QR_OPT_PREFETCH: if (v < 0 || v > 31) return fail(QR_EINVAL, "prefetch must be in [0, 31]"); c->opt_prefetch = v; break;
         case QR_OPT_STAGED: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad staged mode"); c->opt_staged = v; break;
         case QR_OPT_DEBUG: c->opt_debug = v; break;
+        case QR_OPT_PAIR: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad pair mode"); c->opt_pair = v; break;
         case QR_OPT_SRC_ORDER: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad source-order mode"); c->opt_src_order = v; break;
         case QR_OPT_LOW_BITS_PASS: if (v < -1 || v > 15) return fail(QR_EINVAL, "bad low-bits pass"); c->opt_low_bits_pass = v; break;
         case QR_OPT_CACHE_HINTS: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad cache hints"); c->opt_cache_hints = v; break;
@@ -359,6 +361,7 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_DEBUG: *v = c->opt_debug; break;
         case QR_OPT_CACHE_HINTS: *v = c->opt_cache_hints; break;
         case QR_OPT_SRC_ORDER: *v = c->opt_src_order; break;
+        case QR_OPT_PAIR: *v = c->opt_pair; break;
         case QR_OPT_LOW_BITS_PASS: *v = c->opt_low_bits_pass; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
@@ -1069,15 +1072,25 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         if (nv == 2 && !staged && (c->opt_staged & 8)) staged = 2;   // bit 3: psi-only staging for the other backward passes
         const int K = pp.k;   // 12, or 11 (half-size tiles, direct loads only)
         if (K == 11) staged = 0;
+        // pair kernel: a cluster of two half-size CTAs per 12-bit tile (two backward CTAs per SM without losing a gate bit)
+        bool pair = K == 12 && (c->opt_pair & (nv == 2 ? 1 : 2)) && !(c->opt_staged & 3) && pp.ngroups >= 1 && pp.ngroups <= 4 &&
+                    (c->opt_cluster & (nv == 2 ? 3 : 12)) == 0;
+#ifdef QR_HOST_EMUL
+        pair = false;   // the emulation runs blocks one after another
+#endif
+        if (pair) staged = 0;
         lean_fn lfn;
-        if (K == 11) lfn = nv == 1 ? (ph ? k_tile12<1, true, 0, 11> : k_tile12<1, false, 0, 11>) : (ph ? k_tile12<2, true, 0, 11> : k_tile12<2, false, 0, 11>);
+        if (pair) lfn = nv == 1 ? (ph ? k_tile12<1, true, 0, 11, true> : k_tile12<1, false, 0, 11, true>)
+                                : (ph ? k_tile12<2, true, 0, 11, true> : k_tile12<2, false, 0, 11, true>);
+        else if (K == 11) lfn = nv == 1 ? (ph ? k_tile12<1, true, 0, 11> : k_tile12<1, false, 0, 11>) : (ph ? k_tile12<2, true, 0, 11> : k_tile12<2, false, 0, 11>);
         else if (staged == 2 && nv == 2) lfn = ph ? k_tile12<2, true, 2> : k_tile12<2, false, 2>;
         else if (staged) lfn = nv == 1 ? (ph ? k_tile12<1, true, 1> : k_tile12<1, false, 1>) : (ph ? k_tile12<2, true, 1> : k_tile12<2, false, 1>);
         else lfn = nv == 1 ? (ph ? k_tile12<1, true, 0> : k_tile12<1, false, 0>) : (ph ? k_tile12<2, true, 0> : k_tile12<2, false, 0>);
-        static bool lean_attr[2][2][2][3] = {};
-        if (!lean_attr[K - 11][nv - 1][ph][staged]) {
+        static bool lean_attr[3][2][2][3] = {};
+        const int ksel = pair ? 2 : K - 11;
+        if (!lean_attr[ksel][nv - 1][ph][staged]) {
             CUDA_TRY(cudaFuncSetAttribute(lfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (int)sizeof(double2) << QR_MAX_TILE_BITS));
-            lean_attr[K - 11][nv - 1][ph][staged] = true;
+            lean_attr[ksel][nv - 1][ph][staged] = true;
         }
         if (staged == 1) tp.prefetch = 0;
         Tile12X x;
@@ -1088,15 +1101,18 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
             x.cache_hints = (int)(c->opt_cache_hints & 3) | (oop ? (int)((c->opt_cache_hints >> 2) & 3) : 0);
         }
         const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2, K};
-        x.last_group = pp.ngroups == 1 ? K - 3 : (pp.ngroups == 5 ? 5 : 6);
+        const int KK = pair ? 11 : K;   // tile bits of the kernel instance
+        x.last_group = pp.ngroups == 1 ? KK - 3 : (pp.ngroups == 5 ? 5 : 6);
         for (int r = 0; r < 8; ++r) {
-            const u64 lf = (u64)r << (K - 3), ll = (u64)r << x.last_group;
+            const u64 lf = (u64)r << (KK - 3);
+            u64 ll = (u64)r << x.last_group;
+            if (pair && pp.ngroups == 1) ll = ((u64)(r & 3) << 8) | ((u64)(r >> 2) << 11);   // registers = tile bits 8, 9, 11 after the pair round
             x.droff_first[r] = geo12_local(geo, lf);
             x.roff_first[r] = tp.ladder ? ladder_map(x.droff_first[r], tp.M1, tp.M2) : x.droff_first[r];
             x.roff_last[r] = geo12_local(geo, ll);
         }
-        const long long lctas = K == 11 ? (nv == 1 ? 4 : 2) : ((nv == 1 && !staged) ? std::min<long long>(2, c->opt_ctas_fwd) : 1);
-        const i64 lgrid = std::min<i64>(tp.num_tiles, (i64)c->sm_count * lctas);
+        const long long lctas = KK == 11 ? (nv == 1 ? 4 : 2) : ((nv == 1 && !staged) ? std::min<long long>(2, c->opt_ctas_fwd) : 1);
+        const i64 lgrid = pair ? 2 * std::min<i64>(tp.num_tiles, (i64)c->sm_count * lctas / 2) : std::min<i64>(tp.num_tiles, (i64)c->sm_count * lctas);
         if (nv == 2) {
             const i64 nunits = flush_per_tile ? tp.num_tiles : lgrid;
             QR_TRY(ensure_scratch(c, (size_t)nunits * QR_SLOTS));
@@ -1106,14 +1122,16 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         // backward passes: clusters of 2 CTAs take adjacent tiles and align their loads (see k_tile12)
         const int want_cluster = (nv == 2 ? (int)(c->opt_cluster & 3) : (int)((c->opt_cluster >> 2) & 3));
         const bool strided_pass = pp.c < K;
-        x.cluster = (want_cluster == 2 || (want_cluster == 1 && strided_pass)) && lgrid % 2 == 0 ? 2 : 1;
+        x.cluster = pair ? 2 : ((want_cluster == 2 || (want_cluster == 1 && strided_pass)) && lgrid % 2 == 0 ? 2 : 1);
         // L2 prefetch of the next tile: opt_prefetch bit 4 = contiguous passes only
         if ((c->opt_prefetch & 16) && strided_pass) tp.prefetch = 0;
-        const size_t lsmem = staged ? (size_t)(nv + 1) * tile_bytes : (pp.ngroups > 1 ? (size_t)nv * tile_bytes : 0);
+        // pair: nv half-tile exchange buffers (32 KiB each) + nv * 4 * 256 amplitudes for the partner (16 KiB each)
+        const size_t lsmem = pair ? (size_t)nv * (tile_bytes / 2 + tile_bytes / 4)
+                                  : (staged ? (size_t)(nv + 1) * tile_bytes : (pp.ngroups > 1 ? (size_t)nv * tile_bytes : 0));
         if (x.cluster > 1) {
-            CUDA_TRY(QR_LAUNCH_CLUSTER(lfn, (unsigned)lgrid, 1u << (K - 3), lsmem, c->stream, 2u, tp, x));
+            CUDA_TRY(QR_LAUNCH_CLUSTER(lfn, (unsigned)lgrid, 1u << (KK - 3), lsmem, c->stream, 2u, tp, x));
         } else {
-            QR_LAUNCH(lfn, (unsigned)lgrid, 1 << (K - 3), lsmem, c->stream, tp, x);
+            QR_LAUNCH(lfn, (unsigned)lgrid, 1 << (KK - 3), lsmem, c->stream, tp, x);
         }
         KERNEL_CHECK();
         c->perf.kernel_launches++;

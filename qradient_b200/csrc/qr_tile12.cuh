@@ -211,6 +211,45 @@ __device__ __forceinline__ void qr_cp_async_commit() {}
 __device__ __forceinline__ void qr_cp_async_wait_all() {}
 #endif
 
+// ---- thread-block cluster helpers (pair kernel): rank, distributed-shared-memory loads, split barrier ----
+#ifndef QR_HOST_EMUL
+__device__ __forceinline__ unsigned qr_cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned qr_map_remote(const void* smem_ptr, unsigned rank) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(smem_ptr), o;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(o) : "r"(a), "r"(rank));
+    return o;
+}
+__device__ __forceinline__ double2 qr_ld_remote(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void qr_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void qr_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// 16-byte store into the partner CTA's shared memory that credits `bytes` to the partner's mbarrier on completion:
+// no fence on the producer side, the consumer's mbarrier wait orders the data (async proxy)
+__device__ __forceinline__ void qr_st_async_remote(unsigned remote_addr, double2 v, unsigned remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(remote_addr), "d"(v.x), "d"(v.y),
+                 "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ void qr_mbar_arrive_remote(unsigned remote_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+#else   // the emulation runs blocks one after another: the pair kernel is never launched there
+__device__ __forceinline__ void qr_st_async_remote(unsigned, double2, unsigned) {}
+__device__ __forceinline__ void qr_mbar_arrive_remote(unsigned) {}
+__device__ __forceinline__ unsigned qr_cluster_rank() { return 0; }
+__device__ __forceinline__ unsigned qr_map_remote(const void*, unsigned) { return 0; }
+__device__ __forceinline__ double2 qr_ld_remote(unsigned) { return make_double2(0.0, 0.0); }
+__device__ __forceinline__ void qr_cluster_arrive() {}
+__device__ __forceinline__ void qr_cluster_wait() {}
+#endif
+
 // diagonal phase exp(-i angle H[d]) from the integer look-up table or, for general H, sincos
 __device__ __noinline__ double2 qr12_phase_slow(const double* __restrict__ ham, u64 d, double angle, double* hv) {
     const double v = ham[d];
@@ -234,9 +273,18 @@ __device__ __noinline__ double2 qr12_phase_slow(const double* __restrict__ ham, 
 // exchange keeps its two buffers and single barrier: [exchange psi][exchange lambda][stage psi].
 // K = 11: half-size tiles (2048 amplitudes, 256 threads, 64 KiB of shared memory for the backward pass): two
 // backward CTAs per SM, whose load / FP64 / exchange phases overlap; used where it does not cost a pass.
-template <int NV, bool PHASE, int STAGED, int K = QR_MAX_TILE_BITS>
+//
+// PAIR (K = 11 only): a cluster of two such CTAs covers one 12-bit tile -- rank rho owns the half with local bit
+// 11 = rho -- so a pass keeps its 12 gate bits AND two backward CTAs fit on an SM (2 x 96 KiB of shared memory,
+// 2 x 256 x 128 registers).  After the gates of bits 8-10 the CTAs trade, through distributed shared memory, the
+// halves of their registers that differ in bit 10: rank rho keeps bit 10 = rho and receives the partner's
+// amplitudes with the other value of bit 11, which land in the register slots just vacated.  Bit 11 is then a
+// register bit (gate applied), bit 10 is the rank bit for the rest of the pass (its gate is done), and only the
+// store addresses notice the swap.  One cluster barrier per tile (+ one split arrive/wait pair).
+template <int NV, bool PHASE, int STAGED, int K = QR_MAX_TILE_BITS, bool PAIR = false>
 __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 1 ? 4 : 2)) : ((NV == 1 && !STAGED) ? 2 : 1)))
     k_tile12(const TilePass p, const Tile12X x) {
+    static_assert(!PAIR || (K == 11 && STAGED == 0), "pair kernel: half-size tiles, direct loads");
     constexpr int NSV = STAGED == 1 ? NV : (STAGED == 2 ? 1 : 0);   // staged vectors
     constexpr int T = 1 << K;
     constexpr int LG = K - 3;   // first local bit of the register group held at load time
@@ -248,7 +296,25 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
     __shared__ int s_flags[2];                  // [0]: the pass needs its diagonal (an Rz, or an odd number of sign flips)
     __shared__ double2 lut_sm[QR_LUT_MAX];
     const int tid = threadIdx.x;
-    const Geo12 geo = {p.c, p.h, p.m1, p.h2, K};
+    const Geo12 geo = {p.c, p.h, p.m1, p.h2, PAIR ? 12 : K};   // PAIR: addresses follow the 12-bit tile geometry
+    const unsigned rho = PAIR ? qr_cluster_rank() : 0u;            // which half of the 12-bit tile (local bit 11 at load time)
+    double2* const pairbuf = smem + NV * T;                        // PAIR: [NV][4][256] amplitudes handed over by the partner CTA
+    __shared__ u64 bar_full, bar_empty;                            // PAIR: hand-over landed / hand-over consumed by the partner
+    unsigned remote_buf = 0, remote_full = 0, remote_empty = 0;
+    if (PAIR) {
+#ifndef QR_HOST_EMUL
+        if (threadIdx.x == 0) {
+            qr_mbar_init(&bar_full, 1);                            // my expect_tx arrival + the partner's bytes
+            qr_mbar_init(&bar_empty, (1 << LG) / 32);              // one arrival per partner warp
+        }
+        __syncthreads();
+        qr_cluster_arrive();                                       // both CTAs run and their barriers are initialised
+        qr_cluster_wait();
+        remote_buf = qr_map_remote(pairbuf, rho ^ 1u);
+        remote_full = qr_map_remote(&bar_full, rho ^ 1u);
+        remote_empty = qr_map_remote(&bar_empty, rho ^ 1u);
+#endif
+    }
     const u64 tmask = ((u64)1 << p.tiles_log2) - 1;
     const int ng = x.ngroups;
     // destination base index of tile t.  Ladder passes may enumerate the tiles in SOURCE order: the gather map
@@ -258,7 +324,7 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
     // bits, so the tile bits of the inverse map depend on the tile bits of the source only.
     auto dest_base = [&](u64 t) -> u64 {
         const u64 g0 = geo12_tile(geo, t);
-        return p.src_order ? (ladder_map(g0, p.iM1, p.iM2) & ~(u64)(T - 1)) : g0;
+        return p.src_order ? (ladder_map(g0, p.iM1, p.iM2) & ~(u64)((PAIR ? 2 * T : T) - 1)) : g0;
     };
 
     double acc_all[QR_SLOTS];
@@ -267,10 +333,12 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
     double wtot = 0.0;   // running sum of Im(conj(lambda) psi) over this thread's amplitudes
 
     // per-thread global offsets (local bits 0-8 at load time; the last group's thread bits at store time)
-    const u64 toff_d = geo12_local(geo, (u64)tid);                                       // destination index bits
+    const u64 toff_d = geo12_local(geo, (u64)tid | (PAIR ? (u64)rho << 11 : 0));          // destination index bits
     const u64 toff_s = p.ladder ? ladder_map(toff_d, p.M1, p.M2) : toff_d;               // gathered source bits
     const int tbl = ng > 1 ? qr12_tb(tid, K == 12 ? 6 : x.last_group) : tid;   // K = 12: the last group is always 6
-    const u64 toff_l = geo12_local(geo, (u64)tbl);
+    // PAIR: at store time local bit 10 of the half tile is tile bit 11 and the rank is tile bit 10
+    const u64 toff_l = PAIR ? geo12_local(geo, (u64)(tbl & 0x3FF) | ((u64)rho << 10) | ((u64)((tbl >> 10) & 1) << 11))
+                            : geo12_local(geo, (u64)tbl);
 
     const bool use_lut = PHASE && p.hidx != nullptr && (p.pre_phase || p.post_phase);
     if (use_lut) {
@@ -288,6 +356,7 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
             const int m = sg[b].mode;
             double v = acc_all[b];
             if (b < LG && m == 4) v = ((tid >> b) & 1) ? -wtot : wtot;
+            if (PAIR && b == 11 && m == 4) v = rho ? -wtot : wtot;
             acc_all[b] = v;
         }
     };
@@ -314,14 +383,18 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
 
     // Uniform trip count over the grid: with x.cluster > 1 every CTA of a cluster must reach the
     // per-tile cluster barrier the same number of times (a CTA without a tile just arrives).
-    const i64 iters = (p.num_tiles + gridDim.x - 1) / gridDim.x;
+    // PAIR: the two CTAs of a cluster work on the same tile; the tile loop runs over clusters.
+    const i64 nworkers = PAIR ? (i64)(gridDim.x >> 1) : (i64)gridDim.x;
+    const i64 worker = PAIR ? (i64)(blockIdx.x >> 1) : (i64)blockIdx.x;
+    const i64 iters = (p.num_tiles + nworkers - 1) / nworkers;
+    unsigned pair_count = 0;     // PAIR: hand-overs done so far (mbarrier phase parities)
     for (i64 it = 0; it < iters; ++it) {
-        const i64 tile = (i64)blockIdx.x + it * gridDim.x;
+        const i64 tile = worker + it * nworkers;
 #ifndef QR_HOST_EMUL
         // CTAs of a cluster own ADJACENT tiles (rows 128 B apart in the strided passes).  Aligning their
         // loads in time lets the DRAM controller serve both halves of a 256 B chunk from one row
         // activation: measured 4.8 -> 5.8 TB/s on the bare two-vector access pattern (scripts/membench.cu).
-        if (x.cluster > 1 && (STAGED == 0 || it + 1 < iters)) asm volatile("barrier.cluster.arrive.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory");
+        if (!PAIR && x.cluster > 1 && (STAGED == 0 || it + 1 < iters)) asm volatile("barrier.cluster.arrive.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory");
 #endif
         if (tile >= p.num_tiles) continue;
         const i64 b = tile >> p.tiles_log2;
@@ -331,7 +404,7 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
             __syncthreads();
             if (tid < QR_GATE_SLOTS) {
                 GateP g = p.gates[b * p.gate_stride + tid];
-                if (K < QR_GATE_SLOTS && tid >= K) g.axis = -1;
+                if (!PAIR && K < QR_GATE_SLOTS && tid >= K) g.axis = -1;
                 Gate12 o;
                 o.tau = 0.0; o.sig = 0.0; o.mode = -1; o.neg = 0;
                 double2 z0 = make_double2(1.0, 0.0), z1 = z0;
@@ -372,6 +445,7 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
             zt = make_double2(s_flags[1] ? -1.0 : 1.0, 0.0);
 #pragma unroll
             for (int j = 0; j < LG; ++j) zt = cmul(zt, szb[j][(tid >> j) & 1]);
+            if (PAIR) zt = cmul(zt, szb[11][rho]);
             cur_b = b;
         }
         // batch element offset: state_stride is a multiple of 2^n, so it can be OR-ed into the index bits
@@ -399,13 +473,13 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
         }
 #ifndef QR_HOST_EMUL
         if (p.prefetch) {   // pull the next tile of this CTA into L2 while this one is computed
-            const i64 nt = tile + (i64)gridDim.x * p.prefetch;
+            const i64 nt = tile + nworkers * p.prefetch;
             if (nt < p.num_tiles) {
                 const i64 nb = nt >> p.tiles_log2;
                 const u64 t2 = (u64)nt & tmask;
                 const u64 nbase = dest_base(t2);
                 const int l = tid << 3;   // one 128 B line per thread
-                const u64 d = nbase | geo12_local(geo, (u64)l);
+                const u64 d = nbase | geo12_local(geo, (u64)l | (PAIR ? (u64)rho << 11 : 0));
                 const u64 s = p.ladder ? (ladder_map(d, p.M1, p.M2) ^ p.src_xor) : d;
                 if (STAGED != 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src0 + nb * p.state_stride + s));
                 if (NV == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src1 + nb * p.state_stride + s));
@@ -451,6 +525,42 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
         // ---- rounds ----
 #define QR12_X(GP, GN) do { if (STAGED == 1) qr12_exchange_1buf<NV, GP, GN>(a, smem, tid); else qr12_exchange<NV, GP, GN, K>(a, smem, tid); } while (0)
         qr12_round<NV, LG>(a, sg, acc_all);
+        if (PAIR) {
+            // Hand the register half with bit 10 != rho to the partner CTA (asynchronous stores into ITS buffer, credited
+            // to ITS `full` mbarrier) and take its half with bit 10 == rho, bit 11 = 1 - rho, from my own buffer.  No
+            // cluster-wide barrier or fence per tile: a release fence would wait for the previous tile's global stores.
+            if (pair_count > 0) qr_mbar_wait(&bar_empty, (pair_count - 1) & 1u);   // the partner has read my previous hand-over
+            if (tid == 0) qr_mbar_expect_tx(&bar_full, (unsigned)(NV * 4 * (1 << LG) * sizeof(double2)));
+            if (rho == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                        qr_st_async_remote(remote_buf + (unsigned)(((v * 4 + k) * (1 << LG) + tid) * sizeof(double2)), a[v][k | 4], remote_full);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                        qr_st_async_remote(remote_buf + (unsigned)(((v * 4 + k) * (1 << LG) + tid) * sizeof(double2)), a[v][k], remote_full);
+            }
+            qr_mbar_wait(&bar_full, pair_count & 1u);   // the partner's half has landed in my buffer
+            if (rho == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) a[v][k | 4] = pairbuf[(v * 4 + k) * (1 << LG) + tid];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) a[v][k] = pairbuf[(v * 4 + k) * (1 << LG) + tid];
+            }
+            qr12_gate<NV, 2>(a, sg[11], acc_all[11]);   // register bit 2 is tile bit 11 now
+            __syncwarp();
+            if ((tid & 31) == 0) qr_mbar_arrive_remote(remote_empty);   // my buffer may be overwritten (one arrival per warp)
+            ++pair_count;
+        }
         if (ng == 4) {
             QR12_X(LG, 0);
             qr12_round<NV, 0>(a, sg, acc_all);
@@ -508,6 +618,10 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
             for (int i = 0; i < QR_SLOTS; ++i) acc_all[i] = 0.0;
             wtot = 0.0;
         }
+    }
+    if (PAIR) {   // do not exit while the partner may still store into my buffer or arrive on my barriers
+        qr_cluster_arrive();
+        qr_cluster_wait();
     }
     if (NV == 2 && !p.flush_per_tile) {
         if (cur_b >= 0) finalize();

@@ -170,3 +170,35 @@ def test_batched_14_qubits_matches_single():
     for b in (0, 17, 63):
         e_ref, g_ref = orc.mcclean_grad_run(n, zz01(n), axes[b], angles[b])
         assert_parity(e[b], g[b], e_ref, g_ref, 1.0, 1e-10)
+
+
+@pytest.mark.parametrize("n,L", [(12, 3), (15, 2), (20, 2), (23, 2)])
+def test_pair_kernel_matches_default(n, L):
+    """k_tile12 pair kernel (QR_OPT_PAIR: a cluster of two half-size CTAs shares a 12-bit tile over distributed
+    shared memory; st.async + mbarrier hand-over) against the default kernels.  GPU only: the CPU emulation runs
+    thread blocks one after another and cannot host a cluster."""
+    from qradient_b200.circuit_logic import McClean, Qaoa
+    from qradient_b200.optimization_problems import MaxCut
+    rng = np.random.default_rng(100 + n)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    zz = np.full((n, n), None)
+    zz[0, 1] = 1.0
+    zz[2, n - 1] = -0.5
+    obs = {"zz": zz, "x": np.array([0.3] + [None] * (n - 1), dtype=object)}
+    c = McClean(n, obs, L, axes=axes, angles=angles)
+    c.state.set_option("tile_bits", 12)
+    e0, g0 = c.grad_run()
+    r0 = c.run_expec_val()
+    for mode in (1, 2, 3):
+        c.state.set_option("pair", mode)
+        for _ in range(2):          # a race would show up as a run-to-run difference
+            e1, g1 = c.grad_run()
+            assert_parity(e1, g1, e0, g0, 1.8, 1e-12)
+        assert abs(c.run_expec_val() - r0) < 1e-12
+    q = Qaoa(n, MaxCut(n, edge_set=[(i, i + 1) for i in range(n - 1)]).to_observable(), 2)
+    q.state.set_option("tile_bits", 12)
+    b, gm = rng.random(2), rng.random(2)
+    e0, g0 = q.grad_run(b, gm)
+    q.state.set_option("pair", 3)
+    e1, g1 = q.grad_run(b, gm)
+    assert_parity(e1, g1, e0, g0, float(n - 1), 1e-12)
