@@ -356,6 +356,19 @@ def main():
                   "frac_of_peak": perf["algorithmic_bytes"] / (max(perf["ms_total"], 1e-9) * 1e-3) / 1e9 / peak,
                   "ms_forward": perf["ms_forward"], "ms_observable": perf["ms_observable"], "ms_backward": perf["ms_backward"]},
     }
+    # ---- BASELINE config 3: "... exact grad_run plus 100-shot sampling": the sampling leg, timed after the gradient steps ----
+    if w["kind"] == "qaoa" and rank == 0:
+        u = np.random.RandomState(0).uniform(size=100)
+        circ.run_expec_val(betas, gammas)
+        circ.sample_cost(100, u)                       # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e_fwd = circ.run_expec_val(betas, gammas)      # psi_final (grad_run leaves the co-state in state.vec)
+        t1 = time.perf_counter()
+        mean_cost = circ.sample_cost(100, u)           # prefix-sum sampler + H gather on the device
+        t2 = time.perf_counter()
+        line["sampling"] = {"shots": 100, "ms_forward_sweep": 1e3 * (t1 - t0), "ms_sampling": 1e3 * (t2 - t1),
+                            "mean_cost_of_samples": float(mean_cost), "E_exact": float(e_fwd), "uniforms": "RandomState(0).uniform(size=100)"}
     # ---- the HBM-bound north-star size, measured in the same run (N = 1, default workload only) ----
     if rank == 0 and world == 1 and args.hbm_target and args.workload == "mcclean20":
         try:

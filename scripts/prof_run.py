@@ -17,7 +17,7 @@ ap.add_argument("--ctas-bwd", type=int, default=1)
 ap.add_argument("--ctas-fwd", type=int, default=2)
 ap.add_argument("--r-fwd", type=int, default=3)
 ap.add_argument("--r-bwd", type=int, default=3)
-ap.add_argument("--tile-bits", type=int, default=12)
+ap.add_argument("--tile-bits", type=int, default=0)
 ap.add_argument("--async-fwd", type=int, default=0)
 ap.add_argument("--tile-bits-x", type=int, default=0)
 ap.add_argument("--decoupled", type=int, default=0)
