@@ -17,7 +17,7 @@ ap.add_argument("--qubits", dest="n", type=int, default=31)
 ap.add_argument("--layers", dest="L", type=int, default=3)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--check", action="store_true", help="compare with the CPU oracle (small n only)")
-ap.add_argument("--tile-bits", type=int, default=12)
+ap.add_argument("--tile-bits", type=int, default=0)
 ap.add_argument("--check-single", action="store_true", help="compare with the single-GPU path on rank 0")
 args = ap.parse_args()
 
