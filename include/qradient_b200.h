@@ -61,7 +61,6 @@ enum {
     QR_OPT_CLUSTER = 18,      /* CTA pairs (thread-block clusters of 2) on adjacent tiles: bits 0-1 backward, 2-3 forward; 0 none, 1 strided passes, 2 all */
     QR_OPT_STAGED = 19,       /* k_tile12: next tile staged in shared memory by asynchronous copies: bit0 backward, bit1 forward, bit2 (default) auto */
     QR_OPT_STAGED_MIN_BIT = 20, /* auto mode: strided backward passes whose lowest gate bit is >= this (default 21) are staged */
-    QR_OPT_DEBUG = 21,        /* timing diagnostics only (results are wrong): bit0 no ladder gather map, bit1 ladder passes in place */
     QR_OPT_CACHE_HINTS = 22,  /* k_tile12: bit0 streaming stores, bit1 streaming loads; bits 2-3: the same for out-of-place (ladder) passes only */
     QR_OPT_LOW_BITS_PASS = 23, /* k_tile12: pass applying the gates on index bits 0-2: 0 = contiguous pass, k = k-th strided pass, -1 = last */
     QR_OPT_SRC_ORDER = 24,    /* k_tile12 ladder passes enumerate tiles in source order (sequential reads): bit0 backward, bit1 forward (default 0: measured neutral) */

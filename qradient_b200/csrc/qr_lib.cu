@@ -116,7 +116,6 @@ struct qr_ctx {
     long long opt_src_order = 0;   // k_tile12 ladder passes enumerate tiles in source order: bit0 backward, bit1 forward
     long long opt_low_bits_pass = 0;   // k_tile12: pass that applies the gates on index bits 0-2 (0 = contiguous pass, -1 = last strided pass)
     long long opt_cache_hints = 0; // k_tile12: bit0 streaming stores, bit1 streaming loads (all passes); bits 2-3: same, out-of-place passes only
-    long long opt_debug = 0;       // timing diagnostics (results are wrong): bit0 no ladder gather map, bit1 ladder passes in place
     long long opt_buf_skew = 0;    // bytes between the start offsets of consecutive state buffers (multiple of 256)
     qr_perf perf;
     // ---- sharded states: this context holds one shard of an n_total-qubit register ----
@@ -299,7 +298,6 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
             c->opt_tile_bits = v; break;
         case QR_OPT_PREFETCH: if (v < 0 || v > 31) return fail(QR_EINVAL, "prefetch must be in [0, 31]"); c->opt_prefetch = v; break;
         case QR_OPT_STAGED: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad staged mode"); c->opt_staged = v; break;
-        case QR_OPT_DEBUG: c->opt_debug = v; break;
         case QR_OPT_PAIR: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad pair mode"); c->opt_pair = v; break;
         case QR_OPT_SRC_ORDER: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad source-order mode"); c->opt_src_order = v; break;
         case QR_OPT_LOW_BITS_PASS: if (v < -1 || v > 15) return fail(QR_EINVAL, "bad low-bits pass"); c->opt_low_bits_pass = v; break;
@@ -358,7 +356,6 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_CLUSTER: *v = c->opt_cluster; break;
         case QR_OPT_STAGED: *v = c->opt_staged; break;
         case QR_OPT_STAGED_MIN_BIT: *v = c->opt_staged_min_bit; break;
-        case QR_OPT_DEBUG: *v = c->opt_debug; break;
         case QR_OPT_CACHE_HINTS: *v = c->opt_cache_hints; break;
         case QR_OPT_SRC_ORDER: *v = c->opt_src_order; break;
         case QR_OPT_PAIR: *v = c->opt_pair; break;
@@ -1032,12 +1029,10 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
             ladder_masks(lp.n, ladder_stacking, &tp.iM1, &tp.iM2);
         }
     }
-    if (c->opt_debug & 1) tp.ladder = 0;          // timing diagnostics only (wrong results): no gather map
     tp.tiles_log2 = lp.n - pp.k;
     tp.num_tiles = batch << tp.tiles_log2;
     tp.state_stride = state_stride;
     tp.src0 = io.src0; tp.src1 = io.src1; tp.dst0 = io.dst0; tp.dst1 = io.dst1;
-    if (c->opt_debug & 2) { tp.dst0 = (double2*)io.src0; tp.dst1 = (double2*)io.src1; }   // timing diagnostics only: in place
     tp.gates = d_gates; tp.gate_stride = gate_stride;
     tp.ham = ham; tp.pre_phase = pre_phase; tp.post_phase = post_phase;
     if (lut && c->ham_integer) { tp.hidx = c->d_hidx; tp.lut = lut; tp.lut_size = c->ham_range; tp.hmin = c->ham_min; }
