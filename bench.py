@@ -109,10 +109,11 @@ class ClockSampler:
 
 
 # per-launch DRAM traffic of the backward tile pass at n = 30 (ncu dram__bytes_read.sum + dram__bytes_write.sum,
-# averaged over the 9 backward launches of profiles/r1_launches_mcclean30_L3_tile12_default.csv; algorithmic: 68.72e9)
+# averaged over the 9 backward launches of profiles/r1_launches_mcclean30_L3_tile12_final.csv; algorithmic: 68.72e9)
+TRAFFIC20_BWD = 33.64e6   # n = 20 (L2 resident): ncu cold-cache capture, reads 33.6 MB, writes stay in L2 (profiles/r1_launches_mcclean20_dram.csv)
 TRAFFIC30_BWD = 69.3e9
 TRAFFIC30_SRC = ("ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 9 backward launches in "
-                 "profiles/r1_launches_mcclean30_L3_tile12_default.csv (reads 35.0 GB incl. ~2 % L2-prefetch over-fetch, writes 34.3 GB)")
+                 "profiles/r1_launches_mcclean30_L3_tile12_final.csv (reads 35.0 GB incl. ~2 % L2-prefetch over-fetch, writes 34.3 GB)")
 
 
 def measured_peak():
@@ -348,7 +349,7 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "k_tile12<2,*> (backward tile pass: psi and lambda, qr_tile12.cuh)",
                      "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak, "peak_source": peak_src,
                      "bytes_per_launch": perf["bwd_pass_bytes"], "ms_per_launch": perf["bwd_pass_ms_avg"],
-                     "traffic": None,
+                     "traffic": TRAFFIC20_BWD if (n == 20 and w["kind"] == "mcclean") else None,
                      "note": "state vector is L2-resident at n<=21 (2 x %.0f MiB): fraction of the HBM peak is reported "
                              "but launch latency / L2 bound; see hbm_target for the HBM-bound size" % (16 * 2.0 ** n / 2 ** 20)
                      if n <= 21 else "HBM-bound size"},
