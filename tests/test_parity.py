@@ -565,3 +565,28 @@ def test_state_snapshots(backend):
     st.free_snapshots()
     with pytest.raises(ValueError):
         st.load(0)
+
+
+def test_options_and_permutation_api_validation(backend):
+    """Argument checks of the kernel-selection options and of qr_perm_load / qr_state_permute."""
+    n = 6
+    st = State(n)
+    for name, bad in (("tile_bits", 3), ("tile_bits", 13), ("prefetch", 32), ("staged", 16), ("cluster", 16), ("pair", 4),
+                      ("src_order", 4), ("cache_hints", 16), ("lean", 4), ("buf_skew", 100), ("page_bits", 5), ("min_row_bits", 12)):
+        with pytest.raises(ValueError):
+            st.set_option(name, bad)
+    st.set_option("tile_bits", 0)                     # auto
+    with pytest.raises(ValueError):
+        st.load_permutation(np.arange(2 ** n - 1))    # wrong length
+    with pytest.raises(ValueError):
+        st.load_permutation(np.zeros(2 ** n, dtype=np.int64))   # not a permutation
+    fresh = State(n)
+    with pytest.raises(RuntimeError):
+        fresh.permute()                                # nothing loaded
+    rng = np.random.default_rng(3)
+    v = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    perm = rng.permutation(2 ** n)
+    st.vec = v
+    st.load_permutation(perm)
+    st.permute()
+    np.testing.assert_array_equal(np.array(st.vec), v[perm])
