@@ -101,7 +101,7 @@ class McClean(ParametrizedCircuit):
             axes = np.broadcast_to(axes, angles.shape)
         if axes.shape != angles.shape:
             raise ValueError('axes must have shape (B, L, n) or (L, n)')
-        if np.any((axes < 0) | (axes > 2)):
+        if axes.size and (axes.min() < 0 or axes.max() > 2):     # two reductions, no B*L*n temporaries
             raise ValueError('Invalid axis')
         axes = _lib.as_i32(axes)
         e = np.empty(B, dtype=np.float64)
