@@ -167,6 +167,15 @@ int qr_qaoa_expec(qr_ctx* ctx, int n_layers, const double* betas, const double* 
 int qr_qaoa_grad(qr_ctx* ctx, int n_layers, const double* betas, const double* gammas,
                  int use_current_state, double* e_out, double* grad_out);
 
+/* ---- optimiser loop on the device (optimization.py:41-91 McCleanOpt.step, :131-194 update rules) ---------- */
+/* `steps` x (grad_run, update) without host round trips.  rule: 0 Adam, 1 GradientDescent (constant step),
+ * 2 RateDecayOnPlateau.  hyper[8] = {step_size, beta1, beta2, eps, plateau_length, decay_rate, cost, plateau_counter}
+ * (step_size, cost and plateau_counter are updated); m / v: Adam moments [L*n] in/out (null otherwise);
+ * angles [L*n] in/out; cost_history [steps]; param_history [steps][L*n] (parameters after each step) or null. */
+int qr_mcclean_optimize(qr_ctx* ctx, int n_layers, const int32_t* axes, double* angles, const qr_obs* obs, int rule,
+                        double* hyper, int* iter_inout, double* m_inout, double* v_inout, int steps,
+                        double* cost_history, double* param_history);
+
 /* ---- finite-shot sampling (qaoa.py:196-198, mc_clean.py:259-261) ------------------------ */
 /* index = first k with cumsum(|vec|^2)[k] >= u  (scipy rv_discrete inverse CDF); uniforms are
  * supplied by the caller from the numpy stream so the draw order matches the reference. */

@@ -72,6 +72,8 @@ _SIGNATURES = {
     "qr_qaoa_grad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, P(c_double), c_void_p]),
     "qr_sample_bitstrings": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "qr_ham_gather": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "qr_mcclean_optimize": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                    c_void_p, c_void_p]),
     "qr_perm_load": (c_int, [c_void_p, c_void_p, c_size_t]),
     "qr_state_permute": (c_int, [c_void_p]),
     "qr_shard_create": (c_int, [c_int, c_int, c_int, c_int, P(c_void_p)]),

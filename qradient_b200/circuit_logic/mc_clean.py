@@ -88,6 +88,30 @@ class McClean(ParametrizedCircuit):
                        comp_obs._handle, use_current, ctypes.byref(e), _lib.ptr(grad))
         return expec_val, grad
 
+    # -- extension: optimiser loop on the device (optimization.py:69-91 repeated, no host round trips) --
+    def optimize_on_device(self, rule, hyper, iteration, steps, m=None, v=None, keep_param_history=True):
+        """`steps` x (grad_run, parameter update) enqueued back to back on the device.
+
+        rule: 0 Adam, 1 GradientDescent (constant step), 2 RateDecayOnPlateau; hyper: float64[8] =
+        (step_size, beta1, beta2, eps, plateau_length, decay_rate, cost, plateau_counter), updated in place;
+        m, v: Adam moments float64[L, n], updated in place.  self.angles is updated in place.
+        Returns (cost_history float64[steps], param_history float64[steps, L, n] or None, iteration)."""
+        axes, angles = self._params()
+        hyper = np.ascontiguousarray(hyper, dtype=np.float64)
+        cost = np.zeros(steps, dtype=np.float64)
+        hist = np.zeros((steps, self.lnum, self.qnum), dtype=np.float64) if keep_param_history else None
+        it = ctypes.c_int(int(iteration))
+        mm = np.ascontiguousarray(m, dtype=np.float64) if m is not None else None
+        vv = np.ascontiguousarray(v, dtype=np.float64) if v is not None else None
+        self._lib.call('qr_mcclean_optimize', self.state._ctx, self.lnum, _lib.ptr(axes), _lib.ptr(angles), self.observable._handle,
+                       int(rule), _lib.ptr(hyper), ctypes.byref(it), _lib.ptr(mm) if mm is not None else None,
+                       _lib.ptr(vv) if vv is not None else None, int(steps), _lib.ptr(cost), _lib.ptr(hist) if hist is not None else None)
+        self.angles = angles
+        if m is not None:
+            m[...] = mm
+            v[...] = vv
+        return cost, hist, it.value, hyper
+
     # -- extension: many parameter sets at once (timing-test.ipynb cell 6 host loop) -------------
     def grad_run_batch(self, angles, axes=None):
         """angles: [B, L, n]; axes: [B, L, n] or [L, n] (default: self.axes).

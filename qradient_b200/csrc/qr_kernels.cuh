@@ -436,6 +436,65 @@ __global__ void k_build_gates(const int* __restrict__ axes, const double* __rest
 }
 
 
+// ------------------------------------------------------------------------------------------
+// Device-side optimiser step (optimization.py:131-194: Adam, GradientDescent with a constant step,
+// RateDecayOnPlateau).  One block: scatter the slot sums of the backward sweep into grad[L][n], record the
+// cost, update the parameters in place.  Enqueued right after the gradient's kernels, so a whole optimisation
+// run needs no host round trip.
+// ------------------------------------------------------------------------------------------
+struct OptDev {
+    int rule;              // 0 Adam, 1 GradientDescent, 2 RateDecayOnPlateau
+    int iter;
+    int plateau_length, plateau_counter;
+    double step_size, beta1, beta2, eps, decay_rate, cost;
+};
+
+__global__ void k_opt_step(const double* __restrict__ result, const int* __restrict__ slot_qubit, int L, int n, int P, int GS, int SL,
+                           double* __restrict__ params, double* __restrict__ m, double* __restrict__ v, double* __restrict__ grad,
+                           OptDev* st, double* __restrict__ cost_hist, double* __restrict__ param_hist, int it) {
+    __shared__ double sh[3];   // step size of this step, 1 - beta1^iter, 1 - beta2^iter
+    const int total_slots = L * P * GS, np_ = L * n;
+    for (int idx = threadIdx.x; idx < total_slots; idx += blockDim.x) {
+        const int s = idx % GS, p = (idx / GS) % P, i = idx / (GS * P);
+        const int q = slot_qubit[p * GS + s];
+        if (q >= 0) grad[i * n + q] = result[1 + (size_t)(i * P + p) * SL + s];
+    }
+    if (threadIdx.x == 0) {
+        const double e = result[0];
+        cost_hist[it] = e;
+        st->iter += 1;
+        if (st->rule == 2) {               // optimization.py:183-192
+            if (e > st->cost) {
+                st->plateau_counter += 1;
+                if (st->plateau_counter >= st->plateau_length) { st->step_size *= st->decay_rate; st->plateau_counter = 0; }
+            } else {
+                st->cost = e;
+                st->plateau_counter = 0;
+            }
+        }
+        sh[0] = st->step_size;
+        sh[1] = 1.0 - pow(st->beta1, (double)st->iter);
+        sh[2] = 1.0 - pow(st->beta2, (double)st->iter);
+    }
+    __syncthreads();
+    const double step = sh[0];
+    for (int k = threadIdx.x; k < np_; k += blockDim.x) {
+        const double g = grad[k];
+        double x = params[k];
+        if (st->rule == 0) {               // optimization.py:148-154
+            const double mk = st->beta1 * m[k] + (1.0 - st->beta1) * g;
+            const double vk = st->beta2 * v[k] + (1.0 - st->beta2) * (g * g);
+            m[k] = mk;
+            v[k] = vk;
+            x -= step * (mk / sh[1]) / (sqrt(vk / sh[2]) + st->eps);
+        } else {
+            x -= step * g;
+        }
+        params[k] = x;
+        if (param_hist) param_hist[(size_t)it * np_ + k] = x;
+    }
+}
+
 // integer-valued diagonal Hamiltonian -> 16-bit index table: hidx[j] = H[j] - hmin
 __global__ void k_ham_index(const double* __restrict__ ham, short* __restrict__ hidx, u64 N, double hmin) {
     for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (u64)gridDim.x * blockDim.x)

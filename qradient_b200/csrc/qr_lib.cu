@@ -1251,8 +1251,17 @@ struct GradLayout {   // where the per-(layer, pass) slot sums land in d_result
 
 // fused McClean forward (+ backward when grad != null) for `batch` parameter sets laid out
 // contiguously in the state buffers (state b at offset b * N)
+// Device-resident parameters (optimiser loop, qr_mcclean_optimize): the angles are read from device memory, the gate
+// tables are built on the device, and nothing is read back -- E and the slot sums stay in d_result
+// ([E][L][P][QR_SLOTS]) for the update kernel that is enqueued next.
+struct DevParams {
+    const double* d_angles;      // [L * n] on the device
+    int* slot_qubit_out;         // host [P * QR_GATE_SLOTS]: qubit of each backward gradient slot (or -1)
+    int* passes_out;             // host: P
+};
+
 static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const double* angles, const qr_obs* o,
-                         int use_current, double* e_out, double* grad) {
+                         int use_current, double* e_out, double* grad, const DevParams* dev = nullptr) {
     const int n = c->n;
     LayerPlan lpf, lp;   // forward / backward plans: same tile geometry, different register blocking
     const bool dc_f = batch == 1 && !c->opt_async_fwd && (c->opt_decoupled & 2);
@@ -1272,17 +1281,18 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     const size_t terms_bytes = (o->terms.size() + 1) * sizeof(ObsTerm);
     const size_t tab_off = (terms_bytes + 255) & ~(size_t)255;
     const size_t raw_off = (tab_off + tab_bytes + 1024 + 255) & ~(size_t)255;   // batched: raw axes/angles/qmap staging
-    const size_t raw_bytes = batch > 1 ? (size_t)batch * L * n * (sizeof(double) + sizeof(int32_t)) + 2 * (size_t)P * GS * sizeof(int) + 1024 : 0;
+    const bool dev_tables = batch > 1 || dev != nullptr;   // build the gate tables on the device from raw axes / angles
+    const size_t raw_bytes = dev_tables ? (size_t)batch * L * n * (sizeof(double) + sizeof(int32_t)) + 2 * (size_t)P * GS * sizeof(int) + 1024 : 0;
     QR_TRY(ensure_small(c, raw_off + raw_bytes + 1024));
-    QR_TRY(ensure_pin(c, batch > 1 ? std::max((size_t)1 << 16, (size_t)batch * (1 + (size_t)L * P * QR_SLOTS) * sizeof(double) + 8192)
-                                   : tab_off + tab_bytes + 1024));
-    if (batch > 1) {
+    QR_TRY(ensure_pin(c, dev_tables ? std::max((size_t)1 << 16, (size_t)batch * (1 + (size_t)L * P * QR_SLOTS) * sizeof(double) + 8192)
+                                    : tab_off + tab_bytes + 1024));
+    if (dev_tables) {
         // device-side table build: upload raw parameters + the slot->qubit maps of both directions
         char* d_raw = (char*)c->d_small + raw_off;
         double* d_angles = (double*)d_raw;
         int* d_axes = (int*)(d_raw + (size_t)batch * L * n * sizeof(double));
         int* d_qmap = d_axes + (size_t)batch * L * n;
-        int* qmap = (int*)c->h_pin;
+        int* qmap = (int*)(c->h_pin + tab_off);   // own staging slot: offset 0 is reused for the observable terms below
         for (int dir = 0; dir < 2; ++dir)
             for (int p = 0; p < P; ++p)
                 for (int s2 = 0; s2 < GS; ++s2) {
@@ -1290,10 +1300,10 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
                     qmap[((size_t)dir * P + p) * GS + s2] = gb < 0 ? -1 : n - 1 - gb;
                 }
         CUDA_TRY(cudaMemcpyAsync(d_qmap, qmap, 2 * (size_t)P * GS * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(d_angles, angles, (size_t)batch * L * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        if (!dev) CUDA_TRY(cudaMemcpyAsync(d_angles, angles, (size_t)batch * L * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaMemcpyAsync(d_axes, axes, (size_t)batch * L * n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         const i64 total = (i64)batch * per_batch;
-        QR_LAUNCH(k_build_gates, grid_for(c, (u64)total), QR_BLOCK, 0, c->stream, (const int*)d_axes, (const double*)d_angles,
+        QR_LAUNCH(k_build_gates, grid_for(c, (u64)total), QR_BLOCK, 0, c->stream, (const int*)d_axes, dev ? dev->d_angles : (const double*)d_angles,
                   (const int*)d_qmap, (GatePOut*)((char*)c->d_small + tab_off), batch, L, n, P, GS, want_grad ? 2 : 1);
         KERNEL_CHECK();
         c->perf.kernel_launches++;
@@ -1428,6 +1438,16 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
         }
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    if (dev) {   // results stay on the device; tell the caller how to read the slot sums
+        for (int p = 0; p < P; ++p)
+            for (int s2 = 0; s2 < GS; ++s2) {
+                const int gb = lp.pass[p].gbit[s2];
+                dev->slot_qubit_out[p * GS + s2] = gb < 0 ? -1 : n - 1 - gb;
+            }
+        *dev->passes_out = P;
+        c->psi = lam;
+        return 0;
+    }
     // ---- results ----
     const size_t nres = (size_t)batch * (1 + (want_grad ? slots_per_state : 0));
     QR_TRY(ensure_pin(c, nres * sizeof(double)));
@@ -1530,6 +1550,83 @@ extern "C" int qr_mcclean_grad_batch(qr_ctx* c, int batch, int L, const int32_t*
     c->perf = total;
     // leave a valid single state in psi (state 0 of the last chunk)
     return 0;
+}
+
+// Optimiser loop on the device (optimization.py:41-91 McCleanOpt.step repeated `steps` times):
+// gradient -> parameter update -> gate tables -> next gradient, all stream ordered, one synchronisation at the end.
+extern "C" int qr_mcclean_optimize(qr_ctx* c, int L, const int32_t* axes, double* angles, const qr_obs* o, int rule,
+                                   double* hyper, int* iter_inout, double* m_inout, double* v_inout, int steps,
+                                   double* cost_history, double* param_history) {
+    QR_TRY(check_mcclean_args(c, L, axes, angles, o));
+    if (!use_fused(c)) return fail(QR_EINVAL, "the device optimiser loop needs the fused path (>= 4 qubits, QR_OPT_FUSION)");
+    if (rule < 0 || rule > 2 || !hyper || !iter_inout || steps < 0 || (steps > 0 && !cost_history)) return fail(QR_EINVAL, "bad optimiser arguments");
+    if (rule == 0 && (!m_inout || !v_inout)) return fail(QR_EINVAL, "Adam needs the moment arrays");
+    if (steps == 0 || L == 0) return 0;
+    QR_TRY(use_device(c));
+    perf_reset(c);
+    const size_t np_ = (size_t)L * c->n;
+    // device block: params | m | v | grad | cost history | parameter history | slot map | state
+    const size_t doubles = 4 * np_ + (size_t)steps + (param_history ? (size_t)steps * np_ : 0);
+    const size_t map_ints = 16 * QR_GATE_SLOTS;
+    char* d_blk = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_blk, doubles * sizeof(double) + map_ints * sizeof(int) + sizeof(OptDev) + 64));
+    double* d_params = (double*)d_blk;
+    double *d_m = d_params + np_, *d_v = d_m + np_, *d_grad = d_v + np_, *d_cost = d_grad + np_;
+    double* d_hist = param_history ? d_cost + steps : nullptr;
+    int* d_map = (int*)(d_params + doubles);
+    OptDev* d_st = (OptDev*)(d_map + map_ints);
+    OptDev st;
+    memset(&st, 0, sizeof(st));
+    st.rule = rule; st.iter = *iter_inout;
+    st.step_size = hyper[0]; st.beta1 = hyper[1]; st.beta2 = hyper[2]; st.eps = hyper[3];
+    st.plateau_length = (int)hyper[4]; st.decay_rate = hyper[5]; st.cost = hyper[6]; st.plateau_counter = (int)hyper[7];
+    int rc = 0;
+    std::vector<int> slot_q(16 * QR_GATE_SLOTS, -1);
+    int P = 0;
+    do {
+        cudaError_t e;
+        if ((e = cudaMemcpyAsync(d_params, angles, np_ * sizeof(double), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
+            (e = cudaMemsetAsync(d_m, 0, 3 * np_ * sizeof(double), c->stream)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(d_st, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) {
+            rc = fail(QR_ECUDA, "optimiser setup: %s", cudaGetErrorString(e));
+            break;
+        }
+        if (rule == 0) {
+            cudaMemcpyAsync(d_m, m_inout, np_ * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+            cudaMemcpyAsync(d_v, v_inout, np_ * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+        }
+        if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { rc = fail(QR_ECUDA, "optimiser setup: %s", cudaGetErrorString(e)); break; }
+        double dummy_grad = 0.0, dummy_e = 0.0;
+        for (int it = 0; it < steps && rc == 0; ++it) {
+            DevParams dev = {d_params, slot_q.data(), &P};
+            rc = mcclean_fused(c, 1, L, axes, nullptr, o, 0, &dummy_e, &dummy_grad, &dev);
+            if (rc) break;
+            if (it == 0) {   // the slot map is the same for every step
+                if (P > 16) { rc = fail(QR_EINVAL, "internal: too many passes"); break; }
+                if ((e = cudaMemcpyAsync(d_map, slot_q.data(), (size_t)P * QR_GATE_SLOTS * sizeof(int), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
+                    (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { rc = fail(QR_ECUDA, "optimiser: %s", cudaGetErrorString(e)); break; }
+            }
+            QR_LAUNCH(k_opt_step, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_result, (const int*)d_map, L, c->n, P, QR_GATE_SLOTS, QR_SLOTS,
+                      d_params, d_m, d_v, d_grad, d_st, d_cost, d_hist, it);
+            if ((e = cudaGetLastError()) != cudaSuccess) { rc = fail(QR_ECUDA, "optimiser step: %s", cudaGetErrorString(e)); break; }
+            c->perf.kernel_launches++;
+        }
+        if (rc) break;
+        cudaMemcpyAsync(angles, d_params, np_ * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(cost_history, d_cost, (size_t)steps * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (param_history) cudaMemcpyAsync(param_history, d_hist, (size_t)steps * np_ * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (rule == 0) {
+            cudaMemcpyAsync(m_inout, d_m, np_ * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+            cudaMemcpyAsync(v_inout, d_v, np_ * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        }
+        cudaMemcpyAsync(&st, d_st, sizeof(st), cudaMemcpyDeviceToHost, c->stream);
+        if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { rc = fail(QR_ECUDA, "optimiser loop: %s", cudaGetErrorString(e)); break; }
+        *iter_inout = st.iter;
+        hyper[0] = st.step_size; hyper[6] = st.cost; hyper[7] = (double)st.plateau_counter;
+    } while (0);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_blk);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -46,6 +46,7 @@ class GradientDescent(_Rule):
     def __init__(self, parameters, hyper_parameters):
         super().__init__(parameters, hyper_parameters)
         self.decay_function = hyper_parameters.get('decay_function', lambda step_size, it: step_size)
+        self.constant_step = 'decay_function' not in hyper_parameters
 
     def step(self, gradient, *_):
         self.iter += 1
@@ -137,6 +138,40 @@ class McCleanOpt(ParametrizedCircuitOptimizer):
         self.iter += 1
         self.param_history[self.iter] = self.optimizer.parameters
         self.circuit.angles = self.optimizer.parameters
+
+    def run(self, steps):
+        """`steps` exact-gradient steps (the same sequence as `steps` calls of `step()`), executed as ONE device-side
+        loop when the circuit and the update rule support it (`McClean.optimize_on_device`: Adam, GradientDescent with a
+        constant step, RateDecayOnPlateau): gradient, parameter update and the next gate tables stay on the GPU, the
+        histories come back once at the end.  Falls back to `step()` otherwise."""
+        opt = self.optimizer
+        steps = int(min(steps, self.max_iter - 1 - self.iter))
+        rule = {Adam: 0, GradientDescent: 1, RateDecayOnPlateau: 2}.get(type(opt))
+        device_ok = (steps > 0 and rule is not None and hasattr(self.circuit, 'optimize_on_device')
+                     and self.circuit.qnum >= 4 and (rule != 1 or opt.constant_step))
+        if not device_ok:
+            for _ in range(max(steps, 0)):
+                self.step()
+            return
+        hyper = np.array([opt.step_size, getattr(opt, 'beta1', 0.), getattr(opt, 'beta2', 0.), getattr(opt, 'eps', 0.),
+                          getattr(opt, 'plateau_length', 0), getattr(opt, 'decay_rate', 0.), getattr(opt, 'cost', 0.),
+                          getattr(opt, 'plateau_counter', 0)], dtype=np.float64)
+        self.circuit.angles = np.ascontiguousarray(opt.parameters, dtype=np.float64)
+        m = opt.m if rule == 0 else None
+        v = opt.v if rule == 0 else None
+        cost, hist, it, hyper = self.circuit.optimize_on_device(rule, hyper, opt.iter, steps, m=m, v=v)
+        self.cost_history[self.iter:self.iter + steps] = cost
+        self.param_history[self.iter + 1:self.iter + 1 + steps] = hist
+        self.iter += steps
+        opt.iter = it
+        opt.step_size = hyper[0]
+        if rule == 0:
+            opt.m_hat = opt.m / (1 - opt.beta1 ** opt.iter)
+            opt.v_hat = opt.v / (1 - opt.beta2 ** opt.iter)
+        if rule == 2:
+            opt.cost, opt.plateau_counter = hyper[6], int(hyper[7])
+        opt.parameters[...] = self.circuit.angles
+        self.circuit.angles = opt.parameters
 
     def reset(self, **kwargs):
         self.__init__(self.circuit, kwargs.get('optimizer', self.optimizer_info), kwargs.get('max_iter', self.max_iter),

@@ -1,0 +1,26 @@
+"""Optimiser loop: host loop (McCleanOpt.step, one grad_run + host update per step) vs device loop (McCleanOpt.run)."""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from qradient_b200.circuit_logic import McClean
+from qradient_b200.optimization import McCleanOpt
+
+for n, L, steps in ((8, 8, 200), (12, 12, 200), (16, 16, 100), (20, 20, 50), (24, 10, 10)):
+    rng = np.random.default_rng(n)
+    zz = np.full((n, n), None); zz[0, 1] = 1.0
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    res = {}
+    for mode in ("host", "device"):
+        c = McClean(n, {"zz": zz}, L, axes=axes, angles=angles.copy())
+        o = McCleanOpt(c, {"name": "Adam", "step_size": 0.05}, max_iter=steps + 8, ini_parameters=angles.copy())
+        (o.run if mode == "device" else (lambda k: [o.step() for _ in range(k)]))(3)     # warm-up
+        t0 = time.perf_counter()
+        if mode == "device":
+            o.run(steps)
+        else:
+            for _ in range(steps):
+                o.step()
+        res[mode] = (time.perf_counter() - t0, o.cost_history[:steps + 3].copy())
+    d = np.abs(res["host"][1] - res["device"][1]).max()
+    print("n=%d L=%d steps=%d host %.3f ms/step device %.3f ms/step (x%.2f) max|dcost|=%.1e" % (
+        n, L, steps, 1e3 * res["host"][0] / steps, 1e3 * res["device"][0] / steps, res["host"][0] / res["device"][0], d), flush=True)
