@@ -7,26 +7,39 @@
 #include <cuda_runtime.h>
 #define QR_LAUNCH(kernel, grid, block, smem, stream, ...) \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
-// launch with a thread-block cluster of `cluster` CTAs along x (grid must be a multiple of it)
+// launch through cudaLaunchKernelEx: optional thread-block cluster of `cluster` CTAs along x (grid must be a
+// multiple of it) and optional programmatic dependent launch (PDL): the CTAs of this grid may be scheduled while
+// the previous kernel on the stream drains; the kernel itself orders its memory accesses with griddepcontrol.wait.
 template <class... KArgs, class... Args>
-static inline cudaError_t qr_launch_cluster(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
-                                            unsigned cluster, Args... args) {
+static inline cudaError_t qr_launch_ex(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
+                                       unsigned cluster, bool pdl, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(block);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = cluster;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute at[2];
+    unsigned na = 0;
+    if (cluster > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = cluster;
+        at[na].val.clusterDim.y = 1;
+        at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 #define QR_LAUNCH_CLUSTER(kernel, grid, block, smem, stream, cluster, ...) \
-    qr_launch_cluster(kernel, (grid), (block), (smem), (stream), (cluster), __VA_ARGS__)
+    qr_launch_ex(kernel, (grid), (block), (smem), (stream), (cluster), false, __VA_ARGS__)
+#define QR_LAUNCH_EX(kernel, grid, block, smem, stream, cluster, pdl, ...) \
+    qr_launch_ex(kernel, (grid), (block), (smem), (stream), (cluster), (pdl), __VA_ARGS__)
 #define QR_DYN_SMEM(type, name)                                   \
     extern __shared__ __align__(16) unsigned char qr_dyn_smem_[]; \
     type* name = reinterpret_cast<type*>(qr_dyn_smem_)

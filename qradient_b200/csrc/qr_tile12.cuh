@@ -211,6 +211,18 @@ __device__ __forceinline__ void qr_cp_async_commit() {}
 __device__ __forceinline__ void qr_cp_async_wait_all() {}
 #endif
 
+// ---- programmatic dependent launch (QR_OPT_PDL): the CTAs of a pass may become resident while the previous pass
+// drains (its CTAs that ran out of tiles free their slots); nothing is read from or written to global memory before
+// qr_pdl_wait(), which returns once the previous kernel on the stream has completed and its stores are visible.
+// Both instructions are no-ops when the kernel was launched without the attribute.
+#ifndef QR_HOST_EMUL
+__device__ __forceinline__ void qr_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void qr_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+__device__ __forceinline__ void qr_pdl_wait() {}
+__device__ __forceinline__ void qr_pdl_launch_dependents() {}
+#endif
+
 // ---- thread-block cluster helpers (pair kernel): rank, distributed-shared-memory loads, split barrier ----
 #ifndef QR_HOST_EMUL
 __device__ __forceinline__ unsigned qr_cluster_rank() {
@@ -340,6 +352,11 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
     const u64 toff_l = PAIR ? geo12_local(geo, (u64)(tbl & 0x3FF) | ((u64)rho << 10) | ((u64)((tbl >> 10) & 1) << 11))
                             : geo12_local(geo, (u64)tbl);
 
+    // Everything above is index arithmetic on kernel parameters.  From here on global memory is touched: wait for the
+    // previous pass (no-op without PDL), then let the next pass's CTAs queue up behind this one (at most two grids are
+    // ever co-resident because the trigger comes after the wait).
+    qr_pdl_wait();
+    qr_pdl_launch_dependents();
     const bool use_lut = PHASE && p.hidx != nullptr && (p.pre_phase || p.post_phase);
     if (use_lut) {
         for (int i = tid; i < p.lut_size; i += blockDim.x) lut_sm[i] = p.lut[i];

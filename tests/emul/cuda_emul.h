@@ -124,4 +124,6 @@ static inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = *t = (size
     emul::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kernel(__VA_ARGS__); })
 #define QR_LAUNCH_CLUSTER(kernel, grid, block, smem, stream, cluster, ...) \
     (emul::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kernel(__VA_ARGS__); }), cudaSuccess)   /* clusters: blocks run one after another */
+#define QR_LAUNCH_EX(kernel, grid, block, smem, stream, cluster, pdl, ...) \
+    (emul::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kernel(__VA_ARGS__); }), cudaSuccess)   /* PDL: kernels run one after another */
 #define QR_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emul::g_smem)

@@ -202,3 +202,44 @@ def test_pair_kernel_matches_default(n, L):
     q.state.set_option("pair", 3)
     e1, g1 = q.grad_run(b, gm)
     assert_parity(e1, g1, e0, g0, float(n - 1), 1e-12)
+
+
+@pytest.mark.parametrize("n,L", [(12, 3), (14, 6), (20, 8), (24, 3)])
+def test_programmatic_dependent_launch_is_bit_identical(n, L):
+    """QR_OPT_PDL: tile passes launched with programmatic stream serialization (the next pass's CTAs queue up while
+    the previous pass drains; every pass orders its memory accesses with griddepcontrol.wait).  Same kernels, same
+    grids, same reduction order => results must be IDENTICAL to the serialized launches; a missing dependency would
+    show up as a difference (or a run-to-run variation) because consecutive passes read what the previous one wrote."""
+    from qradient_b200.circuit_logic import McClean, Qaoa
+    from qradient_b200.optimization_problems import MaxCut
+    rng = np.random.default_rng(200 + n)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    zz = np.full((n, n), None)
+    zz[0, 1] = 1.0
+    obs = {"zz": zz, "x": np.array([0.3] + [None] * (n - 1), dtype=object)}
+    c = McClean(n, obs, L, axes=axes, angles=angles)
+    c.state.set_option("pdl", 0)
+    e0, g0 = c.grad_run()
+    r0 = c.run_expec_val()
+    for mode in (1, 2):
+        c.state.set_option("pdl", mode)
+        for _ in range(4):
+            e1, g1 = c.grad_run()
+            assert e1 == e0 and np.array_equal(g1, g0)
+        assert c.run_expec_val() == r0
+    if n <= 20:
+        B = 8
+        ax, an = rng.integers(0, 3, (B, L, n)), rng.uniform(0, 2 * np.pi, (B, L, n))
+        c.state.set_option("pdl", 0)
+        eb0, gb0 = c.grad_run_batch(an, ax)
+        c.state.set_option("pdl", 2)
+        eb1, gb1 = c.grad_run_batch(an, ax)
+        assert np.array_equal(eb0, eb1) and np.array_equal(gb0, gb1)
+    q = Qaoa(n, MaxCut(n, edge_set=[(i, i + 1) for i in range(n - 1)]).to_observable(), 3)
+    b, gm = rng.random(3), rng.random(3)
+    q.state.set_option("pdl", 0)
+    e0, g0 = q.grad_run(b, gm)
+    q.state.set_option("pdl", 2)
+    for _ in range(3):
+        e1, g1 = q.grad_run(b, gm)
+        assert e1 == e0 and np.array_equal(g1, g0)

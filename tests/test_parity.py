@@ -571,7 +571,7 @@ def test_options_and_permutation_api_validation(backend):
     """Argument checks of the kernel-selection options and of qr_perm_load / qr_state_permute."""
     n = 6
     st = State(n)
-    for name, bad in (("tile_bits", 3), ("tile_bits", 13), ("prefetch", 32), ("staged", 16), ("cluster", 16), ("pair", 4),
+    for name, bad in (("tile_bits", 3), ("tile_bits", 13), ("prefetch", 32), ("staged", 16), ("cluster", 16), ("pair", 4), ("pdl", 3),
                       ("src_order", 4), ("cache_hints", 16), ("lean", 4), ("buf_skew", 100), ("page_bits", 5), ("min_row_bits", 12)):
         with pytest.raises(ValueError):
             st.set_option(name, bad)
