@@ -72,7 +72,7 @@ struct LayerPlan {
 };
 
 #define QR_NBUF 4
-#define QR_PDL_AUTO_MAX_QUBITS 22
+#define QR_PDL_AUTO_MAX_QUBITS 21   // measured: +12 % at n = 20 (L2 resident), -4 % at n = 26 and n = 30
 
 struct qr_ctx {
     int n = 0;
@@ -117,7 +117,8 @@ struct qr_ctx {
     long long opt_src_order = 0;   // k_tile12 ladder passes enumerate tiles in source order: bit0 backward, bit1 forward
     long long opt_low_bits_pass = 0;   // k_tile12: pass that applies the gates on index bits 0-2 (0 = contiguous pass, -1 = last strided pass)
     long long opt_cache_hints = 0; // k_tile12: bit0 streaming stores, bit1 streaming loads (all passes); bits 2-3: same, out-of-place passes only
-    long long opt_pdl = 0;         // k_tile12 passes launched with programmatic stream serialization: 0 off, 1 auto (n <= 22), 2 always
+    long long opt_pair_order = 0;  // k_tile12 strided passes take their tiles in adjacent pairs: bit0 backward, bit1 forward, bit2: force the pair prefetch on
+    long long opt_pdl = 1;         // k_tile12 passes launched with programmatic stream serialization: 0 off, 1 auto (n <= 21), 2 always
     long long opt_buf_skew = 0;    // bytes between the start offsets of consecutive state buffers (multiple of 256)
     qr_perf perf;
     // ---- sharded states: this context holds one shard of an n_total-qubit register ----
@@ -319,6 +320,7 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
         case QR_OPT_BATCH_CHUNK_MB: if (v < 0 || v > 65536) return fail(QR_EINVAL, "bad batch chunk"); c->opt_batch_chunk_mb = v; break;
         case QR_OPT_DECOUPLED: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad decoupled mode"); c->opt_decoupled = v; break;
         case QR_OPT_LEAN: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad lean mode"); c->opt_lean = v; break;
+        case QR_OPT_PAIR_ORDER: if (v < 0 || v > 7) return fail(QR_EINVAL, "bad pair-order mode"); c->opt_pair_order = v; break;
         case QR_OPT_PDL: if (v < 0 || v > 2) return fail(QR_EINVAL, "bad PDL mode"); c->opt_pdl = v; break;
         case QR_OPT_PAGE_BITS: if (v != 0 && (v < 13 || v > 40)) return fail(QR_EINVAL, "bad page bits"); c->opt_page_bits = v; break;
         case QR_OPT_BUF_SKEW:
@@ -363,6 +365,7 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_SRC_ORDER: *v = c->opt_src_order; break;
         case QR_OPT_PAIR: *v = c->opt_pair; break;
         case QR_OPT_PDL: *v = c->opt_pdl; break;
+        case QR_OPT_PAIR_ORDER: *v = c->opt_pair_order; break;
         case QR_OPT_LOW_BITS_PASS: *v = c->opt_low_bits_pass; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
@@ -1124,12 +1127,17 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         x.cluster = pair ? 2 : ((want_cluster == 2 || (want_cluster == 1 && strided_pass)) && lgrid % 2 == 0 ? 2 : 1);
         // L2 prefetch of the next tile: opt_prefetch bit 4 = contiguous passes only
         if ((c->opt_prefetch & 16) && strided_pass) tp.prefetch = 0;
+        // pair order (strided in-place passes): a CTA takes adjacent tiles back to back and fetches them into L2 together
+        x.pair_order = ((c->opt_pair_order & (nv == 2 ? 1 : 2)) && strided_pass && !tp.ladder && !pair && x.cluster == 1 &&
+                        tp.tiles_log2 >= 1 && pp.c >= 1) ? 1 : 0;
+        if (x.pair_order && (c->opt_pair_order & 4)) tp.prefetch = staged == 1 ? 0 : 1;   // bit 2: with the pair prefetch in both directions
         // pair: nv half-tile exchange buffers (32 KiB each) + nv * 4 * 256 amplitudes for the partner (16 KiB each)
         const size_t lsmem = pair ? (size_t)nv * (tile_bytes / 2 + tile_bytes / 4)
                                   : (staged ? (size_t)(nv + 1) * tile_bytes : (pp.ngroups > 1 ? (size_t)nv * tile_bytes : 0));
         // programmatic dependent launch: the next pass's CTAs queue up while this one drains.  Auto (1): only where a
         // pass is short enough for the launch ramp to matter (states that fit in L2); 2: every pass.
         const bool pdl = c->opt_pdl == 2 || (c->opt_pdl == 1 && lp.n <= QR_PDL_AUTO_MAX_QUBITS);
+        if (x.pair_order && lgrid > tp.num_tiles / 2) x.pair_order = 0;   // fewer tile pairs than CTAs: keep every CTA busy
         if (x.cluster > 1 || pdl) {
             CUDA_TRY(QR_LAUNCH_EX(lfn, (unsigned)lgrid, 1u << (KK - 3), lsmem, c->stream, (unsigned)x.cluster, pdl, tp, x));
         } else {

@@ -57,6 +57,8 @@ struct Tile12X {
     int last_group;         // first local bit of the register group held at store time
     int cluster;            // thread-block cluster size of the launch (1 or 2)
     int cache_hints;        // bit0: streaming (evict-first) stores, bit1: streaming loads
+    int pair_order;         // strided passes: a CTA takes its tiles in ADJACENT pairs (t, t ^ 1: the two 128 B halves of the same
+                            // 256 B chunks) and fetches the partner / the next pair into L2 together, so DRAM sees 256 B requests
     u64 roff_first[8];      // global offset of register r at load time (group G3), gather map applied
     u64 roff_last[8];       // global offset of register r at store time (G2, or G3 when ngroups == 1)
     u64 droff_first[8];     // same as roff_first without the gather map (destination index: phase tables)
@@ -378,6 +380,18 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
         }
     };
 
+    // pull tile `nt` into L2: one 128 B line per thread and vector
+    auto prefetch_tile = [&](i64 nt, bool both) {
+#ifndef QR_HOST_EMUL
+        const i64 nb = nt >> p.tiles_log2;
+        const u64 nbase = dest_base((u64)nt & tmask);
+        const int l = tid << 3;
+        const u64 d = nbase | geo12_local(geo, (u64)l | (PAIR ? (u64)rho << 11 : 0));
+        const u64 s = p.ladder ? (ladder_map(d, p.M1, p.M2) ^ p.src_xor) : d;
+        if (both || STAGED != 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src0 + nb * p.state_stride + s));
+        if (NV == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src1 + nb * p.state_stride + s));
+#endif
+    };
     // issue the asynchronous copies of this thread's amplitudes of tile `tl` into its stage slots
     auto issue_stage = [&](i64 tl) {
         const i64 nb = tl >> p.tiles_log2;
@@ -390,23 +404,27 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
             if (NSV == 2) qr_cp_async16(stage + T + tid + (r << LG), p.src1 + nb * p.state_stride + sidx);
         }
         qr_cp_async_commit();
+        if (x.pair_order && !(tl & 1) && tl + 1 < p.num_tiles) prefetch_tile(tl + 1, true);   // the other halves of the same 256 B chunks
     };
-    if (STAGED && (i64)blockIdx.x < p.num_tiles) {
-#ifndef QR_HOST_EMUL
-        if (x.cluster > 1) asm volatile("barrier.cluster.arrive.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory");
-#endif
-        issue_stage(blockIdx.x);
-    }
 
     // Uniform trip count over the grid: with x.cluster > 1 every CTA of a cluster must reach the
     // per-tile cluster barrier the same number of times (a CTA without a tile just arrives).
     // PAIR: the two CTAs of a cluster work on the same tile; the tile loop runs over clusters.
     const i64 nworkers = PAIR ? (i64)(gridDim.x >> 1) : (i64)gridDim.x;
     const i64 worker = PAIR ? (i64)(blockIdx.x >> 1) : (i64)blockIdx.x;
-    const i64 iters = (p.num_tiles + nworkers - 1) / nworkers;
+    const bool po = x.pair_order != 0;   // (the host sets it only for an even number of tiles per state)
+    const i64 iters = po ? 2 * (((p.num_tiles >> 1) + nworkers - 1) / nworkers) : (p.num_tiles + nworkers - 1) / nworkers;
+    auto tile_at = [&](i64 it) -> i64 { return po ? 2 * (worker + (it >> 1) * nworkers) + (it & 1) : worker + it * nworkers; };
+    if (STAGED && tile_at(0) < p.num_tiles) {
+#ifndef QR_HOST_EMUL
+        if (x.cluster > 1) asm volatile("barrier.cluster.arrive.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory");
+#endif
+        issue_stage(tile_at(0));
+    }
+
     unsigned pair_count = 0;     // PAIR: hand-overs done so far (mbarrier phase parities)
     for (i64 it = 0; it < iters; ++it) {
-        const i64 tile = worker + it * nworkers;
+        const i64 tile = tile_at(it);
 #ifndef QR_HOST_EMUL
         // CTAs of a cluster own ADJACENT tiles (rows 128 B apart in the strided passes).  Aligning their
         // loads in time lets the DRAM controller serve both halves of a 256 B chunk from one row
@@ -479,7 +497,7 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
                 if (NSV == 2) a[NV - 1][r] = stage[T + tid + (r << LG)];
                 else if (NV == 2) a[NV - 1][r] = p.src1[sbt ^ x.roff_first[r]];
             }
-            if (tile + gridDim.x < p.num_tiles) issue_stage(tile + gridDim.x);   // lands while this tile is computed
+            if (it + 1 < iters && tile_at(it + 1) < p.num_tiles) issue_stage(tile_at(it + 1));   // lands while this tile is computed
         } else {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
@@ -488,21 +506,18 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
                 if (NV == 2) a[NV - 1][r] = (x.cache_hints & 2) ? qr_ldcs(p.src1 + s) : p.src1[s];
             }
         }
-#ifndef QR_HOST_EMUL
         if (p.prefetch) {   // pull the next tile of this CTA into L2 while this one is computed
-            const i64 nt = tile + nworkers * p.prefetch;
-            if (nt < p.num_tiles) {
-                const i64 nb = nt >> p.tiles_log2;
-                const u64 t2 = (u64)nt & tmask;
-                const u64 nbase = dest_base(t2);
-                const int l = tid << 3;   // one 128 B line per thread
-                const u64 d = nbase | geo12_local(geo, (u64)l | (PAIR ? (u64)rho << 11 : 0));
-                const u64 s = p.ladder ? (ladder_map(d, p.M1, p.M2) ^ p.src_xor) : d;
-                if (STAGED != 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src0 + nb * p.state_stride + s));
-                if (NV == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src1 + nb * p.state_stride + s));
+            if (po) {       // pairs: the partner of the very first tile, then both tiles of the next pair at once
+                if (it == 0 && tile + 1 < p.num_tiles) prefetch_tile(tile + 1, false);
+                if ((it & 1) && it + 1 < iters) {
+                    const i64 nt = tile_at(it + 1);
+                    if (nt + 1 < p.num_tiles) { prefetch_tile(nt, false); prefetch_tile(nt + 1, false); }
+                }
+            } else {
+                const i64 nt = tile + nworkers * p.prefetch;
+                if (nt < p.num_tiles) prefetch_tile(nt, false);
             }
         }
-#endif
         // ---- Z gradients: w = Im(conj(lambda) psi), signed sums over the register bits, total for the thread bits ----
         if (NV == 2 && has_zgate) {
             double w[8];

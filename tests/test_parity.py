@@ -187,6 +187,41 @@ def test_kernel_variants_vs_oracle(backend, opts, n, L, tile_bits):
     assert_parity(e, g, e_ref, g_ref, float(n - 1), TOL)
 
 
+@pytest.mark.parametrize("opts", [dict(pair_order=7), dict(pair_order=3, prefetch=5), dict(pair_order=1, staged=1, tile_bits=12),
+                                  dict(pair_order=7, staged=3, tile_bits=12), dict(pair_order=7, tile_bits=12), dict(pair_order=2)])
+@pytest.mark.parametrize("n,L", [(15, 2), (16, 2)])
+def test_pair_order_matches_default(backend, opts, n, L):
+    """QR_OPT_PAIR_ORDER: in the strided passes a CTA takes its tiles in adjacent pairs (the two 128 B halves of the
+    same 256 B chunks) -- a different tile enumeration (and prefetch / staging schedule), same arithmetic per tile."""
+    rng = np.random.default_rng(1500 + n)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    obs = mixed_obs(n)
+    c = McClean(n, obs, L, axes=axes, angles=angles)
+    e0, g0 = c.grad_run()
+    v0 = np.array(c.state.vec)
+    r0 = c.run_expec_val()
+    for k, v in opts.items():
+        c.state.set_option(k, v)
+    e1, g1 = c.grad_run()
+    assert_parity(e1, g1, e0, g0, obs_scale(obs), 1e-12)
+    np.testing.assert_allclose(c.state.vec, v0, atol=1e-13 * obs_scale(obs))
+    assert abs(c.run_expec_val() - r0) < 1e-12 * obs_scale(obs)
+    B = 3
+    ax, an = rng.integers(0, 3, (B, L, n)), rng.uniform(0, 2 * np.pi, (B, L, n))
+    eb, gb = c.grad_run_batch(an, ax)
+    d = McClean(n, obs, L, axes=ax[2], angles=an[2])
+    e2, g2 = d.grad_run()
+    assert_parity(eb[2], gb[2], e2, g2, obs_scale(obs), 1e-12)
+    edges = [(i, i + 1) for i in range(n - 1)]
+    q = Qaoa(n, MaxCut(n, edge_set=edges).to_observable(), 2)
+    b, gm = rng.random(2), rng.random(2)
+    e0, g0 = q.grad_run(b, gm)
+    for k, v in opts.items():
+        q.state.set_option(k, v)
+    e1, g1 = q.grad_run(b, gm)
+    assert_parity(e1, g1, e0, g0, float(n - 1), 1e-12)
+
+
 @pytest.mark.parametrize("n,L", [(12, 3), (14, 2), (16, 2), (17, 1), (19, 1)])
 def test_lean_tile_kernel_group_counts(backend, n, L):
     """k_tile12 (qr_tile12.cuh): strided passes with 1, 2 and 3 register groups next to the 4-group first
@@ -571,7 +606,7 @@ def test_options_and_permutation_api_validation(backend):
     """Argument checks of the kernel-selection options and of qr_perm_load / qr_state_permute."""
     n = 6
     st = State(n)
-    for name, bad in (("tile_bits", 3), ("tile_bits", 13), ("prefetch", 32), ("staged", 16), ("cluster", 16), ("pair", 4), ("pdl", 3),
+    for name, bad in (("tile_bits", 3), ("tile_bits", 13), ("prefetch", 32), ("staged", 16), ("cluster", 16), ("pair", 4), ("pdl", 3), ("pair_order", 8),
                       ("src_order", 4), ("cache_hints", 16), ("lean", 4), ("buf_skew", 100), ("page_bits", 5), ("min_row_bits", 12)):
         with pytest.raises(ValueError):
             st.set_option(name, bad)
