@@ -117,6 +117,7 @@ struct qr_ctx {
     long long opt_src_order = 0;   // k_tile12 ladder passes enumerate tiles in source order: bit0 backward, bit1 forward
     long long opt_low_bits_pass = 0;   // k_tile12: pass that applies the gates on index bits 0-2 (0 = contiguous pass, -1 = last strided pass)
     long long opt_cache_hints = 0; // k_tile12: bit0 streaming stores, bit1 streaming loads (all passes); bits 2-3: same, out-of-place passes only
+    long long opt_defer_reduce = 1; // single circuits: one reduction launch per gradient instead of a last-CTA reduction in every backward pass
     long long opt_pair_order = 0;  // k_tile12 strided passes take their tiles in adjacent pairs: bit0 backward, bit1 forward, bit2: force the pair prefetch on
     long long opt_pdl = 1;         // k_tile12 passes launched with programmatic stream serialization: 0 off, 1 auto (n <= 21), 2 always
     long long opt_buf_skew = 0;    // bytes between the start offsets of consecutive state buffers (multiple of 256)
@@ -321,6 +322,7 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
         case QR_OPT_DECOUPLED: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad decoupled mode"); c->opt_decoupled = v; break;
         case QR_OPT_LEAN: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad lean mode"); c->opt_lean = v; break;
         case QR_OPT_PAIR_ORDER: if (v < 0 || v > 7) return fail(QR_EINVAL, "bad pair-order mode"); c->opt_pair_order = v; break;
+        case QR_OPT_DEFER_REDUCE: c->opt_defer_reduce = v ? 1 : 0; break;
         case QR_OPT_PDL: if (v < 0 || v > 2) return fail(QR_EINVAL, "bad PDL mode"); c->opt_pdl = v; break;
         case QR_OPT_PAGE_BITS: if (v != 0 && (v < 13 || v > 40)) return fail(QR_EINVAL, "bad page bits"); c->opt_page_bits = v; break;
         case QR_OPT_BUF_SKEW:
@@ -365,6 +367,7 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_SRC_ORDER: *v = c->opt_src_order; break;
         case QR_OPT_PAIR: *v = c->opt_pair; break;
         case QR_OPT_PDL: *v = c->opt_pdl; break;
+        case QR_OPT_DEFER_REDUCE: *v = c->opt_defer_reduce; break;
         case QR_OPT_PAIR_ORDER: *v = c->opt_pair_order; break;
         case QR_OPT_LOW_BITS_PASS: *v = c->opt_low_bits_pass; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
@@ -995,6 +998,14 @@ static void fill_gates(const LayerPlan& lp, int pass, GateP* out, F gate_of_qubi
     }
 }
 
+// every pass runs k_tile12 on tiles of the same size => every backward pass of a gradient uses the same grid
+// (precondition of the deferred reduction, which reads the same number of per-CTA partials for every pass)
+static bool uniform_lean_plan(const LayerPlan& lp) {
+    for (int i = 0; i < lp.npasses; ++i)
+        if (!lp.pass[i].lean || lp.pass[i].k != lp.pass[0].k) return false;
+    return true;
+}
+
 typedef void (*tile_fn)(const TilePass);
 
 static tile_fn tile_kernel(int nv, int R, int async) {
@@ -1017,7 +1028,7 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
                        int gate_stride, int ladder_stacking /* -1 none, else gather of ladder(stacking) */,
                        i64 batch, i64 state_stride, int flush_per_tile, const double* ham, int pre_phase,
                        double angle_pre, int post_phase, double angle_post, int* units, const LadderSpec* spec = nullptr,
-                       double* final_out = nullptr, const double2* lut = nullptr) {
+                       double* final_out = nullptr, const double2* lut = nullptr, double* partials_at = nullptr) {
     const PassPlan& pp = lp.pass[pass];
     TilePass tp;
     memset(&tp, 0, sizeof(tp));
@@ -1060,7 +1071,7 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         QR_TRY(ensure_scratch(c, (size_t)nunits * QR_SLOTS));
         *units = (int)nunits;
     }
-    tp.partials = c->d_scratch;
+    tp.partials = partials_at ? partials_at : c->d_scratch;   // partials_at: a slice of d_scratch the caller has sized (deferred reduction)
     tp.final_out = (nv == 2 && !flush_per_tile) ? final_out : nullptr;
     tp.done_counter = c->d_counter;
     if (pp.lean) {   // lean static kernel (k = 12, 512 threads)
@@ -1119,7 +1130,7 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
             const i64 nunits = flush_per_tile ? tp.num_tiles : lgrid;
             QR_TRY(ensure_scratch(c, (size_t)nunits * QR_SLOTS));
             *units = (int)nunits;
-            tp.partials = c->d_scratch;
+            tp.partials = partials_at ? partials_at : c->d_scratch;
         }
         // backward passes: clusters of 2 CTAs take adjacent tiles and align their loads (see k_tile12)
         const int want_cluster = (nv == 2 ? (int)(c->opt_cluster & 3) : (int)((c->opt_cluster >> 2) & 3));
@@ -1394,7 +1405,10 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     int lam = -1;
     if (want_grad) { lam = other_buf(c, c->psi); QR_TRY(ensure_buf(c, lam)); }
     const int ogrid = grid_for(c, c->N);
-    QR_TRY(ensure_scratch(c, (size_t)ogrid * std::max<i64>(batch, 1)));
+    // deferred second-stage reduction: each backward pass keeps its per-CTA partials in its own slice of d_scratch
+    const bool defer = want_grad && batch == 1 && c->opt_defer_reduce && L > 0 && uniform_lean_plan(lp);
+    const size_t unit_cap = (size_t)c->sm_count * 16;   // upper bound on the CTAs of a pass (launch_pass: per_sm <= 16)
+    QR_TRY(ensure_scratch(c, std::max<size_t>((size_t)ogrid * (size_t)std::max<i64>(batch, 1), defer ? (size_t)L * P * unit_cap * QR_SLOTS : (size_t)0)));
     QR_TRY(ensure_result(c, (size_t)batch * (1 + (want_grad ? (size_t)L * P * QR_SLOTS : 0)) + 16));
     {
         QR_LAUNCH(k_apply_obs, dim3((unsigned)ogrid, (unsigned)batch), QR_BLOCK, 0, c->stream, (const double2*)c->buf[c->psi],
@@ -1413,6 +1427,7 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     double* d_slots = c->d_result + batch;
     const int slots_per_state = L * P * QR_SLOTS;
     int n_bwd_pass = 0;
+    int defer_units = -1;
     if (want_grad) {
         for (int i = L - 1; i >= 0; --i, ++lay) {
             // table index of backward layer i: forward tables come first, backward tables are stored in layer order
@@ -1430,7 +1445,12 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
                 int units = 0;
                 QR_TRY(launch_pass(c, lp, p, 2, io, d_tab + ((size_t)tlay * P + p) * GS, gate_stride, lad, batch, stride,
                                    flush, nullptr, 0, 0, 0, 0, &units, nullptr,
-                                   batch == 1 ? d_slots + ((size_t)i * P + p) * QR_SLOTS : nullptr));
+                                   (batch == 1 && !defer) ? d_slots + ((size_t)i * P + p) * QR_SLOTS : nullptr, nullptr,
+                                   defer ? c->d_scratch + ((size_t)i * P + p) * unit_cap * QR_SLOTS : nullptr));
+                if (defer) {
+                    if (defer_units >= 0 && units != defer_units) return fail(QR_ESTATE, "internal: passes of one gradient use different grids");
+                    defer_units = units;
+                }
                 c->psi = dpsi;
                 lam = dlam;
                 ++n_bwd_pass;
@@ -1443,6 +1463,12 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
                 KERNEL_CHECK();
                 c->perf.kernel_launches++;
             }
+        }
+        if (defer) {
+            QR_LAUNCH(k_reduce_slots_strided, (unsigned)(L * P), 32 * 16, 0, c->stream, (const double*)c->d_scratch, defer_units,
+                      (u64)unit_cap * QR_SLOTS, d_slots, QR_SLOTS);
+            KERNEL_CHECK();
+            c->perf.kernel_launches++;
         }
         if (c->opt_final_ladder && n >= 2 && L > 0 && batch == 1) {   // mc_clean.py:77 for layer 0
             const int d = other_buf(c, c->psi, lam);
@@ -1763,7 +1789,9 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
         }
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     const int g = grid_for(c, c->N);
-    QR_TRY(ensure_scratch(c, g));
+    const bool defer = want_grad && c->opt_defer_reduce && p > 0 && uniform_lean_plan(lp);   // see mcclean_fused
+    const size_t unit_cap = (size_t)c->sm_count * 16;
+    QR_TRY(ensure_scratch(c, std::max<size_t>((size_t)g, defer ? (size_t)p * P * unit_cap * QR_SLOTS : (size_t)0)));
     QR_TRY(ensure_result(c, 1 + (size_t)p * P * QR_SLOTS + 16));
     int lam = -1;
     if (want_grad) { lam = other_buf(c, c->psi); QR_TRY(ensure_buf(c, lam)); }
@@ -1776,16 +1804,28 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
     double* d_slots = c->d_result + 1;
     int n_bwd_pass = 0;
+    int defer_units = -1;
     if (want_grad) {
         for (int i = p - 1; i >= 0; --i)
             for (int q = 0; q < P; ++q) {
                 PassIO io = {c->buf[c->psi], c->buf[lam], c->buf[c->psi], c->buf[lam]};
                 int units = 0;
                 QR_TRY(launch_pass(c, lp, q, 2, io, d_tab + ((size_t)(p + i) * P + q) * GS, 0, -1, 1, stride, 0, c->d_ham, 0, 0.0,
-                                   q == P - 1 ? 1 : 0, -gammas[i], &units, nullptr, d_slots + ((size_t)i * P + q) * QR_SLOTS,
-                                   d_lut ? d_lut + (size_t)(p + i) * c->ham_range : nullptr));
+                                   q == P - 1 ? 1 : 0, -gammas[i], &units, nullptr, defer ? nullptr : d_slots + ((size_t)i * P + q) * QR_SLOTS,
+                                   d_lut ? d_lut + (size_t)(p + i) * c->ham_range : nullptr,
+                                   defer ? c->d_scratch + ((size_t)i * P + q) * unit_cap * QR_SLOTS : nullptr));
+                if (defer) {
+                    if (defer_units >= 0 && units != defer_units) return fail(QR_ESTATE, "internal: passes of one gradient use different grids");
+                    defer_units = units;
+                }
                 ++n_bwd_pass;
             }
+        if (defer) {
+            QR_LAUNCH(k_reduce_slots_strided, (unsigned)(p * P), 32 * 16, 0, c->stream, (const double*)c->d_scratch, defer_units,
+                      (u64)unit_cap * QR_SLOTS, d_slots, QR_SLOTS);
+            KERNEL_CHECK();
+            c->perf.kernel_launches++;
+        }
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
     const size_t nres = 1 + (want_grad ? (size_t)p * P * QR_SLOTS : 0);

@@ -74,6 +74,12 @@ struct TilePass {
     int prefetch;
 };
 
+// Deferred second stage of the gradient reductions (QR_OPT_DEFER_REDUCE): every backward pass of a gradient leaves its
+// per-CTA partials in its own slice of the scratch buffer, and ONE launch after the sweep adds them -- block g handles
+// (layer, pass) g, warp w slot w: lane l adds the units l, l+32, ... and a fixed shuffle tree finishes.  Same order of
+// additions as the fused last-CTA reduction of k_tile12, without its fence + atomic + tail on every pass.
+__global__ void k_reduce_slots_strided(const double* __restrict__ partial, int units, u64 group_stride, double* __restrict__ out,
+                                       int out_stride);
 template <int R>
 __device__ __forceinline__ int qr_swz(int l) { return l ^ ((l >> R) & 7); }
 
@@ -708,4 +714,16 @@ __global__ void __launch_bounds__(256) k_global_gates(const GlobalGates p) {
             if (threadIdx.x == 0) p.partials[(u64)blockIdx.x * 4 + i] = s;
         }
     }
+}
+
+__global__ void k_reduce_slots_strided(const double* __restrict__ partial, int units, u64 group_stride, double* __restrict__ out,
+                                       int out_stride) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double* base = partial + (u64)blockIdx.x * group_stride;
+    double v = 0.0;
+    if (w < QR_SLOTS)
+        for (int u = lane; u < units; u += 32) v += base[(u64)u * QR_SLOTS + w];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (w < QR_SLOTS && lane == 0) out[(u64)blockIdx.x * out_stride + w] = v;
 }
