@@ -65,7 +65,7 @@ enum {
     QR_OPT_LOW_BITS_PASS = 23, /* k_tile12: pass applying the gates on index bits 0-2: 0 = contiguous pass, k = k-th strided pass, -1 = last */
     QR_OPT_SRC_ORDER = 24,    /* k_tile12 ladder passes enumerate tiles in source order (sequential reads): bit0 backward, bit1 forward (default 0: measured neutral) */
     QR_OPT_PAIR = 25,         /* k_tile12 pair kernel: clusters of two half-size CTAs share a 12-bit tile over distributed shared memory: bit0 backward, bit1 forward */
-    QR_OPT_PDL = 26,          /* k_tile12 passes use programmatic dependent launch (griddepcontrol): 0 off, 1 (default) auto: registers that fit in L2 (n <= 21), 2 always */
+    QR_OPT_PDL = 26,          /* k_tile12 passes use programmatic dependent launch (griddepcontrol): 0 off, 1 (default) auto: short passes (n <= 22), 2 always */
     QR_OPT_PAIR_ORDER = 27,   /* k_tile12 strided passes: a CTA takes adjacent tiles (the two 128 B halves of the same 256 B chunks) back to back and prefetches them together: bit0 backward, bit1 forward, bit2 force the prefetch on */
     QR_OPT_DEFER_REDUCE = 28, /* 1 (default): single circuits add the per-CTA gradient partials of all backward passes in ONE launch after the sweep; 0: last-CTA reduction fused into every pass */
     QR_OPT_PAGE_BITS = 17     /* log2 amplitudes per memory page (17 = 2 MiB): strided passes share the index bits above it; 0 (default) = off */

@@ -72,7 +72,7 @@ struct LayerPlan {
 };
 
 #define QR_NBUF 4
-#define QR_PDL_AUTO_MAX_QUBITS 21   // measured: +12 % at n = 20 (L2 resident), -4 % at n = 26 and n = 30
+#define QR_PDL_AUTO_MAX_QUBITS 22   // measured (profiles/r1_pdl_sweep.log, r1_ab_pdl.log): +24 % at n = 16, +12 % at 20, +3.5 % at 22, +1 % at 24; -4 % for QAOA-26 and n = 30
 
 struct qr_ctx {
     int n = 0;
@@ -119,7 +119,7 @@ struct qr_ctx {
     long long opt_cache_hints = 0; // k_tile12: bit0 streaming stores, bit1 streaming loads (all passes); bits 2-3: same, out-of-place passes only
     long long opt_defer_reduce = 1; // single circuits: one reduction launch per gradient instead of a last-CTA reduction in every backward pass
     long long opt_pair_order = 0;  // k_tile12 strided passes take their tiles in adjacent pairs: bit0 backward, bit1 forward, bit2: force the pair prefetch on
-    long long opt_pdl = 1;         // k_tile12 passes launched with programmatic stream serialization: 0 off, 1 auto (n <= 21), 2 always
+    long long opt_pdl = 1;         // k_tile12 passes launched with programmatic stream serialization: 0 off, 1 auto (n <= 22), 2 always
     long long opt_buf_skew = 0;    // bytes between the start offsets of consecutive state buffers (multiple of 256)
     qr_perf perf;
     // ---- sharded states: this context holds one shard of an n_total-qubit register ----
