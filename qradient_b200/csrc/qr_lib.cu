@@ -121,6 +121,7 @@ struct qr_ctx {
     long long opt_pair_order = 0;  // k_tile12 strided passes take their tiles in adjacent pairs: bit0 backward, bit1 forward, bit2: force the pair prefetch on
     long long opt_pdl = 1;         // k_tile12 passes launched with programmatic stream serialization: 0 off, 1 auto (n <= 22), 2 always
     long long opt_buf_skew = 0;    // bytes between the start offsets of consecutive state buffers (multiple of 256)
+    bool tables_fresh = true;      // gate / phase tables were (re)written since the last tile pass: see launch_pass
     qr_perf perf;
     // ---- sharded states: this context holds one shard of an n_total-qubit register ----
     int n_total = 0, g = 0, rank = 0;
@@ -1147,7 +1148,10 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
                                   : (staged ? (size_t)(nv + 1) * tile_bytes : (pp.ngroups > 1 ? (size_t)nv * tile_bytes : 0));
         // programmatic dependent launch: the next pass's CTAs queue up while this one drains.  Auto (1): only where a
         // pass is short enough for the launch ramp to matter (states that fit in L2); 2: every pass.
-        const bool pdl = c->opt_pdl == 2 || (c->opt_pdl == 1 && lp.n <= QR_PDL_AUTO_MAX_QUBITS);
+        // The first pass after the gate / phase tables were written is launched fully serialized: k_tile12 reads the
+        // tables BEFORE griddepcontrol.wait, which is only safe once a serialized launch separates it from their writer.
+        const bool pdl = (c->opt_pdl == 2 || (c->opt_pdl == 1 && lp.n <= QR_PDL_AUTO_MAX_QUBITS)) && !c->tables_fresh;
+        c->tables_fresh = false;
         if (x.pair_order && lgrid > tp.num_tiles / 2) x.pair_order = 0;   // fewer tile pairs than CTAs: keep every CTA busy
         if (x.cluster > 1 || pdl) {
             CUDA_TRY(QR_LAUNCH_EX(lfn, (unsigned)lgrid, 1u << (KK - 3), lsmem, c->stream, (unsigned)x.cluster, pdl, tp, x));
@@ -1289,6 +1293,7 @@ struct DevParams {
 static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const double* angles, const qr_obs* o,
                          int use_current, double* e_out, double* grad, const DevParams* dev = nullptr) {
     const int n = c->n;
+    c->tables_fresh = true;
     LayerPlan lpf, lp;   // forward / backward plans: same tile geometry, different register blocking
     const bool dc_f = batch == 1 && !c->opt_async_fwd && (c->opt_decoupled & 2);
     const bool dc_b = batch == 1 && !c->opt_async_bwd && (c->opt_decoupled & 1);
@@ -1731,6 +1736,7 @@ static int qaoa_unfused(qr_ctx* c, int p, const double* betas, const double* gam
 static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gammas, int use_current, double* e_out,
                       double* grad) {
     const int n = c->n;
+    c->tables_fresh = true;
     LayerPlan lpf, lp;
     QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, pick_min_row_bits(c, n),
                      !c->opt_async_fwd && (c->opt_decoupled & 2),
@@ -2197,6 +2203,7 @@ static int shard_global_step(qr_ctx* c, ShardRun* run, int layer, int nv) {
 }
 
 extern "C" int qr_shard_step(qr_ctx* c, int step) {
+    if (c) c->tables_fresh = true;   // every step is stream-synchronised: no programmatic launch across steps
     QR_TRY(need_shard(c));
     ShardRun* run = c->run;
     if (!run) return fail(QR_ESTATE, "no sharded run in progress");

@@ -354,19 +354,81 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
     const u64 toff_l = PAIR ? geo12_local(geo, (u64)(tbl & 0x3FF) | ((u64)rho << 10) | ((u64)((tbl >> 10) & 1) << 11))
                             : geo12_local(geo, (u64)tbl);
 
-    // Everything above is index arithmetic on kernel parameters.  From here on global memory is touched: wait for the
-    // previous pass (no-op without PDL), then let the next pass's CTAs queue up behind this one (at most two grids are
-    // ever co-resident because the trigger comes after the wait).
-    qr_pdl_wait();
-    qr_pdl_launch_dependents();
-    const bool use_lut = PHASE && p.hidx != nullptr && (p.pre_phase || p.post_phase);
-    if (use_lut) {
-        for (int i = tid; i < p.lut_size; i += blockDim.x) lut_sm[i] = p.lut[i];
-    }
+    // Uniform trip count over the grid: with x.cluster > 1 every CTA of a cluster must reach the
+    // per-tile cluster barrier the same number of times (a CTA without a tile just arrives).
+    // PAIR: the two CTAs of a cluster work on the same tile; the tile loop runs over clusters.
+    const i64 nworkers = PAIR ? (i64)(gridDim.x >> 1) : (i64)gridDim.x;
+    const i64 worker = PAIR ? (i64)(blockIdx.x >> 1) : (i64)blockIdx.x;
+    const bool po = x.pair_order != 0;   // (the host sets it only for an even number of tiles per state)
+    const i64 iters = po ? 2 * (((p.num_tiles >> 1) + nworkers - 1) / nworkers) : (p.num_tiles + nworkers - 1) / nworkers;
+    auto tile_at = [&](i64 it) -> i64 { return po ? 2 * (worker + (it >> 1) * nworkers) + (it & 1) : worker + it * nworkers; };
     i64 cur_b = -1;
     double2 zt = make_double2(1.0, 0.0);   // thread factor of the merged diagonal (includes F)
     bool has_z = false;       // apply the diagonal zt * zr after the load
     bool has_zgate = false;   // the pass has an Rz: take the Z-gradient product w
+    // convert the gate table of batch element b (block-uniform): reduced shears, merged Z diagonal, per-thread factors
+    auto convert_gates = [&](i64 b) {
+        __syncthreads();
+        if (tid < QR_GATE_SLOTS) {
+            GateP g = p.gates[b * p.gate_stride + tid];
+            if (!PAIR && K < QR_GATE_SLOTS && tid >= K) g.axis = -1;
+            Gate12 o;
+            o.tau = 0.0; o.sig = 0.0; o.mode = -1; o.neg = 0;
+            double2 z0 = make_double2(1.0, 0.0), z1 = z0;
+            if (g.axis == 0 || g.axis == 1) {
+                // reduce to |phi| <= pi/2 (c >= 0): R(c, s) = -R(-c, -s)
+                const double cc = g.c < 0.0 ? -g.c : g.c, ss = g.c < 0.0 ? -g.s : g.s;
+                o.neg = g.c < 0.0 ? 1 : 0;
+                o.tau = ss / (1.0 + cc);
+                o.sig = ss;
+                o.mode = g.axis;
+            } else if (g.axis == 2) {   // Rz: (c - i s) on bit value 0, (c + i s) on bit value 1 (state.py:168-170)
+                o.mode = 4;
+                z0 = make_double2(g.c, -g.s);
+                z1 = make_double2(g.c, g.s);
+            }
+            sg[tid] = o;
+            szb[tid][0] = z0;
+            szb[tid][1] = z1;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int z = 0, neg = 0;
+            for (int i = 0; i < QR_GATE_SLOTS; ++i) { z |= (sg[i].mode == 4); neg ^= sg[i].neg; }
+            s_flags[0] = z | neg;
+            s_flags[1] = neg;
+        }
+        if (tid < 8) {
+            double2 z = make_double2(1.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) z = cmul(z, szb[LG + j][(tid >> j) & 1]);
+            szr[tid] = z;
+        }
+        __syncthreads();
+        has_z = s_flags[0] != 0;
+        has_zgate = false;
+#pragma unroll
+        for (int j = 0; j < QR_GATE_SLOTS; ++j) has_zgate = has_zgate || sg[j].mode == 4;
+        zt = make_double2(s_flags[1] ? -1.0 : 1.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < LG; ++j) zt = cmul(zt, szb[j][(tid >> j) & 1]);
+        if (PAIR) zt = cmul(zt, szb[11][rho]);
+        cur_b = b;
+    };
+
+    // Programmatic dependent launch: everything up to qr_pdl_wait() may run while the previous pass is still draining.
+    // That part touches no state vector and no reduction scratch -- only kernel parameters and the gate / phase tables,
+    // which are written once per API call BEFORE its first pass; the host launches that first pass fully serialized
+    // (launch_pass: tables_fresh), so every later pass may read them early.  The table conversion (an L2 round trip, a
+    // division, three barriers: ~1 us) thus leaves the critical path of a short pass.  After the wait, let the next
+    // pass's CTAs queue up behind this one (at most two grids are ever co-resident: the trigger comes after the wait).
+    const bool use_lut = PHASE && p.hidx != nullptr && (p.pre_phase || p.post_phase);
+    if (use_lut) {
+        for (int i = tid; i < p.lut_size; i += blockDim.x) lut_sm[i] = p.lut[i];
+    }
+    if (tile_at(0) < p.num_tiles) convert_gates(tile_at(0) >> p.tiles_log2);
+    qr_pdl_wait();
+    qr_pdl_launch_dependents();
 
     // flush helper state: sign pattern of the thread-bit Z gates is applied when partials leave the thread
     auto finalize = [&]() {
@@ -407,14 +469,6 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
         if (x.pair_order && !(tl & 1) && tl + 1 < p.num_tiles) prefetch_tile(tl + 1, true);   // the other halves of the same 256 B chunks
     };
 
-    // Uniform trip count over the grid: with x.cluster > 1 every CTA of a cluster must reach the
-    // per-tile cluster barrier the same number of times (a CTA without a tile just arrives).
-    // PAIR: the two CTAs of a cluster work on the same tile; the tile loop runs over clusters.
-    const i64 nworkers = PAIR ? (i64)(gridDim.x >> 1) : (i64)gridDim.x;
-    const i64 worker = PAIR ? (i64)(blockIdx.x >> 1) : (i64)blockIdx.x;
-    const bool po = x.pair_order != 0;   // (the host sets it only for an even number of tiles per state)
-    const i64 iters = po ? 2 * (((p.num_tiles >> 1) + nworkers - 1) / nworkers) : (p.num_tiles + nworkers - 1) / nworkers;
-    auto tile_at = [&](i64 it) -> i64 { return po ? 2 * (worker + (it >> 1) * nworkers) + (it & 1) : worker + it * nworkers; };
     if (STAGED && tile_at(0) < p.num_tiles) {
 #ifndef QR_HOST_EMUL
         if (x.cluster > 1) asm volatile("barrier.cluster.arrive.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory");
@@ -435,54 +489,7 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
         const i64 b = tile >> p.tiles_log2;
         const u64 t = (u64)tile & tmask;
         const u64 tbase = dest_base(t);
-        if (b != cur_b) {   // block-uniform: convert the gate table of this batch element
-            __syncthreads();
-            if (tid < QR_GATE_SLOTS) {
-                GateP g = p.gates[b * p.gate_stride + tid];
-                if (!PAIR && K < QR_GATE_SLOTS && tid >= K) g.axis = -1;
-                Gate12 o;
-                o.tau = 0.0; o.sig = 0.0; o.mode = -1; o.neg = 0;
-                double2 z0 = make_double2(1.0, 0.0), z1 = z0;
-                if (g.axis == 0 || g.axis == 1) {
-                    // reduce to |phi| <= pi/2 (c >= 0): R(c, s) = -R(-c, -s)
-                    const double cc = g.c < 0.0 ? -g.c : g.c, ss = g.c < 0.0 ? -g.s : g.s;
-                    o.neg = g.c < 0.0 ? 1 : 0;
-                    o.tau = ss / (1.0 + cc);
-                    o.sig = ss;
-                    o.mode = g.axis;
-                } else if (g.axis == 2) {   // Rz: (c - i s) on bit value 0, (c + i s) on bit value 1 (state.py:168-170)
-                    o.mode = 4;
-                    z0 = make_double2(g.c, -g.s);
-                    z1 = make_double2(g.c, g.s);
-                }
-                sg[tid] = o;
-                szb[tid][0] = z0;
-                szb[tid][1] = z1;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                int z = 0, neg = 0;
-                for (int i = 0; i < QR_GATE_SLOTS; ++i) { z |= (sg[i].mode == 4); neg ^= sg[i].neg; }
-                s_flags[0] = z | neg;
-                s_flags[1] = neg;
-            }
-            if (tid < 8) {
-                double2 z = make_double2(1.0, 0.0);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) z = cmul(z, szb[LG + j][(tid >> j) & 1]);
-                szr[tid] = z;
-            }
-            __syncthreads();
-            has_z = s_flags[0] != 0;
-            has_zgate = false;
-#pragma unroll
-            for (int j = 0; j < QR_GATE_SLOTS; ++j) has_zgate = has_zgate || sg[j].mode == 4;
-            zt = make_double2(s_flags[1] ? -1.0 : 1.0, 0.0);
-#pragma unroll
-            for (int j = 0; j < LG; ++j) zt = cmul(zt, szb[j][(tid >> j) & 1]);
-            if (PAIR) zt = cmul(zt, szb[11][rho]);
-            cur_b = b;
-        }
+        if (b != cur_b) convert_gates(b);   // block-uniform: a persistent CTA of a batched pass moves on to the next circuit
         // batch element offset: state_stride is a multiple of 2^n, so it can be OR-ed into the index bits
         const u64 boff = (u64)b * (u64)p.state_stride;
 
