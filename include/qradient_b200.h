@@ -68,6 +68,7 @@ enum {
     QR_OPT_PDL = 26,          /* k_tile12 passes use programmatic dependent launch (griddepcontrol): 0 off, 1 (default) auto: short passes (n <= 22), 2 always */
     QR_OPT_PAIR_ORDER = 27,   /* k_tile12 strided passes: a CTA takes adjacent tiles (the two 128 B halves of the same 256 B chunks) back to back and prefetches them together: bit0 backward, bit1 forward, bit2 force the prefetch on */
     QR_OPT_DEFER_REDUCE = 28, /* 1 (default): single circuits add the per-CTA gradient partials of all backward passes in ONE launch after the sweep; 0: last-CTA reduction fused into every pass */
+    QR_OPT_SHARD_ZSKIP = 29,  /* 1 (default): sharded states apply an Rz on a global qubit as a per-subgroup phase without the NVLink exchange (only X / Y rotations are exchanged) */
     QR_OPT_PAGE_BITS = 17     /* log2 amplitudes per memory page (17 = 2 MiB): strided passes share the index bits above it; 0 (default) = off */
 };
 
@@ -84,6 +85,7 @@ typedef struct qr_perf {
     long long kernel_launches;/* kernels launched by the last fused call                            */
     int passes_per_layer;
     int tile_bits;
+    double link_bytes;        /* sharded states: bytes this rank moved over NVLink (peer loads + peer stores) since the run began */
 } qr_perf;
 
 const char* qr_last_error(void);

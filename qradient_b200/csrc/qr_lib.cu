@@ -121,6 +121,7 @@ struct qr_ctx {
     long long opt_pair_order = 0;  // k_tile12 strided passes take their tiles in adjacent pairs: bit0 backward, bit1 forward, bit2: force the pair prefetch on
     long long opt_pdl = 1;         // k_tile12 passes launched with programmatic stream serialization: 0 off, 1 auto (n <= 22), 2 always
     long long opt_buf_skew = 0;    // bytes between the start offsets of consecutive state buffers (multiple of 256)
+    long long opt_shard_zskip = 1; // sharded states: Rz on a global qubit is applied as a per-subgroup phase, without the exchange
     bool tables_fresh = true;      // gate / phase tables were (re)written since the last tile pass: see launch_pass
     qr_perf perf;
     // ---- sharded states: this context holds one shard of an n_total-qubit register ----
@@ -324,6 +325,7 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
         case QR_OPT_LEAN: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad lean mode"); c->opt_lean = v; break;
         case QR_OPT_PAIR_ORDER: if (v < 0 || v > 7) return fail(QR_EINVAL, "bad pair-order mode"); c->opt_pair_order = v; break;
         case QR_OPT_DEFER_REDUCE: c->opt_defer_reduce = v ? 1 : 0; break;
+        case QR_OPT_SHARD_ZSKIP: c->opt_shard_zskip = v ? 1 : 0; break;
         case QR_OPT_PDL: if (v < 0 || v > 2) return fail(QR_EINVAL, "bad PDL mode"); c->opt_pdl = v; break;
         case QR_OPT_PAGE_BITS: if (v != 0 && (v < 13 || v > 40)) return fail(QR_EINVAL, "bad page bits"); c->opt_page_bits = v; break;
         case QR_OPT_BUF_SKEW:
@@ -368,6 +370,7 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_SRC_ORDER: *v = c->opt_src_order; break;
         case QR_OPT_PAIR: *v = c->opt_pair; break;
         case QR_OPT_PDL: *v = c->opt_pdl; break;
+        case QR_OPT_SHARD_ZSKIP: *v = c->opt_shard_zskip; break;
         case QR_OPT_DEFER_REDUCE: *v = c->opt_defer_reduce; break;
         case QR_OPT_PAIR_ORDER: *v = c->opt_pair_order; break;
         case QR_OPT_LOW_BITS_PASS: *v = c->opt_low_bits_pass; break;
@@ -2169,27 +2172,49 @@ static int shard_global_step(qr_ctx* c, ShardRun* run, int layer, int nv) {
     const int G = 1 << c->g, nt = c->n_total;
     GlobalGates gg;
     memset(&gg, 0, sizeof(gg));
-    gg.g = c->g;
-    gg.slice_len = c->N / G;
-    gg.slice_off = (u64)c->rank * gg.slice_len;
-    for (int rho = 0; rho < G; ++rho) {
-        gg.psi[run->pi[rho]] = c->peer[rho][c->psi];
-        if (nv == 2) gg.lam[run->pi[rho]] = c->peer[rho][run->lam];
-    }
     const double sgn = nv == 2 ? -1.0 : 1.0;
+    const int me = run->pi[c->rank];          // logical shard id held by this rank
+    // X / Y rotations form the exchange group; Rz gates are diagonal (a constant phase per subgroup, no exchange)
+    int active[4], ga = 0;
+    unsigned zmask = 0;
+    gg.zphase = make_double2(1.0, 0.0);
     for (int b = 0; b < c->g; ++b) {
         const int q = c->g - 1 - b;
         const double an = run->angles[(size_t)layer * nt + q];
-        gg.gate[b].c = std::cos(0.5 * an);
-        gg.gate[b].s = sgn * std::sin(0.5 * an);
-        gg.gate[b].axis = run->axes[(size_t)layer * nt + q];
+        const int axis = run->axes[(size_t)layer * nt + q];
+        const double cs = std::cos(0.5 * an), sn = sgn * std::sin(0.5 * an);
+        if (axis == 2 && c->opt_shard_zskip) {
+            const int v = (me >> b) & 1;       // (c - i s) on bit value 0, (c + i s) on bit value 1 (state.py:168-170)
+            const double pr = cs, pi_ = v ? sn : -sn, zr = gg.zphase.x, zi = gg.zphase.y;
+            gg.zphase = make_double2(zr * pr - zi * pi_, zr * pi_ + zi * pr);
+            gg.zslot[gg.nz] = b;
+            gg.zsign[gg.nz] = v ? -1.0 : 1.0;
+            gg.nz++;
+            zmask |= 1u << b;
+        } else {
+            gg.gate[ga].c = cs; gg.gate[ga].s = sn; gg.gate[ga].axis = axis;
+            gg.slot[ga] = b;
+            active[ga++] = b;
+        }
+    }
+    auto member = [&](int shard) { int m = 0; for (int i = 0; i < ga; ++i) m |= ((shard >> active[i]) & 1) << i; return m; };
+    gg.ga = ga;
+    gg.slice_len = c->N >> ga;
+    gg.slice_off = (u64)member(me) * gg.slice_len;
+    for (int rho = 0; rho < G; ++rho) {
+        const int t = run->pi[rho];
+        if ((t & zmask) != (me & zmask)) continue;   // another subgroup
+        gg.psi[member(t)] = c->peer[rho][c->psi];
+        if (nv == 2) gg.lam[member(t)] = c->peer[rho][run->lam];
     }
     const int grid = (int)std::min<u64>((gg.slice_len + 255) / 256, (u64)c->sm_count * 4);
     gg.partials = c->d_scratch;
     typedef void (*gfn)(const GlobalGates);
-    gfn fn = nullptr;
-    if (nv == 1) fn = c->g == 1 ? k_global_gates<1, 1> : c->g == 2 ? k_global_gates<1, 2> : c->g == 3 ? k_global_gates<1, 3> : k_global_gates<1, 4>;
-    else fn = c->g == 1 ? k_global_gates<2, 1> : c->g == 2 ? k_global_gates<2, 2> : c->g == 3 ? k_global_gates<2, 3> : k_global_gates<2, 4>;
+    static const gfn fns[2][5] = {
+        {k_global_gates<1, 0>, k_global_gates<1, 1>, k_global_gates<1, 2>, k_global_gates<1, 3>, k_global_gates<1, 4>},
+        {k_global_gates<2, 0>, k_global_gates<2, 1>, k_global_gates<2, 2>, k_global_gates<2, 3>, k_global_gates<2, 4>}};
+    gfn fn = fns[nv - 1][ga];
+    c->perf.link_bytes += (double)nv * 2.0 * 16.0 * (double)c->N * ((1 << ga) - 1) / (double)(1 << ga);   // in + out, this rank
     QR_LAUNCH(fn, grid, 256, 0, c->stream, gg);
     KERNEL_CHECK();
     c->perf.kernel_launches++;

@@ -676,19 +676,31 @@ __global__ void __launch_bounds__(512, (NV == 1 ? 2 : 1)) k_tile_pass_dc(const T
 // per layer and vector, overlapped with the arithmetic by the usual load/store pipelining.
 // ------------------------------------------------------------------------------------------
 #define QR_MAX_RANKS 16
+// Only X / Y rotations need the exchange.  An Rz on a global qubit is diagonal: the shards split into independent
+// subgroups (fixed values of the Z bits), each subgroup exchanges among its 2^ga members only ((2^ga - 1) / 2^ga of a
+// shard crosses NVLink instead of (G - 1) / G; nothing at all when every global gate of the layer is an Rz), the Z
+// phases of a subgroup are ONE constant factor, and the Z gradients are the signed total of Im(conj(lambda) psi).
 struct GlobalGates {
-    int g;                        // log2(ranks)
-    u64 slice_off, slice_len;     // local index range handled by this rank
-    double2* psi[QR_MAX_RANKS];   // shard base pointers ordered by LOGICAL shard id
+    int ga;                       // rank bits with X / Y rotations (the exchanged ones), 0 .. log2(ranks)
+    u64 slice_off, slice_len;     // local index range handled by this rank: 1 / 2^ga of the shard
+    double2* psi[QR_MAX_RANKS];   // the 2^ga shards of this rank's subgroup, ordered by the active bits of the LOGICAL shard id
     double2* lam[QR_MAX_RANKS];
-    GateP gate[4];                // gate on shard-id bit b (qubit g-1-b)
+    GateP gate[4];                // X / Y gate on active bit i
+    int slot[4];                  // result slot of active gate i (= its rank bit b, qubit g-1-b)
+    int nz;                       // Rz gates on the other rank bits
+    int zslot[4];                 // their result slots
+    double zsign[4];              // +1 if this subgroup's value of the bit is 0, else -1
+    double2 zphase;               // product of their phases for this subgroup
     double* partials;             // [grid][4]
 };
 
-template <int NV, int GL>
+template <int NV, int GA>
 __global__ void __launch_bounds__(256) k_global_gates(const GlobalGates p) {
-    constexpr int NA = 1 << GL;
+    constexpr int NA = 1 << GA;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double wtot = 0.0;
+    const bool zg = p.nz > 0;
+    const double2 zp = p.zphase;
     for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < p.slice_len; j += (u64)gridDim.x * blockDim.x) {
         const u64 idx = p.slice_off + j;
         double2 a[NV][NA];
@@ -697,22 +709,35 @@ __global__ void __launch_bounds__(256) k_global_gates(const GlobalGates p) {
             a[0][s] = p.psi[s][idx];
             if (NV == 2) a[NV - 1][s] = p.lam[s][idx];
         }
-        qr_gate_on_bit<NV, NA, 0>(a, p.gate[0], acc[0]);
-        if (GL > 1) qr_gate_on_bit<NV, NA, (GL > 1 ? 1 : 0)>(a, p.gate[1], acc[1]);
-        if (GL > 2) qr_gate_on_bit<NV, NA, (GL > 2 ? 2 : 0)>(a, p.gate[2], acc[2]);
-        if (GL > 3) qr_gate_on_bit<NV, NA, (GL > 3 ? 3 : 0)>(a, p.gate[3], acc[3]);
+        if (NV == 2 && zg) {
+#pragma unroll
+            for (int s = 0; s < NA; ++s) wtot += im_conj_mul(a[NV - 1][s], a[0][s]);
+        }
+        if (GA > 0) qr_gate_on_bit<NV, NA, 0>(a, p.gate[0], acc[0]);
+        if (GA > 1) qr_gate_on_bit<NV, NA, (GA > 1 ? 1 : 0)>(a, p.gate[1], acc[1]);
+        if (GA > 2) qr_gate_on_bit<NV, NA, (GA > 2 ? 2 : 0)>(a, p.gate[2], acc[2]);
+        if (GA > 3) qr_gate_on_bit<NV, NA, (GA > 3 ? 3 : 0)>(a, p.gate[3], acc[3]);
 #pragma unroll
         for (int s = 0; s < NA; ++s) {
+            if (zg) {
+                a[0][s] = cmul(a[0][s], zp);
+                if (NV == 2) a[NV - 1][s] = cmul(a[NV - 1][s], zp);
+            }
             p.psi[s][idx] = a[0][s];
             if (NV == 2) p.lam[s][idx] = a[NV - 1][s];
         }
     }
     if (NV == 2) {
+        double out[4] = {0.0, 0.0, 0.0, 0.0};
+        const double wsum = block_reduce_sum(wtot);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const double s = block_reduce_sum(acc[i]);
-            if (threadIdx.x == 0) p.partials[(u64)blockIdx.x * 4 + i] = s;
+            if (i < GA) out[p.slot[i] & 3] = s;
         }
+        for (int k = 0; k < p.nz; ++k) out[p.zslot[k] & 3] = p.zsign[k] * wsum;
+        if (threadIdx.x == 0)
+            for (int i = 0; i < 4; ++i) p.partials[(u64)blockIdx.x * 4 + i] = out[i];
     }
 }
 

@@ -19,6 +19,7 @@ ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--check", action="store_true", help="compare with the CPU oracle (small n only)")
 ap.add_argument("--tile-bits", type=int, default=0)
 ap.add_argument("--check-single", action="store_true", help="compare with the single-GPU path on rank 0")
+ap.add_argument("--opt", action="append", default=[], help="library option name=value")
 args = ap.parse_args()
 
 import torch
@@ -47,6 +48,9 @@ zz[0, 1] = 1.0
 obs = {"zz": zz, "x": np.array([0.25] + [None] * (n - 1), dtype=object)}
 circ = ShardedMcClean(n, obs, L, TorchDistComm(), axes, angles, device=device)
 circ.set_option("tile_bits", args.tile_bits)
+for o in args.opt:
+    k_, v_ = o.split("=")
+    circ.set_option(k_, int(v_))
 times = []
 for _ in range(args.reps):
     dist.barrier()
@@ -57,7 +61,7 @@ for _ in range(args.reps):
 if rank == 0:
     out = {"n": n, "L": L, "world": world, "E": e, "grad_norm": float(np.linalg.norm(g)), "s_per_gradient": min(times),
            "bytes_sched_per_gpu": 16.0 * 2.0 ** n / world * (1 + 2 * 3 * L + 2 + 4 * 3 * L),
-           "step_seconds": {k: round(v, 4) for k, v in circ.step_seconds.items()},
+           "step_seconds": {k: round(v, 4) for k, v in circ.step_seconds.items()}, "opts": args.opt,
            "nvlink_bytes_per_direction_per_global_vector_step": 16.0 * 2.0 ** n / world * (world - 1) / world}
     print(json.dumps(out))
     if args.check:

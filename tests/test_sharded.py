@@ -45,6 +45,32 @@ def test_virtual_shards_vs_oracle(backend, n, L, G, tile_bits):
         c.close()
 
 
+@pytest.mark.parametrize("n,G", [(8, 2), (8, 4), (9, 8), (10, 16)])
+def test_diagonal_global_gates_skip_the_exchange(backend, n, G):
+    """Rz on a global (rank-bit) qubit is applied as a per-subgroup phase and only X / Y rotations are exchanged
+    (QR_OPT_SHARD_ZSKIP): every Z / non-Z pattern on the global qubits against the oracle and against the full exchange."""
+    g = int(np.log2(G))
+    patterns = [[2] * g, [0] * g, [2] + [1] * (g - 1), [1] * (g - 1) + [2], [(2 if i % 2 else 0) for i in range(g)],
+                [(2 if i % 2 == 0 else 1) for i in range(g)]]
+    L = len(patterns)
+    rng = np.random.default_rng(77 + n)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    for i, pat in enumerate(patterns):
+        axes[i, :g] = pat
+    obs = mixed_obs(n)
+    e_ref, g_ref = orc.mcclean_grad_run(n, obs, axes, angles)
+    c = ShardedMcClean(n, obs, L, LocalComm(G), axes, angles)
+    try:
+        e, gr = c.grad_run()
+        assert_parity(e, gr, e_ref, g_ref, obs_scale(obs), 1e-10)
+        assert abs(c.run_expec_val() - e_ref) <= 1e-10 * obs_scale(obs)
+        c.set_option("shard_zskip", 0)
+        e0, g0 = c.grad_run()
+        assert_parity(e, gr, e0, g0, obs_scale(obs), 1e-12)
+    finally:
+        c.close()
+
+
 def test_sharded_argument_checks(backend):
     with pytest.raises(ValueError):
         ShardedMcClean(6, mixed_obs(6), 1, LocalComm(3), np.zeros((1, 6), int), np.zeros((1, 6)))
