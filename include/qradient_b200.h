@@ -54,7 +54,7 @@ enum {
     QR_OPT_ASYNC_BWD = 10,    /* same for the backward pass                                        */
     QR_OPT_TILE_BITS_STRIDED = 11, /* tile bits of the strided (non-first) passes; 0 = same as first */
     QR_OPT_MIN_ROW_BITS = 12, /* log2 of the minimum contiguous run (amplitudes) in strided passes */
-    QR_OPT_BATCH_CHUNK_MB = 13, /* batched circuits: MiB of state per buffer processed per chunk (0 = 256) */
+    QR_OPT_BATCH_CHUNK_MB = 13, /* batched circuits: MiB of state per buffer processed per chunk (0 = 512) */
     QR_OPT_DECOUPLED = 14,    /* decoupled-exchange tile kernel: bit0 backward, bit1 forward           */
     QR_OPT_LEAN = 15,         /* lean static 12-bit tile kernel (default 3): bit0 backward, bit1 forward */
     QR_OPT_BUF_SKEW = 16,     /* bytes between the start offsets of consecutive state buffers (multiple of 256) */

@@ -1506,14 +1506,23 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     for (i64 b = 0; b < batch; ++b) e_out[b] = res[b];
     if (want_grad) {
         const double* slots = res + batch;
+        // (slot offset within a layer, qubit) of the n gradient slots, once per call: the scatter below runs
+        // batch * L * n times (1.6 M for BASELINE config 4)
+        int soff[64], sq[64], ns = 0;
+        for (int p = 0; p < P; ++p)
+            for (int s = 0; s < GS; ++s) {
+                const int gb = lp.pass[p].gbit[s];
+                if (gb < 0 || ns >= 64) continue;
+                soff[ns] = p * QR_SLOTS + s;
+                sq[ns] = n - 1 - gb;
+                ++ns;
+            }
         for (i64 b = 0; b < batch; ++b)
-            for (int i = 0; i < L; ++i)
-                for (int p = 0; p < P; ++p)
-                    for (int s = 0; s < GS; ++s) {
-                        const int gb = lp.pass[p].gbit[s];
-                        if (gb < 0) continue;
-                        grad[((size_t)b * L + i) * n + (n - 1 - gb)] = slots[(size_t)b * slots_per_state + ((size_t)i * P + p) * QR_SLOTS + s];
-                    }
+            for (int i = 0; i < L; ++i) {
+                const double* src = slots + (size_t)b * slots_per_state + (size_t)i * P * QR_SLOTS;
+                double* dst = grad + ((size_t)b * L + i) * n;
+                for (int k = 0; k < ns; ++k) dst[sq[k]] = src[soff[k]];
+            }
         c->psi = lam;   // state.vec = back-propagated co-state (mc_clean.py:68-77)
     }
     // ---- perf ----
@@ -1573,7 +1582,7 @@ extern "C" int qr_mcclean_grad_batch(qr_ctx* c, int batch, int L, const int32_t*
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     const u64 per_state = c->N * sizeof(double2) * QR_NBUF;
-    const u64 chunk_bytes = c->opt_batch_chunk_mb > 0 ? (u64)c->opt_batch_chunk_mb << 20 : (u64)1 << 28;   // per buffer
+    const u64 chunk_bytes = c->opt_batch_chunk_mb > 0 ? (u64)c->opt_batch_chunk_mb << 20 : (u64)1 << 29;   // per buffer (measured: 512 MiB 81.5 ms, 256 MiB 84.4 ms, 128 MiB 88.9 ms per 8192 14x14 gradients)
     u64 chunk = std::max<u64>(1, std::min<u64>((u64)batch, chunk_bytes / std::max<u64>(per_state / QR_NBUF, 1)));
     // (re)allocate the buffers for `chunk` states
     if (c->buf_amps < c->N * chunk) {
