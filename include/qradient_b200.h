@@ -161,6 +161,14 @@ int qr_mcclean_expec(qr_ctx* ctx, int n_layers, const int32_t* axes, const doubl
  * the back-propagated co-state exactly as the reference leaves it. */
 int qr_mcclean_grad(qr_ctx* ctx, int n_layers, const int32_t* axes, const double* angles,
                     const qr_obs* obs, int use_current_state, double* e_out, double* grad_out);
+
+/* Layered circuit: |0..0> (or the current state), then n_layers x { CNOT ladder iff ladder_before[i]; one Pauli rotation
+ * per qubit, axes/angles [n_layers * n] }; E = <O>, grad[i*n+q] = dE/d angles[i,q] (grad may be NULL: forward only,
+ * state.vec = psi_final).  Engine of MeynardClassifier.run / grad_run (tutorials/meynard-classifier.ipynb cells 3, 11,
+ * 14; the class has no source in the reference snapshot): a classifier layer [ladder] Rx Ry Rz is three
+ * such sub-layers. */
+int qr_layered_grad(qr_ctx* ctx, int n_layers, const int32_t* axes, const double* angles, const unsigned char* ladder_before,
+                    int use_current_state, const qr_obs* obs, double* e_out, double* grad_out);
 /* batched extension (timing-test.ipynb cell 6 loop): B independent parameter sets on one device.
  * axes/angles: [B*L*n]; e_out[B]; grad_out[B*L*n].  ctx must have been created with n qubits. */
 int qr_mcclean_grad_batch(qr_ctx* ctx, int batch, int n_layers, const int32_t* axes, const double* angles,

@@ -385,6 +385,59 @@ def mcclean_grad_run(n, observable, axes, angles, ini_state=None, return_state=F
     return (e, grad, st.vec) if return_state else (e, grad)
 
 
+# ------------------------------------------------------------------------------------------
+# MeynardClassifier (tutorials/meynard-classifier.ipynb cells 3, 7-8, 11, 14).  PARITY UNPINNED: the class has no
+# source in the reference snapshot; the circuit below is this repo's documented definition:
+#   |0..0>;  encoding layer l:    [ladder(0) unless l == 0]  Rx(data[l,q])  Ry(enc[l,q,0])  Rz(enc[l,q,1])   on every q
+#            classifying layer l: [ladder(0) unless it is the very first layer]  Rx(cls[l,q,0]) Ry(cls[l,q,1]) Rz(cls[l,q,2])
+#   observable: Z on qubit 0 unless given.  Gradients by the exact parameter-shift rule
+#   dE/dtheta = (E(theta + pi/2) - E(theta - pi/2)) / 2  -- independent of the adjoint sweep the CUDA path uses.
+# ------------------------------------------------------------------------------------------
+def classifier_default_observable(n):
+    return {"z": np.array([1.0] + [None] * (n - 1), dtype=object)}
+
+
+def classifier_run(n, data, enc_angles, cls_angles, observable=None, return_state=False):
+    obs_dict = classifier_default_observable(n) if observable is None else observable
+    obs = obs_dict if isinstance(obs_dict, OracleObservable) else OracleObservable(n, obs_dict)
+    data, enc, cls = np.asarray(data, dtype=float), np.asarray(enc_angles, dtype=float), np.asarray(cls_angles, dtype=float)
+    st = OracleState(n)
+    first = True
+    for l in range(data.shape[0]):
+        if not first:
+            st.cnot_ladder(0)
+        first = False
+        for q in range(n):
+            st.rot(0, data[l, q], q)
+            st.rot(1, enc[l, q, 0], q)
+            st.rot(2, enc[l, q, 1], q)
+    for l in range(cls.shape[0]):
+        if not first:
+            st.cnot_ladder(0)
+        first = False
+        for q in range(n):
+            for a in range(3):
+                st.rot(a, cls[l, q, a], q)
+    e = expec_val(obs, st.vec)
+    return (e, st.vec) if return_state else e
+
+
+def classifier_grad_run(n, data, enc_angles, cls_angles, observable=None):
+    enc, cls = np.array(enc_angles, dtype=float), np.array(cls_angles, dtype=float)
+    e = classifier_run(n, data, enc, cls, observable)
+    enc_grad, cls_grad = np.empty_like(enc), np.empty_like(cls)
+    for arr, grad, which in ((enc, enc_grad, 0), (cls, cls_grad, 1)):
+        for idx in np.ndindex(arr.shape):
+            keep = arr[idx]
+            arr[idx] = keep + np.pi / 2
+            ep = classifier_run(n, data, enc, cls, observable)
+            arr[idx] = keep - np.pi / 2
+            em = classifier_run(n, data, enc, cls, observable)
+            arr[idx] = keep
+            grad[idx] = 0.5 * (ep - em)
+    return e, enc_grad, cls_grad
+
+
 def mcclean_sample_grad(n, observable, axes, angles, shot_num, rng_uniform=None):
     """mc_clean.py:117-156 parameter-shift gradient with finite shots (exact E returned)."""
     obs = observable if isinstance(observable, OracleObservable) else OracleObservable(n, observable)

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "qr_apply_ham": (c_int, [c_void_p, c_int]),
     "qr_mcclean_expec": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, P(c_double)]),
     "qr_mcclean_grad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, P(c_double), c_void_p]),
+    "qr_layered_grad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, P(c_double), c_void_p]),
     "qr_mcclean_grad_batch": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "qr_qaoa_expec": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, P(c_double)]),
     "qr_qaoa_grad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, P(c_double), c_void_p]),

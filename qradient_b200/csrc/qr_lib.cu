@@ -1223,16 +1223,22 @@ static int init_mcclean_product(qr_ctx* c) {
 }
 
 // --- un-fused McClean (gate-at-a-time kernels): QR_OPT_FUSION=0, n < 4, or cross-checks ---
+// init_mode (McClean: 0 / 1; layered circuits, qr_layered_grad: 2 / 3):
+//   0  Ry(pi/4)^n |0..0>            1  Ry(pi/4)^n applied to the current state (ini_state)
+//   2  |0..0>, no Ry layer          3  the current state, no Ry layer
+// lad_flags (null = every layer): layer i starts with the CNOT ladder iff lad_flags[i] != 0
 static int mcclean_unfused(qr_ctx* c, int L, const int32_t* axes, const double* angles, const qr_obs* o,
-                           int use_current, double* e_out, double* grad) {
+                           int use_current, double* e_out, double* grad, const unsigned char* lad_flags = nullptr) {
     const int n = c->n;
-    if (!use_current) {
+    auto has_ladder = [&](int i) { return n >= 2 && (!lad_flags || lad_flags[i]); };
+    if (use_current == 0 || use_current == 2) {
         QR_LAUNCH(k_init_basis, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[c->psi], c->N, 0, 0.0);
         KERNEL_CHECK();
     }
-    for (int q = 0; q < n; ++q) QR_TRY(launch_1q(c, c->buf[c->psi], n - 1 - q, rot_matrix(1, M_PI / 4.0)));
+    if (use_current < 2)
+        for (int q = 0; q < n; ++q) QR_TRY(launch_1q(c, c->buf[c->psi], n - 1 - q, rot_matrix(1, M_PI / 4.0)));
     for (int i = 0; i < L; ++i) {
-        if (n >= 2) {
+        if (has_ladder(i)) {
             const int dst = other_buf(c, c->psi);
             QR_TRY(ensure_buf(c, dst));
             QR_TRY(launch_ladder(c, c->psi, dst, 0));
@@ -1260,7 +1266,7 @@ static int mcclean_unfused(qr_ctx* c, int L, const int32_t* axes, const double* 
             QR_TRY(launch_1q(c, c->buf[c->psi], n - 1 - q, m));
             QR_TRY(launch_1q(c, c->buf[lam], n - 1 - q, m));
         }
-        if (n >= 2) {
+        if (has_ladder(i)) {
             const int d1 = other_buf(c, c->psi, lam);
             const int d2 = other_buf(c, c->psi, lam, d1);
             QR_TRY(ensure_buf(c, d1));
@@ -1294,7 +1300,8 @@ struct DevParams {
 };
 
 static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const double* angles, const qr_obs* o,
-                         int use_current, double* e_out, double* grad, const DevParams* dev = nullptr) {
+                         int use_current, double* e_out, double* grad, const DevParams* dev = nullptr,
+                         const unsigned char* lad_flags = nullptr) {
     const int n = c->n;
     c->tables_fresh = true;
     LayerPlan lpf, lp;   // forward / backward plans: same tile geometry, different register blocking
@@ -1307,7 +1314,8 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     const int P = lp.npasses;
     const int GS = QR_GATE_SLOTS;                 // gate entries per (layer, pass)
     const bool want_grad = grad != nullptr;
-    const bool ry_layer = use_current != 0;       // ini_state given: apply the Ry(pi/4) layer as gates
+    const bool ry_layer = use_current == 1;       // ini_state given: apply the Ry(pi/4) layer as gates (init modes: mcclean_unfused)
+    auto has_ladder = [&](int i) { return n >= 2 && (!lad_flags || lad_flags[i]); };
     // ---- gate tables: [batch][ (ry layer) + L forward + L backward ][P][GS] ----
     const int nlay_tab = (ry_layer ? 1 : 0) + L + (want_grad ? L : 0);
     const size_t per_batch = (size_t)nlay_tab * P * GS;
@@ -1372,7 +1380,12 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     // ---- forward ----
     int lay = 0;
-    if (!ry_layer) {
+    if (use_current == 2) {          // layered circuits: |0..0>, no Ry layer
+        QR_LAUNCH(k_init_basis, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[c->psi], c->N, 0, 0.0);
+        KERNEL_CHECK();
+        c->perf.kernel_launches++;
+    } else if (use_current == 3) {   // layered circuits: the current state as it is
+    } else if (!ry_layer) {
         if (batch == 1) QR_TRY(init_mcclean_product(c));
         else {
             // same product state for every batch element: N*batch amplitudes, popcount of the low n bits
@@ -1398,7 +1411,7 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
         for (int p = 0; p < P; ++p) {
             int dst = c->psi;
             int lad = -1;
-            if (p == 0 && n >= 2) { dst = other_buf(c, c->psi); QR_TRY(ensure_buf(c, dst)); lad = 0; }
+            if (p == 0 && has_ladder(i)) { dst = other_buf(c, c->psi); QR_TRY(ensure_buf(c, dst)); lad = 0; }
             PassIO io = {c->buf[c->psi], nullptr, c->buf[dst], nullptr};
             QR_TRY(launch_pass(c, lpf, p, 1, io, d_tab + ((size_t)lay * P + p) * GS, gate_stride, lad, batch, stride, 0,
                                nullptr, 0, 0, 0, 0, nullptr));
@@ -1442,7 +1455,7 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
             const int tlay = (ry_layer ? 1 : 0) + L + i;
             for (int p = 0; p < P; ++p) {
                 int dpsi = c->psi, dlam = lam, lad = -1;
-                if (p == 0 && i < L - 1 && n >= 2) {
+                if (p == 0 && i < L - 1 && has_ladder(i + 1)) {
                     dpsi = other_buf(c, c->psi, lam);
                     dlam = other_buf(c, c->psi, lam, dpsi);
                     QR_TRY(ensure_buf(c, dpsi));
@@ -1478,7 +1491,7 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
             KERNEL_CHECK();
             c->perf.kernel_launches++;
         }
-        if (c->opt_final_ladder && n >= 2 && L > 0 && batch == 1) {   // mc_clean.py:77 for layer 0
+        if (c->opt_final_ladder && L > 0 && batch == 1 && has_ladder(0)) {   // mc_clean.py:77 for layer 0
             const int d = other_buf(c, c->psi, lam);
             QR_TRY(ensure_buf(c, d));
             QR_TRY(launch_ladder(c, lam, d, 1));
@@ -1541,7 +1554,7 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     c->perf.bwd_pass_ms_avg = n_bwd_pass ? c->perf.ms_backward / n_bwd_pass : 0.0;
     // B_sched: init write 16, forward 32 per pass, observable 32 (+16 read-only if no grad), backward 64 per pass
     c->perf.algorithmic_bytes = amps * (16.0 + 32.0 * n_fwd_pass + (want_grad ? 32.0 : 16.0) + 64.0 * n_bwd_pass +
-                                        (want_grad && c->opt_final_ladder && batch == 1 && L > 0 ? 32.0 : 0.0));
+                                        (want_grad && c->opt_final_ladder && batch == 1 && L > 0 && has_ladder(0) ? 32.0 : 0.0));
     return 0;
 }
 
@@ -1566,6 +1579,21 @@ extern "C" int qr_mcclean_grad(qr_ctx* c, int L, const int32_t* axes, const doub
     double dummy;
     if (use_fused(c)) return mcclean_fused(c, 1, L, axes, angles, o, use_current_state, e_out, grad_out ? grad_out : &dummy);
     return mcclean_unfused(c, L, axes, angles, o, use_current_state, e_out, grad_out ? grad_out : &dummy);
+}
+
+// Layered circuit = McClean's layer structure with the ladder optional per layer and without the Ry(pi/4) layer:
+// the engine behind MeynardClassifier (tutorials/meynard-classifier.ipynb cells 3, 11, 14), whose layers are
+// [ladder] Rx Ry Rz on every qubit, i.e. three ladder-free / ladder-first "sub-layers" of one rotation per qubit.
+extern "C" int qr_layered_grad(qr_ctx* c, int L, const int32_t* axes, const double* angles, const unsigned char* ladder_before,
+                               int use_current_state, const qr_obs* o, double* e_out, double* grad_out) {
+    QR_TRY(check_mcclean_args(c, L, axes, angles, o));
+    if (!e_out) return fail(QR_EINVAL, "null output");
+    if (L > 0 && !ladder_before) return fail(QR_EINVAL, "null ladder flags");
+    QR_TRY(use_device(c));
+    perf_reset(c);
+    const int mode = use_current_state ? 3 : 2;
+    if (use_fused(c)) return mcclean_fused(c, 1, L, axes, angles, o, mode, e_out, grad_out, nullptr, ladder_before);
+    return mcclean_unfused(c, L, axes, angles, o, mode, e_out, grad_out, ladder_before);
 }
 
 extern "C" int qr_mcclean_grad_batch(qr_ctx* c, int batch, int L, const int32_t* axes, const double* angles,
