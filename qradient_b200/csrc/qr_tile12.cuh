@@ -189,6 +189,104 @@ __device__ __forceinline__ void qr12_exchange_1buf(double2 (&a)[NV][8], double2*
     }
 }
 
+// ---- split rounds (QR_T12_SPLIT_XCHG): the shared-memory writes of psi are issued between the FP64 work of psi and
+// lambda, and the first FP64 instructions of the next round need psi only, so the shared-memory pipe and the FP64 pipe
+// overlap inside a warp instead of taking turns (ncu at n = 30: mio_throttle 2.0, math_pipe_throttle 1.5 stalls per issue
+// with the all-FP64-then-all-exchange order).  Round = shear psi; write psi; shear lambda; inner products; write lambda.
+// The inner products are taken AFTER the un-rotations of the round: <lambda|P_q|psi> is invariant under a rotation about
+// P_q and under rotations of other qubits as long as they are applied to BOTH vectors.
+#ifndef QR_T12_SPLIT_XCHG
+#define QR_T12_SPLIT_XCHG 1
+#endif
+template <int BIT>
+__device__ __forceinline__ void qr12_shear(double2 (&av)[8], const Gate12& g) {
+    const int m = g.mode;
+    if (m != 0 && m != 1) return;
+    const double tau = g.tau, sig = g.sig;
+    if (m == 0) {   // a -= i tau b ; b -= i sig a ; a -= i tau b
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (r & (1 << BIT)) continue;
+            const int r1 = r | (1 << BIT);
+            av[r].x += tau * av[r1].y;
+            av[r].y -= tau * av[r1].x;
+            av[r1].x += sig * av[r].y;
+            av[r1].y -= sig * av[r].x;
+            av[r].x += tau * av[r1].y;
+            av[r].y -= tau * av[r1].x;
+        }
+    } else {        // a -= tau b ; b += sig a ; a -= tau b
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (r & (1 << BIT)) continue;
+            const int r1 = r | (1 << BIT);
+            av[r].x -= tau * av[r1].x;
+            av[r].y -= tau * av[r1].y;
+            av[r1].x += sig * av[r].x;
+            av[r1].y += sig * av[r].y;
+            av[r].x -= tau * av[r1].x;
+            av[r].y -= tau * av[r1].y;
+        }
+    }
+}
+template <int BIT>
+__device__ __forceinline__ void qr12_ip(const double2 (&l)[8], const double2 (&p)[8], const Gate12& g, double& acc) {
+    const int m = g.mode;
+    if (m != 0 && m != 1) return;
+    double s = 0.0;
+    if (m == 0) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (r & (1 << BIT)) continue;
+            const int r1 = r | (1 << BIT);
+            s += im_conj_mul(l[r], p[r1]) + im_conj_mul(l[r1], p[r]);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (r & (1 << BIT)) continue;
+            const int r1 = r | (1 << BIT);
+            s += re_conj_mul(l[r1], p[r]) - re_conj_mul(l[r], p[r1]);
+        }
+    }
+    acc += s;
+}
+template <int NV, int G, int NB, int K>
+__device__ __forceinline__ void qr12_round_split(double2 (&a)[NV][8], const Gate12* sg, double (&acc)[QR_SLOTS], double2* smem, int tid,
+                                                 bool write) {
+    constexpr int T = 1 << K;
+    const int bp = qr12_sbase<G>(tid);
+    qr12_shear<0>(a[0], sg[G + 0]);
+    if (NB > 1) qr12_shear<1>(a[0], sg[G + (NB > 1 ? 1 : 0)]);
+    if (NB > 2) qr12_shear<2>(a[0], sg[G + (NB > 2 ? 2 : 0)]);
+    if (write) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) smem[bp ^ qr12_cr<G>(r)] = a[0][r];
+    }
+    if (NV == 2) {
+        qr12_shear<0>(a[NV - 1], sg[G + 0]);
+        if (NB > 1) qr12_shear<1>(a[NV - 1], sg[G + (NB > 1 ? 1 : 0)]);
+        if (NB > 2) qr12_shear<2>(a[NV - 1], sg[G + (NB > 2 ? 2 : 0)]);
+        qr12_ip<0>(a[NV - 1], a[0], sg[G + 0], acc[G + 0]);
+        if (NB > 1) qr12_ip<1>(a[NV - 1], a[0], sg[G + (NB > 1 ? 1 : 0)], acc[G + (NB > 1 ? 1 : 0)]);
+        if (NB > 2) qr12_ip<2>(a[NV - 1], a[0], sg[G + (NB > 2 ? 2 : 0)], acc[G + (NB > 2 ? 2 : 0)]);
+        if (write) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) smem[T + (bp ^ qr12_cr<G>(r))] = a[NV - 1][r];
+        }
+    }
+}
+// second half of an exchange: the registers of group GN (psi first: the next round starts with psi)
+template <int NV, int GN, int K>
+__device__ __forceinline__ void qr12_xread(double2 (&a)[NV][8], const double2* smem, int tid) {
+    constexpr int T = 1 << K;
+    const int bn = qr12_sbase<GN>(tid);
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) a[v][r] = smem[v * T + (bn ^ qr12_cr<GN>(r))];
+}
+
 // streaming (evict-first) accesses: every amplitude is read once and written once per pass
 #ifndef QR_HOST_EMUL
 __device__ __forceinline__ double2 qr_ldcs(const double2* p) { return __ldcs(p); }
@@ -562,6 +660,42 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
             }
         }
         // ---- rounds ----
+        if (QR_T12_SPLIT_XCHG && !PAIR && STAGED != 1) {
+#define QR12_RS(G, NB, W) qr12_round_split<NV, G, NB, K>(a, sg, acc_all, smem, tid, W)
+#define QR12_XR(GN) qr12_xread<NV, GN, K>(a, smem, tid)
+            // one block barrier per exchange: a thread writes only the slots it read itself in the previous exchange
+            QR12_RS(LG, 3, ng > 1);
+            if (ng > 1) __syncthreads();
+            if (ng == 4) {
+                QR12_XR(0);
+                QR12_RS(0, 3, true);
+                __syncthreads();
+                QR12_XR(3);
+            } else if (ng == 3) {
+                QR12_XR(3);
+            }
+            if (K == 12 ? ng >= 3 : (ng == 3 || ng == 4)) {
+                QR12_RS(3, 3, true);
+                __syncthreads();
+                QR12_XR(6);
+            } else if (ng == 2) {
+                QR12_XR(6);
+            }
+            if (K == 12 ? ng >= 2 : (ng >= 2 && ng <= 4)) {
+                QR12_RS(6, (K == 12 ? 3 : 2), false);   // K = 11: bit 8 belongs to the load group
+                __syncthreads();   // every thread has read its last exchange: smem is free for the next tile
+            }
+            if (K == 11 && ng == 5) {   // 64 B rows: gate bits 2-10 = groups 8 | 2 | 5
+                QR12_XR(2);
+                QR12_RS(2, 3, true);
+                __syncthreads();
+                QR12_XR(5);
+                QR12_RS(5, 3, false);
+                __syncthreads();
+            }
+#undef QR12_RS
+#undef QR12_XR
+        } else {
 #define QR12_X(GP, GN) do { if (STAGED == 1) qr12_exchange_1buf<NV, GP, GN>(a, smem, tid); else qr12_exchange<NV, GP, GN, K>(a, smem, tid); } while (0)
         qr12_round<NV, LG>(a, sg, acc_all);
         if (PAIR) {
@@ -625,6 +759,7 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
             __syncthreads();
         }
 #undef QR12_X
+        }
         // ---- registers -> global (QAOA backward: diagonal-generator inner product and un-phase) ----
         const u64 dlt = tbase | toff_l | boff;
 #pragma unroll
