@@ -195,8 +195,10 @@ __device__ __forceinline__ void qr12_exchange_1buf(double2 (&a)[NV][8], double2*
 // with the all-FP64-then-all-exchange order).  Round = shear psi; write psi; shear lambda; inner products; write lambda.
 // The inner products are taken AFTER the un-rotations of the round: <lambda|P_q|psi> is invariant under a rotation about
 // P_q and under rotations of other qubits as long as they are applied to BOTH vectors.
+// MEASURED SLOWER (profiles/r1_ab_split_rounds.log: backward sweep +1 % at n = 30, +2 % at n = 26 and n = 20), so it is
+// compiled out by default and kept for A/B builds (-DQR_T12_SPLIT_XCHG=1).
 #ifndef QR_T12_SPLIT_XCHG
-#define QR_T12_SPLIT_XCHG 1
+#define QR_T12_SPLIT_XCHG 0
 #endif
 template <int BIT>
 __device__ __forceinline__ void qr12_shear(double2 (&av)[8], const Gate12& g) {
