@@ -601,6 +601,29 @@ def test_state_snapshots(backend):
         st.load(0)
 
 
+@pytest.mark.parametrize("n,L", [(12, 3), (14, 2)])
+def test_deferred_reduction_matches_per_pass_reduction(backend, n, L):
+    """QR_OPT_DEFER_REDUCE: one reduction launch per gradient (k_reduce_slots_strided) against the last-CTA reduction
+    fused into every backward pass -- same partials, same order of additions."""
+    rng = np.random.default_rng(900 + n)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    obs = mixed_obs(n)
+    c = McClean(n, obs, L, axes=axes, angles=angles)
+    e1, g1 = c.grad_run()
+    c.state.set_option("defer_reduce", 0)
+    e0, g0 = c.grad_run()
+    assert e0 == e1
+    np.testing.assert_allclose(g1, g0, rtol=0, atol=1e-15 * obs_scale(obs))
+    edges = [(i, i + 1) for i in range(n - 1)]
+    q = Qaoa(n, MaxCut(n, edge_set=edges).to_observable(), 2)
+    b, gm = rng.random(2), rng.random(2)
+    e1, g1 = q.grad_run(b, gm)
+    q.state.set_option("defer_reduce", 0)
+    e0, g0 = q.grad_run(b, gm)
+    assert e0 == e1
+    np.testing.assert_allclose(g1, g0, rtol=0, atol=1e-15 * (n - 1))
+
+
 def test_options_and_permutation_api_validation(backend):
     """Argument checks of the kernel-selection options and of qr_perm_load / qr_state_permute."""
     n = 6
