@@ -197,6 +197,10 @@ int qr_sample_bitstrings(qr_ctx* ctx, int n_shots, const double* uniforms, int64
  * eigenvalues of a diagonal observable (McClean.sample_grad_dense, mc_clean.py:207-268, matrix-free) */
 int qr_perm_load(qr_ctx* ctx, const int64_t* perm, size_t n_amps);
 int qr_state_permute(qr_ctx* ctx);
+/* dense basis change psi <- M psi (M: 2^n x 2^n, row major, interleaved re/im; n <= 12): the eigenbasis measurement of
+ * observables with x / y terms, replaces eigenvectors.transpose().conj() / lhs.dot(vec) of mc_clean.py:221-224, 255-256 */
+int qr_dense_load(qr_ctx* ctx, const double* m_re_im, size_t dim);
+int qr_state_apply_dense(qr_ctx* ctx);
 /* mean of H[idx] over the sampled indices, computed on the device from the loaded H table */
 int qr_ham_gather(qr_ctx* ctx, int n, const int64_t* idx, double* out_vals);
 

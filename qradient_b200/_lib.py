@@ -77,6 +77,8 @@ _SIGNATURES = {
                                     c_void_p, c_void_p]),
     "qr_perm_load": (c_int, [c_void_p, c_void_p, c_size_t]),
     "qr_state_permute": (c_int, [c_void_p]),
+    "qr_dense_load": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "qr_state_apply_dense": (c_int, [c_void_p]),
     "qr_shard_create": (c_int, [c_int, c_int, c_int, c_int, P(c_void_p)]),
     "qr_shard_ipc_handle": (c_int, [c_void_p, c_int, c_void_p]),
     "qr_shard_ipc_open": (c_int, [c_void_p, c_int, c_int, c_void_p]),

@@ -178,20 +178,27 @@ class McClean(ParametrizedCircuit):
         state is pushed through the remaining layers on the device, re-ordered by the ascending
         eigenvalues (`numpy.linalg.eigh` order; ties do not change which eigenvalue a draw selects) and
         sampled by the prefix-sum sampler with the uniforms scipy's `rvs` would draw.  Observables with
-        x / y terms need the dense eigensystem and are not supported."""
+        x / y terms use the dense eigensystem like the reference (numpy.linalg.eigh on the host, one dense
+        matrix-vector product per measurement on the device; n <= 12)."""
         obs = self.observable
-        if np.any(obs.term_kinds < 2):
-            raise NotImplementedError('sample_grad_dense: only observables made of z / zz terms can be measured matrix-free; '
-                                      'x / y terms need the dense 2^n x 2^n eigensystem of the reference (mc_clean.py:221)')
+        dense = bool(np.any(obs.term_kinds < 2))               # x / y terms: dense eigensystem like the reference (small n)
+        if dense and self.qnum > 12:
+            raise NotImplementedError('sample_grad_dense: observables with x / y terms are measured in the eigenbasis of the '
+                                      'dense 2^n x 2^n observable (mc_clean.py:221), which is limited to 12 qubits here')
         axes, angles = self._params()
         n, L = self.qnum, self.lnum
         st = self.state
         if getattr(self, '_eig_order', None) is None:          # the reference's has_loaded_eigensystem
-            st._load_ham(obs)
-            ham = st._download_ham()
-            self._eig_order = np.argsort(ham, kind='stable')
-            self.eigenvalues = ham[self._eig_order]
-            st.load_permutation(self._eig_order)
+            if dense:
+                self.eigenvalues, eigenvectors = np.linalg.eigh(obs.matrix.toarray())     # mc_clean.py:221
+                st.load_dense(eigenvectors.transpose().conj())                             # mc_clean.py:222
+                self._eig_order = 'dense'
+            else:
+                st._load_ham(obs)
+                ham = st._download_ham()
+                self._eig_order = np.argsort(ham, kind='stable')
+                self.eigenvalues = ham[self._eig_order]
+                st.load_permutation(self._eig_order)
         if ini_state is None:
             st.reset()
         else:
@@ -212,7 +219,10 @@ class McClean(ParametrizedCircuit):
                 st.cnot_ladder(0)
                 for q in range(n):
                     self._rot(j, q)
-            st.permute()
+            if dense:
+                st.apply_dense()                                # amplitudes in the eigenbasis (mc_clean.py:255)
+            else:
+                st.permute()
             return self.eigenvalues[self.sample_bitstrings(shot_num)].mean()
 
         for i in range(L):

@@ -396,6 +396,24 @@ __global__ void k_permute_gather(const double2* __restrict__ src, const i64* __r
     for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (u64)gridDim.x * blockDim.x) dst[k] = src[perm[k]];
 }
 
+// psi' = M psi for a dense N x N matrix (row major): the change into the eigenbasis of an observable with x / y terms
+// (mc_clean.py:221-224 diagonalises the dense observable; small registers only).  One warp per row, fp64 complex dot
+// product, fixed shuffle tree.  HBM bound on the matrix: 16 B per entry.
+__global__ void k_dense_matvec(const double2* __restrict__ M, const double2* __restrict__ x, double2* __restrict__ y, u64 N) {
+    const int lane = threadIdx.x & 31;
+    const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 row = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < N; row += warps) {
+        double2 acc = make_double2(0.0, 0.0);
+        for (u64 c = lane; c < N; c += 32) acc = cadd(acc, cmul(M[row * N + c], x[c]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        }
+        if (lane == 0) y[row] = acc;
+    }
+}
+
 __global__ void k_gather_f64(const double* __restrict__ table, const i64* __restrict__ idx, int n, double* __restrict__ out) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = table[idx[i]];
 }

@@ -86,6 +86,7 @@ struct qr_ctx {
     int psi = 0;                 // buffer holding the state vector
     double* d_ham = nullptr;     // diagonal Hamiltonian table [N]
     i64* d_perm = nullptr;       // index permutation for qr_state_permute [N]
+    double2* d_dense = nullptr;  // dense N x N basis change for qr_state_apply_dense (small registers)
     bool ham_loaded = false;
     short* d_hidx = nullptr;     // integer-valued H: H = hmin + hidx (phase look-up table path)
     bool ham_integer = false;
@@ -282,6 +283,7 @@ extern "C" int qr_ctx_destroy(qr_ctx* c) {
     for (int i = 0; i < QR_NBUF; ++i) if (c->buf_base[i]) cudaFree(c->buf_base[i]);
     if (c->d_ham) cudaFree(c->d_ham);
     if (c->d_perm) cudaFree(c->d_perm);
+    if (c->d_dense) cudaFree(c->d_dense);
     if (c->d_hidx) cudaFree(c->d_hidx);
     for (double2* sp : c->snapshots) if (sp) cudaFree(sp);
     if (c->d_scratch) cudaFree(c->d_scratch);
@@ -1991,6 +1993,37 @@ extern "C" int qr_state_permute(qr_ctx* c) {
     const int dst = other_buf(c, c->psi);
     QR_TRY(ensure_buf(c, dst));
     QR_LAUNCH(k_permute_gather, grid_for(c, c->N), QR_BLOCK, 0, c->stream, (const double2*)c->buf[c->psi], (const i64*)c->d_perm, c->buf[dst], c->N);
+    KERNEL_CHECK();
+    c->psi = dst;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// Dense basis change (observables with x / y terms are measured in the eigenbasis of the dense 2^n x 2^n observable,
+// mc_clean.py:221-224, 255-256): the caller supplies M = V^dagger of numpy.linalg.eigh, row major, interleaved re/im.
+#define QR_DENSE_MAX_QUBITS 12
+extern "C" int qr_dense_load(qr_ctx* c, const double* m_re_im, size_t dim) {
+    if (!c || !m_re_im) return fail(QR_EINVAL, "null argument");
+    if (c->n > QR_DENSE_MAX_QUBITS) return fail(QR_EINVAL, "dense basis changes are limited to %d qubits (2^n x 2^n matrix)", QR_DENSE_MAX_QUBITS);
+    if (dim != c->N) return fail(QR_EINVAL, "matrix must be 2^n x 2^n with 2^n = %llu, got %llu", (unsigned long long)c->N, (unsigned long long)dim);
+    QR_TRY(use_device(c));
+    if (!c->d_dense) {
+        cudaError_t e = cudaMalloc((void**)&c->d_dense, c->N * c->N * sizeof(double2));
+        if (e != cudaSuccess) { c->d_dense = nullptr; return fail(QR_ENOMEM, "cannot allocate the dense matrix: %s", cudaGetErrorString(e)); }
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_dense, m_re_im, c->N * c->N * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int qr_state_apply_dense(qr_ctx* c) {
+    if (!c) return fail(QR_EINVAL, "null context");
+    if (!c->d_dense) return fail(QR_ESTATE, "no dense matrix loaded (qr_dense_load)");
+    QR_TRY(use_device(c));
+    const int dst = other_buf(c, c->psi);
+    QR_TRY(ensure_buf(c, dst));
+    const int grid = (int)std::min<u64>((c->N * 32 + QR_BLOCK - 1) / QR_BLOCK, (u64)c->sm_count * 8);
+    QR_LAUNCH(k_dense_matvec, grid, QR_BLOCK, 0, c->stream, (const double2*)c->d_dense, (const double2*)c->buf[c->psi], c->buf[dst], c->N);
     KERNEL_CHECK();
     c->psi = dst;
     CUDA_TRY(cudaStreamSynchronize(c->stream));

@@ -172,6 +172,17 @@ class State:
         """vec[k] <- vec[perm[k]] on the device."""
         self._lib.call('qr_state_permute', self._ctx)
 
+    def load_dense(self, matrix):
+        """Keep a dense 2^n x 2^n matrix on the device for `apply_dense()` (eigenbasis of an observable, n <= 12)."""
+        m = np.ascontiguousarray(matrix, dtype=np.complex128)
+        if m.ndim != 2 or m.shape[0] != m.shape[1]:
+            raise ValueError('matrix must be square')
+        self._lib.call('qr_dense_load', self._ctx, _lib.ptr(m), int(m.shape[0]))
+
+    def apply_dense(self):
+        """vec <- M vec on the device."""
+        self._lib.call('qr_state_apply_dense', self._ctx)
+
     def norm_error(self):                          # state.py:331-332
         out = ctypes.c_double()
         self._lib.call('qr_norm2', self._ctx, ctypes.byref(out))

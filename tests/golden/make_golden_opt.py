@@ -70,5 +70,28 @@ def gv14_mcclean_sample_grad_dense():
     mg.save("gv14_mcclean_sample_grad_dense", **out)
 
 
+def gv15_mcclean_sample_grad_dense_xy():
+    """GV15: McClean.sample_grad_dense (mc_clean.py:207-268) for observables with x / y terms (dense eigensystem):
+    a generic one and X(0) + ZZ(0,1) (degenerate spectrum)."""
+    out = {}
+    for tag, n, L, shots, seed in (("a", 4, 3, 20, 4), ("b", 5, 2, 12, 9)):
+        rng = np.random.default_rng(31 + seed)
+        obs = {"zz": np.full((n, n), None), "x": np.array([0.5] + [None] * (n - 1), dtype=object)}
+        obs["zz"][0, 1] = 1.0
+        if tag == "a":
+            obs["y"] = np.array([None, None, 0.3, None], dtype=object)
+            obs["z"] = np.array([0.4, None, -0.7, 0.15], dtype=object)
+            obs["zz"][1, 3] = 0.5
+        axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+        c = mg.McClean(n, obs, L, axes=axes, angles=angles)
+        np.random.seed(seed)
+        e, g = c.sample_grad_dense(shot_num=shots)
+        out.update({tag + "_n": n, tag + "_L": L, tag + "_shots": shots, tag + "_seed": seed, tag + "_axes": axes, tag + "_angles": angles,
+                    tag + "_E": e, tag + "_grad": g, tag + "_eigenvalues": c.eigenvalues,
+                    **{tag + "_" + k: v for k, v in mg.obs_to_arrays(n, obs).items()}})
+    mg.save("gv15_mcclean_sample_grad_dense_xy", **out)
+
+
 if __name__ == "__main__":
     gv14_mcclean_sample_grad_dense()
+    gv15_mcclean_sample_grad_dense_xy()
