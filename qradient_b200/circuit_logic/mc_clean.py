@@ -8,6 +8,7 @@ two-vector adjoint recurrence  grad[i,q] = Im<lambda_i| P_q |psi_i>  executed in
 tile passes (qradient_b200/csrc/qr_tile.cuh); results agree to ~1e-15.
 """
 import ctypes
+import warnings
 
 import numpy as np
 
@@ -167,38 +168,109 @@ class McClean(ParametrizedCircuit):
                 grad[i, dq] = .5 * (shifted[0] - shifted[1])
         return expec_val, grad
 
+    # -- mc_clean.py:158-198: the same with one observable component drawn per parameter --------
+    def sample_grad_with_component_sampling(self, hide_progbar=True, shot_num=1, exact_expec_val=True, ini_state=None):
+        if not getattr(self.observable, 'store_components', False):
+            raise AttributeError('construct the circuit with use_observable_components=True')
+        axes, angles = self._params()
+        n, L = self.qnum, self.lnum
+        st = self.state
+        if ini_state is None:
+            st.reset()
+        else:
+            st.vec = ini_state
+        grad = np.ndarray([L, n], dtype='double')
+        for q in range(n):
+            st.yrot(np.pi / 4., q)
+        for i in range(L):
+            st.cnot_ladder(0)
+            for q in range(n):
+                self._rot(i, q)
+            st.save(i)                                  # mc_clean.py:173 state_history[i] (device snapshot)
+        expec_val = self.expec_val() if exact_expec_val else self.sample_expec_val(shot_num)
+        for i in range(L):
+            for dq in range(n):
+                component = np.random.choice(np.arange(self.observable.num_components), p=self.observable.weight_distribution)
+                shifted = []
+                for shift in (np.pi / 2, -np.pi / 2):
+                    st.load(i)
+                    self._manual_rot(i, dq, shift)
+                    for j in range(i + 1, L):
+                        st.cnot_ladder(0)
+                        for q in range(n):
+                            self._rot(j, q)
+                    shifted.append(self.sample_component_expec_val(shot_num, component))
+                grad[i, dq] = .5 * (shifted[0] - shifted[1])
+        st.free_snapshots()
+        return expec_val, grad
+
+    # -- mc_clean.py:200-205, 270-275: renamed methods keep their deprecation stubs -------------
+    def sample_grad_observable(self, *args):
+        warnings.warn('Method sample_grad_observable is now called sample_grad_dense.', DeprecationWarning, stacklevel=2)
+
+    def sample_grad_observable_with_component_sampling(self, *args):
+        warnings.warn('Method sample_grad_observable_with_component_sampling is now called '
+                      'sample_grad_dense_with_component_sampling.', DeprecationWarning, stacklevel=2)
+
     # -- mc_clean.py:207-268: finite-shot gradient, observable measured in its eigenbasis ---------
     def sample_grad_dense(self, shot_num=1, hide_progbar=True, exact_expec_val=True, ini_state=None):
         """Parameter-shift gradient where every shifted circuit is measured `shot_num` times in the eigenbasis
         of the observable (returns the exact expectation value, like the reference).
 
         The reference diagonalises the dense 2^n x 2^n observable and propagates dense left-hand-side
-        matrices (mc_clean.py:221-244).  Matrix-free here, for observables made of z / zz terms: their
-        eigenbasis is the computational basis and the eigenvalues are the diagonal H, so each shifted
-        state is pushed through the remaining layers on the device, re-ordered by the ascending
-        eigenvalues (`numpy.linalg.eigh` order; ties do not change which eigenvalue a draw selects) and
-        sampled by the prefix-sum sampler with the uniforms scipy's `rvs` would draw.  Observables with
-        x / y terms use the dense eigensystem like the reference (numpy.linalg.eigh on the host, one dense
-        matrix-vector product per measurement on the device; n <= 12)."""
+        matrices (mc_clean.py:221-244).  Here each shifted state is pushed through the remaining layers on the
+        device and then measured: observables made of z / zz terms matrix-free (their eigenbasis is the
+        computational basis and the eigenvalues are the diagonal H: the state is re-ordered by the ascending
+        eigenvalues, `numpy.linalg.eigh` order; ties do not change which eigenvalue a draw selects);
+        observables with x / y terms through the dense eigensystem like the reference (numpy.linalg.eigh on
+        the host, one dense matrix-vector product per measurement on the device; n <= 12).  The draws are those
+        scipy's `rvs` would make on the global numpy stream."""
+        if getattr(self, '_eig_basis', None) is None:          # the reference's has_loaded_eigensystem
+            self._eig_basis = self._measurement_basis(self.observable, self.observable.matrix)
+            self.eigenvalues = self._eig_basis[1]
+        return self._sample_grad_measured(self._eig_basis, shot_num, exact_expec_val, ini_state)
+
+    # -- mc_clean.py:277-350: the same with ONE observable component, drawn per call ----------------
+    def sample_grad_dense_with_component_sampling(self, shot_num=1, hide_progbar=True, exact_expec_val=True, ini_state=None):
+        """Like sample_grad_dense, but every shifted circuit is measured in the eigenbasis of ONE component of the
+        observable, drawn with np.random.choice(p=weight_distribution) before the circuit runs (mc_clean.py:301).
+        Needs use_observable_components=True at construction, like the reference.  Returns the exact expectation
+        value under the FULL observable."""
         obs = self.observable
-        dense = bool(np.any(obs.term_kinds < 2))               # x / y terms: dense eigensystem like the reference (small n)
-        if dense and self.qnum > 12:
-            raise NotImplementedError('sample_grad_dense: observables with x / y terms are measured in the eigenbasis of the '
-                                      'dense 2^n x 2^n observable (mc_clean.py:221), which is limited to 12 qubits here')
+        if not getattr(obs, 'store_components', False):
+            raise AttributeError('construct the circuit with use_observable_components=True')
+        if getattr(self, '_component_bases', None) is None:    # the reference's has_loaded_component_eigensystems
+            self._component_bases = [None] * obs.num_components
+        component = np.random.choice(np.arange(obs.num_components), p=obs.weight_distribution)
+        if self._component_bases[component] is None:
+            self._component_bases[component] = self._measurement_basis(obs.component(component), obs.component_array[component])
+        return self._sample_grad_measured(self._component_bases[component], shot_num, exact_expec_val, ini_state)
+
+    def _measurement_basis(self, obs, host_matrix):
+        """('perm', eigenvalues, order) for z / zz observables, ('dense', eigenvalues, V^dagger) otherwise."""
+        if np.any(obs.term_kinds < 2):
+            if self.qnum > 12:
+                raise NotImplementedError('observables with x / y terms are measured in the eigenbasis of the dense 2^n x 2^n '
+                                          'observable (mc_clean.py:221), which is limited to 12 qubits here')
+            eigenvalues, eigenvectors = np.linalg.eigh(host_matrix.toarray())           # mc_clean.py:221
+            return ('dense', eigenvalues, np.ascontiguousarray(eigenvectors.transpose().conj()))   # mc_clean.py:222
+        st = self.state
+        st._load_ham(obs)
+        ham = st._download_ham()
+        order = np.argsort(ham, kind='stable')
+        return ('perm', ham[order], order)
+
+    def _sample_grad_measured(self, basis, shot_num, exact_expec_val, ini_state):
+        kind, eigenvalues, table = basis
         axes, angles = self._params()
         n, L = self.qnum, self.lnum
         st = self.state
-        if getattr(self, '_eig_order', None) is None:          # the reference's has_loaded_eigensystem
-            if dense:
-                self.eigenvalues, eigenvectors = np.linalg.eigh(obs.matrix.toarray())     # mc_clean.py:221
-                st.load_dense(eigenvectors.transpose().conj())                             # mc_clean.py:222
-                self._eig_order = 'dense'
+        if self.__dict__.get('_loaded_basis') is not table:    # the device holds one permutation / one dense matrix
+            if kind == 'dense':
+                st.load_dense(table)
             else:
-                st._load_ham(obs)
-                ham = st._download_ham()
-                self._eig_order = np.argsort(ham, kind='stable')
-                self.eigenvalues = ham[self._eig_order]
-                st.load_permutation(self._eig_order)
+                st.load_permutation(table)
+            self._loaded_basis = table
         if ini_state is None:
             st.reset()
         else:
@@ -219,11 +291,11 @@ class McClean(ParametrizedCircuit):
                 st.cnot_ladder(0)
                 for q in range(n):
                     self._rot(j, q)
-            if dense:
+            if kind == 'dense':
                 st.apply_dense()                                # amplitudes in the eigenbasis (mc_clean.py:255)
             else:
                 st.permute()
-            return self.eigenvalues[self.sample_bitstrings(shot_num)].mean()
+            return eigenvalues[self.sample_bitstrings(shot_num)].mean()
 
         for i in range(L):
             for q in range(n):

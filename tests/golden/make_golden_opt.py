@@ -39,7 +39,7 @@ def run_qaoa(name, optimizer, steps, n=6, p=2):
             "qa_edges": edges, "qa_betas": betas, "qa_gammas": gammas}
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and (len(sys.argv) < 2 or "gv13" in sys.argv[1:]):
     d = {"steps": 6}
     d.update(run_mcclean("mc_adam", {"name": "Adam", "step_size": 0.05}, 6))
     d.update(run_mcclean("mc_gd", {"name": "GradientDescent", "step_size": 0.1}, 6))
@@ -92,6 +92,51 @@ def gv15_mcclean_sample_grad_dense_xy():
     mg.save("gv15_mcclean_sample_grad_dense_xy", **out)
 
 
+def gv16_mcclean_sample_grad_dense_component_sampling():
+    """GV16: McClean.sample_grad_dense_with_component_sampling (mc_clean.py:277-350): one observable component drawn with
+    np.random.choice, measured in ITS eigenbasis."""
+    out = {}
+    for tag, n, L, shots, seed in (("a", 4, 2, 16, 6), ("b", 4, 2, 10, 11)):
+        rng = np.random.default_rng(41 + seed)
+        obs = {"zz": np.full((n, n), None), "x": np.array([0.5] + [None] * (n - 1), dtype=object),
+               "z": np.array([None, 0.8, None, 0.3], dtype=object)}
+        obs["zz"][0, 1] = 1.0
+        obs["zz"][1, 3] = 0.6
+        if tag == "b":
+            obs["y"] = np.array([None, None, 0.7, None], dtype=object)
+        axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+        c = mg.McClean(n, obs, L, use_observable_components=True, axes=axes, angles=angles)
+        np.random.seed(seed)
+        e, g = c.sample_grad_dense_with_component_sampling(shot_num=shots)
+        out.update({tag + "_n": n, tag + "_L": L, tag + "_shots": shots, tag + "_seed": seed, tag + "_axes": axes, tag + "_angles": angles,
+                    tag + "_E": e, tag + "_grad": g, **{tag + "_" + k: v for k, v in mg.obs_to_arrays(n, obs).items()}})
+    mg.save("gv16_mcclean_sample_grad_dense_component_sampling", **out)
+
+
+def gv17_mcclean_sample_grad_with_component_sampling():
+    """GV17: McClean.sample_grad_with_component_sampling (mc_clean.py:158-198): per parameter one component drawn with
+    np.random.choice, per-term Bernoulli estimates (base.py:35-46) of the two shifted circuits."""
+    n, L, shots, seed = 4, 2, 30, 14
+    rng = np.random.default_rng(55)
+    obs = {"zz": np.full((n, n), None), "x": np.array([0.5] + [None] * (n - 1), dtype=object),
+           "y": np.array([None, None, 0.7, None], dtype=object), "z": np.array([None, 0.8, None, 0.3], dtype=object)}
+    obs["zz"][0, 1] = 1.0
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    c = mg.McClean(n, obs, L, use_observable_components=True, axes=axes, angles=angles)
+    np.random.seed(seed)
+    e, g = c.sample_grad_with_component_sampling(shot_num=shots)
+    mg.save("gv17_mcclean_sample_grad_component_sampling", n=n, L=L, shots=shots, seed=seed, axes=axes, angles=angles, E=e, grad=g,
+            **mg.obs_to_arrays(n, obs))
+
+
 if __name__ == "__main__":
-    gv14_mcclean_sample_grad_dense()
-    gv15_mcclean_sample_grad_dense_xy()
+    import sys as _sys
+    which = _sys.argv[1:] or ["gv14", "gv15", "gv16", "gv17"]
+    if "gv14" in which:
+        gv14_mcclean_sample_grad_dense()
+    if "gv15" in which:
+        gv15_mcclean_sample_grad_dense_xy()
+    if "gv16" in which:
+        gv16_mcclean_sample_grad_dense_component_sampling()
+    if "gv17" in which:
+        gv17_mcclean_sample_grad_with_component_sampling()
