@@ -35,6 +35,36 @@ class Projector:
     def __repr__(self):
         return 'Projector({!r}, {})'.format(self.key, ', '.join(map(str, self.qubits)))
 
+    qnum = None                 # class attribute like the reference's (observable.py:170-171)
+
+    @staticmethod
+    def set_qnum(qnum):
+        Projector.qnum = qnum
+
+    def dot(self, vec):
+        """Host-side inspection aid with the semantics of observable.py:173-177: the +1-eigenspace projector applied to a
+        host vector, matrix-free (x / y: (1 + P)/2 on the strided pairs; z / zz: the 0/1 mask of observable.py:142-166).
+        The device path never calls it -- it takes the term's expectation value instead."""
+        n = Projector.qnum
+        v = np.asarray(vec, dtype=complex)
+        if n is None or v.shape != (2 ** n,):
+            raise ValueError('Projector.dot needs Projector.set_qnum(n) and a vector with 2^n entries')
+        if self.key in ('x', 'y'):
+            q = self.qubits[0]
+            w = v.reshape(2 ** q, 2, 2 ** (n - 1 - q))
+            out = np.empty_like(w)
+            off = 1. if self.key == 'x' else -1.j          # [[.5, .5], [.5, .5]] resp. [[.5, -.5j], [.5j, .5]]
+            out[:, 0, :] = .5 * w[:, 0, :] + .5 * off * w[:, 1, :]
+            out[:, 1, :] = .5 * np.conj(off) * w[:, 0, :] + .5 * w[:, 1, :]
+            return out.reshape(-1)
+        idx = np.arange(2 ** n)
+        bit = lambda q: (idx >> (n - 1 - q)) & 1
+        if self.key == 'z':
+            mask = bit(self.qubits[0]) == 0
+        else:
+            mask = bit(self.qubits[0]) == bit(self.qubits[1])
+        return mask.astype(complex) * v
+
 
 class Observable:
     def __init__(self, qubit_number, observable, store_components=False):
@@ -130,6 +160,7 @@ class Observable:
         if self.has_loaded_projectors:
             return None
         projs = []
+        Projector.set_qnum(self.qnum)                  # observable.py:89
         for k in range(self.num_components):
             kind = ('x', 'y', 'z', 'zz')[int(self.term_kinds[k])]
             if kind == 'zz':

@@ -219,6 +219,25 @@ class State:
         self._lib.call('qr_perf_last', self._ctx, ctypes.byref(p))
         return p.as_dict()
 
+    # -- state.py:39-59: dense-operator tracking attributes (host-side scipy objects, as in the reference; every gate
+    #    variant that would use them is a 'Not implemented.' stub there and here) ---------------------------------
+    def activate_lefthandside(self):
+        if 'lhs' not in self.__dict__:
+            import scipy.sparse as sp
+            self.lhs = sp.identity(2**self.qnum, dtype='complex', format='csr')
+
+    def activate_center_matrix(self):
+        if 'center_matrix' not in self.__dict__:
+            import scipy.sparse as sp
+            self.center_matrix = sp.csr_matrix((2**self.qnum, 2**self.qnum), dtype='complex')
+            self._center_matrix_ini = sp.csr_matrix((2**self.qnum, 2**self.qnum), dtype='complex')
+
+    def set_center_matrix(self, matrix):
+        if 'center_matrix' not in self.__dict__:
+            raise AttributeError('center_matrix is not initialized yet.')     # state.py:57
+        self.center_matrix = matrix.copy()
+        self._center_matrix_ini = matrix.copy()
+
     # the reference's *_lhs / *_center_matrix variants are 'Not implemented.' stubs (state.py:99-103 ...)
     def __getattr__(self, name):
         if name.endswith('_lhs') or name.endswith('_center_matrix'):

@@ -624,6 +624,44 @@ def test_deferred_reduction_matches_per_pass_reduction(backend, n, L):
     np.testing.assert_allclose(g1, g0, rtol=0, atol=1e-15 * (n - 1))
 
 
+def test_projector_dot_and_dense_tracking_attributes(backend):
+    """API parity rows outside the hot path: Projector.dot (observable.py:126-177) against the Kronecker constructions of
+    the reference, and State.activate_lefthandside / activate_center_matrix / set_center_matrix (state.py:39-59)."""
+    import scipy.sparse as sp
+    n = 4
+    x = np.array([[.5, .5], [.5, .5]], dtype=complex)
+    y = np.array([[.5, -.5j], [.5j, .5]], dtype=complex)
+    up, dn = np.diag([1., 0.]).astype(complex), np.diag([0., 1.]).astype(complex)
+
+    def kron_at(ops):
+        m = np.eye(1, dtype=complex)
+        for q in range(n):
+            m = np.kron(m, ops.get(q, np.eye(2, dtype=complex)))
+        return m
+
+    zz = np.full((n, n), None)
+    zz[1, 3] = 0.6
+    obs = Observable(n, {"x": np.array([0.5, None, None, None], dtype=object), "y": np.array([None, None, 0.7, None], dtype=object),
+                         "z": np.array([None, 0.8, None, None], dtype=object), "zz": zz})
+    obs.load_projectors()
+    rng = np.random.default_rng(5)
+    v = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    expected = [kron_at({0: x}), kron_at({2: y}), kron_at({1: up}), kron_at({1: up, 3: up}) + kron_at({1: dn, 3: dn})]
+    assert len(obs.projectors) == 4
+    for proj, m in zip(obs.projectors, expected):
+        np.testing.assert_allclose(proj.dot(v), m.dot(v), atol=1e-14)
+    st = State(n)
+    with pytest.raises(AttributeError):
+        st.set_center_matrix(sp.identity(2 ** n, format='csr'))
+    st.activate_lefthandside()
+    st.activate_center_matrix()
+    assert st.lhs.shape == (2 ** n, 2 ** n) and st.lhs.nnz == 2 ** n and st.center_matrix.nnz == 0
+    st.set_center_matrix(sp.identity(2 ** n, dtype=complex, format='csr'))
+    assert st.center_matrix.nnz == 2 ** n
+    with pytest.warns(UserWarning):
+        st.xrot_lhs(0.1, 0)                      # still the reference's 'Not implemented.' stub
+
+
 def test_options_and_permutation_api_validation(backend):
     """Argument checks of the kernel-selection options and of qr_perm_load / qr_state_permute."""
     n = 6
