@@ -22,6 +22,9 @@ class _Rule:
         self.iter = 0
 
 
+GradientDescentOptimizer = _Rule      # the reference's name of the base class (optimization.py:131)
+
+
 class Adam(_Rule):
     def __init__(self, parameters, hyper_parameters):
         super().__init__(parameters, hyper_parameters)
