@@ -160,10 +160,7 @@ class McClean(ParametrizedCircuit):
                 for shift in (np.pi / 2, -np.pi / 2):
                     st.vec = history[i]
                     self._manual_rot(i, dq, shift)
-                    for j in range(i + 1, L):
-                        st.cnot_ladder(0)
-                        for q in range(n):
-                            self._rot(j, q)
+                    self._forward_tail(i + 1)
                     shifted.append(self.sample_expec_val(shot_num))
                 grad[i, dq] = .5 * (shifted[0] - shifted[1])
         return expec_val, grad
@@ -195,10 +192,7 @@ class McClean(ParametrizedCircuit):
                 for shift in (np.pi / 2, -np.pi / 2):
                     st.load(i)
                     self._manual_rot(i, dq, shift)
-                    for j in range(i + 1, L):
-                        st.cnot_ladder(0)
-                        for q in range(n):
-                            self._rot(j, q)
+                    self._forward_tail(i + 1)
                     shifted.append(self.sample_component_expec_val(shot_num, component))
                 grad[i, dq] = .5 * (shifted[0] - shifted[1])
         st.free_snapshots()
@@ -287,10 +281,7 @@ class McClean(ParametrizedCircuit):
 
         def measure(i):
             """layers i+1 .. L-1 on the current state, then shot_num draws of the eigenvalue"""
-            for j in range(i + 1, L):
-                st.cnot_ladder(0)
-                for q in range(n):
-                    self._rot(j, q)
+            self._forward_tail(i + 1)
             if kind == 'dense':
                 st.apply_dense()                                # amplitudes in the eigenbasis (mc_clean.py:255)
             else:
@@ -309,6 +300,21 @@ class McClean(ParametrizedCircuit):
                 grad[i, q] = (sample1 - sample2) / 2.
         st.free_snapshots()
         return expec_val, grad
+
+    def _forward_tail(self, first_layer):
+        """Layers first_layer .. L-1 applied to the CURRENT state in fused tile passes (one call, P launches per layer,
+        instead of n + 1 gate-at-a-time launches per layer): the tail every shifted circuit of the sampled-gradient
+        estimators runs (mc_clean.py:142-145, 148-151, 257-261)."""
+        L = self.lnum
+        if first_layer >= L:
+            return
+        axes, angles = self._params()
+        k = L - first_layer
+        ladder = np.ones(k, dtype=np.uint8)
+        e = ctypes.c_double()
+        self._lib.call('qr_layered_grad', self.state._ctx, int(k), _lib.ptr(np.ascontiguousarray(axes[first_layer:])),
+                       _lib.ptr(np.ascontiguousarray(angles[first_layer:])), _lib.ptr(ladder), 1, self.observable._handle,
+                       ctypes.byref(e), None)
 
     def _rot(self, i, q, angle_sign=1.):
         self._manual_rot(i, q, angle_sign * self.angles[i, q])
