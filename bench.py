@@ -291,7 +291,7 @@ def main():
             sec = dt.item() / args.steps
             P = 3
             bsched = 16.0 * 2.0 ** n / world * (1 + 2 * P * L + 2 + 4 * P * L)
-            nvl = 2 * 16.0 * 2.0 ** n / world * (world - 1) / world * 3 * L     # bytes per direction per GPU: peer loads in + peer stores out
+            nvl = getattr(sh, "link_bytes", 0.0) or 2 * 16.0 * 2.0 ** n / world * (world - 1) / world * 3 * L   # bytes per direction per GPU (counted by the library: peer loads in + peer stores out, less for Rz on global qubits)
             peak, peak_src = measured_peak()
             print(json.dumps({"metric": "McClean grad_run full gradients/sec", "value": 1.0 / sec, "unit": "gradients/s",
                               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec,

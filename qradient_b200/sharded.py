@@ -188,6 +188,11 @@ class ShardedMcClean:
             self._lib.call('qr_shard_mcclean_finish', s.ctx, ctypes.byref(e), _lib.ptr(grad[1:]) if want_grad else None)
             grad[0] = e.value
             parts.append(grad)
+        # NVLink volume of this gradient as counted by the library (peer loads + peer stores of the first local shard):
+        # smaller than the full exchange when global qubits carry Rz gates (QR_OPT_SHARD_ZSKIP)
+        perf = _lib.QrPerf()
+        self._lib.call('qr_perf_last', self.shards[0].ctx, ctypes.byref(perf))
+        self.link_bytes = perf.link_bytes
         total = self.comm.allreduce_sum(parts)
         return float(total[0]), np.array(total[1:]).reshape(self.lnum, self.qnum)
 

@@ -62,7 +62,8 @@ if rank == 0:
     out = {"n": n, "L": L, "world": world, "E": e, "grad_norm": float(np.linalg.norm(g)), "s_per_gradient": min(times),
            "bytes_sched_per_gpu": 16.0 * 2.0 ** n / world * (1 + 2 * 3 * L + 2 + 4 * 3 * L),
            "step_seconds": {k: round(v, 4) for k, v in circ.step_seconds.items()}, "opts": args.opt,
-           "nvlink_bytes_per_direction_per_global_vector_step": 16.0 * 2.0 ** n / world * (world - 1) / world}
+           "nvlink_bytes_per_direction_per_global_vector_step": 16.0 * 2.0 ** n / world * (world - 1) / world,
+           "nvlink_bytes_per_direction_per_gradient_counted": getattr(circ, "link_bytes", None)}
     print(json.dumps(out))
     if args.check:
         from oracle import qr_oracle as orc

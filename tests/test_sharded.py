@@ -63,10 +63,15 @@ def test_diagonal_global_gates_skip_the_exchange(backend, n, G):
     try:
         e, gr = c.grad_run()
         assert_parity(e, gr, e_ref, g_ref, obs_scale(obs), 1e-10)
+        link_skip = c.link_bytes
         assert abs(c.run_expec_val() - e_ref) <= 1e-10 * obs_scale(obs)
         c.set_option("shard_zskip", 0)
         e0, g0 = c.grad_run()
         assert_parity(e, gr, e0, g0, obs_scale(obs), 1e-12)
+        # counted NVLink volume per direction and rank: full exchange = 3 vector-steps per layer x 2 x 16 B x N_loc x (G-1)/G
+        n_loc = 2 ** (n - g)
+        assert c.link_bytes == pytest.approx(3 * L * 2 * 16.0 * n_loc * (G - 1) / G)
+        assert link_skip < c.link_bytes
     finally:
         c.close()
 
