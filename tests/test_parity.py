@@ -484,6 +484,53 @@ def test_error_behaviour(backend):
         q.run_expec_val(np.zeros(2), np.zeros(1))
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5])
+def test_empty_and_tiny_inputs(n):
+    """Edge cases: zero layers, one- and two-qubit registers (below the fused path), observables without terms.
+    CPU tier only (added after the round's GPU budget was spent; the GPU tier covers 3-qubit registers elsewhere)."""
+    from backends import activate
+    from qradient_b200 import _lib as _l
+    prev = _l._LIB
+    activate("emul")
+    try:
+        _empty_and_tiny_inputs(n)
+    finally:
+        _l._restore(prev)
+
+
+def _empty_and_tiny_inputs(n):
+    rng = np.random.default_rng(40 + n)
+    obs = {"z": np.array([0.7] + [None] * (n - 1), dtype=object), "x": np.array([None] * (n - 1) + [0.4], dtype=object)}
+    # zero layers: E of Ry(pi/4)^n |0>, empty gradient
+    c0 = McClean(n, obs, 0, axes=np.zeros((0, n), dtype=int), angles=np.zeros((0, n)))
+    e, g = c0.grad_run()
+    e_ref, g_ref = orc.mcclean_grad_run(n, obs, np.zeros((0, n), dtype=int), np.zeros((0, n)))
+    assert g.shape == (0, n) and abs(e - e_ref) < 1e-12 and abs(c0.run_expec_val() - e_ref) < 1e-12
+    # a few layers on tiny registers
+    L = 3
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    c = McClean(n, obs, L, axes=axes, angles=angles)
+    e, g = c.grad_run()
+    e_ref, g_ref = orc.mcclean_grad_run(n, obs, axes, angles)
+    assert_parity(e, g, e_ref, g_ref, 1.1, TOL)
+    # an observable without any term: E = 0, zero gradient
+    empty = {"z": np.array([None] * n, dtype=object)}
+    ce = McClean(n, empty, L, axes=axes, angles=angles)
+    e, g = ce.grad_run()
+    assert e == 0.0 and not np.any(g)
+    if n >= 2:
+        zz = np.full((n, n), None)
+        zz[0, n - 1] = 1.0
+        q = Qaoa(n, {"zz": zz}, 0)                      # zero QAOA layers: |+>^n, <ZZ> = 0
+        e, g = q.grad_run(np.zeros(0), np.zeros(0))
+        assert abs(e) < 1e-15 and g.shape == (0, 2)
+        q1 = Qaoa(n, {"zz": zz}, 1)
+        b, gm = rng.random(1), rng.random(1)
+        e, g = q1.grad_run(b, gm)
+        e_ref, g_ref = orc.qaoa_grad_run(n, {"zz": zz}, b, gm)
+        assert_parity(e, g, e_ref, g_ref, 1.0, TOL)
+
+
 def test_optimizer_style_parameter_updates(backend):
     """optimization.py:61,91 assign circuit.angles between grad_run calls."""
     n, L = 6, 2
