@@ -187,8 +187,7 @@ def test_kernel_variants_vs_oracle(backend, opts, n, L, tile_bits):
     assert_parity(e, g, e_ref, g_ref, float(n - 1), TOL)
 
 
-@pytest.mark.parametrize("n,L,opts", [(15, 2, dict(pair_order=7)), (16, 1, dict(pair_order=3, prefetch=5)),
-                                      (15, 2, dict(pair_order=1, staged=1, tile_bits=12)), (15, 1, dict(pair_order=7, staged=3, tile_bits=12))])
+@pytest.mark.parametrize("n,L,opts", [(15, 1, dict(pair_order=7, prefetch=5)), (15, 1, dict(pair_order=7, staged=3, tile_bits=12))])
 def test_pair_order_matches_default(backend, opts, n, L):
     """QR_OPT_PAIR_ORDER: in the strided passes a CTA takes its tiles in adjacent pairs (the two 128 B halves of the
     same 256 B chunks) -- a different tile enumeration (and prefetch / staging schedule), same arithmetic per tile."""
