@@ -39,7 +39,7 @@ enum { QR_OK = 0, QR_EINVAL = 1, QR_ECUDA = 2, QR_ENOMEM = 3, QR_ESTATE = 4 };
 /* observable term kinds (physical_components/observable.py:45-73) */
 enum { QR_TERM_X = 0, QR_TERM_Y = 1, QR_TERM_Z = 2, QR_TERM_ZZ = 3 };
 
-/* qr_set_option keys */
+/* qr_set_option keys (numbering is stable; retired round-1 experiment keys 7-10, 14-18, 22-25, 27 are rejected) */
 enum {
     QR_OPT_FUSION = 0,        /* 1 (default): fused tile passes; 0: one kernel per gate          */
     QR_OPT_TILE_BITS = 1,     /* log2 amplitudes per shared-memory tile; 0 (default) = auto: 11 or 12 */
@@ -48,28 +48,14 @@ enum {
     QR_OPT_CTAS_PER_SM_BWD = 4,
     QR_OPT_FINAL_LADDER = 5,  /* 1 (default): leave state.vec exactly as mc_clean.py:77 does     */
     QR_OPT_HAM_LUT = 6,       /* 1 (default): integer-valued diagonal Hamiltonians use a phase LUT */
-    QR_OPT_REG_BITS_FWD = 7,  /* index bits per round held in registers, forward pass: 3 or 4     */
-    QR_OPT_REG_BITS_BWD = 8,  /* same for the backward pass                                        */
-    QR_OPT_ASYNC_FWD = 9,     /* 1: stage forward tiles with bulk async copies (TMA) + mbarrier    */
-    QR_OPT_ASYNC_BWD = 10,    /* same for the backward pass                                        */
     QR_OPT_TILE_BITS_STRIDED = 11, /* tile bits of the strided (non-first) passes; 0 = same as first */
     QR_OPT_MIN_ROW_BITS = 12, /* log2 of the minimum contiguous run (amplitudes) in strided passes */
     QR_OPT_BATCH_CHUNK_MB = 13, /* batched circuits: MiB of state per buffer processed per chunk (0 = 512) */
-    QR_OPT_DECOUPLED = 14,    /* decoupled-exchange tile kernel: bit0 backward, bit1 forward           */
-    QR_OPT_LEAN = 15,         /* lean static 12-bit tile kernel (default 3): bit0 backward, bit1 forward */
-    QR_OPT_BUF_SKEW = 16,     /* bytes between the start offsets of consecutive state buffers (multiple of 256) */
-    QR_OPT_CLUSTER = 18,      /* CTA pairs (thread-block clusters of 2) on adjacent tiles: bits 0-1 backward, 2-3 forward; 0 none, 1 strided passes, 2 all */
     QR_OPT_STAGED = 19,       /* k_tile12: next tile staged in shared memory by asynchronous copies: bit0 backward, bit1 forward, bit2 (default) auto */
     QR_OPT_STAGED_MIN_BIT = 20, /* auto mode: strided backward passes whose lowest gate bit is >= this (default 21) are staged */
-    QR_OPT_CACHE_HINTS = 22,  /* k_tile12: bit0 streaming stores, bit1 streaming loads; bits 2-3: the same for out-of-place (ladder) passes only */
-    QR_OPT_LOW_BITS_PASS = 23, /* k_tile12: pass applying the gates on index bits 0-2: 0 = contiguous pass, k = k-th strided pass, -1 = last */
-    QR_OPT_SRC_ORDER = 24,    /* k_tile12 ladder passes enumerate tiles in source order (sequential reads): bit0 backward, bit1 forward (default 0: measured neutral) */
-    QR_OPT_PAIR = 25,         /* k_tile12 pair kernel: clusters of two half-size CTAs share a 12-bit tile over distributed shared memory: bit0 backward, bit1 forward */
     QR_OPT_PDL = 26,          /* k_tile12 passes use programmatic dependent launch (griddepcontrol): 0 off, 1 (default) auto: short passes (n <= 22), 2 always */
-    QR_OPT_PAIR_ORDER = 27,   /* k_tile12 strided passes: a CTA takes adjacent tiles (the two 128 B halves of the same 256 B chunks) back to back and prefetches them together: bit0 backward, bit1 forward, bit2 force the prefetch on */
     QR_OPT_DEFER_REDUCE = 28, /* 1 (default): single circuits add the per-CTA gradient partials of all backward passes in ONE launch after the sweep; 0: last-CTA reduction fused into every pass */
-    QR_OPT_SHARD_ZSKIP = 29,  /* 1 (default): sharded states apply an Rz on a global qubit as a per-subgroup phase without the NVLink exchange (only X / Y rotations are exchanged) */
-    QR_OPT_PAGE_BITS = 17     /* log2 amplitudes per memory page (17 = 2 MiB): strided passes share the index bits above it; 0 (default) = off */
+    QR_OPT_SHARD_ZSKIP = 29   /* 1 (default): sharded states apply an Rz on a global qubit as a per-subgroup phase without the NVLink exchange (only X / Y rotations are exchanged) */
 };
 
 typedef struct qr_perf {

@@ -59,9 +59,7 @@ struct PassPlan {
     int k, c, h, nrounds;
     int g[QR_MAXROUNDS];
     int gbit[QR_GATE_SLOTS];   // global index bit handled by slot (round * R + register bit) or -1
-    bool dc;                   // decoupled-exchange kernel (k == 12, R == 3)
-    DcPlan dcp;
-    bool lean;                 // lean static kernel k_tile12 (k == 12): slot = local bit
+    bool lean;                 // lean static kernel k_tile12 (k == 12 or 11): slot = local bit
     int ngroups;               // lean: active register groups (1..4)
     int m1, h2;                // lean: two-segment geometry (Geo12); single segment: m1 = k - c, h2 = h + m1
 };
@@ -81,7 +79,7 @@ struct qr_ctx {
     int sm_count = 1;
     cudaStream_t stream = nullptr;
     double2* buf[QR_NBUF] = {nullptr, nullptr, nullptr, nullptr};
-    void* buf_base[QR_NBUF] = {nullptr, nullptr, nullptr, nullptr};   // raw allocations (buf[i] = base + i * skew)
+    void* buf_base[QR_NBUF] = {nullptr, nullptr, nullptr, nullptr};   // raw allocations
     u64 buf_amps = 0;            // capacity of each buffer in amplitudes (>= N; batch paths grow it)
     int psi = 0;                 // buffer holding the state vector
     double* d_ham = nullptr;     // diagonal Hamiltonian table [N]
@@ -105,23 +103,11 @@ struct qr_ctx {
     // options
     long long opt_fusion = 1, opt_tile_bits = 0 /* auto */, opt_prefetch = 1;
     long long opt_ctas_fwd = 2, opt_ctas_bwd = 1, opt_final_ladder = 1, opt_ham_lut = 1;
-    long long opt_r_fwd = 3, opt_r_bwd = 3;
-    long long opt_async_fwd = 0, opt_async_bwd = 0;
     long long opt_tile_bits_x = 0, opt_min_row_bits = 3, opt_batch_chunk_mb = 0;
-    long long opt_decoupled = 0;   // bit0: backward, bit1: forward use the decoupled-exchange kernel
-    long long opt_lean = 3;        // bit0: backward, bit1: forward use the lean static 12-bit tile kernel
-    long long opt_page_bits = 0;   // log2 amplitudes per memory page (2 MiB): strided passes share the index bits above it; 0 = off
     long long opt_staged = 4;      // bit0 backward, bit1 forward: next tile staged in shared memory by asynchronous copies; bit2: auto (backward)
     long long opt_staged_min_bit = 21;   // auto mode: strided backward passes whose lowest gate bit is >= this are staged
-    long long opt_cluster = 0;     // bits 0-1 backward, bits 2-3 forward: 0 none, 1 CTA pairs in the strided passes, 2 in every pass
-    long long opt_pair = 0;        // k_tile12 pair kernel (cluster of two half-size CTAs per 12-bit tile): bit0 backward, bit1 forward
-    long long opt_src_order = 0;   // k_tile12 ladder passes enumerate tiles in source order: bit0 backward, bit1 forward
-    long long opt_low_bits_pass = 0;   // k_tile12: pass that applies the gates on index bits 0-2 (0 = contiguous pass, -1 = last strided pass)
-    long long opt_cache_hints = 0; // k_tile12: bit0 streaming stores, bit1 streaming loads (all passes); bits 2-3: same, out-of-place passes only
     long long opt_defer_reduce = 1; // single circuits: one reduction launch per gradient instead of a last-CTA reduction in every backward pass
-    long long opt_pair_order = 0;  // k_tile12 strided passes take their tiles in adjacent pairs: bit0 backward, bit1 forward, bit2: force the pair prefetch on
     long long opt_pdl = 1;         // k_tile12 passes launched with programmatic stream serialization: 0 off, 1 auto (n <= 22), 2 always
-    long long opt_buf_skew = 0;    // bytes between the start offsets of consecutive state buffers (multiple of 256)
     long long opt_shard_zskip = 1; // sharded states: Rz on a global qubit is applied as a per-subgroup phase, without the exchange
     bool tables_fresh = true;      // gate / phase tables were (re)written since the last tile pass: see launch_pass
     qr_perf perf;
@@ -176,12 +162,8 @@ static int ensure_pin(qr_ctx* c, size_t bytes) {
 
 static int ensure_buf(qr_ctx* c, int i) {
     if (c->buf[i]) return 0;
-    // Buffer i starts i * skew bytes into its allocation, so that the same amplitude index of psi,
-    // lambda and their ping-pong partners does not land on the same DRAM channel / bank (the
-    // allocations themselves are a power of two apart).
-    const size_t skew = (size_t)c->opt_buf_skew * (size_t)i;
-    cudaError_t e = cudaMalloc(&c->buf_base[i], c->buf_amps * sizeof(double2) + skew);
-    if (e == cudaSuccess) c->buf[i] = (double2*)((char*)c->buf_base[i] + skew);
+    cudaError_t e = cudaMalloc(&c->buf_base[i], c->buf_amps * sizeof(double2));
+    if (e == cudaSuccess) c->buf[i] = (double2*)c->buf_base[i];
     if (e != cudaSuccess) {
         c->buf[i] = nullptr;
         c->buf_base[i] = nullptr;
@@ -305,40 +287,18 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
             if (v != 0 && (v < 4 || v > QR_MAX_TILE_BITS)) return fail(QR_EINVAL, "tile bits must be 0 (auto) or in [4, %d]", QR_MAX_TILE_BITS);
             c->opt_tile_bits = v; break;
         case QR_OPT_PREFETCH: if (v < 0 || v > 31) return fail(QR_EINVAL, "prefetch must be in [0, 31]"); c->opt_prefetch = v; break;
-        case QR_OPT_STAGED: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad staged mode"); c->opt_staged = v; break;
-        case QR_OPT_PAIR: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad pair mode"); c->opt_pair = v; break;
-        case QR_OPT_SRC_ORDER: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad source-order mode"); c->opt_src_order = v; break;
-        case QR_OPT_LOW_BITS_PASS: if (v < -1 || v > 15) return fail(QR_EINVAL, "bad low-bits pass"); c->opt_low_bits_pass = v; break;
-        case QR_OPT_CACHE_HINTS: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad cache hints"); c->opt_cache_hints = v; break;
+        case QR_OPT_STAGED: if (v < 0 || v > 7) return fail(QR_EINVAL, "bad staged mode"); c->opt_staged = v; break;
         case QR_OPT_STAGED_MIN_BIT: if (v < 0 || v > 64) return fail(QR_EINVAL, "bad staged min bit"); c->opt_staged_min_bit = v; break;
-        case QR_OPT_CLUSTER: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad cluster mode"); c->opt_cluster = v; break;
         case QR_OPT_CTAS_PER_SM_FWD: if (v < 1 || v > 8) return fail(QR_EINVAL, "bad CTAs/SM"); c->opt_ctas_fwd = v; break;
         case QR_OPT_CTAS_PER_SM_BWD: if (v < 1 || v > 8) return fail(QR_EINVAL, "bad CTAs/SM"); c->opt_ctas_bwd = v; break;
         case QR_OPT_FINAL_LADDER: c->opt_final_ladder = v ? 1 : 0; break;
         case QR_OPT_HAM_LUT: c->opt_ham_lut = v ? 1 : 0; break;
-        case QR_OPT_REG_BITS_FWD: if (v != 3 && v != 4) return fail(QR_EINVAL, "register bits must be 3 or 4"); c->opt_r_fwd = v; break;
-        case QR_OPT_REG_BITS_BWD: if (v != 3 && v != 4) return fail(QR_EINVAL, "register bits must be 3 or 4"); c->opt_r_bwd = v; break;
-        case QR_OPT_ASYNC_FWD: c->opt_async_fwd = v ? 1 : 0; break;
-        case QR_OPT_ASYNC_BWD: c->opt_async_bwd = v ? 1 : 0; break;
         case QR_OPT_TILE_BITS_STRIDED: if (v != 0 && (v < 4 || v > QR_MAX_TILE_BITS)) return fail(QR_EINVAL, "bad strided tile bits"); c->opt_tile_bits_x = v; break;
         case QR_OPT_MIN_ROW_BITS: if (v < 1 || v > 11) return fail(QR_EINVAL, "bad min row bits"); c->opt_min_row_bits = v; break;
         case QR_OPT_BATCH_CHUNK_MB: if (v < 0 || v > 65536) return fail(QR_EINVAL, "bad batch chunk"); c->opt_batch_chunk_mb = v; break;
-        case QR_OPT_DECOUPLED: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad decoupled mode"); c->opt_decoupled = v; break;
-        case QR_OPT_LEAN: if (v < 0 || v > 3) return fail(QR_EINVAL, "bad lean mode"); c->opt_lean = v; break;
-        case QR_OPT_PAIR_ORDER: if (v < 0 || v > 7) return fail(QR_EINVAL, "bad pair-order mode"); c->opt_pair_order = v; break;
         case QR_OPT_DEFER_REDUCE: c->opt_defer_reduce = v ? 1 : 0; break;
         case QR_OPT_SHARD_ZSKIP: c->opt_shard_zskip = v ? 1 : 0; break;
         case QR_OPT_PDL: if (v < 0 || v > 2) return fail(QR_EINVAL, "bad PDL mode"); c->opt_pdl = v; break;
-        case QR_OPT_PAGE_BITS: if (v != 0 && (v < 13 || v > 40)) return fail(QR_EINVAL, "bad page bits"); c->opt_page_bits = v; break;
-        case QR_OPT_BUF_SKEW:
-            if (v < 0 || v > (1ll << 30) || (v & 255)) return fail(QR_EINVAL, "buffer skew must be a multiple of 256 bytes");
-            if (v != c->opt_buf_skew) {   // takes effect for buffers allocated from now on: drop all but the state
-                CUDA_TRY(cudaStreamSynchronize(c->stream));
-                for (int i = 0; i < QR_NBUF; ++i)
-                    if (i != c->psi && c->buf_base[i]) { cudaFree(c->buf_base[i]); c->buf[i] = nullptr; c->buf_base[i] = nullptr; }
-            }
-            c->opt_buf_skew = v;
-            break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -354,28 +314,14 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_CTAS_PER_SM_BWD: *v = c->opt_ctas_bwd; break;
         case QR_OPT_FINAL_LADDER: *v = c->opt_final_ladder; break;
         case QR_OPT_HAM_LUT: *v = c->opt_ham_lut; break;
-        case QR_OPT_REG_BITS_FWD: *v = c->opt_r_fwd; break;
-        case QR_OPT_REG_BITS_BWD: *v = c->opt_r_bwd; break;
-        case QR_OPT_ASYNC_FWD: *v = c->opt_async_fwd; break;
-        case QR_OPT_ASYNC_BWD: *v = c->opt_async_bwd; break;
         case QR_OPT_TILE_BITS_STRIDED: *v = c->opt_tile_bits_x; break;
         case QR_OPT_MIN_ROW_BITS: *v = c->opt_min_row_bits; break;
         case QR_OPT_BATCH_CHUNK_MB: *v = c->opt_batch_chunk_mb; break;
-        case QR_OPT_DECOUPLED: *v = c->opt_decoupled; break;
-        case QR_OPT_LEAN: *v = c->opt_lean; break;
-        case QR_OPT_BUF_SKEW: *v = c->opt_buf_skew; break;
-        case QR_OPT_PAGE_BITS: *v = c->opt_page_bits; break;
-        case QR_OPT_CLUSTER: *v = c->opt_cluster; break;
         case QR_OPT_STAGED: *v = c->opt_staged; break;
         case QR_OPT_STAGED_MIN_BIT: *v = c->opt_staged_min_bit; break;
-        case QR_OPT_CACHE_HINTS: *v = c->opt_cache_hints; break;
-        case QR_OPT_SRC_ORDER: *v = c->opt_src_order; break;
-        case QR_OPT_PAIR: *v = c->opt_pair; break;
         case QR_OPT_PDL: *v = c->opt_pdl; break;
         case QR_OPT_SHARD_ZSKIP: *v = c->opt_shard_zskip; break;
         case QR_OPT_DEFER_REDUCE: *v = c->opt_defer_reduce; break;
-        case QR_OPT_PAIR_ORDER: *v = c->opt_pair_order; break;
-        case QR_OPT_LOW_BITS_PASS: *v = c->opt_low_bits_pass; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -853,40 +799,9 @@ static void plan_rounds(PassPlan& pp, int first, int R) {
         }
 }
 
-// Decoupled-exchange plan of a k = 12 pass whose gate bits are the local bits [first, 12): groups
-// A,B,C,D of 3 bits; D is in the registers at load time (natural, coalesced layout), the other
-// groups that carry gates are swapped in through the slot that currently holds them.
-static void plan_dc(PassPlan& pp, int first) {
-    int cont[3] = {0, 1, 2}, reg = 3;   // group held by S0, S1, S2 and by the registers
-    DcPlan& d = pp.dcp;
-    int nr = 0;
-    auto record = [&]() {
-        for (int s = 0; s < 3; ++s) d.gp[nr][s] = 3 * cont[s];
-        d.gp[nr][3] = 3 * reg;
-        for (int b = 0; b < 3; ++b) {
-            const int lb = 3 * reg + b;
-            pp.gbit[nr * 3 + b] = lb < first ? -1 : (lb < pp.c ? lb : pp.h + (lb - pp.c));
-        }
-        ++nr;
-    };
-    for (int i = 0; i < QR_GATE_SLOTS; ++i) pp.gbit[i] = -1;
-    record();
-    for (int grp = 0; grp < 3; ++grp) {
-        if (3 * grp + 2 < first) continue;   // no gate bit in this group
-        int s = 0;
-        while (cont[s] != grp) ++s;
-        d.swap_slot[nr - 1] = s;
-        std::swap(cont[s], reg);
-        record();
-    }
-    d.nrounds = nr;
-    pp.nrounds = nr;
-    pp.dc = true;
-}
-
 // Lean plan of a k = 12 pass whose gate bits are the local bits [first, 12): fixed groups
 // G0..G3 = local bits 0-2, 3-5, 6-8, 9-11, visited G3 [G0] [G1] [G2]; gradient slot = local bit.
-static void plan_lean(PassPlan& pp, int first, bool with_low = false) {
+static void plan_lean(PassPlan& pp, int first) {
     for (int i = 0; i < QR_GATE_SLOTS; ++i) pp.gbit[i] = -1;
     const int K = pp.k;
     const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2, K};
@@ -899,10 +814,6 @@ static void plan_lean(PassPlan& pp, int first, bool with_low = false) {
     // chain of register groups (Tile12X::ngroups): L = K-3 | [0] | [3] | [6], or L | 2 | 5 for K = 11 with 64 B rows
     if (K == 11 && first == 2) pp.ngroups = 5;
     else pp.ngroups = first < 3 ? 4 : (first < 6 ? 3 : (first < K - 3 ? 2 : 1));
-    if (with_low) {   // the gates of index bits 0-2 (inside every tile's 128 B rows) are applied in this strided pass
-        for (int lb = 0; lb < 3; ++lb) pp.gbit[lb] = lb;
-        pp.ngroups = 4;
-    }
     pp.nrounds = pp.ngroups;
     pp.g[0] = K - 3;
     pp.lean = true;
@@ -913,8 +824,7 @@ static void plan_lean(PassPlan& pp, int first, bool with_low = false) {
 // neutral at 20, -10 % at 27: profiles/README.md); 12-bit tiles otherwise.
 static int pick_tile_bits(const qr_ctx* c, int n) {
     if (c->opt_tile_bits != 0) return (int)c->opt_tile_bits;
-    const bool lean_on = (c->opt_lean & 3) == 3 && !c->opt_async_fwd && !c->opt_async_bwd && !c->opt_decoupled &&
-                         c->opt_tile_bits_x == 0 && c->opt_min_row_bits == 3 && c->opt_low_bits_pass == 0;
+    const bool lean_on = c->opt_tile_bits_x == 0 && c->opt_min_row_bits == 3;
     if (lean_on && ((n >= 13 && n <= 20) || (n >= 22 && n <= 26))) return 11;
     return QR_MAX_TILE_BITS;
 }
@@ -924,30 +834,21 @@ static int pick_min_row_bits(const qr_ctx* c, int n) {
     return (int)c->opt_min_row_bits;
 }
 
-static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x = 0, int min_row_bits = 3, bool allow_dc = false,
-                     bool allow_lean = false, int page_bits = 17, int low_bits_pass = 0) {
+// Pass 0 is the contiguous low-k tile; the remaining n - k index bits are split evenly over strided passes whose
+// tiles keep >= 2^min_row_bits contiguous amplitudes per row.  Tiles of 12 or 11 bits run k_tile12 (slot = local
+// bit), smaller ones the generic kernel.
+static int make_plan(int n, int tile_bits, LayerPlan* lp, int tile_bits_x = 0, int min_row_bits = 3) {
     if (n < 4) return fail(QR_EINVAL, "fused path needs at least 4 qubits");
+    const int R = 3;
     const int k = std::min(n, tile_bits);
     lp->n = n;
     lp->k = k;
     lp->R = R;
     int np = 0;
     PassPlan& p0 = lp->pass[np++];
-    p0.k = k; p0.c = k; p0.h = k; p0.dc = false; p0.lean = false; p0.ngroups = 0; p0.m1 = 0; p0.h2 = k;
-    // lean kernel: the gates on index bits 0-2 may be moved from the (on-chip bound) contiguous pass to a
-    // (memory bound) strided pass, whose tiles contain those bits as well
-    const int rem0 = n - k;
-    int low_pass = 0;
-    if (allow_lean && k == 12 && low_bits_pass != 0 && rem0 > 0) {   // (12-bit tiles only)
-        const int kx0 = tile_bits_x > 0 ? std::min(n, tile_bits_x) : k;
-        const int umax0 = std::max(kx0 - std::min(min_row_bits, kx0 - 1), 1);
-        const int nx0 = (rem0 + umax0 - 1) / umax0;
-        low_pass = low_bits_pass < 0 ? nx0 : std::min(low_bits_pass, nx0);
-        if (kx0 != 12 || rem0 / nx0 < 7) low_pass = 0;   // only into a pass with >= 7 strided gate bits (3 other groups are active anyway)
-    }
-    const bool lean_k = allow_lean && (k == 12 || k == 11) && (tile_bits_x == 0 || tile_bits_x == k) && (k == 12 || min_row_bits >= 2);
-    if (lean_k) plan_lean(p0, low_pass ? 3 : 0);
-    else if (allow_dc && k == 12 && R == 3) plan_dc(p0, 0); else plan_rounds(p0, 0, R);
+    p0.k = k; p0.c = k; p0.h = k; p0.lean = false; p0.ngroups = 0; p0.m1 = 0; p0.h2 = k;
+    const bool lean_k = (k == 12 || k == 11) && (tile_bits_x == 0 || tile_bits_x == k) && (k == 12 || min_row_bits >= 2);
+    if (lean_k) plan_lean(p0, 0); else plan_rounds(p0, 0, R);
     const int rem = n - k;
     if (rem > 0) {
         // strided passes: tile of kx bits = c contiguous low bits (rows of 2^c amplitudes) + m gate bits
@@ -955,35 +856,14 @@ static int make_plan(int n, int tile_bits, int R, LayerPlan* lp, int tile_bits_x
         const int umax = std::max(kx - std::min(min_row_bits, kx - 1), 1);
         const int nx = (rem + umax - 1) / umax;
         int h = k;
-        // lean kernel: the index bits >= page_bit select the 2 MiB page; share them evenly between the
-        // strided passes (each pass = a run of the remaining low bits + a run of the page bits)
-        const int page_bit = page_bits;
-        const bool split = lean_k && kx == 12 && nx > 1 && page_bit > k && n > page_bit;
-        const int hi_total = split ? n - page_bit : 0;
-        int lo_next = k, hi_next = page_bit;
         for (int i = 0; i < nx; ++i) {
             const int m = rem / nx + (i < rem % nx ? 1 : 0);
             PassPlan& pp = lp->pass[np++];
-            pp.k = kx; pp.c = kx - m; pp.h = h; pp.dc = false; pp.lean = false; pp.ngroups = 0;
+            pp.k = kx; pp.c = kx - m; pp.h = h; pp.lean = false; pp.ngroups = 0;
             pp.m1 = m; pp.h2 = h + m;
-            if (split) {
-                int mh = hi_total / nx + (i < hi_total % nx ? 1 : 0);          // page bits of this pass
-                int ml = m - mh;                                                // low bits of this pass
-                const int lo_left = page_bit - lo_next;
-                if (ml > lo_left) { ml = lo_left; mh = m - ml; }
-                if (ml < 0) { ml = 0; mh = m; }
-                if (i == nx - 1) { ml = page_bit - lo_next; mh = m - ml; }      // last pass takes what is left
-                pp.h = ml > 0 ? lo_next : hi_next;
-                pp.m1 = ml > 0 ? ml : mh;
-                pp.h2 = ml > 0 ? hi_next : pp.h + pp.m1;
-                lo_next += ml;
-                hi_next += mh;
-            }
-            if (lean_k) plan_lean(pp, pp.c, low_pass == i + 1);
-            else if (allow_dc && kx == 12 && R == 3) plan_dc(pp, pp.c); else plan_rounds(pp, pp.c, R);
+            if (lean_k) plan_lean(pp, pp.c); else plan_rounds(pp, pp.c, R);
             h += m;
         }
-        if (split && (lo_next != page_bit || hi_next != n)) return fail(QR_EINVAL, "internal: page-bit split does not cover the register");
     }
     lp->npasses = np;
     for (int i = 0; i < np; ++i)
@@ -1014,20 +894,23 @@ static bool uniform_lean_plan(const LayerPlan& lp) {
 
 typedef void (*tile_fn)(const TilePass);
 
-static tile_fn tile_kernel(int nv, int R, int async) {
-    if (async) {
-        if (nv == 1) return R == 3 ? k_tile_pass<1, 3, true> : k_tile_pass<1, 4, true>;
-        return R == 3 ? k_tile_pass<2, 3, true> : k_tile_pass<2, 4, true>;
-    }
-    if (nv == 1) return R == 3 ? k_tile_pass<1, 3, false> : k_tile_pass<1, 4, false>;
-    return R == 3 ? k_tile_pass<2, 3, false> : k_tile_pass<2, 4, false>;
-}
-
 struct PassIO {
     const double2* src0; const double2* src1; double2* dst0; double2* dst1;
 };
 
 struct LadderSpec { u64 M1, M2, src_xor; };   // explicit gather map (sharded states)
+
+// opt in to > 48 KiB of dynamic shared memory: the attribute is PER DEVICE, so remember it per (kernel, device)
+static int ensure_smem_attr(qr_ctx* c, const void* fn, int slot) {
+    static bool done[64][32] = {};   // [device][kernel slot]
+    const int dev = c->device & 63;
+    if (slot < 0 || slot >= 32) return fail(QR_EINVAL, "internal: kernel slot %d", slot);
+    if (!done[dev][slot]) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (int)sizeof(double2) << QR_MAX_TILE_BITS));
+        done[dev][slot] = true;
+    }
+    return 0;
+}
 
 // launch one tile pass; returns the number of partial units written (backward) through *units
 static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const PassIO& io, const GateP* d_gates,
@@ -1048,10 +931,6 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
     } else if (ladder_stacking >= 0) {
         tp.ladder = 1;
         ladder_masks(lp.n, 1 - ladder_stacking, &tp.M1, &tp.M2);
-        if (pp.lean && (c->opt_src_order & (nv == 2 ? 1 : 2))) {   // k_tile12: enumerate the tiles in source order
-            tp.src_order = 1;
-            ladder_masks(lp.n, ladder_stacking, &tp.iM1, &tp.iM2);
-        }
     }
     tp.tiles_log2 = lp.n - pp.k;
     tp.num_tiles = batch << tp.tiles_log2;
@@ -1064,23 +943,10 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
     tp.flush_per_tile = flush_per_tile;
     tp.prefetch = nv == 2 ? (int)(c->opt_prefetch & 3) : (int)((c->opt_prefetch >> 2) & 3);   // tiles ahead: bits 0-1 backward, bits 2-3 forward
     const int R = lp.R;
-    const int async = (nv == 1 ? c->opt_async_fwd : c->opt_async_bwd) ? 1 : 0;
-    const int threads = 1 << (pp.k - R);
-    const int full = 1 << (QR_MAX_TILE_BITS - R);
-    const long long ctas = async ? 1 : (nv == 1 ? c->opt_ctas_fwd : c->opt_ctas_bwd);
-    const long long per_sm = std::min<long long>(16, ctas * std::max(1, full / threads));
-    const i64 grid = std::min<i64>(tp.num_tiles, (i64)c->sm_count * per_sm);
     const size_t tile_bytes = sizeof(double2) << pp.k;
-    size_t smem = async ? (size_t)(nv + 1) * tile_bytes : (pp.nrounds > 1 ? (size_t)nv * tile_bytes : 0);
-    if (nv == 2) {
-        const i64 nunits = flush_per_tile ? tp.num_tiles : grid;
-        QR_TRY(ensure_scratch(c, (size_t)nunits * QR_SLOTS));
-        *units = (int)nunits;
-    }
-    tp.partials = partials_at ? partials_at : c->d_scratch;   // partials_at: a slice of d_scratch the caller has sized (deferred reduction)
     tp.final_out = (nv == 2 && !flush_per_tile) ? final_out : nullptr;
     tp.done_counter = c->d_counter;
-    if (pp.lean) {   // lean static kernel (k = 12, 512 threads)
+    if (pp.lean) {   // k_tile12 (k = 12: 512 threads; k = 11: 256 threads)
         typedef void (*lean_fn)(const TilePass, const Tile12X);
         const int ph = (pre_phase || post_phase) ? 1 : 0;
         // staged (asynchronous shared-memory copies of the next tile) vs direct loads + L2 prefetch, per pass:
@@ -1088,104 +954,68 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         // below 32 MiB, and loses badly (22 vs 17 ms) when all gate bits are >= 21 -> auto mode (bit 2).
         int staged = (nv == 2 ? (c->opt_staged & 1) : (c->opt_staged & 2)) ? 1 : 0;
         if (nv == 2 && (c->opt_staged & 4) && pp.c < pp.k && pp.h >= c->opt_staged_min_bit) staged = 1;
-        if (nv == 2 && !staged && (c->opt_staged & 8)) staged = 2;   // bit 3: psi-only staging for the other backward passes
         const int K = pp.k;   // 12, or 11 (half-size tiles, direct loads only)
         if (K == 11) staged = 0;
-        // pair kernel: a cluster of two half-size CTAs per 12-bit tile (two backward CTAs per SM without losing a gate bit)
-        bool pair = K == 12 && (c->opt_pair & (nv == 2 ? 1 : 2)) && !(c->opt_staged & 3) && pp.ngroups >= 1 && pp.ngroups <= 4 &&
-                    (c->opt_cluster & (nv == 2 ? 3 : 12)) == 0;
-#ifdef QR_HOST_EMUL
-        pair = false;   // the emulation runs blocks one after another
-#endif
-        if (pair) staged = 0;
         lean_fn lfn;
-        if (pair) lfn = nv == 1 ? (ph ? k_tile12<1, true, 0, 11, true> : k_tile12<1, false, 0, 11, true>)
-                                : (ph ? k_tile12<2, true, 0, 11, true> : k_tile12<2, false, 0, 11, true>);
-        else if (K == 11) lfn = nv == 1 ? (ph ? k_tile12<1, true, 0, 11> : k_tile12<1, false, 0, 11>) : (ph ? k_tile12<2, true, 0, 11> : k_tile12<2, false, 0, 11>);
-        else if (staged == 2 && nv == 2) lfn = ph ? k_tile12<2, true, 2> : k_tile12<2, false, 2>;
+        if (K == 11) lfn = nv == 1 ? (ph ? k_tile12<1, true, 0, 11> : k_tile12<1, false, 0, 11>) : (ph ? k_tile12<2, true, 0, 11> : k_tile12<2, false, 0, 11>);
         else if (staged) lfn = nv == 1 ? (ph ? k_tile12<1, true, 1> : k_tile12<1, false, 1>) : (ph ? k_tile12<2, true, 1> : k_tile12<2, false, 1>);
         else lfn = nv == 1 ? (ph ? k_tile12<1, true, 0> : k_tile12<1, false, 0>) : (ph ? k_tile12<2, true, 0> : k_tile12<2, false, 0>);
-        static bool lean_attr[3][2][2][3] = {};
-        const int ksel = pair ? 2 : K - 11;
-        if (!lean_attr[ksel][nv - 1][ph][staged]) {
-            CUDA_TRY(cudaFuncSetAttribute(lfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (int)sizeof(double2) << QR_MAX_TILE_BITS));
-            lean_attr[ksel][nv - 1][ph][staged] = true;
-        }
+        QR_TRY(ensure_smem_attr(c, (const void*)lfn, ((K - 11) * 2 + (nv - 1)) * 4 + ph * 2 + staged));
         if (staged == 1) tp.prefetch = 0;
         Tile12X x;
         memset(&x, 0, sizeof(x));
         x.ngroups = pp.ngroups;
-        {   // cache hints: opt bits 0-1 = all passes, bits 2-3 = out-of-place (ladder) passes only
-            const bool oop = io.src0 != io.dst0;
-            x.cache_hints = (int)(c->opt_cache_hints & 3) | (oop ? (int)((c->opt_cache_hints >> 2) & 3) : 0);
-        }
         const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2, K};
-        const int KK = pair ? 11 : K;   // tile bits of the kernel instance
-        x.last_group = pp.ngroups == 1 ? KK - 3 : (pp.ngroups == 5 ? 5 : 6);
+        x.last_group = pp.ngroups == 1 ? K - 3 : (pp.ngroups == 5 ? 5 : 6);
         for (int r = 0; r < 8; ++r) {
-            const u64 lf = (u64)r << (KK - 3);
-            u64 ll = (u64)r << x.last_group;
-            if (pair && pp.ngroups == 1) ll = ((u64)(r & 3) << 8) | ((u64)(r >> 2) << 11);   // registers = tile bits 8, 9, 11 after the pair round
+            const u64 lf = (u64)r << (K - 3);
+            const u64 ll = (u64)r << x.last_group;
             x.droff_first[r] = geo12_local(geo, lf);
             x.roff_first[r] = tp.ladder ? ladder_map(x.droff_first[r], tp.M1, tp.M2) : x.droff_first[r];
             x.roff_last[r] = geo12_local(geo, ll);
         }
-        const long long lctas = KK == 11 ? (nv == 1 ? 4 : 2) : ((nv == 1 && !staged) ? std::min<long long>(2, c->opt_ctas_fwd) : 1);
-        const i64 lgrid = pair ? 2 * std::min<i64>(tp.num_tiles, (i64)c->sm_count * lctas / 2) : std::min<i64>(tp.num_tiles, (i64)c->sm_count * lctas);
+        const long long lctas = K == 11 ? (nv == 1 ? 4 : 2) : ((nv == 1 && !staged) ? std::min<long long>(2, c->opt_ctas_fwd) : 1);
+        const i64 lgrid = std::min<i64>(tp.num_tiles, (i64)c->sm_count * lctas);
         if (nv == 2) {
             const i64 nunits = flush_per_tile ? tp.num_tiles : lgrid;
             QR_TRY(ensure_scratch(c, (size_t)nunits * QR_SLOTS));
             *units = (int)nunits;
-            tp.partials = partials_at ? partials_at : c->d_scratch;
         }
-        // backward passes: clusters of 2 CTAs take adjacent tiles and align their loads (see k_tile12)
-        const int want_cluster = (nv == 2 ? (int)(c->opt_cluster & 3) : (int)((c->opt_cluster >> 2) & 3));
+        tp.partials = partials_at ? partials_at : c->d_scratch;   // partials_at: a slice of d_scratch the caller has sized (deferred reduction)
         const bool strided_pass = pp.c < K;
-        x.cluster = pair ? 2 : ((want_cluster == 2 || (want_cluster == 1 && strided_pass)) && lgrid % 2 == 0 ? 2 : 1);
         // L2 prefetch of the next tile: opt_prefetch bit 4 = contiguous passes only
         if ((c->opt_prefetch & 16) && strided_pass) tp.prefetch = 0;
-        // pair order (strided in-place passes): a CTA takes adjacent tiles back to back and fetches them into L2 together
-        x.pair_order = ((c->opt_pair_order & (nv == 2 ? 1 : 2)) && strided_pass && !tp.ladder && !pair && x.cluster == 1 &&
-                        tp.tiles_log2 >= 1 && pp.c >= 1) ? 1 : 0;
-        if (x.pair_order && (c->opt_pair_order & 4)) tp.prefetch = staged == 1 ? 0 : 1;   // bit 2: with the pair prefetch in both directions
-        // pair: nv half-tile exchange buffers (32 KiB each) + nv * 4 * 256 amplitudes for the partner (16 KiB each)
-        const size_t lsmem = pair ? (size_t)nv * (tile_bytes / 2 + tile_bytes / 4)
-                                  : (staged ? (size_t)(nv + 1) * tile_bytes : (pp.ngroups > 1 ? (size_t)nv * tile_bytes : 0));
+        const size_t lsmem = staged ? (size_t)(nv + 1) * tile_bytes : (pp.ngroups > 1 ? (size_t)nv * tile_bytes : 0);
         // programmatic dependent launch: the next pass's CTAs queue up while this one drains.  Auto (1): only where a
         // pass is short enough for the launch ramp to matter (states that fit in L2); 2: every pass.
         // The first pass after the gate / phase tables were written is launched fully serialized: k_tile12 reads the
         // tables BEFORE griddepcontrol.wait, which is only safe once a serialized launch separates it from their writer.
         const bool pdl = (c->opt_pdl == 2 || (c->opt_pdl == 1 && lp.n <= QR_PDL_AUTO_MAX_QUBITS)) && !c->tables_fresh;
         c->tables_fresh = false;
-        if (x.pair_order && lgrid > tp.num_tiles / 2) x.pair_order = 0;   // fewer tile pairs than CTAs: keep every CTA busy
-        if (x.cluster > 1 || pdl) {
-            CUDA_TRY(QR_LAUNCH_EX(lfn, (unsigned)lgrid, 1u << (KK - 3), lsmem, c->stream, (unsigned)x.cluster, pdl, tp, x));
+        if (pdl) {
+            CUDA_TRY(QR_LAUNCH_EX(lfn, (unsigned)lgrid, 1u << (K - 3), lsmem, c->stream, 1u, pdl, tp, x));
         } else {
-            QR_LAUNCH(lfn, (unsigned)lgrid, 1 << (KK - 3), lsmem, c->stream, tp, x);
+            QR_LAUNCH(lfn, (unsigned)lgrid, 1 << (K - 3), lsmem, c->stream, tp, x);
         }
         KERNEL_CHECK();
         c->perf.kernel_launches++;
         return 0;
     }
-    if (pp.dc) {   // decoupled-exchange kernel (single state, k = 12, R = 3)
-        typedef void (*dc_fn)(const TilePass, const DcPlan);
-        dc_fn dfn = nv == 1 ? k_tile_pass_dc<1> : k_tile_pass_dc<2>;
-        static bool dc_attr[2] = {false, false};
-        if (!dc_attr[nv - 1]) {
-            CUDA_TRY(cudaFuncSetAttribute(dfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(double2) << QR_MAX_TILE_BITS));
-            dc_attr[nv - 1] = true;
-        }
-        QR_LAUNCH(dfn, (unsigned)grid, threads, (size_t)nv * tile_bytes, c->stream, tp, pp.dcp);
-        KERNEL_CHECK();
-        c->perf.kernel_launches++;
-        return 0;
+    // generic kernel (tiles of fewer than 11 bits)
+    const int threads = 1 << (pp.k - R);
+    const int full = 1 << (QR_MAX_TILE_BITS - R);
+    const long long ctas = nv == 1 ? c->opt_ctas_fwd : c->opt_ctas_bwd;
+    const long long per_sm = std::min<long long>(16, ctas * std::max(1, full / threads));
+    const i64 grid = std::min<i64>(tp.num_tiles, (i64)c->sm_count * per_sm);
+    const size_t smem = pp.nrounds > 1 ? (size_t)nv * tile_bytes : 0;
+    if (nv == 2) {
+        const i64 nunits = flush_per_tile ? tp.num_tiles : grid;
+        QR_TRY(ensure_scratch(c, (size_t)nunits * QR_SLOTS));
+        *units = (int)nunits;
     }
-    tile_fn fn = tile_kernel(nv, R, async);
-    static bool attr_done[2][5][2] = {{{false}}};
-    if (!attr_done[nv - 1][R][async]) {
-        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (int)sizeof(double2) << QR_MAX_TILE_BITS));
-        attr_done[nv - 1][R][async] = true;
-    }
+    tp.partials = partials_at ? partials_at : c->d_scratch;
+    tile_fn fn = nv == 1 ? k_tile_pass<1, 3> : k_tile_pass<2, 3>;
+    QR_TRY(ensure_smem_attr(c, (const void*)fn, 24 + nv));
     QR_LAUNCH(fn, (unsigned)grid, threads, smem, c->stream, tp);
     KERNEL_CHECK();
     c->perf.kernel_launches++;
@@ -1307,12 +1137,8 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     const int n = c->n;
     c->tables_fresh = true;
     LayerPlan lpf, lp;   // forward / backward plans: same tile geometry, different register blocking
-    const bool dc_f = batch == 1 && !c->opt_async_fwd && (c->opt_decoupled & 2);
-    const bool dc_b = batch == 1 && !c->opt_async_bwd && (c->opt_decoupled & 1);
-    QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, pick_min_row_bits(c, n), dc_f,
-                     !dc_f && !c->opt_async_fwd && (c->opt_lean & 2), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
-    QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, pick_min_row_bits(c, n), dc_b,
-                     !dc_b && !c->opt_async_bwd && (c->opt_lean & 1), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
+    QR_TRY(make_plan(n, pick_tile_bits(c, n), &lpf, (int)c->opt_tile_bits_x, pick_min_row_bits(c, n)));
+    lp = lpf;
     const int P = lp.npasses;
     const int GS = QR_GATE_SLOTS;                 // gate entries per (layer, pass)
     const bool want_grad = grad != nullptr;
@@ -1780,12 +1606,8 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
     const int n = c->n;
     c->tables_fresh = true;
     LayerPlan lpf, lp;
-    QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_fwd, &lpf, (int)c->opt_tile_bits_x, pick_min_row_bits(c, n),
-                     !c->opt_async_fwd && (c->opt_decoupled & 2),
-                     !c->opt_async_fwd && !(c->opt_decoupled & 2) && (c->opt_lean & 2), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
-    QR_TRY(make_plan(n, pick_tile_bits(c, n), (int)c->opt_r_bwd, &lp, (int)c->opt_tile_bits_x, pick_min_row_bits(c, n),
-                     !c->opt_async_bwd && (c->opt_decoupled & 1),
-                     !c->opt_async_bwd && !(c->opt_decoupled & 1) && (c->opt_lean & 1), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
+    QR_TRY(make_plan(n, pick_tile_bits(c, n), &lpf, (int)c->opt_tile_bits_x, pick_min_row_bits(c, n)));
+    lp = lpf;
     const int P = lp.npasses;
     const int GS = QR_GATE_SLOTS;
     const bool want_grad = grad != nullptr;
@@ -2127,7 +1949,7 @@ extern "C" int qr_shard_ipc_open(qr_ctx* c, int peer_rank, int buf, const void* 
     memcpy(&h, handle64, 64);
     void* p = nullptr;
     CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-    c->peer[peer_rank][buf] = (double2*)((char*)p + (size_t)c->opt_buf_skew * (size_t)buf);   // every rank uses the same skew
+    c->peer[peer_rank][buf] = (double2*)p;
     c->peer_mapped[peer_rank][buf] = true;
     return 0;
 }
@@ -2193,12 +2015,8 @@ extern "C" int qr_shard_mcclean_begin(qr_ctx* c, int L, const int32_t* axes, con
     run->axes.assign(axes, axes + (size_t)L * nt);
     run->angles.assign(angles, angles + (size_t)L * nt);
     run->terms = o->terms;
-    QR_TRY(make_plan(nl, pick_tile_bits(c, nl), (int)c->opt_r_fwd, &run->lpf, (int)c->opt_tile_bits_x, pick_min_row_bits(c, nl),
-                     !c->opt_async_fwd && (c->opt_decoupled & 2),
-                     !c->opt_async_fwd && !(c->opt_decoupled & 2) && (c->opt_lean & 2), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
-    QR_TRY(make_plan(nl, pick_tile_bits(c, nl), (int)c->opt_r_bwd, &run->lpb, (int)c->opt_tile_bits_x, pick_min_row_bits(c, nl),
-                     !c->opt_async_bwd && (c->opt_decoupled & 1),
-                     !c->opt_async_bwd && !(c->opt_decoupled & 1) && (c->opt_lean & 1), (int)c->opt_page_bits, (int)c->opt_low_bits_pass));
+    QR_TRY(make_plan(nl, pick_tile_bits(c, nl), &run->lpf, (int)c->opt_tile_bits_x, pick_min_row_bits(c, nl)));
+    run->lpb = run->lpf;
     const int P = run->P = run->lpb.npasses;
     run->pi.resize(G);
     for (int r = 0; r < G; ++r) run->pi[r] = r;

@@ -49,8 +49,6 @@ struct TilePass {
     int ladder;                  // 1: gather through the ladder map on load
     u64 M1, M2;
     u64 src_xor;                 // sharded states: carry of the rank bits into the local source index
-    int src_order;               // k_tile12 ladder passes: tiles are enumerated in SOURCE order (sequential reads, scattered writes)
-    u64 iM1, iM2;                // masks of the inverse gather map (destination tile of a source tile)
     int tiles_log2;              // log2(tiles per state) = n - k
     i64 num_tiles;               // batch * tiles per state
     i64 state_stride;            // amplitudes between consecutive states of a batch
@@ -172,75 +170,23 @@ __device__ __forceinline__ void qr_round_compute(double2 (&a)[NV][1 << R], const
     if (R > 3) qr_gate_on_bit<NV, (1 << R), (R > 3 ? 3 : 0)>(a, gt[R > 3 ? 3 : 0], acc[R > 3 ? 3 : 0]);
 }
 
-// ---- async bulk-copy (TMA) + mbarrier helpers ------------------------------------------------
-// Product build: cp.async.bulk (UBLKCP in SASS) completing on an mbarrier.  Emulation build: the
-// copy is a synchronous memcpy, so a missing barrier shows up as wrong data rather than a hang.
-#ifndef QR_HOST_EMUL
-__device__ __forceinline__ unsigned qr_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void qr_mbar_init(u64* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(qr_smem_addr(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void qr_mbar_expect_tx(u64* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(qr_smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void qr_mbar_wait(u64* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(qr_smem_addr(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void qr_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, u64* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     qr_smem_addr(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(qr_smem_addr(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void qr_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-#else
-__device__ __forceinline__ void qr_mbar_init(u64*, int) {}
-__device__ __forceinline__ void qr_mbar_expect_tx(u64*, unsigned) {}
-__device__ __forceinline__ void qr_mbar_wait(u64*, unsigned) { __syncthreads(); }   // all issuing threads have copied
-__device__ __forceinline__ void qr_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, u64*) { memcpy(smem_dst, gsrc, bytes); }
-__device__ __forceinline__ void qr_fence_proxy_async() {}
-#endif
-
-// R = index bits per round held in registers (2^R amplitudes per thread per vector);
-// threads per tile = 2^(k-R).  The round loop is a run-time loop so the code stays inside the
-// instruction cache; per-round accumulators are folded into a small per-thread array.
-//
-// ASYNC = true: the tile is staged through shared memory by bulk async copies (one 64 KiB copy per
-// vector for contiguous tiles, one copy per >=128 B row otherwise) that complete on an mbarrier,
-// and the copies for the CTA's NEXT tile are issued as soon as the current tile has been read
-// into registers, so HBM reads overlap the gate arithmetic.  Shared memory: NV raw tiles + one
-// exchange tile (the vectors take turns in the exchange buffer) = 192 KiB for the backward pass.
-template <int NV, int R, bool ASYNC>
-__global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASYNC) ? 2 : 1)) k_tile_pass(const TilePass p) {
+// Generic tile pass for tiles of fewer than 11 bits (registers of fewer than 11 qubits) and explicit QR_OPT_TILE_BITS:
+// R = index bits per round held in registers (2^R amplitudes per thread per vector); threads per tile = 2^(k-R).
+// The round loop is a run-time loop so the code stays inside the instruction cache; per-round accumulators are
+// folded into a small per-thread array.  Registers of >= 11 qubits run k_tile12 (qr_tile12.cuh).
+template <int NV, int R>
+__global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), (NV == 1 ? 2 : 1)) k_tile_pass(const TilePass p) {
     constexpr int RA = 1 << R;
     QR_DYN_SMEM(double2, smem);
-    __shared__ u64 full_bar;
     __shared__ GateP sgt[QR_GATE_SLOTS];    // this pass's gate table (a dependent global load per gate
                                             // would put an L2 round trip on every tile's critical path)
     __shared__ double2 lut_sm[QR_LUT_MAX];  // QAOA phase factors by integer Hamiltonian value
     const int tid = threadIdx.x;
     const int T = 1 << p.k;
-    double2* exch = ASYNC ? smem + NV * T : smem;   // ASYNC: [raw psi][raw lambda][exchange]
-    // Backward pass: the 13 per-thread gradient accumulators live in shared memory ([slot][thread],
-    // conflict free) so that the 64 data registers + addressing fit 128 registers without spills.
-    constexpr bool ACC_SMEM = false;   // measured: 25.0 ms vs 23.9 ms per n=30 backward pass with registers (+53 KiB smem shrinks L1)
-    double* acc_sm = reinterpret_cast<double*>(smem + NV * T);
+    double2* exch = smem;
     double acc_all[QR_SLOTS];
 #pragma unroll
     for (int i = 0; i < QR_SLOTS; ++i) acc_all[i] = 0.0;
-    if (ACC_SMEM) {
-#pragma unroll
-        for (int i = 0; i < QR_SLOTS; ++i) acc_sm[i * blockDim.x + tid] = 0.0;
-    }
     const int c = p.c, h = p.h;
     const int lomask = (1 << c) - 1;
     const int nlo = h - c;
@@ -249,28 +195,6 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
     const int g_first = p.g[0], g_last = p.g[nrounds - 1];
     const int tb_first = (tid & ((1 << g_first) - 1)) | ((tid >> g_first) << (g_first + R));
     const int tb_last = (tid & ((1 << g_last) - 1)) | ((tid >> g_last) << (g_last + R));
-    const int nrows = 1 << (p.k - c);            // rows of 2^c contiguous amplitudes per tile
-    const unsigned row_bytes = (unsigned)sizeof(double2) << c;
-
-    // issue the bulk copies of tile `tl` into the raw buffers
-    auto issue_tile = [&](i64 tl) {
-        const i64 nb = tl >> p.tiles_log2;
-        const u64 t2 = (u64)tl & tmask;
-        u64 nbase = ((t2 & (((u64)1 << nlo) - 1)) << c) | ((t2 >> nlo) << (h + p.k - c));
-        if (p.ladder) nbase = (ladder_map(nbase, p.M1, p.M2) ^ p.src_xor) & ~(u64)(T - 1);
-        if (tid == 0) qr_mbar_expect_tx(&full_bar, (unsigned)(NV * T * sizeof(double2)));
-        for (int r = tid; r < nrows; r += blockDim.x) {
-            const u64 src = nbase | ((u64)r << h);
-            qr_bulk_load(smem + ((size_t)r << c), p.src0 + nb * p.state_stride + src, row_bytes, &full_bar);
-            if (NV == 2) qr_bulk_load(smem + T + ((size_t)r << c), p.src1 + nb * p.state_stride + src, row_bytes, &full_bar);
-        }
-    };
-    if (ASYNC) {
-        if (tid == 0) qr_mbar_init(&full_bar, 1);
-        __syncthreads();
-        if ((i64)blockIdx.x < p.num_tiles) issue_tile(blockIdx.x);
-    }
-    unsigned parity = 0;
     i64 cur_b = -1;
     const bool use_lut = p.hidx != nullptr && (p.pre_phase || p.post_phase);
     if (use_lut) {
@@ -295,31 +219,14 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
         double2* __restrict__ d1 = (NV == 2) ? p.dst1 + b * p.state_stride : nullptr;
 
         double2 a[NV][RA];
-        if (ASYNC) {
-            // ---- raw shared tile -> registers (ladder permutation applied to the read index) ----
-            const int off = p.ladder ? (int)((ladder_map(tbase, p.M1, p.M2) ^ p.src_xor) & (u64)(T - 1)) : 0;
-            qr_mbar_wait(&full_bar, parity);
-            parity ^= 1u;
+        // ---- global -> registers (ladder gather folded into the load addresses) ----
 #pragma unroll
-            for (int r = 0; r < RA; ++r) {
-                const int l = tb_first | (r << g_first);
-                const int sl = p.ladder ? (((int)ladder_map((u64)l, p.M1, p.M2) ^ off) & (T - 1)) : l;
-                a[0][r] = smem[sl];
-                if (NV == 2) a[NV - 1][r] = smem[T + sl];
-            }
-            __syncthreads();                       // every thread has consumed the raw tile
-            const i64 nt = tile + gridDim.x;
-            if (nt < p.num_tiles) issue_tile(nt);  // next tile streams in while this one is computed
-        } else {
-            // ---- global -> registers (ladder gather folded into the load addresses) ----
-#pragma unroll
-            for (int r = 0; r < RA; ++r) {
-                const int l = tb_first | (r << g_first);
-                const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
-                const u64 s = p.ladder ? (ladder_map(d, p.M1, p.M2) ^ p.src_xor) : d;
-                a[0][r] = s0[s];
-                if (NV == 2) a[NV - 1][r] = s1[s];
-            }
+        for (int r = 0; r < RA; ++r) {
+            const int l = tb_first | (r << g_first);
+            const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
+            const u64 s = p.ladder ? (ladder_map(d, p.M1, p.M2) ^ p.src_xor) : d;
+            a[0][r] = s0[s];
+            if (NV == 2) a[NV - 1][r] = s1[s];
         }
         if (p.pre_phase) {
 #pragma unroll
@@ -338,7 +245,7 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
             }
         }
 #ifndef QR_HOST_EMUL
-        if (!ASYNC && p.prefetch) {   // pull the next tile of this CTA into L2 while this one is computed
+        if (p.prefetch) {   // pull the next tile of this CTA into L2 while this one is computed
             const i64 nt = tile + (i64)gridDim.x * p.prefetch;   // p.prefetch = distance in tiles
             if (nt < p.num_tiles) {
                 const i64 nb = nt >> p.tiles_log2;
@@ -359,10 +266,7 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
         for (int rd = 0; rd < nrounds; ++rd) {
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
             qr_round_compute<NV, R>(a, gt + rd * R, acc);
-            if (ACC_SMEM) {
-#pragma unroll
-                for (int i = 0; i < R; ++i) acc_sm[(rd * R + i) * blockDim.x + tid] += acc[i];
-            } else if (NV == 2) {   // static indices keep the accumulators in registers
+            if (NV == 2) {   // static indices keep the accumulators in registers
 #pragma unroll
                 for (int rr = 0; rr < QR_MAXROUNDS; ++rr)
                     if (rr == rd) {
@@ -375,32 +279,20 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
                 const int gp = p.g[rd], gn = p.g[rd + 1];
                 const int tbp = (tid & ((1 << gp) - 1)) | ((tid >> gp) << (gp + R));
                 const int tbn = (tid & ((1 << gn) - 1)) | ((tid >> gn) << (gn + R));
-                if (ASYNC) {   // one exchange tile: the vectors take turns
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) {
+                for (int r = 0; r < RA; ++r) {
+                    const int l = qr_swz<R>(tbp | (r << gp));
 #pragma unroll
-                        for (int r = 0; r < RA; ++r) exch[qr_swz<R>(tbp | (r << gp))] = a[v][r];
-                        __syncthreads();
-#pragma unroll
-                        for (int r = 0; r < RA; ++r) a[v][r] = exch[qr_swz<R>(tbn | (r << gn))];
-                        __syncthreads();
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < RA; ++r) {
-                        const int l = qr_swz<R>(tbp | (r << gp));
-#pragma unroll
-                        for (int v = 0; v < NV; ++v) exch[v * T + l] = a[v][r];
-                    }
-                    __syncthreads();
-#pragma unroll
-                    for (int r = 0; r < RA; ++r) {
-                        const int l = qr_swz<R>(tbn | (r << gn));
-#pragma unroll
-                        for (int v = 0; v < NV; ++v) a[v][r] = exch[v * T + l];
-                    }
-                    if (rd + 2 == nrounds) __syncthreads();   // smem is free for the next tile's first exchange
+                    for (int v = 0; v < NV; ++v) exch[v * T + l] = a[v][r];
                 }
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < RA; ++r) {
+                    const int l = qr_swz<R>(tbn | (r << gn));
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) a[v][r] = exch[v * T + l];
+                }
+                if (rd + 2 == nrounds) __syncthreads();   // smem is free for the next tile's first exchange
             }
         }
         // ---- registers -> global (QAOA: diagonal-generator inner product and un-phase) ----
@@ -429,20 +321,12 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
             if (NV == 2) d1[d] = a[NV - 1][r];
         }
         if (NV == 2 && p.flush_per_tile) {
-            if (ACC_SMEM) {
-#pragma unroll
-                for (int i = 0; i < QR_GATE_SLOTS; ++i) { acc_all[i] = acc_sm[i * blockDim.x + tid]; acc_sm[i * blockDim.x + tid] = 0.0; }
-            }
             qr_block_reduce_slots(acc_all, p.partials + (u64)tile * QR_SLOTS);
 #pragma unroll
             for (int i = 0; i < QR_SLOTS; ++i) acc_all[i] = 0.0;
         }
     }
     if (NV == 2 && !p.flush_per_tile) {
-        if (ACC_SMEM) {
-#pragma unroll
-            for (int i = 0; i < QR_GATE_SLOTS; ++i) acc_all[i] = acc_sm[i * blockDim.x + tid];
-        }
         qr_block_reduce_slots(acc_all, p.partials + (u64)blockIdx.x * QR_SLOTS);
         // second stage fused in: the last CTA to arrive adds the per-CTA partials in CTA order
         // (fixed order => run-to-run deterministic) and writes the QR_SLOTS sums of this pass.
@@ -462,203 +346,6 @@ __global__ void __launch_bounds__(1 << (QR_MAX_TILE_BITS - R), ((NV == 1 && !ASY
                     p.final_out[i] = v;
                 }
                 if (tid == 0) *p.done_counter = 0u;   // re-arm for the next launch on this stream
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Decoupled-exchange tile pass (k = 12, 512 threads, 3 bits per round).
-//
-// Same arithmetic as k_tile_pass, different thread <-> index-bit bookkeeping.  The 12 local bits
-// are four groups A=(0,1,2) B=(3,4,5) C=(6,7,8) D=(9,10,11); a thread id has three 3-bit slots
-// S0=(t0..t2) S1=(t3..t5) S2=(t6..t8) and the registers hold a fourth group.  An exchange swaps the
-// register group with ONE slot, so only the 8 threads that differ in that slot trade data:
-//     S0: 8 neighbouring lanes  -> __syncwarp
-//     S1: a pair of warps       -> named barrier, 64 threads
-//     S2: every other warp      -> named barrier, 256 threads
-// No block-wide barrier is left in the gate loop, so the 16 warps of the single resident CTA drift
-// apart and their FP64, shared-memory and global-memory phases overlap.  Every thread writes an
-// amplitude back to the address it read it from (address = swizzled local index), which removes
-// all write-after-read hazards inside a tile; the one hazard between consecutive tiles is covered
-// by an arrive-early / wait-late mbarrier.
-// ------------------------------------------------------------------------------------------
-struct DcPlan {
-    int nrounds;
-    int gp[QR_MAXROUNDS][4];   // bit position of the group held by S0, S1, S2, REG in each round
-    int swap_slot[QR_MAXROUNDS];   // slot exchanged with the registers after round r (r < nrounds-1)
-};
-
-#ifndef QR_HOST_EMUL
-__device__ __forceinline__ void qr_named_barrier(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void qr_mbar_arrive(u64* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(qr_smem_addr(bar)) : "memory");
-}
-#else
-__device__ __forceinline__ void qr_named_barrier(int, int) { __syncthreads(); }   // over-synchronises: fine
-__device__ __forceinline__ void qr_mbar_arrive(u64*) {}
-#endif
-
-// bank swizzle for the decoupled kernel: the 8 lanes of a quarter warp always differ in exactly one
-// 3-bit group, whichever it is, so the 16-byte column is the XOR of all four groups
-__device__ __forceinline__ int qr_swz_dc(int l) { return l ^ (((l >> 3) ^ (l >> 6) ^ (l >> 9)) & 7); }
-
-template <int NV>
-__global__ void __launch_bounds__(512, (NV == 1 ? 2 : 1)) k_tile_pass_dc(const TilePass p, const DcPlan dc) {
-    constexpr int R = 3, RA = 8, K = 12, T = 1 << K;
-    QR_DYN_SMEM(double2, smem);
-    __shared__ u64 tile_bar;
-    __shared__ GateP sgt[QR_GATE_SLOTS];
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int s0 = tid & 7, s1 = (tid >> 3) & 7, s2 = tid >> 6;
-    double acc_all[QR_SLOTS];
-#pragma unroll
-    for (int i = 0; i < QR_SLOTS; ++i) acc_all[i] = 0.0;
-    const int c = p.c, h = p.h;
-    const int lomask = (1 << c) - 1;
-    const int nlo = h - c;
-    const u64 tmask = ((u64)1 << p.tiles_log2) - 1;
-    const int nrounds = dc.nrounds;
-    __shared__ double2 lut_sm[QR_LUT_MAX];
-    const bool use_lut = p.hidx != nullptr && (p.pre_phase || p.post_phase);
-    if (tid == 0) qr_mbar_init(&tile_bar, 512);
-    for (int i = tid; i < QR_GATE_SLOTS; i += blockDim.x) sgt[i] = p.gates[i];
-    if (use_lut)
-        for (int i = tid; i < p.lut_size; i += blockDim.x) lut_sm[i] = p.lut[i];
-    __syncthreads();
-    const int lb_first = (s0 << dc.gp[0][0]) | (s1 << dc.gp[0][1]) | (s2 << dc.gp[0][2]);
-    const int gr_first = dc.gp[0][3];
-    const int lb_last = (s0 << dc.gp[nrounds - 1][0]) | (s1 << dc.gp[nrounds - 1][1]) | (s2 << dc.gp[nrounds - 1][2]);
-    const int gr_last = dc.gp[nrounds - 1][3];
-    unsigned iter = 0;
-
-    for (i64 tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
-        const u64 t = (u64)tile & tmask;
-        const u64 tbase = ((t & (((u64)1 << nlo) - 1)) << c) | ((t >> nlo) << (h + K - c));
-        double2 a[NV][RA];
-#pragma unroll
-        for (int r = 0; r < RA; ++r) {
-            const int l = lb_first | (r << gr_first);
-            const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
-            const u64 s = p.ladder ? (ladder_map(d, p.M1, p.M2) ^ p.src_xor) : d;
-            a[0][r] = p.src0[s];
-            if (NV == 2) a[NV - 1][r] = p.src1[s];
-        }
-        if (p.pre_phase) {
-#pragma unroll
-            for (int r = 0; r < RA; ++r) {
-                const int l = lb_first | (r << gr_first);
-                const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
-                double2 ph;
-                if (use_lut) ph = lut_sm[p.hidx[d]];
-                else {
-                    double sn, cs;
-                    sincos(p.angle_pre * p.ham[d], &sn, &cs);
-                    ph = make_double2(cs, -sn);
-                }
-#pragma unroll
-                for (int v = 0; v < NV; ++v) a[v][r] = cmul(a[v][r], ph);
-            }
-        }
-#ifndef QR_HOST_EMUL
-        if (p.prefetch) {
-            const i64 nt = tile + (i64)gridDim.x * p.prefetch;
-            if (nt < p.num_tiles) {
-                const u64 t2 = (u64)nt & tmask;
-                const u64 nbase = ((t2 & (((u64)1 << nlo) - 1)) << c) | ((t2 >> nlo) << (h + K - c));
-                for (int line = tid; line < (T >> 3); line += blockDim.x) {
-                    const int l = line << 3;
-                    const u64 d = nbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
-                    const u64 s = p.ladder ? (ladder_map(d, p.M1, p.M2) ^ p.src_xor) : d;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src0 + s));
-                    if (NV == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src1 + s));
-                }
-            }
-        }
-#endif
-#pragma unroll 1
-        for (int rd = 0; rd < nrounds; ++rd) {
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            qr_round_compute<NV, R>(a, sgt + rd * R, acc);
-            if (NV == 2) {
-#pragma unroll
-                for (int rr = 0; rr < QR_MAXROUNDS; ++rr)
-                    if (rr == rd) {
-#pragma unroll
-                        for (int i = 0; i < R; ++i) acc_all[rr * R + i] += acc[i];
-                    }
-            }
-            if (rd + 1 < nrounds) {
-                const int lbp = (s0 << dc.gp[rd][0]) | (s1 << dc.gp[rd][1]) | (s2 << dc.gp[rd][2]);
-                const int grp = dc.gp[rd][3];
-                const int lbn = (s0 << dc.gp[rd + 1][0]) | (s1 << dc.gp[rd + 1][1]) | (s2 << dc.gp[rd + 1][2]);
-                const int grn = dc.gp[rd + 1][3];
-                if (rd == 0 && iter > 0) qr_mbar_wait(&tile_bar, (iter - 1) & 1u);   // previous tile fully read
-#pragma unroll
-                for (int r = 0; r < RA; ++r) {
-                    const int l = qr_swz_dc(lbp | (r << grp));
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) smem[v * T + l] = a[v][r];
-                }
-                const int slot = dc.swap_slot[rd];
-                if (slot == 0) __syncwarp();
-                else if (slot == 1) qr_named_barrier(1 + (warp >> 1), 64);
-                else qr_named_barrier(9 + (warp & 1), 256);
-#pragma unroll
-                for (int r = 0; r < RA; ++r) {
-                    const int l = qr_swz_dc(lbn | (r << grn));
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) a[v][r] = smem[v * T + l];
-                }
-                if (rd + 2 == nrounds) qr_mbar_arrive(&tile_bar);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < RA; ++r) {
-            const int l = lb_last | (r << gr_last);
-            const u64 d = tbase | (u64)(l & lomask) | ((u64)(l >> c) << h);
-            if (p.post_phase) {
-                double hv;
-                double2 ph;
-                if (use_lut) {
-                    const int hi = p.hidx[d];
-                    hv = p.hmin + (double)hi;
-                    ph = lut_sm[hi];
-                } else {
-                    hv = p.ham[d];
-                    double sn, cs;
-                    sincos(p.angle_post * hv, &sn, &cs);
-                    ph = make_double2(cs, -sn);
-                }
-                if (NV == 2) acc_all[QR_SLOTS - 1] += hv * im_conj_mul(a[NV - 1][r], a[0][r]);
-#pragma unroll
-                for (int v = 0; v < NV; ++v) a[v][r] = cmul(a[v][r], ph);
-            }
-            p.dst0[d] = a[0][r];
-            if (NV == 2) p.dst1[d] = a[NV - 1][r];
-        }
-    }
-    if (NV == 2) {
-        __syncthreads();
-        qr_block_reduce_slots(acc_all, p.partials + (u64)blockIdx.x * QR_SLOTS);
-        if (p.final_out) {
-            __shared__ int is_last;
-            __threadfence();
-            if (tid == 0) {
-                const unsigned prev = atomicAdd(p.done_counter, 1u);
-                is_last = (prev + 1 == gridDim.x);
-            }
-            __syncthreads();
-            if (is_last) {
-                __threadfence();
-                for (int i = tid; i < QR_SLOTS; i += blockDim.x) {
-                    double v = 0.0;
-                    for (unsigned b = 0; b < gridDim.x; ++b) v += ((volatile double*)p.partials)[(u64)b * QR_SLOTS + i];
-                    p.final_out[i] = v;
-                }
-                if (tid == 0) *p.done_counter = 0u;
             }
         }
     }

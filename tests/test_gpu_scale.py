@@ -32,34 +32,11 @@ def test_config2_mcclean_20x20_golden():
     assert_parity(e, g, float(d["E"]), d["grad"], 1.0, 1e-10)
     assert abs(c.run_expec_val() - float(d["E"])) < 1e-10
     assert abs(c.state.norm_error()) < 1e-12
-    for opt in (("async_bwd", 0), ("async_fwd", 1), ("reg_bits_bwd", 4), ("reg_bits_fwd", 4), ("async_bwd", 1),
-                ("prefetch", 1), ("tile_bits", 10), ("ctas_per_sm_fwd", 1), ("async_fwd", 0), ("reg_bits_bwd", 3),
-                ("tile_bits", 12), ("reg_bits_fwd", 3), ("async_bwd", 0), ("decoupled", 1), ("decoupled", 3), ("decoupled", 2)):
+    for opt in (("prefetch", 1), ("tile_bits", 10), ("ctas_per_sm_fwd", 1), ("tile_bits", 12), ("staged", 3), ("staged", 0),
+                ("prefetch", 5), ("defer_reduce", 0), ("pdl", 2), ("tile_bits", 11)):
         c.state.set_option(*opt)       # options accumulate: every kernel variant is exercised
         e2, g2 = c.grad_run()
         assert_parity(e2, g2, float(d["E"]), d["grad"], 1.0, 1e-10)
-
-
-def test_decoupled_kernel_24_qubits_matches_default():
-    """Decoupled-exchange kernel (named barriers, warp-local exchanges) vs the default kernel."""
-    from qradient_b200.circuit_logic import McClean, Qaoa
-    from qradient_b200.optimization_problems import MaxCut
-    n, L = 25, 4
-    rng = np.random.default_rng(25)
-    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
-    c = McClean(n, zz01(n), L, axes=axes, angles=angles)
-    e0, g0 = c.grad_run()
-    for mode in (1, 2, 3):
-        c.state.set_option("decoupled", mode)
-        for _ in range(3):     # races would show up as run-to-run differences
-            e1, g1 = c.grad_run()
-            assert_parity(e1, g1, e0, g0, 1.0, 1e-12)
-    q = Qaoa(22, MaxCut(22, edge_set=MaxCut.random_regular(22, 3, seed=3)).to_observable(), 3)
-    b, gm = rng.random(3), rng.random(3)
-    e0, g0 = q.grad_run(b, gm)
-    q.state.set_option("decoupled", 3)
-    e1, g1 = q.grad_run(b, gm)
-    assert_parity(e1, g1, e0, g0, 33.0, 1e-12)
 
 
 def test_mcclean_16x8_mixed_vs_oracle():
@@ -170,38 +147,6 @@ def test_batched_14_qubits_matches_single():
     for b in (0, 17, 63):
         e_ref, g_ref = orc.mcclean_grad_run(n, zz01(n), axes[b], angles[b])
         assert_parity(e[b], g[b], e_ref, g_ref, 1.0, 1e-10)
-
-
-@pytest.mark.parametrize("n,L", [(12, 3), (15, 2), (20, 2), (23, 2)])
-def test_pair_kernel_matches_default(n, L):
-    """k_tile12 pair kernel (QR_OPT_PAIR: a cluster of two half-size CTAs shares a 12-bit tile over distributed
-    shared memory; st.async + mbarrier hand-over) against the default kernels.  GPU only: the CPU emulation runs
-    thread blocks one after another and cannot host a cluster."""
-    from qradient_b200.circuit_logic import McClean, Qaoa
-    from qradient_b200.optimization_problems import MaxCut
-    rng = np.random.default_rng(100 + n)
-    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
-    zz = np.full((n, n), None)
-    zz[0, 1] = 1.0
-    zz[2, n - 1] = -0.5
-    obs = {"zz": zz, "x": np.array([0.3] + [None] * (n - 1), dtype=object)}
-    c = McClean(n, obs, L, axes=axes, angles=angles)
-    c.state.set_option("tile_bits", 12)
-    e0, g0 = c.grad_run()
-    r0 = c.run_expec_val()
-    for mode in (1, 2, 3):
-        c.state.set_option("pair", mode)
-        for _ in range(2):          # a race would show up as a run-to-run difference
-            e1, g1 = c.grad_run()
-            assert_parity(e1, g1, e0, g0, 1.8, 1e-12)
-        assert abs(c.run_expec_val() - r0) < 1e-12
-    q = Qaoa(n, MaxCut(n, edge_set=[(i, i + 1) for i in range(n - 1)]).to_observable(), 2)
-    q.state.set_option("tile_bits", 12)
-    b, gm = rng.random(2), rng.random(2)
-    e0, g0 = q.grad_run(b, gm)
-    q.state.set_option("pair", 3)
-    e1, g1 = q.grad_run(b, gm)
-    assert_parity(e1, g1, e0, g0, float(n - 1), 1e-12)
 
 
 @pytest.mark.parametrize("n,L", [(12, 3), (14, 6), (20, 8), (24, 3)])

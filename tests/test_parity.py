@@ -157,16 +157,12 @@ def test_mcclean_tile_geometries_vs_oracle(backend, n, L, tile_bits):
     assert abs(c.state.norm_error()) < 1e-12
 
 
-@pytest.mark.parametrize("opts", [dict(lean=0, async_bwd=0, async_fwd=0, reg_bits_fwd=4, reg_bits_bwd=4),
-                                  dict(async_bwd=1, async_fwd=1, reg_bits_fwd=4, reg_bits_bwd=4),
-                                  dict(async_bwd=1, async_fwd=1, reg_bits_fwd=3, reg_bits_bwd=3),
-                                  dict(lean=0, async_bwd=0, async_fwd=0, reg_bits_fwd=3, reg_bits_bwd=3, prefetch=1),
-                                  dict(lean=3, prefetch=1), dict(lean=1), dict(lean=2), dict(staged=3), dict(staged=1, cluster=2), dict(staged=8), dict(staged=12, prefetch=1), dict(src_order=3), dict(src_order=1, tile_bits=12),
-                                  dict(tile_bits_strided=5, min_row_bits=2), dict(tile_bits_strided=4, min_row_bits=1, async_bwd=1),
-                                  dict(decoupled=3)])
+@pytest.mark.parametrize("opts", [dict(prefetch=1), dict(prefetch=5), dict(staged=3), dict(staged=1), dict(staged=0, prefetch=0),
+                                  dict(tile_bits_strided=5, min_row_bits=2), dict(tile_bits_strided=4, min_row_bits=1),
+                                  dict(defer_reduce=0), dict(pdl=2)])
 @pytest.mark.parametrize("n,L,tile_bits", [(7, 2, 5), (10, 2, 12), (13, 1, 12), (9, 2, 4), (12, 2, 12)])
 def test_kernel_variants_vs_oracle(backend, opts, n, L, tile_bits):
-    """Register blocking (3 or 4 bits per round) x staging (direct loads or bulk async copies)."""
+    """Loads (direct, L2 prefetch, staged by asynchronous copies), strided tile sizes, reduction and launch modes."""
     rng = np.random.default_rng(7 * n + tile_bits)
     axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
     obs = mixed_obs(n)
@@ -187,43 +183,10 @@ def test_kernel_variants_vs_oracle(backend, opts, n, L, tile_bits):
     assert_parity(e, g, e_ref, g_ref, float(n - 1), TOL)
 
 
-@pytest.mark.parametrize("n,L,opts", [(15, 1, dict(pair_order=7, prefetch=5)), (15, 1, dict(pair_order=7, staged=3, tile_bits=12))])
-def test_pair_order_matches_default(backend, opts, n, L):
-    """QR_OPT_PAIR_ORDER: in the strided passes a CTA takes its tiles in adjacent pairs (the two 128 B halves of the
-    same 256 B chunks) -- a different tile enumeration (and prefetch / staging schedule), same arithmetic per tile."""
-    rng = np.random.default_rng(1500 + n)
-    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
-    obs = mixed_obs(n)
-    c = McClean(n, obs, L, axes=axes, angles=angles)
-    e0, g0 = c.grad_run()
-    v0 = np.array(c.state.vec)
-    r0 = c.run_expec_val()
-    for k, v in opts.items():
-        c.state.set_option(k, v)
-    e1, g1 = c.grad_run()
-    assert_parity(e1, g1, e0, g0, obs_scale(obs), 1e-12)
-    np.testing.assert_allclose(c.state.vec, v0, atol=1e-13 * obs_scale(obs))
-    assert abs(c.run_expec_val() - r0) < 1e-12 * obs_scale(obs)
-    B = 3
-    ax, an = rng.integers(0, 3, (B, L, n)), rng.uniform(0, 2 * np.pi, (B, L, n))
-    eb, gb = c.grad_run_batch(an, ax)
-    d = McClean(n, obs, L, axes=ax[2], angles=an[2])
-    e2, g2 = d.grad_run()
-    assert_parity(eb[2], gb[2], e2, g2, obs_scale(obs), 1e-12)
-    edges = [(i, i + 1) for i in range(n - 1)]
-    q = Qaoa(n, MaxCut(n, edge_set=edges).to_observable(), 2)
-    b, gm = rng.random(2), rng.random(2)
-    e0, g0 = q.grad_run(b, gm)
-    for k, v in opts.items():
-        q.state.set_option(k, v)
-    e1, g1 = q.grad_run(b, gm)
-    assert_parity(e1, g1, e0, g0, float(n - 1), 1e-12)
-
-
 @pytest.mark.parametrize("n,L", [(12, 3), (14, 2), (16, 2), (17, 1), (19, 1)])
 def test_lean_tile_kernel_group_counts(backend, n, L):
     """k_tile12 (qr_tile12.cuh): strided passes with 1, 2 and 3 register groups next to the 4-group first
-    pass, against the generic tile kernel (lean=0) and, where it finishes in seconds, the oracle."""
+    pass, against the generic tile kernel (10-bit tiles) and, where it finishes in seconds, the oracle."""
     rng = np.random.default_rng(1200 + n)
     axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
     obs = mixed_obs(n)
@@ -231,43 +194,15 @@ def test_lean_tile_kernel_group_counts(backend, n, L):
     c.state.set_option("tile_bits", 12)
     e1, g1 = c.grad_run()
     v1 = np.array(c.state.vec)
-    c.state.set_option("lean", 0)
+    c.state.set_option("tile_bits", 10)
     e0, g0 = c.grad_run()
     assert_parity(e1, g1, e0, g0, obs_scale(obs), 1e-12)
     np.testing.assert_allclose(v1, c.state.vec, atol=1e-13)
     if n <= 14:
         e_ref, g_ref = orc.mcclean_grad_run(n, obs, axes, angles)
         assert_parity(e1, g1, e_ref, g_ref, obs_scale(obs), TOL)
-    c.state.set_option("lean", 3)
+    c.state.set_option("tile_bits", 12)
     np.testing.assert_allclose(c.run_expec_val(), e0, atol=1e-12 * obs_scale(obs))
-
-
-@pytest.mark.parametrize("n,min_row_bits,page_bits", [(17, 9, 13), (19, 8, 13), (18, 9, 14), (16, 10, 13)])
-def test_lean_tile_kernel_two_segment_geometry(backend, n, min_row_bits, page_bits):
-    """Strided passes whose gate bits are two runs of index bits (the planner shares the page-selecting bits between
-    the passes): forced at small n by a small page size and wide rows; against the single-run generic kernel."""
-    L = 2
-    rng = np.random.default_rng(50 + n)
-    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
-    obs = mixed_obs(n)
-    c = McClean(n, obs, L, axes=axes, angles=angles)
-    c.state.set_option("min_row_bits", min_row_bits)
-    c.state.set_option("page_bits", page_bits)
-    e1, g1 = c.grad_run()
-    v1 = np.array(c.state.vec)
-    c.state.set_option("lean", 0)
-    e0, g0 = c.grad_run()
-    assert_parity(e1, g1, e0, g0, obs_scale(obs), 1e-12)
-    np.testing.assert_allclose(v1, c.state.vec, atol=1e-13)
-    c.state.set_option("lean", 3)
-    q = Qaoa(n, MaxCut(n, edge_set=[(i, i + 1) for i in range(n - 1)]).to_observable(), 2)
-    q.state.set_option("min_row_bits", min_row_bits)
-    q.state.set_option("page_bits", page_bits)
-    b, gm = rng.random(2), rng.random(2)
-    e1, g1 = q.grad_run(b, gm)
-    q.state.set_option("lean", 0)
-    e0, g0 = q.grad_run(b, gm)
-    assert_parity(e1, g1, e0, g0, float(n - 1), 1e-12)
 
 
 @pytest.mark.parametrize("n,L,min_row_bits", [(11, 3, 3), (12, 2, 3), (14, 2, 3), (17, 2, 3), (19, 1, 3), (13, 2, 2), (20, 1, 2)])
@@ -299,30 +234,6 @@ def test_lean_tile_kernel_half_size_tiles(backend, n, L, min_row_bits):
         q.state.set_option("min_row_bits", min_row_bits)
         e1, g1 = q.grad_run(b, gm)
         assert_parity(e1, g1, e0, g0, float(n - 1), 1e-12)
-
-
-def test_lean_tile_kernel_low_bits_in_strided_pass(backend):
-    """The gates on index bits 0-2 applied by the strided pass (4 register groups there, 3 in the contiguous pass)."""
-    n, L = 19, 2
-    rng = np.random.default_rng(19)
-    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
-    obs = mixed_obs(n)
-    c = McClean(n, obs, L, axes=axes, angles=angles)
-    e0, g0 = c.grad_run()
-    v0 = np.array(c.state.vec)
-    c.state.set_option("low_bits_pass", -1)
-    e1, g1 = c.grad_run()
-    assert_parity(e1, g1, e0, g0, obs_scale(obs), 1e-12)
-    np.testing.assert_allclose(v0, c.state.vec, atol=1e-13)
-    c.state.set_option("staged", 3)
-    e2, g2 = c.grad_run()
-    assert_parity(e2, g2, e0, g0, obs_scale(obs), 1e-12)
-    q = Qaoa(n, MaxCut(n, edge_set=[(i, i + 1) for i in range(n - 1)]).to_observable(), 2)
-    b, gm = rng.random(2), rng.random(2)
-    e0, g0 = q.grad_run(b, gm)
-    q.state.set_option("low_bits_pass", 1)
-    e1, g1 = q.grad_run(b, gm)
-    assert_parity(e1, g1, e0, g0, float(n - 1), 1e-12)
 
 
 @pytest.mark.parametrize("case", ["all_x", "all_y", "all_z", "special_angles"])
@@ -712,10 +623,11 @@ def test_options_and_permutation_api_validation(backend):
     """Argument checks of the kernel-selection options and of qr_perm_load / qr_state_permute."""
     n = 6
     st = State(n)
-    for name, bad in (("tile_bits", 3), ("tile_bits", 13), ("prefetch", 32), ("staged", 16), ("cluster", 16), ("pair", 4), ("pdl", 3), ("pair_order", 8),
-                      ("src_order", 4), ("cache_hints", 16), ("lean", 4), ("buf_skew", 100), ("page_bits", 5), ("min_row_bits", 12)):
+    for name, bad in (("tile_bits", 3), ("tile_bits", 13), ("prefetch", 32), ("staged", 16), ("pdl", 3), ("min_row_bits", 12)):
         with pytest.raises(ValueError):
             st.set_option(name, bad)
+    with pytest.raises(ValueError):                   # retired round-1 experiment key (decoupled exchange)
+        st._lib.call("qr_set_option", st._ctx, 14, 1)
     st.set_option("tile_bits", 0)                     # auto
     with pytest.raises(ValueError):
         st.load_permutation(np.arange(2 ** n - 1))    # wrong length
