@@ -55,6 +55,8 @@ enum {
     QR_OPT_STAGED_MIN_BIT = 20, /* auto mode: strided backward passes whose lowest gate bit is >= this (default 21) are staged */
     QR_OPT_PDL = 26,          /* k_tile12 passes use programmatic dependent launch (griddepcontrol): 0 off, 1 (default) auto: short passes (n <= 22), 2 always */
     QR_OPT_DEFER_REDUCE = 28, /* 1 (default): single circuits add the per-CTA gradient partials of all backward passes in ONE launch after the sweep; 0: last-CTA reduction fused into every pass */
+    QR_OPT_SHARD_MODE = 30,   /* sharded registers: 0 (default) auto, 1 "peer" engine (peer loads + peer stores per global step; any size), 2 "swap" engine (one NVLink crossing per exchange fused into a tile pass; >= 12 + log2(ranks) local qubits) */
+    QR_OPT_SHARD_LOCKSTEP = 31, /* swap engine: 1 (default) the caller runs qr_shard_step in lockstep over the ranks; 0: all steps are enqueued at once and device-side flags order the ranks */
     QR_OPT_SHARD_ZSKIP = 29   /* 1 (default): sharded states apply an Rz on a global qubit as a per-subgroup phase without the NVLink exchange (only X / Y rotations are exchanged) */
 };
 
@@ -194,6 +196,7 @@ int qr_ham_gather(qr_ctx* ctx, int n, const int64_t* idx, double* out_vals);
 /* One context per rank holds 2^(n_total - log2_world) amplitudes: the top log2_world qubits are the
  * rank bits.  All four ping-pong buffers are allocated so their IPC handles can be exchanged once. */
 int qr_shard_create(int n_total, int log2_world, int rank, int device, qr_ctx** out);
+/* buf = 0..3: the ping-pong state buffers; buf = 4: the rank's array of device-side ordering flags (swap engine) */
 int qr_shard_ipc_handle(qr_ctx* ctx, int buf, void* handle64);                    /* cudaIpcGetMemHandle  */
 int qr_shard_ipc_open(qr_ctx* ctx, int peer_rank, int buf, const void* handle64); /* cudaIpcOpenMemHandle */
 int qr_shard_set_peer_ptr(qr_ctx* ctx, int peer_rank, int buf, void* ptr, int peer_device); /* same process */

@@ -116,6 +116,13 @@ struct qr_ctx {
     double2* peer[QR_MAX_RANKS][QR_NBUF];
     bool peer_mapped[QR_MAX_RANKS][QR_NBUF];
     struct ShardRun* run = nullptr;
+    struct SwapRun* srun = nullptr;                       // swap engine (qr_shard.cuh)
+    unsigned long long* d_flags = nullptr;                // device-side ordering flags of this rank (READY / DONE / ERR per rank)
+    unsigned long long* peer_flags[QR_MAX_RANKS];         // every rank's flag array (own entry = d_flags)
+    bool flags_mapped[QR_MAX_RANKS];
+    long long flag_gen = 0;                               // last generation used by a swap-engine run
+    long long opt_shard_mode = 0;                         // 0 auto, 1 "peer" engine (round 1), 2 "swap" engine
+    long long opt_shard_lockstep = 1;                     // 1: the caller runs the steps in lockstep over the ranks; 0: device-side flags
     std::vector<double2*> snapshots;   // device copies of the state vector (qr_state_save / qr_state_load)
 };
 
@@ -238,6 +245,8 @@ extern "C" int qr_ctx_create(int n_qubits, int device, qr_ctx** out) {
     memset(&c->perf, 0, sizeof(c->perf));
     memset(c->peer, 0, sizeof(c->peer));
     memset(c->peer_mapped, 0, sizeof(c->peer_mapped));
+    memset(c->peer_flags, 0, sizeof(c->peer_flags));
+    memset(c->flags_mapped, 0, sizeof(c->flags_mapped));
     int rc = 0;
     do {
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(QR_ECUDA, "stream creation failed"); break; }
@@ -271,6 +280,7 @@ extern "C" int qr_ctx_destroy(qr_ctx* c) {
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_result) cudaFree(c->d_result);
     if (c->d_counter) cudaFree(c->d_counter);
+    if (c->d_flags) cudaFree(c->d_flags);
     if (c->d_small) cudaFree(c->d_small);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -299,6 +309,8 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
         case QR_OPT_DEFER_REDUCE: c->opt_defer_reduce = v ? 1 : 0; break;
         case QR_OPT_SHARD_ZSKIP: c->opt_shard_zskip = v ? 1 : 0; break;
         case QR_OPT_PDL: if (v < 0 || v > 2) return fail(QR_EINVAL, "bad PDL mode"); c->opt_pdl = v; break;
+        case QR_OPT_SHARD_MODE: if (v < 0 || v > 2) return fail(QR_EINVAL, "bad shard mode"); c->opt_shard_mode = v; break;
+        case QR_OPT_SHARD_LOCKSTEP: c->opt_shard_lockstep = v ? 1 : 0; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -322,6 +334,8 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_PDL: *v = c->opt_pdl; break;
         case QR_OPT_SHARD_ZSKIP: *v = c->opt_shard_zskip; break;
         case QR_OPT_DEFER_REDUCE: *v = c->opt_defer_reduce; break;
+        case QR_OPT_SHARD_MODE: *v = c->opt_shard_mode; break;
+        case QR_OPT_SHARD_LOCKSTEP: *v = c->opt_shard_lockstep; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -960,7 +974,7 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         if (K == 11) lfn = nv == 1 ? (ph ? k_tile12<1, true, 0, 11> : k_tile12<1, false, 0, 11>) : (ph ? k_tile12<2, true, 0, 11> : k_tile12<2, false, 0, 11>);
         else if (staged) lfn = nv == 1 ? (ph ? k_tile12<1, true, 1> : k_tile12<1, false, 1>) : (ph ? k_tile12<2, true, 1> : k_tile12<2, false, 1>);
         else lfn = nv == 1 ? (ph ? k_tile12<1, true, 0> : k_tile12<1, false, 0>) : (ph ? k_tile12<2, true, 0> : k_tile12<2, false, 0>);
-        QR_TRY(ensure_smem_attr(c, (const void*)lfn, ((K - 11) * 2 + (nv - 1)) * 4 + ph * 2 + staged));
+        QR_TRY(ensure_smem_attr(c, (const void*)lfn, ((K - 11) * 2 + (nv - 1)) * 6 + ph * 3 + staged));
         if (staged == 1) tp.prefetch = 0;
         Tile12X x;
         memset(&x, 0, sizeof(x));
@@ -1874,6 +1888,8 @@ extern "C" int qr_ham_gather(qr_ctx* c, int n, const int64_t* idx, double* out) 
 }
 
 
+#include "qr_shard.cuh"
+
 // ------------------------------------------------------------------------------------------
 // Sharded state vector: one shard per rank, top log2(G) qubits = rank bits.
 //   * CNOT ladder: GF(2)-linear and banded towards more significant bits, so a whole destination
@@ -1900,8 +1916,12 @@ static void shard_release(qr_ctx* c) {
     for (int r = 0; r < QR_MAX_RANKS; ++r)
         for (int b = 0; b < QR_NBUF; ++b)
             if (c->peer_mapped[r][b] && c->peer[r][b]) { cudaIpcCloseMemHandle(c->peer[r][b]); c->peer[r][b] = nullptr; c->peer_mapped[r][b] = false; }
+    for (int r = 0; r < QR_MAX_RANKS; ++r)
+        if (c->flags_mapped[r] && c->peer_flags[r]) { cudaIpcCloseMemHandle(c->peer_flags[r]); c->peer_flags[r] = nullptr; c->flags_mapped[r] = false; }
     delete c->run;
     c->run = nullptr;
+    delete c->srun;
+    c->srun = nullptr;
 }
 
 extern "C" int qr_shard_create(int n_total, int log2_world, int rank, int device, qr_ctx** out) {
@@ -1920,6 +1940,13 @@ extern "C" int qr_shard_create(int n_total, int log2_world, int rank, int device
         if (rc) { qr_ctx_destroy(c); *out = nullptr; return rc; }
         c->peer[rank][b] = c->buf[b];
     }
+    if (cudaMalloc((void**)&c->d_flags, QR_FLAG_WORDS * sizeof(unsigned long long)) != cudaSuccess) {
+        qr_ctx_destroy(c); *out = nullptr;
+        return fail(QR_ENOMEM, "flag allocation failed");
+    }
+    cudaMemsetAsync(c->d_flags, 0, QR_FLAG_WORDS * sizeof(unsigned long long), c->stream);
+    cudaStreamSynchronize(c->stream);
+    c->peer_flags[rank] = c->d_flags;
     return 0;
 }
 
@@ -1931,10 +1958,10 @@ static int need_shard(qr_ctx* c) {
 
 extern "C" int qr_shard_ipc_handle(qr_ctx* c, int buf, void* handle64) {
     QR_TRY(need_shard(c));
-    if (buf < 0 || buf >= QR_NBUF || !handle64) return fail(QR_EINVAL, "bad buffer index");
+    if (buf < 0 || buf > QR_NBUF || !handle64) return fail(QR_EINVAL, "bad buffer index");
     QR_TRY(use_device(c));
     cudaIpcMemHandle_t h;
-    CUDA_TRY(cudaIpcGetMemHandle(&h, c->buf_base[buf]));
+    CUDA_TRY(cudaIpcGetMemHandle(&h, buf == QR_NBUF ? (void*)c->d_flags : c->buf_base[buf]));
     static_assert(sizeof(h) == 64, "IPC handle size");
     memcpy(handle64, &h, 64);
     return 0;
@@ -1942,13 +1969,18 @@ extern "C" int qr_shard_ipc_handle(qr_ctx* c, int buf, void* handle64) {
 
 extern "C" int qr_shard_ipc_open(qr_ctx* c, int peer_rank, int buf, const void* handle64) {
     QR_TRY(need_shard(c));
-    if (peer_rank < 0 || peer_rank >= (1 << c->g) || buf < 0 || buf >= QR_NBUF || !handle64) return fail(QR_EINVAL, "bad peer/buffer");
+    if (peer_rank < 0 || peer_rank >= (1 << c->g) || buf < 0 || buf > QR_NBUF || !handle64) return fail(QR_EINVAL, "bad peer/buffer");
     if (peer_rank == c->rank) return 0;
     QR_TRY(use_device(c));
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, 64);
     void* p = nullptr;
     CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    if (buf == QR_NBUF) {   // the peer's ordering flags
+        c->peer_flags[peer_rank] = (unsigned long long*)p;
+        c->flags_mapped[peer_rank] = true;
+        return 0;
+    }
     c->peer[peer_rank][buf] = (double2*)p;
     c->peer_mapped[peer_rank][buf] = true;
     return 0;
@@ -1957,21 +1989,22 @@ extern "C" int qr_shard_ipc_open(qr_ctx* c, int peer_rank, int buf, const void* 
 // same-process peers (one process driving several devices, or the CPU test tier)
 extern "C" int qr_shard_set_peer_ptr(qr_ctx* c, int peer_rank, int buf, void* ptr, int peer_device) {
     QR_TRY(need_shard(c));
-    if (peer_rank < 0 || peer_rank >= (1 << c->g) || buf < 0 || buf >= QR_NBUF || !ptr) return fail(QR_EINVAL, "bad peer/buffer");
+    if (peer_rank < 0 || peer_rank >= (1 << c->g) || buf < 0 || buf > QR_NBUF || !ptr) return fail(QR_EINVAL, "bad peer/buffer");
     if (peer_rank == c->rank) return 0;
     QR_TRY(use_device(c));
     if (peer_device != c->device) {
         cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
         if (e != cudaSuccess) cudaGetLastError();   // already enabled is fine
     }
+    if (buf == QR_NBUF) { c->peer_flags[peer_rank] = (unsigned long long*)ptr; return 0; }
     c->peer[peer_rank][buf] = (double2*)ptr;
     return 0;
 }
 
 extern "C" int qr_shard_buffer_ptr(qr_ctx* c, int buf, void** out) {
     QR_TRY(need_shard(c));
-    if (buf < 0 || buf >= QR_NBUF || !out) return fail(QR_EINVAL, "bad buffer index");
-    *out = c->buf[buf];
+    if (buf < 0 || buf > QR_NBUF || !out) return fail(QR_EINVAL, "bad buffer index");
+    *out = buf == QR_NBUF ? (void*)c->d_flags : (void*)c->buf[buf];
     return 0;
 }
 
@@ -2009,6 +2042,43 @@ extern "C" int qr_shard_mcclean_begin(qr_ctx* c, int L, const int32_t* axes, con
             if (!c->peer[r][b]) return fail(QR_ESTATE, "peer buffers of rank %d are not mapped", r);
     QR_TRY(use_device(c));
     delete c->run;
+    c->run = nullptr;
+    delete c->srun;
+    c->srun = nullptr;
+    const bool swap_ok = swap_engine_ok(nl, c->g) && c->opt_fusion && c->opt_tile_bits == 0 && c->opt_tile_bits_x == 0 && c->opt_min_row_bits == 3;
+    if (c->opt_shard_mode == 2 && !swap_ok)
+        return fail(QR_EINVAL, "the swap engine needs 1..3 rank bits, at least %d local qubits and default tile options", 12 + c->g);
+    if (c->opt_shard_mode == 2 || (c->opt_shard_mode == 0 && swap_ok)) {
+        for (int r = 0; r < G; ++r)
+            if (!c->peer_flags[r]) return fail(QR_ESTATE, "the ordering flags of rank %d are not mapped", r);
+        SwapRun* sr = c->srun = new SwapRun();
+        sr->lockstep = c->opt_shard_lockstep != 0;
+        sr->gen_base = c->flag_gen;
+        std::vector<GateP> tab;
+        QR_TRY(swap_build(c, sr, L, axes, angles, o, want_grad != 0, &tab));
+        c->flag_gen = sr->gen_base;
+        // observable terms (remapped to the final layout of the forward sweep) at offset 0, gate tables behind them
+        const std::vector<ObsTerm>* terms = nullptr;
+        for (const XOp& op : sr->ops) if (op.kind == 2) terms = &op.terms;
+        const size_t terms_bytes = ((terms ? terms->size() : 0) + 1) * sizeof(ObsTerm);
+        sr->tab_off = (terms_bytes + 255) & ~(size_t)255;
+        const size_t tab_bytes = tab.size() * sizeof(GateP);
+        QR_TRY(ensure_small(c, sr->tab_off + tab_bytes + 1024));
+        QR_TRY(ensure_pin(c, std::max(sr->tab_off + tab_bytes + 1024, (sr->n_results + 16) * sizeof(double))));
+        QR_TRY(ensure_result(c, sr->n_results + 16));
+        QR_TRY(ensure_scratch(c, (size_t)c->sm_count * 16 * QR_SLOTS));
+        memcpy(c->h_pin + sr->tab_off, tab.data(), tab_bytes);
+        CUDA_TRY(cudaMemcpyAsync((char*)c->d_small + sr->tab_off, c->h_pin + sr->tab_off, tab_bytes, cudaMemcpyHostToDevice, c->stream));
+        if (terms && !terms->empty()) QR_TRY(upload_small(c, 0, terms->data(), terms->size() * sizeof(ObsTerm), 0));
+        CUDA_TRY(cudaMemsetAsync(c->d_result, 0, (sr->n_results + 16) * sizeof(double), c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        perf_reset(c);
+        c->perf.passes_per_layer = sr->sweeps;
+        c->perf.tile_bits = 12;
+        c->tables_fresh = true;
+        *n_steps = (int)sr->step_first.size();
+        return 0;
+    }
     ShardRun* run = c->run = new ShardRun();
     run->L = L;
     run->want_grad = want_grad != 0;
@@ -2118,6 +2188,16 @@ static int shard_global_step(qr_ctx* c, ShardRun* run, int layer, int nv) {
 extern "C" int qr_shard_step(qr_ctx* c, int step) {
     if (c) c->tables_fresh = true;   // every step is stream-synchronised: no programmatic launch across steps
     QR_TRY(need_shard(c));
+    if (c->srun) {   // swap engine
+        SwapRun* sr = c->srun;
+        if (step < 0 || step >= (int)sr->step_first.size()) return fail(QR_EINVAL, "step %d out of range", step);
+        QR_TRY(use_device(c));
+        const int first = sr->step_first[step];
+        const int last = step + 1 < (int)sr->step_first.size() ? sr->step_first[step + 1] : (int)sr->ops.size();
+        for (int k = first; k < last; ++k) QR_TRY(swap_launch_op(c, sr, sr->ops[k]));
+        if (sr->lockstep) CUDA_TRY(cudaStreamSynchronize(c->stream));   // asynchronous mode: device-side flags order the ranks
+        return 0;
+    }
     ShardRun* run = c->run;
     if (!run) return fail(QR_ESTATE, "no sharded run in progress");
     if (step < 0 || step >= run->n_steps) return fail(QR_EINVAL, "step %d out of range", step);
@@ -2206,6 +2286,37 @@ extern "C" int qr_shard_step(qr_ctx* c, int step) {
 // partial sums of this rank: E and dE/d angles[L * n_total]; the caller adds them over ranks
 extern "C" int qr_shard_mcclean_finish(qr_ctx* c, double* e_partial, double* grad_partial) {
     QR_TRY(need_shard(c));
+    if (c->srun) {   // swap engine
+        SwapRun* sr = c->srun;
+        if (!e_partial) return fail(QR_EINVAL, "null output");
+        QR_TRY(use_device(c));
+        const int nt = c->n_total;
+        unsigned long long* h_flags = (unsigned long long*)(c->h_pin + ((sr->n_results + 1) * sizeof(double) + 63) / 64 * 64);
+        QR_TRY(ensure_pin(c, (sr->n_results + 16) * sizeof(double) + QR_FLAG_WORDS * sizeof(unsigned long long) + 128));
+        h_flags = (unsigned long long*)(c->h_pin + ((sr->n_results + 1) * sizeof(double) + 63) / 64 * 64);
+        CUDA_TRY(cudaMemcpyAsync(c->h_pin, c->d_result, sr->n_results * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(h_flags, c->d_flags, QR_FLAG_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (int r = 0; r < (1 << c->g); ++r)
+            if (h_flags[QR_FLAG_ERR * QR_MAX_RANKS + r]) {
+                cudaMemsetAsync(c->d_flags + QR_FLAG_ERR * QR_MAX_RANKS, 0, QR_MAX_RANKS * sizeof(unsigned long long), c->stream);
+                delete c->srun; c->srun = nullptr;
+                return fail(QR_ESTATE, "sharded run: timed out waiting for rank %d (generation %llu)", r, h_flags[QR_FLAG_ERR * QR_MAX_RANKS + r]);
+            }
+        const double* res = (const double*)c->h_pin;
+        *e_partial = res[0];
+        if (grad_partial) {
+            for (size_t i = 0; i < (size_t)sr->layers * nt; ++i) grad_partial[i] = 0.0;
+            for (const XOp& op : sr->ops)
+                if (op.kind == 1 && op.nv == 2) {
+                    for (int s2 = 0; s2 < QR_GATE_SLOTS; ++s2)
+                        if (op.slot_qubit[s2] >= 0) grad_partial[(size_t)op.layer * nt + op.slot_qubit[s2]] = res[op.res_off + s2];
+                }
+        }
+        delete c->srun;
+        c->srun = nullptr;
+        return 0;
+    }
     ShardRun* run = c->run;
     if (!run || !e_partial) return fail(QR_ESTATE, "no sharded run in progress");
     QR_TRY(use_device(c));

@@ -60,6 +60,21 @@ struct Tile12X {
     u64 droff_first[8];     // same as roff_first without the gather map (destination index: phase tables)
 };
 
+// XMAP passes (sharded registers, qr_shard.cuh): the source of a tile is given by a general GF(2)-linear map instead of
+// the banded ladder masks, and by a table of source POINTERS -- the shard a value is read from (this rank's or a peer's,
+// over NVLink) is selected by the register index (exchange passes: the register bits at load time are the rank bits of
+// the source layout) and / or by up to two bits of the tile index (ladder passes in the swapped layout).
+//   source local index = tmap(tile index) ^ XOR_{thread bit b set} lcol[b] ^ roff_first[register] ^ src_const
+//   source pointer     = src[vector][tile-bit selector][register]
+struct TileXMap {
+    const double2* src[2][4][8];   // [vector][selector][register]
+    u64 tcol[24];                  // image of tile-index bit j (source local index bits)
+    u64 lcol[9];                   // image of tile-local bit b < 9 (the thread bits at load time)
+    u64 src_const;                 // contribution of this rank's id
+    int sel_bit[2];                // tile-index bits forming the selector (or -1)
+    int local_only;                // every pointer is this rank's own buffer: the L2 prefetch of the next tile is useful
+};
+
 // converted gate of local bit b (shared memory, rebuilt per batch element)
 struct Gate12 {
     double tau;    // tan(phi/2) of the reduced rotation
@@ -238,9 +253,9 @@ __device__ __noinline__ double2 qr12_phase_slow(const double* __restrict__ ham, 
 // instead of only reaching L2 (prefetch) or being waited for (direct loads).
 // K = 11: half-size tiles (2048 amplitudes, 256 threads, 64 KiB of shared memory for the backward pass): two
 // backward CTAs per SM, whose load / FP64 / exchange phases overlap; used where it does not cost a pass.
-template <int NV, bool PHASE, int STAGED, int K = QR_MAX_TILE_BITS>
-__global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 1 ? 4 : 2)) : ((NV == 1 && !STAGED) ? 2 : 1)))
-    k_tile12(const TilePass p, const Tile12X x) {
+template <int NV, bool PHASE, int STAGED, int K, bool XMAP>
+__device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, const TileXMap* xmp) {
+    static_assert(!XMAP || (!PHASE && STAGED == 0 && K == 12), "XMAP passes: McClean, direct loads, 12-bit tiles");
     constexpr int T = 1 << K;
     constexpr int LG = K - 3;   // first local bit of the register group held at load time
     QR_DYN_SMEM(double2, smem);
@@ -262,22 +277,45 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
 
     // per-thread global offsets (local bits 0-8 at load time; the last group's thread bits at store time)
     const u64 toff_d = geo12_local(geo, (u64)tid);                                  // destination index bits
-    const u64 toff_s = p.ladder ? ladder_map(toff_d, p.M1, p.M2) : toff_d;          // gathered source bits
+    u64 toff_s = p.ladder ? ladder_map(toff_d, p.M1, p.M2) : toff_d;                // gathered source bits
+    __shared__ u64 xm_tab[XMAP ? 3 : 1][XMAP ? 256 : 1];                            // XMAP: tile index byte -> source index bits
+    if (XMAP) {
+        toff_s = xmp->src_const;
+#pragma unroll
+        for (int b = 0; b < LG; ++b)
+            if ((tid >> b) & 1) toff_s ^= xmp->lcol[b];
+        for (int i = tid; i < 3 * 256; i += blockDim.x) {
+            const int j = i >> 8, v = i & 255;
+            u64 m = 0;
+            for (int b = 0; b < 8; ++b)
+                if ((v >> b) & 1) m ^= xmp->tcol[8 * j + b];
+            xm_tab[j][v] = m;
+        }
+        __syncthreads();
+    }
+    // XMAP: source index bits and pointer selector of tile t
+    auto xm_base = [&](u64 t) -> u64 { return xm_tab[0][t & 255] ^ xm_tab[1][(t >> 8) & 255] ^ xm_tab[2][(t >> 16) & 255]; };
+    auto xm_sel = [&](u64 t) -> int {
+        int s = 0;
+        if (xmp->sel_bit[0] >= 0) s |= (int)((t >> xmp->sel_bit[0]) & 1);
+        if (xmp->sel_bit[1] >= 0) s |= (int)((t >> xmp->sel_bit[1]) & 1) << 1;
+        return s;
+    };
     const int tbl = ng > 1 ? qr12_tb(tid, K == 12 ? 6 : x.last_group) : tid;        // K = 12: the last group is always 6
     const u64 toff_l = geo12_local(geo, (u64)tbl);
 
     const i64 nworkers = (i64)gridDim.x, worker = (i64)blockIdx.x;
-    const i64 iters = (p.num_tiles + nworkers - 1) / nworkers;
-    auto tile_at = [&](i64 it) -> i64 { return worker + it * nworkers; };
-    i64 cur_b = -1;
+    const int iters = (int)((p.num_tiles + nworkers - 1) / nworkers);   // tiles per CTA (32-bit loop state: the kernel sits at its register budget)
+    auto tile_at = [&](int it) -> i64 { return worker + (i64)it * nworkers; };
+    int cur_b = -1;
     double2 zt = make_double2(1.0, 0.0);   // thread factor of the merged diagonal (includes F)
     bool has_z = false;       // apply the diagonal zt * zr after the load
     bool has_zgate = false;   // the pass has an Rz: take the Z-gradient product w
     // convert the gate table of batch element b (block-uniform): reduced shears, merged Z diagonal, per-thread factors
-    auto convert_gates = [&](i64 b) {
+    auto convert_gates = [&](int b) {
         __syncthreads();
         if (tid < QR_GATE_SLOTS) {
-            GateP g = p.gates[b * p.gate_stride + tid];
+            GateP g = p.gates[(i64)b * p.gate_stride + tid];
             if (K < QR_GATE_SLOTS && tid >= K) g.axis = -1;
             Gate12 o;
             o.tau = 0.0; o.sig = 0.0; o.mode = -1; o.neg = 0;
@@ -332,7 +370,7 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
     if (use_lut) {
         for (int i = tid; i < p.lut_size; i += blockDim.x) lut_sm[i] = p.lut[i];
     }
-    if (tile_at(0) < p.num_tiles) convert_gates(tile_at(0) >> p.tiles_log2);
+    if (tile_at(0) < p.num_tiles) convert_gates((int)(tile_at(0) >> p.tiles_log2));
     qr_pdl_wait();
     qr_pdl_launch_dependents();
 
@@ -351,6 +389,17 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
     auto prefetch_tile = [&](i64 nt) {
 #ifndef QR_HOST_EMUL
         const i64 nb = nt >> p.tiles_log2;
+        if (XMAP) {   // line tid of the tile: tile-local bits 3..11 = tid bits 0..8 (bits 9-11 are the load-time register bits)
+            const u64 t2 = (u64)nt & tmask;
+            u64 s = xm_base(t2) ^ xmp->src_const ^ x.roff_first[tid >> 6];
+#pragma unroll
+            for (int b = 3; b < LG; ++b)
+                if ((tid >> (b - 3)) & 1) s ^= xmp->lcol[b];
+            const int sl = xm_sel(t2);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(xmp->src[0][sl][tid >> 6] + s));
+            if (NV == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(xmp->src[1][sl][tid >> 6] + s));
+            return;
+        }
         const u64 nbase = geo12_tile(geo, (u64)nt & tmask);
         const int l = tid << 3;
         const u64 d = nbase | geo12_local(geo, (u64)l);
@@ -375,10 +424,10 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
 
     if (STAGED && tile_at(0) < p.num_tiles) issue_stage(tile_at(0));
 
-    for (i64 it = 0; it < iters; ++it) {
+    for (int it = 0; it < iters; ++it) {
         const i64 tile = tile_at(it);
         if (tile >= p.num_tiles) continue;
-        const i64 b = tile >> p.tiles_log2;
+        const int b = (int)(tile >> p.tiles_log2);
         const u64 t = (u64)tile & tmask;
         const u64 tbase = geo12_tile(geo, t);
         if (b != cur_b) convert_gates(b);   // block-uniform: a persistent CTA of a batched pass moves on to the next circuit
@@ -386,7 +435,7 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
         const u64 boff = (u64)b * (u64)p.state_stride;
 
         // ---- global -> registers (group G3; ladder gather folded into the load addresses) ----
-        const u64 sbt = ((p.ladder ? (ladder_map(tbase, p.M1, p.M2) ^ p.src_xor) : tbase) ^ toff_s) | boff;
+        const u64 sbt = XMAP ? (xm_base(t) ^ toff_s) : (((p.ladder ? (ladder_map(tbase, p.M1, p.M2) ^ p.src_xor) : tbase) ^ toff_s) | boff);
         double2 a[NV][8];
         if (STAGED) {
             qr_cp_async_wait_all();
@@ -396,6 +445,14 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
                 if (NV == 2) a[NV - 1][r] = stage[T + tid + (r << LG)];
             }
             if (it + 1 < iters && tile_at(it + 1) < p.num_tiles) issue_stage(tile_at(it + 1));   // lands while this tile is computed
+        } else if (XMAP) {
+            const int sl = xm_sel(t);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const u64 s = sbt ^ x.roff_first[r];
+                a[0][r] = xmp->src[0][sl][r][s];
+                if (NV == 2) a[NV - 1][r] = xmp->src[1][sl][r][s];
+            }
         } else {
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
@@ -532,4 +589,16 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
             }
         }
     }
+}
+
+template <int NV, bool PHASE, int STAGED, int K = QR_MAX_TILE_BITS>
+__global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 1 ? 4 : 2)) : ((NV == 1 && !STAGED) ? 2 : 1)))
+    k_tile12(const TilePass p, const Tile12X x) {
+    qr12_body<NV, PHASE, STAGED, K, false>(p, x, nullptr);
+}
+
+// sharded registers: general source map and source pointer table (exchange passes read the peers' shards over NVLink)
+template <int NV>
+__global__ void __launch_bounds__(512, (NV == 1 ? 2 : 1)) k_tile12_x(const TilePass p, const Tile12X x, const TileXMap xm) {
+    qr12_body<NV, false, 0, 12, true>(p, x, &xm);
 }

@@ -7,8 +7,12 @@ The reference is single-process; this is the large-register extension named in B
     * local qubits  : the same fused tile passes as on one GPU;
     * CNOT ladder   : a whole destination shard reads exactly one source shard, so the ladder is a
                       relabelling of shards plus a local gather -- no data movement;
-    * global qubits : one kernel per layer and vector reads the G peer shards over NVLink (CUDA IPC
-                      mappings), applies the rotations in registers and writes them back;
+    * global qubits : "swap" engine (default; >= 12 + log2 G local qubits): an EXCHANGE PASS -- an ordinary tile pass
+                      whose loads come from the G peer shards over NVLink (CUDA IPC mappings) and whose stores are
+                      local, so the rank bits trade places with g local bits and every exchanged amplitude crosses the
+                      link once; the passes of all layers are enqueued at once and device-side flags order the ranks.
+                      "peer" engine (small registers): one kernel per layer and vector reads the G peer shards,
+                      applies the rotations in registers and writes them back; a host barrier after every step;
     * E and gradient: per-rank partial sums, one allreduce of L*n+1 doubles at the end.
 
 Two communicators: `TorchDistComm` (one process per GPU, torch.distributed: NCCL on GPUs, gloo in
@@ -22,7 +26,7 @@ import numpy as np
 from . import _lib
 from .physical_components import Observable
 
-NBUF = 4
+NBUF = 4          # state buffers per shard; index NBUF addresses the shard's ordering flags (swap engine)
 
 
 class _Shard:
@@ -36,7 +40,7 @@ class _Shard:
 
     def handles(self):
         out = []
-        for b in range(NBUF):
+        for b in range(NBUF + 1):
             buf = ctypes.create_string_buffer(64)
             self.lib.call('qr_shard_ipc_handle', self.ctx, b, buf)
             out.append(buf.raw)
@@ -44,7 +48,7 @@ class _Shard:
 
     def pointers(self):
         out = []
-        for b in range(NBUF):
+        for b in range(NBUF + 1):
             p = ctypes.c_void_p()
             self.lib.call('qr_shard_buffer_ptr', self.ctx, b, ctypes.byref(p))
             out.append(p.value)
@@ -61,6 +65,7 @@ class _Shard:
 
 class TorchDistComm:
     """One process per GPU; torch.distributed must be initialised by the caller."""
+    lockstep = False   # the swap engine orders the ranks with device-side flags: no host barrier between steps
 
     def __init__(self, group=None):
         import torch.distributed as dist
@@ -97,6 +102,7 @@ class TorchDistComm:
 
 class LocalComm:
     """All G shards live in this process (device d per shard, or one device for tests)."""
+    lockstep = True    # the shards are stepped one after another by this process
 
     def __init__(self, world, devices=None):
         self.world = world
@@ -112,7 +118,7 @@ class LocalComm:
             for peer in range(self.world):
                 if peer == s.rank:
                     continue
-                for b in range(NBUF):
+                for b in range(NBUF + 1):
                     s.lib.call('qr_shard_set_peer_ptr', s.ctx, peer, b, ctypes.c_void_p(ptrs[peer][b]), self.devices[peer])
 
     def barrier(self):
@@ -129,7 +135,7 @@ class ShardedMcClean:
     rank must call the methods collectively with identical arguments.
     """
 
-    def __init__(self, qubit_number, observable, layer_number, comm, axes, angles, device=None):
+    def __init__(self, qubit_number, observable, layer_number, comm, axes, angles, device=None, mode=None):
         self.qnum, self.lnum, self.comm = int(qubit_number), int(layer_number), comm
         g = int(np.log2(comm.world))
         if 2 ** g != comm.world or g < 1:
@@ -145,6 +151,15 @@ class ShardedMcClean:
         comm.barrier()
         comm.exchange_handles(self.shards)
         comm.barrier()
+        nl = self.qnum - g
+        if mode is None:
+            mode = 'swap' if (1 <= g <= 3 and nl >= 12 + g) else 'peer'
+        if mode not in ('swap', 'peer'):
+            raise ValueError("mode must be 'swap' or 'peer'")
+        self.mode = mode
+        self.set_option('shard_mode', 2 if mode == 'swap' else 1)
+        self.set_option('shard_lockstep', 1 if getattr(comm, 'lockstep', True) else 0)
+        self.perf = {}
 
     def set_option(self, name, value):
         for s in self.shards:
@@ -169,6 +184,16 @@ class ShardedMcClean:
         import time
         L = self.lnum
         self.step_seconds = {'fwd_local': 0.0, 'fwd_global': 0.0, 'observable': 0.0, 'bwd_local': 0.0, 'bwd_global': 0.0}
+        if self.mode == 'swap':
+            t0 = time.perf_counter()
+            lockstep = getattr(self.comm, 'lockstep', True)
+            for step in range(nsteps.value):
+                for s in self.shards:
+                    self._lib.call('qr_shard_step', s.ctx, step)
+                if lockstep:
+                    self.comm.barrier()
+            self.step_seconds = {'enqueue': time.perf_counter() - t0}
+            nsteps.value = 0
         for step in range(nsteps.value):
             t0 = time.perf_counter()
             for s in self.shards:
@@ -193,6 +218,8 @@ class ShardedMcClean:
         perf = _lib.QrPerf()
         self._lib.call('qr_perf_last', self.shards[0].ctx, ctypes.byref(perf))
         self.link_bytes = perf.link_bytes
+        self.perf = {'kernel_launches': int(perf.kernel_launches), 'link_bytes': float(perf.link_bytes),
+                     'sweeps_per_layer': int(perf.passes_per_layer) + (1 if self.mode == 'peer' else 0), 'mode': self.mode}
         total = self.comm.allreduce_sum(parts)
         return float(total[0]), np.array(total[1:]).reshape(self.lnum, self.qnum)
 

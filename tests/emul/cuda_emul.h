@@ -66,6 +66,8 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 static inline void __threadfence() {}
+#include <sched.h>
+static inline void emul_yield_cpu() { sched_yield(); }
 static inline int __double2int_rn(double x) { return (int)std::nearbyint(x); }
 
 // ---- runtime subset -------------------------------------------------------------------

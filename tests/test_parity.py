@@ -160,7 +160,7 @@ def test_mcclean_tile_geometries_vs_oracle(backend, n, L, tile_bits):
 @pytest.mark.parametrize("opts", [dict(prefetch=1), dict(prefetch=5), dict(staged=3), dict(staged=1), dict(staged=0, prefetch=0),
                                   dict(tile_bits_strided=5, min_row_bits=2), dict(tile_bits_strided=4, min_row_bits=1),
                                   dict(defer_reduce=0), dict(pdl=2)])
-@pytest.mark.parametrize("n,L,tile_bits", [(7, 2, 5), (10, 2, 12), (13, 1, 12), (9, 2, 4), (12, 2, 12)])
+@pytest.mark.parametrize("n,L,tile_bits", [(7, 2, 5), (10, 2, 12), (13, 1, 12), (9, 2, 4), (12, 2, 12), (14, 2, 11), (15, 1, 12)])
 def test_kernel_variants_vs_oracle(backend, opts, n, L, tile_bits):
     """Loads (direct, L2 prefetch, staged by asynchronous copies), strided tile sizes, reduction and launch modes."""
     rng = np.random.default_rng(7 * n + tile_bits)

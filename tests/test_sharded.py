@@ -45,6 +45,52 @@ def test_virtual_shards_vs_oracle(backend, n, L, G, tile_bits):
         c.close()
 
 
+@pytest.mark.parametrize("n,L,G", [(14, 3, 2), (15, 2, 2), (16, 3, 4), (18, 3, 8)])
+def test_swap_engine_virtual_shards_vs_oracle(backend, n, L, G):
+    """Swap engine (qr_shard.cuh): exchange passes whose loads come from the peer shards and whose stores are local, the
+    layout alternating between 'qubits 0..g-1 on the rank bits' and 'local bits [sigma, sigma+g) on the rank bits', ladder
+    passes with cross-shard tiles in the swapped layout; x / y observable terms on a rank-held qubit and on the lowest bit."""
+    rng = np.random.default_rng(n * 10 + G)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    obs = mixed_obs(n)
+    e_ref, g_ref = orc.mcclean_grad_run(n, obs, axes, angles)
+    c = ShardedMcClean(n, obs, L, LocalComm(G), axes, angles, mode="swap")
+    try:
+        assert c.mode == "swap"
+        e, g = c.grad_run()
+        assert_parity(e, g, e_ref, g_ref, obs_scale(obs), 1e-10)
+        assert c.perf["sweeps_per_layer"] == 3 and c.perf["kernel_launches"] > 0
+        # every exchanged amplitude crosses the link once: (G-1)/G of a shard per exchange pass (+ the cross-shard ladder tiles)
+        n_loc = 2 ** (n - int(np.log2(G)))
+        exchange = 3 * L * 16.0 * n_loc * (G - 1) / G
+        assert exchange <= c.link_bytes <= 2.0 * exchange
+        assert abs(c.run_expec_val() - e_ref) <= 1e-10 * obs_scale(obs)
+        c.angles = angles + 0.1          # parameters can be re-assigned between calls
+        e2, g2 = c.grad_run()
+        e_ref2, g_ref2 = orc.mcclean_grad_run(n, obs, axes, angles + 0.1)
+        assert_parity(e2, g2, e_ref2, g_ref2, obs_scale(obs), 1e-10)
+        if n > 16:
+            return
+        # the round-1 engine on the same register
+        p = ShardedMcClean(n, obs, L, LocalComm(G), axes, angles + 0.1, mode="peer")
+        e3, g3 = p.grad_run()
+        p.close()
+        assert_parity(e3, g3, e2, g2, obs_scale(obs), 1e-12)
+    finally:
+        c.close()
+
+
+def test_swap_engine_needs_enough_local_qubits(backend):
+    n, G = 13, 4      # 11 local qubits < 12 + 2
+    c = ShardedMcClean(n, mixed_obs(n), 1, LocalComm(G), np.zeros((1, n), int), np.zeros((1, n)))
+    assert c.mode == "peer"
+    c.close()
+    c = ShardedMcClean(n, mixed_obs(n), 1, LocalComm(G), np.zeros((1, n), int), np.zeros((1, n)), mode="swap")
+    with pytest.raises(ValueError):
+        c.grad_run()
+    c.close()
+
+
 @pytest.mark.parametrize("n,G", [(8, 2), (8, 4), (9, 8), (10, 16)])
 def test_diagonal_global_gates_skip_the_exchange(backend, n, G):
     """Rz on a global (rank-bit) qubit is applied as a per-subgroup phase and only X / Y rotations are exchanged
@@ -87,12 +133,14 @@ def test_sharded_argument_checks(backend):
     c.close()
 
 
-def test_gloo_world_size_2_on_cpu():
-    """Two processes, torch.distributed gloo, shard buffers mapped across processes."""
+@pytest.mark.parametrize("qubits,port", [(9, "29741"), (14, "29743")])
+def test_gloo_world_size_2_on_cpu(qubits, port):
+    """Two processes, torch.distributed gloo, shard buffers mapped across processes.  9 qubits: the peer engine with a host
+    barrier after every step; 14 qubits: the swap engine, all steps enqueued at once, ranks ordered by device-side flags."""
     script = os.path.join(ROOT, "scripts", "shard_run.py")
-    env = dict(os.environ, QR_SHARD_BACKEND="emul", MASTER_ADDR="127.0.0.1", MASTER_PORT="29741")
+    env = dict(os.environ, QR_SHARD_BACKEND="emul", MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29741", script, "--qubits", "9", "--layers", "3", "--check"]
+           "--master-port", port, script, "--qubits", str(qubits), "--layers", "3", "--check"]
     res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "PARITY OK" in res.stdout, res.stdout + res.stderr
