@@ -220,7 +220,7 @@ class McClean(ParametrizedCircuit):
         the host, one dense matrix-vector product per measurement on the device; n <= 12).  The draws are those
         scipy's `rvs` would make on the global numpy stream."""
         if getattr(self, '_eig_basis', None) is None:          # the reference's has_loaded_eigensystem
-            self._eig_basis = self._measurement_basis(self.observable, self.observable.matrix)
+            self._eig_basis = self._measurement_basis(self.observable, lambda: self.observable.matrix)
             self.eigenvalues = self._eig_basis[1]
         return self._sample_grad_measured(self._eig_basis, shot_num, exact_expec_val, ini_state)
 
@@ -237,16 +237,18 @@ class McClean(ParametrizedCircuit):
             self._component_bases = [None] * obs.num_components
         component = np.random.choice(np.arange(obs.num_components), p=obs.weight_distribution)
         if self._component_bases[component] is None:
-            self._component_bases[component] = self._measurement_basis(obs.component(component), obs.component_array[component])
+            self._component_bases[component] = self._measurement_basis(obs.component(component), lambda: obs._host_matrix([component]))
         return self._sample_grad_measured(self._component_bases[component], shot_num, exact_expec_val, ini_state)
 
     def _measurement_basis(self, obs, host_matrix):
-        """('perm', eigenvalues, order) for z / zz observables, ('dense', eigenvalues, V^dagger) otherwise."""
+        """('perm', eigenvalues, order) for z / zz observables, ('dense', eigenvalues, V^dagger) otherwise.
+        `host_matrix` is a callable: the 2^n x 2^n host matrix is only built on the dense branch (z / zz observables stay
+        matrix-free at any register size)."""
         if np.any(obs.term_kinds < 2):
             if self.qnum > 12:
                 raise NotImplementedError('observables with x / y terms are measured in the eigenbasis of the dense 2^n x 2^n '
                                           'observable (mc_clean.py:221), which is limited to 12 qubits here')
-            eigenvalues, eigenvectors = np.linalg.eigh(host_matrix.toarray())           # mc_clean.py:221
+            eigenvalues, eigenvectors = np.linalg.eigh(host_matrix().toarray())         # mc_clean.py:221
             return ('dense', eigenvalues, np.ascontiguousarray(eigenvectors.transpose().conj()))   # mc_clean.py:222
         st = self.state
         st._load_ham(obs)

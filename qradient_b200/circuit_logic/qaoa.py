@@ -48,6 +48,10 @@ class Qaoa(ParametrizedCircuit):
         self._lib.call('qr_qaoa_expec', self.state._ctx, self.lnum, _lib.ptr(betas), _lib.ptr(gammas), use_current,
                        ctypes.byref(e))
         if exact_expec_val:
+            # qaoa.py:35-36 returns expec_val() under the FULL observable; qr_qaoa_expec reduces <psi|H|psi> over the z / zz
+            # terms (all there is for MaxCut), so observables that also carry x / y terms take the general reduction
+            if np.any(self.observable.term_kinds < 2):
+                return self.expec_val()
             return e.value
         return self.sample_expec_val(shot_num)
 

@@ -61,6 +61,12 @@ class State:
             self._check_ini(ini)
             self._ini = ini
         self._lib.call('qr_state_init', self._ctx, 0 if self._ini == '0' else 1)
+        # state.py:72-77: the dense-operator tracking attributes return to their initial values as well
+        if 'lhs' in self.__dict__:
+            import scipy.sparse as sp
+            self.lhs = sp.identity(2**self.qnum, dtype='complex', format='csr')
+        if 'center_matrix' in self.__dict__:
+            self.center_matrix = self._center_matrix_ini.copy()
 
     @property
     def qnum(self):
@@ -239,8 +245,14 @@ class State:
         self._center_matrix_ini = matrix.copy()
 
     # the reference's *_lhs / *_center_matrix variants are 'Not implemented.' stubs (state.py:99-103 ...)
+    _STUB_GATES = ('xrot', 'xrot_all', 'x_summed', 'yrot', 'zrot', 'cnot', 'cnot_ladder', 'rot_classical_ham',
+                   'rot_classical_ham_component', 'classical_ham', 'exp_ham_classical', 'exp_ham_classical_component', 'ham_classical')
+
     def __getattr__(self, name):
-        if name.endswith('_lhs') or name.endswith('_center_matrix'):
+        for suffix in ('_lhs', '_center_matrix'):
+            if not (name.endswith(suffix) and name[:-len(suffix)] in self._STUB_GATES):
+                continue
+
             def stub(*args, **kwargs):
                 warnings.warn('Not implemented.')
             return stub

@@ -20,6 +20,7 @@ ap.add_argument("--check", action="store_true", help="compare with the CPU oracl
 ap.add_argument("--tile-bits", type=int, default=0)
 ap.add_argument("--check-single", action="store_true", help="compare with the single-GPU path on rank 0")
 ap.add_argument("--opt", action="append", default=[], help="library option name=value")
+ap.add_argument("--mode", default=None, help="sharded engine: swap | peer (default: auto)")
 args = ap.parse_args()
 
 import torch
@@ -46,8 +47,9 @@ axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
 zz = np.full((n, n), None)
 zz[0, 1] = 1.0
 obs = {"zz": zz, "x": np.array([0.25] + [None] * (n - 1), dtype=object)}
-circ = ShardedMcClean(n, obs, L, TorchDistComm(), axes, angles, device=device)
-circ.set_option("tile_bits", args.tile_bits)
+circ = ShardedMcClean(n, obs, L, TorchDistComm(), axes, angles, device=device, mode=args.mode)
+if args.tile_bits:
+    circ.set_option("tile_bits", args.tile_bits)
 for o in args.opt:
     k_, v_ = o.split("=")
     circ.set_option(k_, int(v_))
@@ -59,7 +61,7 @@ for _ in range(args.reps):
     dist.barrier()
     times.append(time.perf_counter() - t0)
 if rank == 0:
-    out = {"n": n, "L": L, "world": world, "E": e, "grad_norm": float(np.linalg.norm(g)), "s_per_gradient": min(times),
+    out = {"n": n, "L": L, "world": world, "mode": circ.mode, "perf": circ.perf, "E": e, "grad_norm": float(np.linalg.norm(g)), "s_per_gradient": min(times),
            "bytes_sched_per_gpu": 16.0 * 2.0 ** n / world * (1 + 2 * 3 * L + 2 + 4 * 3 * L),
            "step_seconds": {k: round(v, 4) for k, v in circ.step_seconds.items()}, "opts": args.opt,
            "nvlink_bytes_per_direction_per_global_vector_step": 16.0 * 2.0 ** n / world * (world - 1) / world,

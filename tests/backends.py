@@ -15,7 +15,20 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
 
 from qradient_b200 import _lib  # noqa: E402
 
-BACKENDS = [pytest.param("emul", id="emul"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+def _cuda_devices():
+    """Number of visible CUDA devices (0 without a driver): plain `pytest tests` on a CPU-only box skips the cuda
+    backend instead of failing in qr_ctx_create."""
+    import ctypes
+    try:
+        n = ctypes.c_int(0)
+        rc = _lib.Library(_lib.LIB_PATH).cdll.qr_device_count(ctypes.byref(n))
+        return n.value if rc == 0 else 0
+    except Exception:
+        return 0
+
+
+_NO_GPU = pytest.mark.skipif(_cuda_devices() == 0, reason="no CUDA device visible")
+BACKENDS = [pytest.param("emul", id="emul"), pytest.param("cuda", id="cuda", marks=[pytest.mark.gpu, _NO_GPU])]
 _handles = {}
 
 

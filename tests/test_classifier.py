@@ -4,7 +4,7 @@ Checked against the oracle's gate-by-gate forward pass and exact parameter-shift
 import numpy as np
 import pytest
 
-from backends import backend, activate  # noqa: F401
+from backends import _NO_GPU, backend, activate  # noqa: F401
 from oracle import qr_oracle as orc
 from qradient_b200.circuit_logic import MeynardClassifier
 
@@ -62,6 +62,7 @@ def test_classifier_custom_observable_and_errors(backend):
 
 
 @pytest.mark.gpu
+@_NO_GPU
 def test_classifier_notebook_sizes_gpu():
     """Notebook cell 18 sweeps 2..14 qubits at 5 + 5 layers; here 14 and 20 qubits with finite differences."""
     activate("cuda")

@@ -395,17 +395,10 @@ def test_error_behaviour(backend):
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5])
-def test_empty_and_tiny_inputs(n):
-    """Edge cases: zero layers, one- and two-qubit registers (below the fused path), observables without terms.
-    CPU tier only (added after the round's GPU budget was spent; the GPU tier covers 3-qubit registers elsewhere)."""
-    from backends import activate
-    from qradient_b200 import _lib as _l
-    prev = _l._LIB
-    activate("emul")
-    try:
-        _empty_and_tiny_inputs(n)
-    finally:
-        _l._restore(prev)
+def test_empty_and_tiny_inputs(backend, n):
+    """Edge cases on both backends: zero layers, one- and two-qubit registers (below the fused path, which starts at
+    4 qubits), observables without terms."""
+    _empty_and_tiny_inputs(n)
 
 
 def _empty_and_tiny_inputs(n):
