@@ -152,7 +152,8 @@ struct XOp {
     bool gather = false;     // plain path: out-of-place gather through `spec`
     LadderSpec spec = {0, 0, 0};
     u64 tcol[24], lcol[9], roff[8], src_const = 0;
-    int sel_bit[2] = {-1, -1};
+    int sel_bit[2] = {-1, -1};   // selector bit k: tile-index bit ...
+    int thr_bit[2] = {-1, -1};   // ... or thread bit (tile-local bit < 9)
     int src_rank[4][8];      // physical source rank per (selector, register)
     bool remote = false;
     double remote_frac = 0.0;   // fraction of the source amplitudes read from peers
@@ -220,18 +221,23 @@ static int xop_set_map(qr_ctx* c, XOp& op, const Lin& M, int nl, int g) {
     op.src_const = cimg & lmask;
     const int r0 = (int)(cimg >> nl);
     int rr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int nsel = 0, srank[2] = {0, 0};
     for (int b = 0; b < 12; ++b) {   // tile-local bits
         const u64 d = geo12_local(geo, (u64)1 << b);
         const u64 img = lin_apply(M, d);
         if (b < 9) {
-            if (img >> nl) return fail(QR_ESTATE, "internal: source rank depends on a thread bit of the tile");
             op.lcol[b] = img & lmask;
+            if (img >> nl) {   // the source shard depends on a thread bit: a per-thread choice of the pointer table
+                if (nsel >= 2) return fail(QR_ESTATE, "internal: source rank depends on more than two selector bits");
+                op.thr_bit[nsel] = b;
+                srank[nsel] = (int)(img >> nl);
+                ++nsel;
+            }
         } else {
             for (int r = 0; r < 8; ++r)
                 if ((r >> (b - 9)) & 1) { op.roff[r] ^= img & lmask; rr[r] ^= (int)(img >> nl); }
         }
     }
-    int nsel = 0, srank[2] = {0, 0};
     const int tiles_log2 = nl - 12;
     if (tiles_log2 > 24) return fail(QR_EINVAL, "sharded registers: at most 36 local qubits");
     for (int j = 0; j < 24; ++j) {
@@ -241,7 +247,7 @@ static int xop_set_map(qr_ctx* c, XOp& op, const Lin& M, int nl, int g) {
         const u64 img = lin_apply(M, d);
         op.tcol[j] = img & lmask;
         if (img >> nl) {
-            if (nsel >= 2) return fail(QR_ESTATE, "internal: source rank depends on more than two tile bits");
+            if (nsel >= 2) return fail(QR_ESTATE, "internal: source rank depends on more than two selector bits");
             op.sel_bit[nsel] = j;
             srank[nsel] = (int)(img >> nl);
             ++nsel;
@@ -314,37 +320,72 @@ static int xop_set_geometry(XOp& op, const std::vector<int>& bits, bool contiguo
 
 static bool swap_engine_ok(int nl, int g) { return g >= 1 && g <= 3 && nl >= 12 + g && nl <= 36; }
 
+// CNOT(control bit pc -> target bit pt) as an index map: j -> j ^ (j_pc ? e_pt : 0) (its own inverse)
+static Lin lin_cnot(int n, int pc, int pt) {
+    Lin f = lin_identity(n);
+    f.col[pc] ^= (u64)1 << pt;
+    return f;
+}
+
+// the CNOT of the ladder whose control is held by a local bit and whose target by the rank bits (at most one in the two
+// layouts the engine uses); returns false if there is none
+static bool layout_offending_cnot(const Layout& ly, int* pc_out, int* pt_out) {
+    const int nt = ly.nl + ly.g;
+    u64 local = 0;
+    for (int k = 0; k < ly.nl; ++k) local |= ly.phi.col[k];
+    int found = 0;
+    for (int c = 0; c + 1 < nt; ++c) {
+        const int pc = nt - 1 - c, pt = nt - 2 - c;
+        if (((local >> pc) & 1) && !((local >> pt) & 1)) { *pc_out = pc; *pt_out = pt; ++found; }
+    }
+    return found == 1;
+}
+
+// does the gather G, run in layout ly, read only this rank's own shard (after the shard relabelling)?
+static bool gather_is_local(const Layout& ly, const Lin& G) {
+    Lin inv;
+    if (!lin_inverse(ly.phi, &inv)) return false;
+    const Lin M0 = lin_mul(inv, lin_mul(G, ly.phi));
+    for (int k = 0; k < ly.nl; ++k)
+        if (M0.col[k] >> ly.nl) return false;
+    return true;
+}
+
 // Build the whole schedule of one gradient (or forward-only run).  Deterministic given (n, g, L): every rank builds the
 // same sequence with the same buffer indices and generations.
+//
+// The CNOT of a ladder whose control is local and whose target sits on a rank bit (swapped layout only) would make the
+// ladder pass read half of its tiles from another shard.  Where the ladder can be written with that CNOT acting first
+// (forward) / last (backward), it is PEELED off and folded into the load addresses of the neighbouring exchange pass,
+// which reads the peers anyway:
+//   forward : the exchange pass that leaves the natural layout applies it on the way (both qubits are still local there);
+//   backward: the exchange pass that returns to the natural layout applies it as a permutation of its source pointers and
+//             also takes over the un-rotation of the CNOT's control qubit (which must follow the CNOT), so that pass's
+//             tile holds the swapped bits, the control bit right above them and 8 - g other local bits.
+// Every exchanged amplitude then crosses NVLink exactly once per layer and vector.
 static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const double* angles, const qr_obs* o, bool want_grad,
                       std::vector<GateP>* gate_tab) {
     const int nl = c->n, g = c->g, nt = c->n_total, G = 1 << g, me = c->rank;
     const int m = 9 - g;                                   // local gate bits of an exchange pass
-    const int h = std::min(12, nl - 9);                    // its gate run is [h, h+9): [h, h+m) local, [h+m, h+9) the swapped bits
+    // gate run of the exchange pass: [h, h+9) = [h, h+m) local + [sigma, sigma+g) swapped.  One local bit must stay above
+    // it (the control of the peeled CNOT), and the peel needs that control to be an odd qubit (it then belongs to the
+    // CNOT group of ladder(0) that acts first): pick h accordingly where the register is large enough.
+    int h = std::min(12, nl - 9);
+    bool peel_geometry = false;
+    {
+        const int hmax = std::min(13, nl - 10);
+        for (int cand = hmax; cand >= std::max(4, hmax - 1); --cand) {
+            const int ctrl_qubit = nt - 1 - (cand + 9);    // qubit held by local bit sigma + g in the natural layout
+            if (ctrl_qubit >= 0 && (ctrl_qubit & 1) && cand + 9 < nl) { h = cand; peel_geometry = true; break; }
+        }
+    }
     const int sigma = h + m;
     sr->h = h; sr->m = m; sr->sigma = sigma; sr->layers = L;
     Layout ly;
     ly.phi = lin_identity(nt);
     ly.nl = nl; ly.g = g;
-    // local gate bits: everything but [h, h+m); pass 0 = contiguous low 12, the rest in strided passes of <= 9 bits
-    std::vector<int> low, high;
-    for (int k = 0; k < nl; ++k) {
-        if (k >= h && k < h + m) continue;
-        (k < 12 ? low : high).push_back(k);
-    }
-    std::vector<std::vector<int>> strided;
-    if (!high.empty()) {
-        const int nx = ((int)high.size() + 8) / 9;
-        size_t pos = 0;
-        for (int i = 0; i < nx; ++i) {
-            const int sz = (int)high.size() / nx + (i < (int)high.size() % nx ? 1 : 0);
-            strided.emplace_back(high.begin() + pos, high.begin() + pos + sz);
-            pos += sz;
-        }
-    }
     std::vector<int> xbits;
     for (int k = h; k < h + 9; ++k) xbits.push_back(k);
-    sr->sweeps = 1 + (int)strided.size() + 1;
     sr->ops.clear();
     gate_tab->clear();
     int psi = 0, lam = -1;
@@ -352,6 +393,7 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
     long long readable[QR_NBUF] = {0, 0, 0, 0};   // generation of the last remote pass in which peers read this buffer
     long long waited = sr->gen_base;              // DONE generation already waited for
     size_t res = 1;                               // d_result[0] = E
+    int max_sweeps = 0;
     auto pick_free = [&](int a, int b, int d) { for (int i = 0; i < QR_NBUF; ++i) if (i != a && i != b && i != d) return i; return -1; };
     auto finish_op = [&](XOp& op, const Layout& dest_ly) -> int {
         // gate table entries and slot -> qubit map in the destination layout
@@ -382,14 +424,38 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
             for (int v = 0; v < op.nv; ++v) readable[op.src_buf[v]] = op.gen;
         return 0;
     };
-    // one layer: optional ladder gather (stacking 0 forward / 1 backward) folded into pass 0, local passes, exchange pass
-    auto add_layer = [&](int layer, int nv, int ladder_stacking) -> int {
-        // ---- pass 0: contiguous tile, gather through the ladder in the current layout ----
+    auto new_op = [&](int layer, int nv) {
+        XOp op;
+        op.kind = 1; op.nv = nv; op.layer = layer;
+        memset(op.tcol, 0, sizeof(op.tcol)); memset(op.lcol, 0, sizeof(op.lcol)); memset(op.roff, 0, sizeof(op.roff));
+        return op;
+    };
+    // One layer.  ladder_stacking >= 0: the gather of that ladder is folded into pass 0.  `pre` (forward): a CNOT already
+    // applied by the previous exchange pass, to be taken out of this ladder.  `next_stacking` (forward): the ladder of the
+    // next layer, whose offending CNOT this layer's exchange pass may apply in advance.
+    std::vector<Lin> pre;   // 0 or 1 entries
+    auto add_layer = [&](int layer, int nv, int ladder_stacking, int next_stacking) -> int {
+        bool owed = false;          // backward: a CNOT peeled off this layer's ladder, owed to this layer's exchange pass
+        Lin owed_f = lin_identity(nt);
+        int ctrl_local = -1;        // local bit holding the control qubit of the owed CNOT
+        // ---- the ladder in the current layout ----
         Lin M = lin_identity(nt);
         if (ladder_stacking >= 0 && nt >= 2) {
+            Lin Gl = lin_ladder_gather(nt, ladder_stacking);
+            if (!pre.empty()) { Gl = lin_mul(pre[0], Gl); pre.clear(); }          // G = F G_rest  =>  G_rest = F G
+            int pc, pt;
+            if (nv == 2 && peel_geometry && !gather_is_local(ly, Gl) && layout_offending_cnot(ly, &pc, &pt)) {
+                const Lin F = lin_cnot(nt, pc, pt);
+                const Lin Grest = lin_mul(Gl, F);                                  // inverse ladder = rest first, then the CNOT
+                int kc = -1;
+                for (int k = 0; k < nl; ++k) if (layout_local_logical(ly, k) == pc) kc = k;
+                if (gather_is_local(ly, Grest) && kc == sigma + g && sigma - 2 >= 3 && h - 1 >= 3) {
+                    owed = true; owed_f = F; ctrl_local = kc; Gl = Grest;
+                }
+            }
             Lin inv;
             if (!lin_inverse(ly.phi, &inv)) return fail(QR_ESTATE, "internal: singular layout");
-            const Lin M0 = lin_mul(inv, lin_mul(lin_ladder_gather(nt, ladder_stacking), ly.phi));
+            const Lin M0 = lin_mul(inv, lin_mul(Gl, ly.phi));
             // absorb the rank-rank block into the layout: T = diag(1, D^-1)
             Lin D = lin_identity(g), Dinv;
             for (int cb = 0; cb < g; ++cb) D.col[cb] = (M0.col[nl + cb] >> nl) & (u64)(G - 1);
@@ -398,11 +464,37 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
             for (int cb = 0; cb < g; ++cb) T.col[nl + cb] = Dinv.col[cb] << nl;
             ly.phi = lin_mul(ly.phi, T);
             M = lin_mul(M0, T);
+        } else pre.clear();
+        // ---- gate bits of this layer's passes ----
+        std::vector<int> xb;        // exchange pass (destination layout)
+        if (!owed) xb = xbits;
+        else {   // [h-1, sigma-2) + [sigma, sigma+g] : 8 - g local bits, the swapped bits, the control bit of the owed CNOT
+            for (int k = h - 1; k < sigma - 2; ++k) xb.push_back(k);
+            for (int k = sigma; k <= sigma + g; ++k) xb.push_back(k);
         }
+        std::vector<int> low, high;
+        for (int k = 0; k < nl; ++k) {
+            bool in_x = false;
+            for (int b : xb) in_x = in_x || b == k;
+            // the exchange pass rotates what its destination tile holds AFTER the swap: the swapped bits [sigma, sigma+g)
+            // still need their local rotation in the current layout
+            if (in_x && !(k >= sigma && k < sigma + g)) continue;
+            (k < 12 ? low : high).push_back(k);
+        }
+        std::vector<std::vector<int>> strided;
+        if (!high.empty()) {
+            const int nx = ((int)high.size() + 8) / 9;
+            size_t pos = 0;
+            for (int i = 0; i < nx; ++i) {
+                const int sz = (int)high.size() / nx + (i < (int)high.size() % nx ? 1 : 0);
+                strided.emplace_back(high.begin() + pos, high.begin() + pos + sz);
+                pos += sz;
+            }
+        }
+        max_sweeps = std::max(max_sweeps, 2 + (int)strided.size());
+        // ---- pass 0: contiguous tile, gather through the ladder ----
         {
-            XOp op;
-            op.kind = 1; op.nv = nv; op.layer = layer;
-            memset(op.tcol, 0, sizeof(op.tcol)); memset(op.lcol, 0, sizeof(op.lcol)); memset(op.roff, 0, sizeof(op.roff));
+            XOp op = new_op(layer, nv);
             QR_TRY(xop_set_geometry(op, low, true));
             QR_TRY(xop_set_map(c, op, M, nl, g));
             const bool oop = op.xmap || op.gather;
@@ -418,9 +510,7 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
         }
         // ---- strided local passes, in place ----
         for (const std::vector<int>& bits : strided) {
-            XOp op;
-            op.kind = 1; op.nv = nv; op.layer = layer;
-            memset(op.tcol, 0, sizeof(op.tcol)); memset(op.lcol, 0, sizeof(op.lcol)); memset(op.roff, 0, sizeof(op.roff));
+            XOp op = new_op(layer, nv);
             QR_TRY(xop_set_geometry(op, bits, false));
             QR_TRY(xop_set_map(c, op, lin_identity(nt), nl, g));
             op.src_buf[0] = psi; op.src_buf[1] = lam; op.dst_buf[0] = psi; op.dst_buf[1] = lam;
@@ -436,14 +526,23 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
                 nw.phi.col[sigma + b] = (u64)1 << held[b];          // the formerly rank-held logical bits, in pure form
                 nw.phi.col[nl + b] = ly.phi.col[sigma + b];         // the local bits that move onto the rank bits
             }
+            Lin F = owed ? owed_f : lin_identity(nt);
+            bool fold = owed;
+            if (!owed && nv == 1 && next_stacking >= 0 && peel_geometry) {
+                // forward: would the next ladder read other shards in the new layout?  Then apply its offending CNOT here.
+                const Lin Gn = lin_ladder_gather(nt, next_stacking);
+                int pc, pt;
+                if (!gather_is_local(nw, Gn) && layout_offending_cnot(nw, &pc, &pt)) {
+                    const Lin Fc = lin_cnot(nt, pc, pt);
+                    if (gather_is_local(nw, lin_mul(Fc, Gn))) { F = Fc; fold = true; pre.push_back(Fc); }
+                }
+            }
             Lin inv;
             if (!lin_inverse(ly.phi, &inv)) return fail(QR_ESTATE, "internal: singular layout");
-            const Lin M = lin_mul(inv, nw.phi);
-            XOp op;
-            op.kind = 1; op.nv = nv; op.layer = layer;
-            memset(op.tcol, 0, sizeof(op.tcol)); memset(op.lcol, 0, sizeof(op.lcol)); memset(op.roff, 0, sizeof(op.roff));
-            QR_TRY(xop_set_geometry(op, xbits, false));
-            QR_TRY(xop_set_map(c, op, M, nl, g));
+            const Lin Mx = fold ? lin_mul(inv, lin_mul(F, nw.phi)) : lin_mul(inv, nw.phi);   // new[j] = old[F j]
+            XOp op = new_op(layer, nv);
+            QR_TRY(xop_set_geometry(op, xb, false));
+            QR_TRY(xop_set_map(c, op, Mx, nl, g));
             if (!op.xmap) return fail(QR_ESTATE, "internal: exchange pass without peers");
             op.src_buf[0] = psi; op.src_buf[1] = lam;
             const int d0 = pick_free(psi, lam, -1);
@@ -453,6 +552,7 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
             psi = d0; if (nv == 2) lam = d1;
             sr->ops.push_back(op);
             ly = nw;
+            (void)ctrl_local;
         }
         return 0;
     };
@@ -464,7 +564,8 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
         op.init_pop = __builtin_popcount((unsigned)layout_shard_value(ly, me));
         sr->ops.push_back(op);
     }
-    for (int i = 0; i < L; ++i) QR_TRY(add_layer(i, 1, 0));
+    for (int i = 0; i < L; ++i) QR_TRY(add_layer(i, 1, 0, i + 1 < L ? 0 : -1));
+    pre.clear();
     // ---- observable in the current layout ----
     {
         XOp op;
@@ -499,13 +600,14 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
         sr->ops.push_back(op);
     }
     if (want_grad)
-        for (int i = L - 1; i >= 0; --i) QR_TRY(add_layer(i, 2, i < L - 1 ? 1 : -1));
+        for (int i = L - 1; i >= 0; --i) QR_TRY(add_layer(i, 2, i < L - 1 ? 1 : -1, -1));
     // ---- steps: a remote pass starts a step, and so does whatever follows it ----
     sr->step_first.clear();
     for (size_t k = 0; k < sr->ops.size(); ++k) {
         const bool after_remote = k > 0 && sr->ops[k - 1].remote;
         if (k == 0 || sr->ops[k].new_step || after_remote) sr->step_first.push_back((int)k);
     }
+    sr->sweeps = max_sweeps;
     sr->n_results = res;
     sr->gen_base = gen;
     (void)psi;
@@ -606,6 +708,7 @@ static int swap_launch_op(qr_ctx* c, SwapRun* sr, const XOp& op) {
             memcpy(xm.lcol, op.lcol, sizeof(xm.lcol));
             xm.src_const = op.src_const;
             xm.sel_bit[0] = op.sel_bit[0]; xm.sel_bit[1] = op.sel_bit[1];
+            xm.thr_bit[0] = op.thr_bit[0]; xm.thr_bit[1] = op.thr_bit[1];
             xm.local_only = op.remote ? 0 : 1;
             // L2 prefetch of the next tile: local sources only (a prefetch of peer memory would warm the PEER's L2)
             tp.prefetch = (!op.remote && op.nv == 2) ? (int)(c->opt_prefetch & 3) : 0;

@@ -65,13 +65,14 @@ struct Tile12X {
 // over NVLink) is selected by the register index (exchange passes: the register bits at load time are the rank bits of
 // the source layout) and / or by up to two bits of the tile index (ladder passes in the swapped layout).
 //   source local index = tmap(tile index) ^ XOR_{thread bit b set} lcol[b] ^ roff_first[register] ^ src_const
-//   source pointer     = src[vector][tile-bit selector][register]
+//   source pointer     = src[vector][selector][register]; selector bit k = tile-index bit sel_bit[k] or thread bit thr_bit[k]
 struct TileXMap {
     const double2* src[2][4][8];   // [vector][selector][register]
     u64 tcol[24];                  // image of tile-index bit j (source local index bits)
     u64 lcol[9];                   // image of tile-local bit b < 9 (the thread bits at load time)
     u64 src_const;                 // contribution of this rank's id
-    int sel_bit[2];                // tile-index bits forming the selector (or -1)
+    int sel_bit[2];                // tile-index bit of selector bit k (or -1)
+    int thr_bit[2];                // thread bit (tile-local bit < 9) of selector bit k (or -1)
     int local_only;                // every pointer is this rank's own buffer: the L2 prefetch of the next tile is useful
 };
 
@@ -295,8 +296,13 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
     }
     // XMAP: source index bits and pointer selector of tile t
     auto xm_base = [&](u64 t) -> u64 { return xm_tab[0][t & 255] ^ xm_tab[1][(t >> 8) & 255] ^ xm_tab[2][(t >> 16) & 255]; };
+    int xm_thr_sel = 0;   // selector bits taken from this thread's id (fixed for the whole kernel)
+    if (XMAP) {
+        if (xmp->thr_bit[0] >= 0) xm_thr_sel |= (tid >> xmp->thr_bit[0]) & 1;
+        if (xmp->thr_bit[1] >= 0) xm_thr_sel |= ((tid >> xmp->thr_bit[1]) & 1) << 1;
+    }
     auto xm_sel = [&](u64 t) -> int {
-        int s = 0;
+        int s = xm_thr_sel;
         if (xmp->sel_bit[0] >= 0) s |= (int)((t >> xmp->sel_bit[0]) & 1);
         if (xmp->sel_bit[1] >= 0) s |= (int)((t >> xmp->sel_bit[1]) & 1) << 1;
         return s;

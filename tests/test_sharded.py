@@ -45,8 +45,8 @@ def test_virtual_shards_vs_oracle(backend, n, L, G, tile_bits):
         c.close()
 
 
-@pytest.mark.parametrize("n,L,G", [(14, 3, 2), (15, 2, 2), (16, 3, 4), (18, 3, 8)])
-def test_swap_engine_virtual_shards_vs_oracle(backend, n, L, G):
+@pytest.mark.parametrize("n,L,G,peeled", [(14, 3, 2, False), (15, 2, 2, True), (16, 3, 4, False), (17, 3, 4, True), (18, 3, 8, True)])
+def test_swap_engine_virtual_shards_vs_oracle(backend, n, L, G, peeled):
     """Swap engine (qr_shard.cuh): exchange passes whose loads come from the peer shards and whose stores are local, the
     layout alternating between 'qubits 0..g-1 on the rank bits' and 'local bits [sigma, sigma+g) on the rank bits', ladder
     passes with cross-shard tiles in the swapped layout; x / y observable terms on a rank-held qubit and on the lowest bit."""
@@ -64,6 +64,9 @@ def test_swap_engine_virtual_shards_vs_oracle(backend, n, L, G):
         n_loc = 2 ** (n - int(np.log2(G)))
         exchange = 3 * L * 16.0 * n_loc * (G - 1) / G
         assert exchange <= c.link_bytes <= 2.0 * exchange
+        # where the geometry allows, the CNOT that would make a ladder pass read another shard is folded into the
+        # neighbouring exchange pass: exactly one crossing per exchange, nothing else on the link
+        assert (c.link_bytes == exchange) == peeled
         assert abs(c.run_expec_val() - e_ref) <= 1e-10 * obs_scale(obs)
         c.angles = angles + 0.1          # parameters can be re-assigned between calls
         e2, g2 = c.grad_run()
