@@ -57,6 +57,8 @@ enum {
     QR_OPT_DEFER_REDUCE = 28, /* 1 (default): single circuits add the per-CTA gradient partials of all backward passes in ONE launch after the sweep; 0: last-CTA reduction fused into every pass */
     QR_OPT_SHARD_MODE = 30,   /* sharded registers: 0 (default) auto, 1 "peer" engine (peer loads + peer stores per global step; any size), 2 "swap" engine (one NVLink crossing per exchange fused into a tile pass; >= 12 + log2(ranks) local qubits) */
     QR_OPT_SHARD_LOCKSTEP = 31, /* swap engine: 1 (default) the caller runs qr_shard_step in lockstep over the ranks; 0: all steps are enqueued at once and device-side flags order the ranks */
+    QR_OPT_SHARD_SLICES = 32, /* swap engine: the last local pass and the exchange pass of a layer are issued in 1 (default), 2, 4 or 8 slices of the index bits 9..11; asynchronous mode runs the exchange pass of a slice on a second stream while the local pass works on the next slice */
+    QR_OPT_SHARD_XSMS = 33,   /* asynchronous mode: SMs given to the exchange pass of a slice (default 60); the concurrent local pass uses the others */
     QR_OPT_SHARD_ZSKIP = 29   /* 1 (default): sharded states apply an Rz on a global qubit as a per-subgroup phase without the NVLink exchange (only X / Y rotations are exchanged) */
 };
 

@@ -123,6 +123,10 @@ struct qr_ctx {
     long long flag_gen = 0;                               // last generation used by a swap-engine run
     long long opt_shard_mode = 0;                         // 0 auto, 1 "peer" engine (round 1), 2 "swap" engine
     long long opt_shard_lockstep = 1;                     // 1: the caller runs the steps in lockstep over the ranks; 0: device-side flags
+    long long opt_shard_slices = 1;                       // swap engine: the last local pass and the exchange pass of a layer are issued in this many slices (1 = off, the default: measured -4 % at 8 GPUs, +11 % at 2, profiles/README.md)
+    long long opt_shard_xsms = 60;                        // asynchronous mode: SMs given to the exchange pass while the local pass of the next slice runs on the others
+    cudaStream_t stream2 = nullptr;                       // second stream of the sliced exchange passes
+    cudaEvent_t ev_pair[2] = {nullptr, nullptr};
     std::vector<double2*> snapshots;   // device copies of the state vector (qr_state_save / qr_state_load)
 };
 
@@ -284,6 +288,8 @@ extern "C" int qr_ctx_destroy(qr_ctx* c) {
     if (c->d_small) cudaFree(c->d_small);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 2; ++i) if (c->ev_pair[i]) cudaEventDestroy(c->ev_pair[i]);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -311,6 +317,8 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
         case QR_OPT_PDL: if (v < 0 || v > 2) return fail(QR_EINVAL, "bad PDL mode"); c->opt_pdl = v; break;
         case QR_OPT_SHARD_MODE: if (v < 0 || v > 2) return fail(QR_EINVAL, "bad shard mode"); c->opt_shard_mode = v; break;
         case QR_OPT_SHARD_LOCKSTEP: c->opt_shard_lockstep = v ? 1 : 0; break;
+        case QR_OPT_SHARD_SLICES: if (v != 1 && v != 2 && v != 4 && v != 8) return fail(QR_EINVAL, "slices must be 1, 2, 4 or 8"); c->opt_shard_slices = v; break;
+        case QR_OPT_SHARD_XSMS: if (v < 1 || v > 1024) return fail(QR_EINVAL, "bad SM count"); c->opt_shard_xsms = v; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -336,6 +344,8 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_DEFER_REDUCE: *v = c->opt_defer_reduce; break;
         case QR_OPT_SHARD_MODE: *v = c->opt_shard_mode; break;
         case QR_OPT_SHARD_LOCKSTEP: *v = c->opt_shard_lockstep; break;
+        case QR_OPT_SHARD_SLICES: *v = c->opt_shard_slices; break;
+        case QR_OPT_SHARD_XSMS: *v = c->opt_shard_xsms; break;
         default: return fail(QR_EINVAL, "unknown option %d", key);
     }
     return 0;
@@ -818,7 +828,7 @@ static void plan_rounds(PassPlan& pp, int first, int R) {
 static void plan_lean(PassPlan& pp, int first) {
     for (int i = 0; i < QR_GATE_SLOTS; ++i) pp.gbit[i] = -1;
     const int K = pp.k;
-    const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2, K};
+    const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2, K, 0};
     for (int lb = first; lb < K; ++lb) {
         u64 gidx = geo12_local(geo, (u64)1 << lb);
         int gb = 0;
@@ -914,6 +924,16 @@ struct PassIO {
 
 struct LadderSpec { u64 M1, M2, src_xor; };   // explicit gather map (sharded states)
 
+// optional launch parameters (sliced passes of sharded registers: qr_shard.cuh)
+struct PassExtra {
+    int hole = 0;                   // index bits [9, 9+hole) are fixed to tile_or >> 9 instead of enumerated
+    u64 tile_or = 0;
+    int max_sms = 0;                // > 0: use at most this many SMs (a concurrent pass runs on the others)
+    double* partials = nullptr;     // per-CTA partials region (default: d_scratch)
+    unsigned* counter = nullptr;    // arrival counter of the fused final reduction (default: d_counter)
+    cudaStream_t stream = nullptr;  // default: the context's stream
+};
+
 // opt in to > 48 KiB of dynamic shared memory: the attribute is PER DEVICE, so remember it per (kernel, device)
 static int ensure_smem_attr(qr_ctx* c, const void* fn, int slot) {
     static bool done[64][32] = {};   // [device][kernel slot]
@@ -931,8 +951,11 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
                        int gate_stride, int ladder_stacking /* -1 none, else gather of ladder(stacking) */,
                        i64 batch, i64 state_stride, int flush_per_tile, const double* ham, int pre_phase,
                        double angle_pre, int post_phase, double angle_post, int* units, const LadderSpec* spec = nullptr,
-                       double* final_out = nullptr, const double2* lut = nullptr, double* partials_at = nullptr) {
+                       double* final_out = nullptr, const double2* lut = nullptr, double* partials_at = nullptr,
+                       const PassExtra* ex = nullptr) {
     const PassPlan& pp = lp.pass[pass];
+    cudaStream_t stream = (ex && ex->stream) ? ex->stream : c->stream;
+    const int sms = (ex && ex->max_sms > 0) ? std::min(ex->max_sms, c->sm_count) : c->sm_count;
     TilePass tp;
     memset(&tp, 0, sizeof(tp));
     tp.k = pp.k; tp.c = pp.c; tp.h = pp.h; tp.nrounds = pp.nrounds;
@@ -946,7 +969,9 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         tp.ladder = 1;
         ladder_masks(lp.n, 1 - ladder_stacking, &tp.M1, &tp.M2);
     }
-    tp.tiles_log2 = lp.n - pp.k;
+    tp.hole = ex ? ex->hole : 0;
+    tp.tile_or = ex ? ex->tile_or : 0;
+    tp.tiles_log2 = lp.n - pp.k - tp.hole;
     tp.num_tiles = batch << tp.tiles_log2;
     tp.state_stride = state_stride;
     tp.src0 = io.src0; tp.src1 = io.src1; tp.dst0 = io.dst0; tp.dst1 = io.dst1;
@@ -959,7 +984,8 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
     const int R = lp.R;
     const size_t tile_bytes = sizeof(double2) << pp.k;
     tp.final_out = (nv == 2 && !flush_per_tile) ? final_out : nullptr;
-    tp.done_counter = c->d_counter;
+    tp.done_counter = (ex && ex->counter) ? ex->counter : c->d_counter;
+    if (ex && ex->partials) partials_at = ex->partials;
     if (pp.lean) {   // k_tile12 (k = 12: 512 threads; k = 11: 256 threads)
         typedef void (*lean_fn)(const TilePass, const Tile12X);
         const int ph = (pre_phase || post_phase) ? 1 : 0;
@@ -967,7 +993,14 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         // measured at n = 30 (profiles/README.md) the L2 prefetch wins for the contiguous pass and for strides
         // below 32 MiB, and loses badly (22 vs 17 ms) when all gate bits are >= 21 -> auto mode (bit 2).
         int staged = (nv == 2 ? (c->opt_staged & 1) : (c->opt_staged & 2)) ? 1 : 0;
-        if (nv == 2 && (c->opt_staged & 4) && pp.c < pp.k && pp.h >= c->opt_staged_min_bit) staged = 1;
+        {   // auto: strided backward passes most of whose gate bits are high-stride bits (two-run tiles: count them)
+            int nbits = 0, nhigh = 0;
+            for (int sb = 0; sb < QR_GATE_SLOTS; ++sb)
+                if (pp.gbit[sb] >= 0) { ++nbits; if (pp.gbit[sb] >= c->opt_staged_min_bit) ++nhigh; }
+            const bool single_run = pp.h2 == pp.h + pp.m1;
+            const bool high = single_run ? pp.h >= c->opt_staged_min_bit : (nbits > 0 && 2 * nhigh > nbits);
+            if (nv == 2 && (c->opt_staged & 4) && pp.c < pp.k && high) staged = 1;
+        }
         const int K = pp.k;   // 12, or 11 (half-size tiles, direct loads only)
         if (K == 11) staged = 0;
         lean_fn lfn;
@@ -979,7 +1012,7 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         Tile12X x;
         memset(&x, 0, sizeof(x));
         x.ngroups = pp.ngroups;
-        const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2, K};
+        const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2, K, 0};
         x.last_group = pp.ngroups == 1 ? K - 3 : (pp.ngroups == 5 ? 5 : 6);
         for (int r = 0; r < 8; ++r) {
             const u64 lf = (u64)r << (K - 3);
@@ -989,7 +1022,7 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
             x.roff_last[r] = geo12_local(geo, ll);
         }
         const long long lctas = K == 11 ? (nv == 1 ? 4 : 2) : ((nv == 1 && !staged) ? std::min<long long>(2, c->opt_ctas_fwd) : 1);
-        const i64 lgrid = std::min<i64>(tp.num_tiles, (i64)c->sm_count * lctas);
+        const i64 lgrid = std::min<i64>(tp.num_tiles, (i64)sms * lctas);
         if (nv == 2) {
             const i64 nunits = flush_per_tile ? tp.num_tiles : lgrid;
             QR_TRY(ensure_scratch(c, (size_t)nunits * QR_SLOTS));
@@ -1007,9 +1040,9 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         const bool pdl = (c->opt_pdl == 2 || (c->opt_pdl == 1 && lp.n <= QR_PDL_AUTO_MAX_QUBITS)) && !c->tables_fresh;
         c->tables_fresh = false;
         if (pdl) {
-            CUDA_TRY(QR_LAUNCH_EX(lfn, (unsigned)lgrid, 1u << (K - 3), lsmem, c->stream, 1u, pdl, tp, x));
+            CUDA_TRY(QR_LAUNCH_EX(lfn, (unsigned)lgrid, 1u << (K - 3), lsmem, stream, 1u, pdl, tp, x));
         } else {
-            QR_LAUNCH(lfn, (unsigned)lgrid, 1 << (K - 3), lsmem, c->stream, tp, x);
+            QR_LAUNCH(lfn, (unsigned)lgrid, 1 << (K - 3), lsmem, stream, tp, x);
         }
         KERNEL_CHECK();
         c->perf.kernel_launches++;
@@ -2053,6 +2086,7 @@ extern "C" int qr_shard_mcclean_begin(qr_ctx* c, int L, const int32_t* axes, con
             if (!c->peer_flags[r]) return fail(QR_ESTATE, "the ordering flags of rank %d are not mapped", r);
         SwapRun* sr = c->srun = new SwapRun();
         sr->lockstep = c->opt_shard_lockstep != 0;
+        sr->slices = (int)c->opt_shard_slices;
         sr->gen_base = c->flag_gen;
         std::vector<GateP> tab;
         QR_TRY(swap_build(c, sr, L, axes, angles, o, want_grad != 0, &tab));
@@ -2066,7 +2100,7 @@ extern "C" int qr_shard_mcclean_begin(qr_ctx* c, int L, const int32_t* axes, con
         QR_TRY(ensure_small(c, sr->tab_off + tab_bytes + 1024));
         QR_TRY(ensure_pin(c, std::max(sr->tab_off + tab_bytes + 1024, (sr->n_results + 16) * sizeof(double))));
         QR_TRY(ensure_result(c, sr->n_results + 16));
-        QR_TRY(ensure_scratch(c, (size_t)c->sm_count * 16 * QR_SLOTS));
+        QR_TRY(ensure_scratch(c, std::max<size_t>(2 * (size_t)c->sm_count * 16 * QR_SLOTS, (size_t)grid_for(c, c->N))));
         memcpy(c->h_pin + sr->tab_off, tab.data(), tab_bytes);
         CUDA_TRY(cudaMemcpyAsync((char*)c->d_small + sr->tab_off, c->h_pin + sr->tab_off, tab_bytes, cudaMemcpyHostToDevice, c->stream));
         if (terms && !terms->empty()) QR_TRY(upload_small(c, 0, terms->data(), terms->size() * sizeof(ObsTerm), 0));
@@ -2194,7 +2228,7 @@ extern "C" int qr_shard_step(qr_ctx* c, int step) {
         QR_TRY(use_device(c));
         const int first = sr->step_first[step];
         const int last = step + 1 < (int)sr->step_first.size() ? sr->step_first[step + 1] : (int)sr->ops.size();
-        for (int k = first; k < last; ++k) QR_TRY(swap_launch_op(c, sr, sr->ops[k]));
+        for (int k = first; k < last; ++k) QR_TRY(swap_launch_op(c, sr, sr->ops[k], k));
         if (sr->lockstep) CUDA_TRY(cudaStreamSynchronize(c->stream));   // asynchronous mode: device-side flags order the ranks
         return 0;
     }
@@ -2303,6 +2337,7 @@ extern "C" int qr_shard_mcclean_finish(qr_ctx* c, double* e_partial, double* gra
                 delete c->srun; c->srun = nullptr;
                 return fail(QR_ESTATE, "sharded run: timed out waiting for rank %d (generation %llu)", r, h_flags[QR_FLAG_ERR * QR_MAX_RANKS + r]);
             }
+        swap_collect_times(c, sr);
         const double* res = (const double*)c->h_pin;
         *e_partial = res[0];
         if (grad_partial) {
@@ -2310,7 +2345,11 @@ extern "C" int qr_shard_mcclean_finish(qr_ctx* c, double* e_partial, double* gra
             for (const XOp& op : sr->ops)
                 if (op.kind == 1 && op.nv == 2) {
                     for (int s2 = 0; s2 < QR_GATE_SLOTS; ++s2)
-                        if (op.slot_qubit[s2] >= 0) grad_partial[(size_t)op.layer * nt + op.slot_qubit[s2]] = res[op.res_off + s2];
+                        if (op.slot_qubit[s2] >= 0) {
+                            double v = 0.0;
+                            for (int sl = 0; sl < op.nslices; ++sl) v += res[op.res_off + (size_t)sl * QR_SLOTS + s2];
+                            grad_partial[(size_t)op.layer * nt + op.slot_qubit[s2]] = v;
+                        }
                 }
         }
         delete c->srun;

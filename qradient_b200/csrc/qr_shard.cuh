@@ -153,7 +153,11 @@ struct XOp {
     LadderSpec spec = {0, 0, 0};
     u64 tcol[24], lcol[9], roff[8], src_const = 0;
     int sel_bit[2] = {-1, -1};   // selector bit k: tile-index bit ...
+    int sel_pos[2] = {-1, -1};   //   (its destination local bit: the tile-index bit depends on the enumeration of a sliced launch)
     int thr_bit[2] = {-1, -1};   // ... or thread bit (tile-local bit < 9)
+    Lin M;                       // source map (dest physical index -> source physical index)
+    int nslices = 1;             // > 1: issued in slices of the index bits [9, 9 + log2 nslices) (last local pass + exchange pass of a layer)
+    long long pair_gen = 0;      // sliced local pass: first generation of its exchange pass (raises READY slice by slice)
     int src_rank[4][8];      // physical source rank per (selector, register)
     bool remote = false;
     double remote_frac = 0.0;   // fraction of the source amplitudes read from peers
@@ -178,9 +182,12 @@ struct SwapRun {
     std::vector<int> step_first;   // first op of each step
     int sigma = 0, h = 0, m = 0;
     int sweeps = 0, layers = 0;
+    int slices = 1;
     size_t tab_off = 0, n_results = 0;
     bool lockstep = true;
     long long gen_base = 0;
+    std::vector<cudaEvent_t> ev;   // two events per op (after its waits / after its kernels): per-kind device times at finish
+    ~SwapRun() { for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e); }
 };
 
 // layout bookkeeping -------------------------------------------------------------------------------------
@@ -216,8 +223,9 @@ static int xop_set_map(qr_ctx* c, XOp& op, const Lin& M, int nl, int g) {
     const int me = c->rank, G = 1 << g;
     const u64 lmask = ((u64)1 << nl) - 1;
     const PassPlan& pp = op.pp;
-    const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2, 12};
+    const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2, 12, 0};
     const u64 cimg = lin_apply(M, (u64)me << nl);
+    op.M = M;
     op.src_const = cimg & lmask;
     const int r0 = (int)(cimg >> nl);
     int rr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -249,6 +257,7 @@ static int xop_set_map(qr_ctx* c, XOp& op, const Lin& M, int nl, int g) {
         if (img >> nl) {
             if (nsel >= 2) return fail(QR_ESTATE, "internal: source rank depends on more than two selector bits");
             op.sel_bit[nsel] = j;
+            op.sel_pos[nsel] = unit_bit(d);
             srank[nsel] = (int)(img >> nl);
             ++nsel;
         }
@@ -412,16 +421,16 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
             }
             gate_tab->push_back(gp);
         }
-        if (op.nv == 2) { op.res_off = res; res += QR_SLOTS; }
-        // ordering
-        if (op.remote) { op.new_step = true; op.gen = ++gen; }
+        if (op.nv == 2) { op.res_off = res; res += (size_t)QR_SLOTS * op.nslices; }
+        // ordering (a sliced exchange pass takes one generation per slice)
+        if (op.remote) { op.new_step = true; op.gen = gen + 1; gen += op.nslices; }
         for (int v = 0; v < op.nv; ++v) {
             const int b = op.dst_buf[v];
             if (readable[b] > waited) { op.wait_done = std::max(op.wait_done, readable[b]); }
         }
         if (op.wait_done > waited) waited = op.wait_done; else op.wait_done = 0;
         if (op.remote)
-            for (int v = 0; v < op.nv; ++v) readable[op.src_buf[v]] = op.gen;
+            for (int v = 0; v < op.nv; ++v) readable[op.src_buf[v]] = op.gen + op.nslices - 1;
         return 0;
     };
     auto new_op = [&](int layer, int nv) {
@@ -437,7 +446,6 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
     auto add_layer = [&](int layer, int nv, int ladder_stacking, int next_stacking) -> int {
         bool owed = false;          // backward: a CNOT peeled off this layer's ladder, owed to this layer's exchange pass
         Lin owed_f = lin_identity(nt);
-        int ctrl_local = -1;        // local bit holding the control qubit of the owed CNOT
         // ---- the ladder in the current layout ----
         Lin M = lin_identity(nt);
         if (ladder_stacking >= 0 && nt >= 2) {
@@ -450,7 +458,7 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
                 int kc = -1;
                 for (int k = 0; k < nl; ++k) if (layout_local_logical(ly, k) == pc) kc = k;
                 if (gather_is_local(ly, Grest) && kc == sigma + g && sigma - 2 >= 3 && h - 1 >= 3) {
-                    owed = true; owed_f = F; ctrl_local = kc; Gl = Grest;
+                    owed = true; owed_f = F; Gl = Grest;
                 }
             }
             Lin inv;
@@ -509,11 +517,16 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
             sr->ops.push_back(op);
         }
         // ---- strided local passes, in place ----
-        for (const std::vector<int>& bits : strided) {
+        // The last one and the exchange pass can be issued in slices of the index bits [9, 12) when those bits are tile-index
+        // bits of both (rows below 9, gate runs from 12 up): the exchange of a slice then overlaps the local pass of the next.
+        bool slice_pair = sr->slices > 1 && !strided.empty() && xb.front() >= 12 && strided.back().front() >= 12 &&
+                          (int)strided.back().size() >= 3 && nl - 12 >= 4;
+        for (size_t si = 0; si < strided.size(); ++si) {
             XOp op = new_op(layer, nv);
-            QR_TRY(xop_set_geometry(op, bits, false));
+            QR_TRY(xop_set_geometry(op, strided[si], false));
             QR_TRY(xop_set_map(c, op, lin_identity(nt), nl, g));
             op.src_buf[0] = psi; op.src_buf[1] = lam; op.dst_buf[0] = psi; op.dst_buf[1] = lam;
+            if (slice_pair && si + 1 == strided.size()) op.nslices = sr->slices;
             QR_TRY(finish_op(op, ly));
             sr->ops.push_back(op);
         }
@@ -548,11 +561,17 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
             const int d0 = pick_free(psi, lam, -1);
             const int d1 = nv == 2 ? pick_free(psi, lam, d0) : -1;
             op.dst_buf[0] = d0; op.dst_buf[1] = d1;
+            if (slice_pair) {   // the slice bits must not select the source shard
+                for (int b = QR_HOLE_POS; b < QR_HOLE_POS + 3; ++b)
+                    if (lin_apply(Mx, (u64)1 << b) >> nl) slice_pair = false;
+                if (!slice_pair) sr->ops.back().nslices = 1;   // (the local pass was already given result slots per slice: harmless)
+            }
+            if (slice_pair) op.nslices = sr->slices;
             QR_TRY(finish_op(op, nw));
+            if (slice_pair) sr->ops.back().pair_gen = op.gen;
             psi = d0; if (nv == 2) lam = d1;
             sr->ops.push_back(op);
             ly = nw;
-            (void)ctrl_local;
         }
         return 0;
     };
@@ -617,29 +636,136 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
 // ------------------------------------------------------------------------------------------
 // execution
 // ------------------------------------------------------------------------------------------
-static int swap_signal(qr_ctx* c, int kind, long long value) {
+static int swap_signal(qr_ctx* c, int kind, long long value, cudaStream_t stream) {
     FlagPeers fp;
     memset(&fp, 0, sizeof(fp));
     const int G = 1 << c->g;
     for (int r = 0; r < G; ++r) fp.p[r] = c->peer_flags[r];
-    QR_LAUNCH(k_flag_signal, 1, 32, 0, c->stream, fp, G, c->rank, kind, (unsigned long long)value);
+    QR_LAUNCH(k_flag_signal, 1, 32, 0, stream, fp, G, c->rank, kind, (unsigned long long)value);
     KERNEL_CHECK();
     return 0;
 }
-static int swap_wait(qr_ctx* c, int kind, long long value) {
-    QR_LAUNCH(k_flag_wait, 1, 32, 0, c->stream, c->d_flags, 1 << c->g, kind, (unsigned long long)value);
+static int swap_wait(qr_ctx* c, int kind, long long value, cudaStream_t stream) {
+    QR_LAUNCH(k_flag_wait, 1, 32, 0, stream, c->d_flags, 1 << c->g, kind, (unsigned long long)value);
     KERNEL_CHECK();
     return 0;
 }
 
-static int swap_launch_op(qr_ctx* c, SwapRun* sr, const XOp& op) {
+// one tile pass (or one slice of it) on `stream`; lane 0 / 1 = the reduction scratch and arrival counter it may use (a
+// local pass and an exchange pass can be in flight together)
+static int swap_launch_tile(qr_ctx* c, SwapRun* sr, const XOp& op, int slice, cudaStream_t stream, int max_sms, int lane) {
+    const int nl = c->n;
+    int hole = 0;
+    while ((1 << hole) < op.nslices) ++hole;
+    const u64 tile_or = op.nslices > 1 ? (u64)slice << QR_HOLE_POS : 0;
+    const size_t lane_doubles = (size_t)c->sm_count * 16 * QR_SLOTS;
+    const GateP* d_tab = (const GateP*)((char*)c->d_small + sr->tab_off) + op.gate_off;
+    double* final_out = op.nv == 2 ? c->d_result + op.res_off + (size_t)slice * QR_SLOTS : nullptr;
+    PassExtra ex;
+    ex.hole = hole; ex.tile_or = tile_or; ex.max_sms = max_sms;
+    ex.partials = c->d_scratch + (size_t)lane * lane_doubles;
+    ex.counter = c->d_counter + lane;
+    ex.stream = stream;
+    if (!op.xmap) {
+        LayerPlan lp;
+        lp.n = nl; lp.k = 12; lp.R = 3; lp.npasses = 1;
+        lp.pass[0] = op.pp;
+        PassIO io = {c->buf[op.src_buf[0]], op.nv == 2 ? c->buf[op.src_buf[1]] : nullptr, c->buf[op.dst_buf[0]],
+                     op.nv == 2 ? c->buf[op.dst_buf[1]] : nullptr};
+        int units = 0;
+        return launch_pass(c, lp, 0, op.nv, io, d_tab, 0, -1, 1, (i64)c->N, 0, nullptr, 0, 0, 0, 0, &units,
+                           op.gather ? &op.spec : nullptr, final_out, nullptr, nullptr, &ex);
+    }
+    const PassPlan& pp = op.pp;
+    const u64 lmask = ((u64)1 << nl) - 1;
+    TilePass tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.k = 12; tp.c = pp.c; tp.h = pp.h; tp.m1 = pp.m1; tp.h2 = pp.h2; tp.nrounds = pp.nrounds;
+    tp.hole = hole; tp.tile_or = tile_or;
+    tp.tiles_log2 = nl - 12 - hole;
+    tp.num_tiles = (i64)1 << tp.tiles_log2;
+    tp.state_stride = (i64)c->N;
+    tp.src0 = c->buf[op.src_buf[0]]; tp.src1 = op.nv == 2 ? c->buf[op.src_buf[1]] : nullptr;
+    tp.dst0 = c->buf[op.dst_buf[0]]; tp.dst1 = op.nv == 2 ? c->buf[op.dst_buf[1]] : nullptr;
+    tp.gates = d_tab; tp.gate_stride = 0;
+    tp.final_out = final_out;
+    tp.done_counter = ex.counter;
+    tp.partials = ex.partials;
+    Tile12X x;
+    memset(&x, 0, sizeof(x));
+    x.ngroups = pp.ngroups;
+    x.last_group = pp.ngroups == 1 ? 9 : 6;
+    const Geo12 geo0 = {pp.c, pp.h, pp.m1, pp.h2, 12, 0};
+    for (int r = 0; r < 8; ++r) {
+        x.droff_first[r] = geo12_local(geo0, (u64)r << 9);
+        x.roff_first[r] = op.roff[r];
+        x.roff_last[r] = geo12_local(geo0, (u64)r << x.last_group);
+    }
+    TileXMap xm;
+    memset(&xm, 0, sizeof(xm));
+    for (int v = 0; v < op.nv; ++v)
+        for (int sl = 0; sl < 4; ++sl)
+            for (int r = 0; r < 8; ++r) xm.src[v][sl][r] = c->peer[op.src_rank[sl][r]][op.src_buf[v]];
+    memcpy(xm.lcol, op.lcol, sizeof(xm.lcol));
+    xm.thr_bit[0] = op.thr_bit[0]; xm.thr_bit[1] = op.thr_bit[1];
+    xm.sel_bit[0] = xm.sel_bit[1] = -1;
+    // tile-index images for this launch's enumeration (the slice bits are fixed: their image joins the constant)
+    const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2, 12, hole};
+    for (int j = 0; j < tp.tiles_log2 && j < 24; ++j) {
+        const u64 d = geo12_tile(geo, (u64)1 << j);
+        xm.tcol[j] = lin_apply(op.M, d) & lmask;
+        for (int k = 0; k < 2; ++k)
+            if (op.sel_pos[k] >= 0 && d == ((u64)1 << op.sel_pos[k])) xm.sel_bit[k] = j;
+    }
+    for (int k = 0; k < 2; ++k)
+        if (op.sel_pos[k] >= 0 && xm.sel_bit[k] < 0) return fail(QR_ESTATE, "internal: selector bit lost in a sliced launch");
+    const u64 simg = lin_apply(op.M, tile_or);
+    if (simg >> nl) return fail(QR_ESTATE, "internal: the slice bits select the source shard");
+    xm.src_const = op.src_const ^ (simg & lmask);
+    xm.local_only = op.remote ? 0 : 1;
+    // L2 prefetch of the next tile: local sources only (a prefetch of peer memory would warm the PEER's L2)
+    tp.prefetch = (!op.remote && op.nv == 2) ? (int)(c->opt_prefetch & 3) : 0;
+    const int sms = max_sms > 0 ? std::min(max_sms, c->sm_count) : c->sm_count;
+    const i64 grid = std::min<i64>(tp.num_tiles, (i64)sms * (op.nv == 1 ? 2 : 1));
+    const size_t smem = (size_t)op.nv * (sizeof(double2) << 12);
+    if (op.nv == 1) {
+        QR_TRY(ensure_smem_attr(c, (const void*)k_tile12_x<1>, 27));
+        QR_LAUNCH(k_tile12_x<1>, (unsigned)grid, 512, smem, stream, tp, x, xm);
+    } else {
+        QR_TRY(ensure_smem_attr(c, (const void*)k_tile12_x<2>, 28));
+        QR_LAUNCH(k_tile12_x<2>, (unsigned)grid, 512, smem, stream, tp, x, xm);
+    }
+    KERNEL_CHECK();
+    c->tables_fresh = false;
+    c->perf.kernel_launches++;
+    return 0;
+}
+
+static int swap_launch_op(qr_ctx* c, SwapRun* sr, const XOp& op, int op_index) {
     const int nl = c->n, G = 1 << c->g;
     const bool async = !sr->lockstep;
-    if (async && op.wait_done > 0) QR_TRY(swap_wait(c, QR_FLAG_DONE, op.wait_done));
-    if (async && op.remote) {
-        QR_TRY(swap_signal(c, QR_FLAG_READY, op.gen));
-        QR_TRY(swap_wait(c, QR_FLAG_READY, op.gen));
+    const bool sliced = op.kind == 1 && op.nslices > 1;
+    // a sliced exchange pass runs on the second stream (asynchronous mode), behind everything issued so far
+    cudaStream_t st = c->stream;
+    if (async && sliced) {
+        if (!c->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) if (!c->ev_pair[i]) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_pair[i], cudaEventDisableTiming));
     }
+    if (async && sliced && op.remote) {
+        st = c->stream2;
+        CUDA_TRY(cudaStreamWaitEvent(st, c->ev_pair[0], 0));   // recorded before the sliced local pass of this layer
+    }
+    if (async && op.wait_done > 0) QR_TRY(swap_wait(c, QR_FLAG_DONE, op.wait_done, st));
+    if (async && op.remote && !sliced) {
+        QR_TRY(swap_signal(c, QR_FLAG_READY, op.gen, st));
+        QR_TRY(swap_wait(c, QR_FLAG_READY, op.gen, st));
+    }
+    if (sr->ev.size() < 2 * sr->ops.size()) {
+        const size_t old = sr->ev.size();
+        sr->ev.resize(2 * sr->ops.size(), nullptr);
+        for (size_t i = old; i < sr->ev.size(); ++i) cudaEventCreate(&sr->ev[i]);
+    }
+    CUDA_TRY(cudaEventRecord(sr->ev[2 * op_index], st));
     if (op.kind == 0) {
         const int nt = c->n_total;
         double table[48];
@@ -656,7 +782,6 @@ static int swap_launch_op(qr_ctx* c, SwapRun* sr, const XOp& op) {
         memset(&peers, 0, sizeof(peers));
         for (int u = 0; u < G; ++u) peers.p[u] = c->peer[op.obs_peer_rank[u]][op.src_buf[0]];
         const int ogrid = grid_for(c, c->N);
-        QR_TRY(ensure_scratch(c, ogrid));
         QR_LAUNCH(k_apply_obs, ogrid, QR_BLOCK, 0, c->stream, (const double2*)c->buf[op.src_buf[0]],
                   op.dst_buf[0] >= 0 ? c->buf[op.dst_buf[0]] : (double2*)nullptr, c->N, (const ObsTerm*)c->d_small, (int)op.terms.size(),
                   c->d_scratch, op.obs_base, nl, peers);
@@ -664,71 +789,59 @@ static int swap_launch_op(qr_ctx* c, SwapRun* sr, const XOp& op) {
         QR_LAUNCH(k_reduce_partials, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_scratch, ogrid, 1, c->d_result);
         KERNEL_CHECK();
         c->perf.kernel_launches += 2;
-    } else {
-        const GateP* d_tab = (const GateP*)((char*)c->d_small + sr->tab_off) + op.gate_off;
-        double* final_out = op.nv == 2 ? c->d_result + op.res_off : nullptr;
-        if (!op.xmap) {
-            LayerPlan lp;
-            lp.n = nl; lp.k = 12; lp.R = 3; lp.npasses = 1;
-            lp.pass[0] = op.pp;
-            PassIO io = {c->buf[op.src_buf[0]], op.nv == 2 ? c->buf[op.src_buf[1]] : nullptr, c->buf[op.dst_buf[0]],
-                         op.nv == 2 ? c->buf[op.dst_buf[1]] : nullptr};
-            int units = 0;
-            QR_TRY(launch_pass(c, lp, 0, op.nv, io, d_tab, 0, -1, 1, (i64)c->N, 0, nullptr, 0, 0, 0, 0, &units,
-                               op.gather ? &op.spec : nullptr, final_out));
-        } else {
-            const PassPlan& pp = op.pp;
-            TilePass tp;
-            memset(&tp, 0, sizeof(tp));
-            tp.k = 12; tp.c = pp.c; tp.h = pp.h; tp.m1 = pp.m1; tp.h2 = pp.h2; tp.nrounds = pp.nrounds;
-            tp.tiles_log2 = nl - 12;
-            tp.num_tiles = (i64)1 << tp.tiles_log2;
-            tp.state_stride = (i64)c->N;
-            tp.src0 = c->buf[op.src_buf[0]]; tp.src1 = op.nv == 2 ? c->buf[op.src_buf[1]] : nullptr;
-            tp.dst0 = c->buf[op.dst_buf[0]]; tp.dst1 = op.nv == 2 ? c->buf[op.dst_buf[1]] : nullptr;
-            tp.gates = d_tab; tp.gate_stride = 0;
-            tp.final_out = final_out;
-            tp.done_counter = c->d_counter;
-            Tile12X x;
-            memset(&x, 0, sizeof(x));
-            x.ngroups = pp.ngroups;
-            x.last_group = pp.ngroups == 1 ? 9 : 6;
-            const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2, 12};
-            for (int r = 0; r < 8; ++r) {
-                x.droff_first[r] = geo12_local(geo, (u64)r << 9);
-                x.roff_first[r] = op.roff[r];
-                x.roff_last[r] = geo12_local(geo, (u64)r << x.last_group);
-            }
-            TileXMap xm;
-            memset(&xm, 0, sizeof(xm));
-            for (int v = 0; v < op.nv; ++v)
-                for (int s = 0; s < 4; ++s)
-                    for (int r = 0; r < 8; ++r) xm.src[v][s][r] = c->peer[op.src_rank[s][r]][op.src_buf[v]];
-            memcpy(xm.tcol, op.tcol, sizeof(xm.tcol));
-            memcpy(xm.lcol, op.lcol, sizeof(xm.lcol));
-            xm.src_const = op.src_const;
-            xm.sel_bit[0] = op.sel_bit[0]; xm.sel_bit[1] = op.sel_bit[1];
-            xm.thr_bit[0] = op.thr_bit[0]; xm.thr_bit[1] = op.thr_bit[1];
-            xm.local_only = op.remote ? 0 : 1;
-            // L2 prefetch of the next tile: local sources only (a prefetch of peer memory would warm the PEER's L2)
-            tp.prefetch = (!op.remote && op.nv == 2) ? (int)(c->opt_prefetch & 3) : 0;
-            const i64 grid = std::min<i64>(tp.num_tiles, (i64)c->sm_count * (op.nv == 1 ? 2 : 1));
-            QR_TRY(ensure_scratch(c, (size_t)grid * QR_SLOTS));
-            tp.partials = c->d_scratch;
-            const size_t smem = (size_t)op.nv * (sizeof(double2) << 12);
-            if (op.nv == 1) {
-                QR_TRY(ensure_smem_attr(c, (const void*)k_tile12_x<1>, 27));
-                QR_LAUNCH(k_tile12_x<1>, (unsigned)grid, 512, smem, c->stream, tp, x, xm);
-            } else {
-                QR_TRY(ensure_smem_attr(c, (const void*)k_tile12_x<2>, 28));
-                QR_LAUNCH(k_tile12_x<2>, (unsigned)grid, 512, smem, c->stream, tp, x, xm);
-            }
-            KERNEL_CHECK();
-            c->tables_fresh = false;
-            c->perf.kernel_launches++;
+    } else if (!sliced) {
+        QR_TRY(swap_launch_tile(c, sr, op, 0, c->stream, 0, 0));
+    } else if (!async) {
+        // lockstep: the slices one after another on the main stream (same kernels, same enumeration as the overlapped run)
+        for (int sl = 0; sl < op.nslices; ++sl) QR_TRY(swap_launch_tile(c, sr, op, sl, c->stream, 0, 0));
+    } else if (!op.remote) {
+        // sliced local pass: raise READY of the exchange pass's generations slice by slice; leave SMs to the exchange pass
+        CUDA_TRY(cudaEventRecord(c->ev_pair[0], c->stream));
+        const int sms = std::max(8, c->sm_count - (int)std::min<long long>(c->opt_shard_xsms, c->sm_count - 8));
+        for (int sl = 0; sl < op.nslices; ++sl) {
+            QR_TRY(swap_launch_tile(c, sr, op, sl, c->stream, sl == 0 ? 0 : sms, 0));   // slice 0 has the GPU to itself
+            QR_TRY(swap_signal(c, QR_FLAG_READY, op.pair_gen + sl, c->stream));
         }
-        c->perf.link_bytes += op.remote_frac * (double)op.nv * 16.0 * (double)c->N;   // bytes this rank reads over NVLink
+    } else {
+        // sliced exchange pass on the second stream: slice s waits for READY(s) of every rank (own local pass included)
+        const int xs = (int)std::min<long long>(c->opt_shard_xsms, c->sm_count);
+        for (int sl = 0; sl < op.nslices; ++sl) {
+            QR_TRY(swap_wait(c, QR_FLAG_READY, op.gen + sl, st));
+            QR_TRY(swap_launch_tile(c, sr, op, sl, st, sl + 1 == op.nslices ? 0 : xs, 1));   // the last slice runs alone
+            QR_TRY(swap_signal(c, QR_FLAG_DONE, op.gen + sl, st));
+        }
     }
-    if (async && op.remote) QR_TRY(swap_signal(c, QR_FLAG_DONE, op.gen));
+    if (op.kind == 1) c->perf.link_bytes += op.remote_frac * (double)op.nv * 16.0 * (double)c->N;   // bytes this rank reads over NVLink
+    CUDA_TRY(cudaEventRecord(sr->ev[2 * op_index + 1], st));
+    if (async && sliced && op.remote) {   // the main stream continues behind the last slice
+        CUDA_TRY(cudaEventRecord(c->ev_pair[1], st));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_pair[1], 0));
+    } else if (async && op.remote) QR_TRY(swap_signal(c, QR_FLAG_DONE, op.gen, st));
     return 0;
+}
+
+// per-kind device times of the finished run (the stream has been synchronised): local passes forward / backward, average
+// exchange pass forward / backward, observable; total = first op to last op (the difference is waiting for peers)
+static void swap_collect_times(qr_ctx* c, SwapRun* sr) {
+    if (sr->ev.size() < 2 * sr->ops.size()) return;
+    double loc[3] = {0, 0, 0}, xch[3] = {0, 0, 0}, obs = 0;
+    int nx[3] = {0, 0, 0};
+    for (size_t k = 0; k < sr->ops.size(); ++k) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sr->ev[2 * k], sr->ev[2 * k + 1]) != cudaSuccess) { cudaGetLastError(); return; }
+        const XOp& op = sr->ops[k];
+        if (op.kind == 2) obs += ms;
+        else if (op.kind == 1 && op.remote) { xch[op.nv] += ms; nx[op.nv]++; }
+        else loc[op.kind == 0 ? 1 : op.nv] += ms;
+    }
+    float tot = 0.f;
+    cudaEventElapsedTime(&tot, sr->ev[0], sr->ev[2 * sr->ops.size() - 1]);
+    c->perf.ms_total = tot;
+    c->perf.ms_forward = loc[1];
+    c->perf.ms_backward = loc[2];
+    c->perf.ms_observable = obs;
+    c->perf.fwd_pass_ms_avg = nx[1] ? xch[1] / nx[1] : 0.0;
+    c->perf.bwd_pass_ms_avg = nx[2] ? xch[2] / nx[2] : 0.0;
+    c->perf.fwd_pass_bytes = (double)nx[1];   // number of exchange passes (forward / backward)
+    c->perf.bwd_pass_bytes = (double)nx[2];
 }

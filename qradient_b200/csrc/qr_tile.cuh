@@ -70,6 +70,8 @@ struct TilePass {
     unsigned* done_counter;      // zero-initialised arrival counter for final_out
     int flush_per_tile;
     int prefetch;
+    int hole;                    // k_tile12, sliced passes: index bits [9, 9+hole) are fixed by tile_or instead of enumerated
+    u64 tile_or;
 };
 
 // Deferred second stage of the gradient reductions (QR_OPT_DEFER_REDUCE): every backward pass of a gradient leaves its

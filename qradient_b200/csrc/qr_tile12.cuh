@@ -41,14 +41,20 @@
 // second segment to spread the page-selecting index bits (>= 2 MiB) over the strided passes, so
 // no pass touches more than ~128 distinct pages per tile and vector (a pass whose 512 rows lie
 // in 512 different pages runs 1.7x slower in the two-vector backward sweep: TLB reach).
-struct Geo12 { int c, h, m1, h2, k; };   // k = tile bits (12, or 11 for the half-size tiles)
+// hole > 0 (sliced passes of sharded registers): the index bits [9, 9+hole) are not enumerated by the tile index -- the
+// launch fixes them (TilePass::tile_or), so that a pass can be issued slice by slice and the exchange pass of a slice can
+// start while the local pass still works on the next one.  They must lie between the rows and the first gate run.
+#define QR_HOLE_POS 9
+struct Geo12 { int c, h, m1, h2, k, hole; };   // k = tile bits (12, or 11 for the half-size tiles)
 __host__ __device__ __forceinline__ u64 geo12_local(const Geo12 g, u64 l) {
     return (l & (((u64)1 << g.c) - 1)) | (((l >> g.c) & (((u64)1 << g.m1) - 1)) << g.h) | ((l >> (g.c + g.m1)) << g.h2);
 }
 __host__ __device__ __forceinline__ u64 geo12_tile(const Geo12 g, u64 t) {
-    const int nlo = g.h - g.c, nmid = g.h2 - g.h - g.m1, m2 = g.k - g.c - g.m1;
-    return ((t & (((u64)1 << nlo) - 1)) << g.c) | (((t >> nlo) & (((u64)1 << nmid) - 1)) << (g.h + g.m1)) |
-           ((t >> (nlo + nmid)) << (g.h2 + m2));
+    const int nlo = g.h - g.c - g.hole, nmid = g.h2 - g.h - g.m1, m2 = g.k - g.c - g.m1;
+    const u64 lo = t & (((u64)1 << nlo) - 1);
+    const u64 lo_placed = g.hole ? (((lo & (((u64)1 << (QR_HOLE_POS - g.c)) - 1)) << g.c) | ((lo >> (QR_HOLE_POS - g.c)) << (QR_HOLE_POS + g.hole)))
+                                 : (lo << g.c);
+    return lo_placed | (((t >> nlo) & (((u64)1 << nmid) - 1)) << (g.h + g.m1)) | ((t >> (nlo + nmid)) << (g.h2 + m2));
 }
 
 struct Tile12X {
@@ -267,7 +273,7 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
     __shared__ int s_flags[2];                  // [0]: the pass needs its diagonal (an Rz, or an odd number of sign flips)
     __shared__ double2 lut_sm[QR_LUT_MAX];
     const int tid = threadIdx.x;
-    const Geo12 geo = {p.c, p.h, p.m1, p.h2, K};
+    const Geo12 geo = {p.c, p.h, p.m1, p.h2, K, p.hole};
     const u64 tmask = ((u64)1 << p.tiles_log2) - 1;
     const int ng = x.ngroups;
 
@@ -406,7 +412,7 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
             if (NV == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(xmp->src[1][sl][tid >> 6] + s));
             return;
         }
-        const u64 nbase = geo12_tile(geo, (u64)nt & tmask);
+        const u64 nbase = geo12_tile(geo, (u64)nt & tmask) | p.tile_or;
         const int l = tid << 3;
         const u64 d = nbase | geo12_local(geo, (u64)l);
         const u64 s = p.ladder ? (ladder_map(d, p.M1, p.M2) ^ p.src_xor) : d;
@@ -417,7 +423,7 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
     // issue the asynchronous copies of this thread's amplitudes of tile `tl` into its stage slots
     auto issue_stage = [&](i64 tl) {
         const i64 nb = tl >> p.tiles_log2;
-        const u64 nbase = geo12_tile(geo, (u64)tl & tmask);
+        const u64 nbase = geo12_tile(geo, (u64)tl & tmask) | p.tile_or;
         const u64 sb = (p.ladder ? (ladder_map(nbase, p.M1, p.M2) ^ p.src_xor) : nbase) ^ toff_s;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -435,7 +441,7 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
         if (tile >= p.num_tiles) continue;
         const int b = (int)(tile >> p.tiles_log2);
         const u64 t = (u64)tile & tmask;
-        const u64 tbase = geo12_tile(geo, t);
+        const u64 tbase = geo12_tile(geo, t) | p.tile_or;
         if (b != cur_b) convert_gates(b);   // block-uniform: a persistent CTA of a batched pass moves on to the next circuit
         // batch element offset: state_stride is a multiple of 2^n, so it can be OR-ed into the index bits
         const u64 boff = (u64)b * (u64)p.state_stride;

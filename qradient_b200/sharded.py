@@ -220,6 +220,14 @@ class ShardedMcClean:
         self.link_bytes = perf.link_bytes
         self.perf = {'kernel_launches': int(perf.kernel_launches), 'link_bytes': float(perf.link_bytes),
                      'sweeps_per_layer': int(perf.passes_per_layer) + (1 if self.mode == 'peer' else 0), 'mode': self.mode}
+        if self.mode == 'swap':   # device times of rank 0's stream: local passes / exchange passes / waiting for peers
+            nxf, nxb = perf.fwd_pass_bytes, perf.bwd_pass_bytes
+            busy = perf.ms_forward + perf.ms_backward + perf.ms_observable + nxf * perf.fwd_pass_ms_avg + nxb * perf.bwd_pass_ms_avg
+            self.perf.update({'ms_total': perf.ms_total, 'ms_local_forward': perf.ms_forward, 'ms_local_backward': perf.ms_backward,
+                              'ms_observable': perf.ms_observable, 'ms_exchange_forward_avg': perf.fwd_pass_ms_avg,
+                              'ms_exchange_backward_avg': perf.bwd_pass_ms_avg, 'exchange_passes': int(nxf + nxb),
+                              'ms_waiting_and_flags': perf.ms_total - busy})
+            self.step_seconds.update({k: v for k, v in self.perf.items() if k.startswith('ms_')})
         total = self.comm.allreduce_sum(parts)
         return float(total[0]), np.array(total[1:]).reshape(self.lnum, self.qnum)
 

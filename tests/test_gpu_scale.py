@@ -160,6 +160,12 @@ def test_sharded_24_qubits_vs_oracle_fixture(G):
         assert sh.mode == "swap"
         e, g = sh.grad_run()
         assert_parity(e, g, float(d["e"]), d["grad"], 1.75, 1e-10)
+        if G == 2:   # the last local pass and the exchange pass issued in 8 slices of the index bits 9..11 (QR_OPT_SHARD_SLICES)
+            sh.set_option("shard_slices", 8)
+            launches = sh.perf["kernel_launches"]
+            e8, g8 = sh.grad_run()
+            assert sh.perf["kernel_launches"] > launches
+            assert_parity(e8, g8, e, g, 1.75, 1e-12)
     finally:
         sh.close()
     if G == 2:
