@@ -211,6 +211,12 @@ int qr_shard_info(qr_ctx* ctx, int* n_total, int* log2_world, int* rank, int* lo
 int qr_shard_mcclean_begin(qr_ctx* ctx, int n_layers, const int32_t* axes, const double* angles, const qr_obs* obs,
                            int want_grad, int* n_steps);
 int qr_shard_step(qr_ctx* ctx, int step);
+/* Qaoa.run_expec_val / grad_run (qaoa.py:23-70) on the sharded register (swap engine; z / zz observable).  Same step /
+ * finish protocol; qr_shard_mcclean_finish then returns this rank's partial E and grad[2 p] (column 0 = d/d beta, column 1 =
+ * d/d gamma).  A forward-only run leaves the state in the natural layout (rank r holds amplitudes r * 2^nl ...), so that
+ * qr_norm2 / qr_sample_bitstrings on every shard give the sharded sampler its local totals and indices (qaoa.py:196-198). */
+int qr_shard_qaoa_begin(qr_ctx* ctx, int n_layers, const double* betas, const double* gammas, const qr_obs* obs,
+                        int want_grad, int* n_steps);
 /* this rank's partial sums of E and of dE/d angles[L * n_total]; sum over ranks (allreduce) */
 int qr_shard_mcclean_finish(qr_ctx* ctx, double* e_partial, double* grad_partial);
 

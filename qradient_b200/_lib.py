@@ -86,6 +86,7 @@ _SIGNATURES = {
     "qr_shard_buffer_ptr": (c_int, [c_void_p, c_int, P(c_void_p)]),
     "qr_shard_info": (c_int, [c_void_p, P(c_int), P(c_int), P(c_int), P(c_int)]),
     "qr_shard_mcclean_begin": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, P(c_int)]),
+    "qr_shard_qaoa_begin": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, P(c_int)]),
     "qr_shard_step": (c_int, [c_void_p, c_int]),
     "qr_shard_mcclean_finish": (c_int, [c_void_p, P(c_double), c_void_p]),
 }

@@ -122,9 +122,10 @@ __device__ __forceinline__ double diag_value(u64 j, const ObsTerm* __restrict__ 
     return d;
 }
 
-__global__ void k_ham_build(double* __restrict__ ham, u64 N, const ObsTerm* __restrict__ terms, int nterms) {
+// idx_off: index bits above the local range (sharded registers: the logical value of the rank-held bits)
+__global__ void k_ham_build(double* __restrict__ ham, u64 N, const ObsTerm* __restrict__ terms, int nterms, u64 idx_off) {
     for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (u64)gridDim.x * blockDim.x)
-        ham[j] = diag_value(j, terms, nterms);
+        ham[j] = diag_value(idx_off | j, terms, nterms);
 }
 
 // vec *= exp(-i angle H)   (state.py:299-301)

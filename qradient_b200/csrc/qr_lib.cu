@@ -121,6 +121,9 @@ struct qr_ctx {
     unsigned long long* peer_flags[QR_MAX_RANKS];         // every rank's flag array (own entry = d_flags)
     bool flags_mapped[QR_MAX_RANKS];
     long long flag_gen = 0;                               // last generation used by a swap-engine run
+    double* d_ham_ly[2] = {nullptr, nullptr};             // sharded QAOA: H over this shard's local index in the natural / swapped layout
+    short* d_hidx_ly[2] = {nullptr, nullptr};
+    std::vector<ObsTerm> ham_ly_terms;                    // terms the tables were built from
     long long opt_shard_mode = 0;                         // 0 auto, 1 "peer" engine (round 1), 2 "swap" engine
     long long opt_shard_lockstep = 1;                     // 1: the caller runs the steps in lockstep over the ranks; 0: device-side flags
     long long opt_shard_slices = 1;                       // swap engine: the last local pass and the exchange pass of a layer are issued in this many slices (1 = off, the default: measured -4 % at 8 GPUs, +11 % at 2, profiles/README.md)
@@ -285,6 +288,7 @@ extern "C" int qr_ctx_destroy(qr_ctx* c) {
     if (c->d_result) cudaFree(c->d_result);
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->d_flags) cudaFree(c->d_flags);
+    for (int i = 0; i < 2; ++i) { if (c->d_ham_ly[i]) cudaFree(c->d_ham_ly[i]); if (c->d_hidx_ly[i]) cudaFree(c->d_hidx_ly[i]); }
     if (c->d_small) cudaFree(c->d_small);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -706,7 +710,7 @@ extern "C" int qr_ham_load(qr_ctx* c, const qr_obs* o) {
     }
     const ObsTerm* d_terms;
     QR_TRY(upload_terms(c, o->terms, &d_terms));
-    QR_LAUNCH(k_ham_build, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->d_ham, c->N, d_terms, (int)o->terms.size());
+    QR_LAUNCH(k_ham_build, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->d_ham, c->N, d_terms, (int)o->terms.size(), (u64)0);
     KERNEL_CHECK();
     // integer weights => H takes at most 2 sum|w| + 1 integer values: phases come from a small table
     double wsum = 0.0;
@@ -932,6 +936,7 @@ struct PassExtra {
     double* partials = nullptr;     // per-CTA partials region (default: d_scratch)
     unsigned* counter = nullptr;    // arrival counter of the fused final reduction (default: d_counter)
     cudaStream_t stream = nullptr;  // default: the context's stream
+    const short* hidx = nullptr;    // integer Hamiltonian index table of the pass's layout (default: d_hidx)
 };
 
 // opt in to > 48 KiB of dynamic shared memory: the attribute is PER DEVICE, so remember it per (kernel, device)
@@ -977,7 +982,7 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
     tp.src0 = io.src0; tp.src1 = io.src1; tp.dst0 = io.dst0; tp.dst1 = io.dst1;
     tp.gates = d_gates; tp.gate_stride = gate_stride;
     tp.ham = ham; tp.pre_phase = pre_phase; tp.post_phase = post_phase;
-    if (lut && c->ham_integer) { tp.hidx = c->d_hidx; tp.lut = lut; tp.lut_size = c->ham_range; tp.hmin = c->ham_min; }
+    if (lut && c->ham_integer) { tp.hidx = (ex && ex->hidx) ? ex->hidx : c->d_hidx; tp.lut = lut; tp.lut_size = c->ham_range; tp.hmin = c->ham_min; }
     tp.angle_pre = angle_pre; tp.angle_post = angle_post;
     tp.flush_per_tile = flush_per_tile;
     tp.prefetch = nv == 2 ? (int)(c->opt_prefetch & 3) : (int)((c->opt_prefetch >> 2) & 3);   // tiles ahead: bits 0-1 backward, bits 2-3 forward
@@ -2062,6 +2067,55 @@ static void shard_relabel(qr_ctx* c, ShardRun* run, u64 m1, u64 m2, LadderSpec* 
     for (int rho = 0; rho < G; ++rho) run->pi[rho] = inv_sigma[run->pi[rho]];
 }
 
+// plan a swap-engine run, upload its tables, reset the result block
+static int shard_swap_begin(qr_ctx* c, const SwapCircuit& circ, const qr_obs* o, bool want_grad, int* n_steps) {
+    const int G = 1 << c->g;
+    for (int r = 0; r < G; ++r)
+        if (!c->peer_flags[r]) return fail(QR_ESTATE, "the ordering flags of rank %d are not mapped", r);
+    delete c->srun;
+    SwapRun* sr = c->srun = new SwapRun();
+    sr->lockstep = c->opt_shard_lockstep != 0;
+    sr->slices = (int)c->opt_shard_slices;
+    sr->gen_base = c->flag_gen;
+    std::vector<GateP> tab;
+    QR_TRY(swap_build(c, sr, circ, o, want_grad, &tab));
+    c->flag_gen = sr->gen_base;
+    // observable terms (remapped to the final layout of the forward sweep) at offset 0, gate tables behind them
+    const std::vector<ObsTerm>* terms = nullptr;
+    for (const XOp& op : sr->ops) if (op.kind == 2) terms = &op.terms;
+    const size_t terms_bytes = ((terms ? terms->size() : 0) + 1) * sizeof(ObsTerm);
+    sr->tab_off = (terms_bytes + 255) & ~(size_t)255;
+    const size_t tab_bytes = tab.size() * sizeof(GateP);
+    const bool lut_on = circ.kind == 1 && c->ham_integer && c->opt_ham_lut;
+    const size_t lut_bytes = lut_on ? (size_t)2 * circ.L * c->ham_range * sizeof(double2) : 0;
+    const size_t lut_off = (sr->tab_off + tab_bytes + 255) & ~(size_t)255;
+    QR_TRY(ensure_small(c, lut_off + lut_bytes + 2048));
+    QR_TRY(ensure_pin(c, std::max(lut_off + lut_bytes + 2048, (sr->n_results + 16) * sizeof(double))));
+    QR_TRY(ensure_result(c, sr->n_results + 16));
+    QR_TRY(ensure_scratch(c, std::max<size_t>(2 * (size_t)c->sm_count * 16 * QR_SLOTS, (size_t)grid_for(c, c->N))));
+    memcpy(c->h_pin + sr->tab_off, tab.data(), tab_bytes);
+    if (lut_on) {   // exp(-i gamma_i h) (forward) and exp(+i gamma_i h) (backward), host libm values (as qaoa_fused)
+        double2* lut = (double2*)(c->h_pin + lut_off);
+        for (int dir = 0; dir < 2; ++dir)
+            for (int i = 0; i < circ.L; ++i)
+                for (int v = 0; v < c->ham_range; ++v) {
+                    const double ang = (dir == 0 ? circ.gammas[i] : -circ.gammas[i]) * (c->ham_min + v);
+                    lut[((size_t)dir * circ.L + i) * c->ham_range + v] = make_double2(std::cos(ang), -std::sin(ang));
+                }
+        sr->lut_off = lut_off;
+    }
+    CUDA_TRY(cudaMemcpyAsync((char*)c->d_small + sr->tab_off, c->h_pin + sr->tab_off, lut_off + lut_bytes - sr->tab_off, cudaMemcpyHostToDevice, c->stream));
+    if (terms && !terms->empty()) QR_TRY(upload_small(c, 0, terms->data(), terms->size() * sizeof(ObsTerm), 0));
+    CUDA_TRY(cudaMemsetAsync(c->d_result, 0, (sr->n_results + 16) * sizeof(double), c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    perf_reset(c);
+    c->perf.passes_per_layer = sr->sweeps;
+    c->perf.tile_bits = 12;
+    c->tables_fresh = true;
+    *n_steps = (int)sr->step_first.size();
+    return 0;
+}
+
 extern "C" int qr_shard_mcclean_begin(qr_ctx* c, int L, const int32_t* axes, const double* angles, const qr_obs* o,
                                       int want_grad, int* n_steps) {
     QR_TRY(need_shard(c));
@@ -2078,40 +2132,15 @@ extern "C" int qr_shard_mcclean_begin(qr_ctx* c, int L, const int32_t* axes, con
     c->run = nullptr;
     delete c->srun;
     c->srun = nullptr;
+    for (int r = 0; r < G; ++r)
+        for (int b2 = 0; b2 < QR_NBUF; ++b2)
+            if (!c->peer[r][b2]) return fail(QR_ESTATE, "peer buffers of rank %d are not mapped", r);
     const bool swap_ok = swap_engine_ok(nl, c->g) && c->opt_fusion && c->opt_tile_bits == 0 && c->opt_tile_bits_x == 0 && c->opt_min_row_bits == 3;
     if (c->opt_shard_mode == 2 && !swap_ok)
         return fail(QR_EINVAL, "the swap engine needs 1..3 rank bits, at least %d local qubits and default tile options", 12 + c->g);
     if (c->opt_shard_mode == 2 || (c->opt_shard_mode == 0 && swap_ok)) {
-        for (int r = 0; r < G; ++r)
-            if (!c->peer_flags[r]) return fail(QR_ESTATE, "the ordering flags of rank %d are not mapped", r);
-        SwapRun* sr = c->srun = new SwapRun();
-        sr->lockstep = c->opt_shard_lockstep != 0;
-        sr->slices = (int)c->opt_shard_slices;
-        sr->gen_base = c->flag_gen;
-        std::vector<GateP> tab;
-        QR_TRY(swap_build(c, sr, L, axes, angles, o, want_grad != 0, &tab));
-        c->flag_gen = sr->gen_base;
-        // observable terms (remapped to the final layout of the forward sweep) at offset 0, gate tables behind them
-        const std::vector<ObsTerm>* terms = nullptr;
-        for (const XOp& op : sr->ops) if (op.kind == 2) terms = &op.terms;
-        const size_t terms_bytes = ((terms ? terms->size() : 0) + 1) * sizeof(ObsTerm);
-        sr->tab_off = (terms_bytes + 255) & ~(size_t)255;
-        const size_t tab_bytes = tab.size() * sizeof(GateP);
-        QR_TRY(ensure_small(c, sr->tab_off + tab_bytes + 1024));
-        QR_TRY(ensure_pin(c, std::max(sr->tab_off + tab_bytes + 1024, (sr->n_results + 16) * sizeof(double))));
-        QR_TRY(ensure_result(c, sr->n_results + 16));
-        QR_TRY(ensure_scratch(c, std::max<size_t>(2 * (size_t)c->sm_count * 16 * QR_SLOTS, (size_t)grid_for(c, c->N))));
-        memcpy(c->h_pin + sr->tab_off, tab.data(), tab_bytes);
-        CUDA_TRY(cudaMemcpyAsync((char*)c->d_small + sr->tab_off, c->h_pin + sr->tab_off, tab_bytes, cudaMemcpyHostToDevice, c->stream));
-        if (terms && !terms->empty()) QR_TRY(upload_small(c, 0, terms->data(), terms->size() * sizeof(ObsTerm), 0));
-        CUDA_TRY(cudaMemsetAsync(c->d_result, 0, (sr->n_results + 16) * sizeof(double), c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        perf_reset(c);
-        c->perf.passes_per_layer = sr->sweeps;
-        c->perf.tile_bits = 12;
-        c->tables_fresh = true;
-        *n_steps = (int)sr->step_first.size();
-        return 0;
+        SwapCircuit circ = {0, L, axes, angles, nullptr, nullptr};
+        return shard_swap_begin(c, circ, o, want_grad != 0, n_steps);
     }
     ShardRun* run = c->run = new ShardRun();
     run->L = L;
@@ -2217,6 +2246,76 @@ static int shard_global_step(qr_ctx* c, ShardRun* run, int layer, int nv) {
         c->perf.kernel_launches++;
     }
     return 0;
+}
+
+// H over this shard's local index for the two layouts of a sharded QAOA run (natural / swapped); rebuilt when the terms change
+static int shard_build_ham_tables(qr_ctx* c, const qr_obs* o, const SwapRun* sr) {
+    bool same = c->d_ham_ly[0] && c->ham_ly_terms.size() == o->terms.size();
+    for (size_t k = 0; same && k < o->terms.size(); ++k)
+        same = memcmp(&c->ham_ly_terms[k], &o->terms[k], sizeof(ObsTerm)) == 0;
+    if (same) return 0;
+    double wsum = 0.0;
+    bool integral = true;
+    for (const ObsTerm& t : o->terms) {
+        if (t.kind < 2) return fail(QR_EINVAL, "the classical Hamiltonian of a QAOA circuit has z / zz terms only");
+        wsum += std::fabs(t.w);
+        if (t.w != std::floor(t.w)) integral = false;
+    }
+    c->ham_integer = integral && 2.0 * wsum + 1.0 <= (double)QR_LUT_MAX;
+    c->ham_min = -wsum;
+    c->ham_range = (int)(2.0 * wsum + 1.0);
+    for (int ly = 0; ly < 2; ++ly) {
+        if (sr->lay[ly].nl == 0) continue;   // (a run without exchange passes never reaches the swapped layout)
+        if (!c->d_ham_ly[ly]) {
+            if (cudaMalloc((void**)&c->d_ham_ly[ly], c->N * sizeof(double)) != cudaSuccess) { c->d_ham_ly[ly] = nullptr; return fail(QR_ENOMEM, "cannot allocate the Hamiltonian table"); }
+            if (cudaMalloc((void**)&c->d_hidx_ly[ly], c->N * sizeof(short)) != cudaSuccess) { c->d_hidx_ly[ly] = nullptr; return fail(QR_ENOMEM, "cannot allocate the Hamiltonian index table"); }
+        }
+        std::vector<ObsTerm> terms = o->terms;
+        QR_TRY(layout_remap_terms(sr->lay[ly], terms, nullptr));
+        const ObsTerm* d_terms;
+        QR_TRY(upload_terms(c, terms, &d_terms));
+        const u64 off = (u64)layout_shard_value(sr->lay[ly], c->rank) << c->n;
+        QR_LAUNCH(k_ham_build, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->d_ham_ly[ly], c->N, d_terms, (int)terms.size(), off);
+        KERNEL_CHECK();
+        if (c->ham_integer) {
+            QR_LAUNCH(k_ham_index, grid_for(c, c->N), QR_BLOCK, 0, c->stream, (const double*)c->d_ham_ly[ly], c->d_hidx_ly[ly], c->N, c->ham_min);
+            KERNEL_CHECK();
+        }
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    c->ham_ly_terms = o->terms;
+    return 0;
+}
+
+// Qaoa.run_expec_val / grad_run (qaoa.py:23-70) on a sharded register: swap engine without a ladder; the diagonal phase
+// exp(-i gamma H) rides on the first pass of a layer, 2 Im<lambda|H|psi> and the un-phase on the backward exchange pass
+extern "C" int qr_shard_qaoa_begin(qr_ctx* c, int p, const double* betas, const double* gammas, const qr_obs* o, int want_grad,
+                                   int* n_steps) {
+    QR_TRY(need_shard(c));
+    if (!o || o->n != c->n_total) return fail(QR_EINVAL, "observable must be defined on all %d qubits", c->n_total);
+    if (p < 0 || (p > 0 && (!betas || !gammas)) || !n_steps) return fail(QR_EINVAL, "bad arguments");
+    const int G = 1 << c->g;
+    for (int r = 0; r < G; ++r)
+        for (int b = 0; b < QR_NBUF; ++b)
+            if (!c->peer[r][b]) return fail(QR_ESTATE, "peer buffers of rank %d are not mapped", r);
+    if (!(swap_engine_ok(c->n, c->g) && c->opt_fusion && c->opt_tile_bits == 0 && c->opt_tile_bits_x == 0 && c->opt_min_row_bits == 3))
+        return fail(QR_EINVAL, "sharded QAOA needs 1..3 rank bits, at least %d local qubits and default tile options", 12 + c->g);
+    QR_TRY(use_device(c));
+    delete c->run;
+    c->run = nullptr;
+    c->psi = 0;
+    // the layouts are fixed by the register shape: plan once without tables to learn them, build H, then plan for real
+    SwapCircuit circ = {1, p, nullptr, nullptr, betas, gammas};
+    {
+        SwapRun probe;
+        probe.lockstep = true; probe.slices = 1; probe.gen_base = 0;
+        std::vector<GateP> tab;
+        const double b1[1] = {0.0};
+        SwapCircuit pc = {1, 1, nullptr, nullptr, b1, b1};
+        QR_TRY(swap_build(c, &probe, pc, o, false, &tab));
+        QR_TRY(shard_build_ham_tables(c, o, &probe));
+    }
+    return shard_swap_begin(c, circ, o, want_grad != 0, n_steps);
 }
 
 extern "C" int qr_shard_step(qr_ctx* c, int step) {
@@ -2338,8 +2437,25 @@ extern "C" int qr_shard_mcclean_finish(qr_ctx* c, double* e_partial, double* gra
                 return fail(QR_ESTATE, "sharded run: timed out waiting for rank %d (generation %llu)", r, h_flags[QR_FLAG_ERR * QR_MAX_RANKS + r]);
             }
         swap_collect_times(c, sr);
+        c->psi = sr->final_psi;
         const double* res = (const double*)c->h_pin;
         *e_partial = res[0];
+        if (sr->circuit == 1) {   // QAOA: grad[2 i] = sum of the X-generator slots of layer i, grad[2 i + 1] = 2 x the H-generator slot (qaoa.py:62-68)
+            if (grad_partial) {
+                for (int i = 0; i < 2 * sr->layers; ++i) grad_partial[i] = 0.0;
+                for (const XOp& op : sr->ops)
+                    if (op.kind == 1 && op.nv == 2 && op.layer >= 0)
+                        for (int sl = 0; sl < op.nslices; ++sl) {
+                            const double* r2 = res + op.res_off + (size_t)sl * QR_SLOTS;
+                            for (int s2 = 0; s2 < QR_GATE_SLOTS; ++s2)
+                                if (op.slot_qubit[s2] >= 0) grad_partial[2 * op.layer] += r2[s2];
+                            if (op.post_phase) grad_partial[2 * op.layer + 1] += 2.0 * r2[QR_SLOTS - 1];
+                        }
+            }
+            delete c->srun;
+            c->srun = nullptr;
+            return 0;
+        }
         if (grad_partial) {
             for (size_t i = 0; i < (size_t)sr->layers * nt; ++i) grad_partial[i] = 0.0;
             for (const XOp& op : sr->ops)

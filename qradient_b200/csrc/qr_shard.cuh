@@ -143,8 +143,13 @@ __global__ void k_flag_wait(unsigned long long* flags, int nranks, int kind, uns
 // ------------------------------------------------------------------------------------------
 // schedule
 // ------------------------------------------------------------------------------------------
+struct Layout {
+    Lin phi;         // physical (rho << nl | l) -> logical index
+    int nl, g;
+};
+
 struct XOp {
-    int kind = 0;            // 0: product-state init, 1: tile pass, 2: observable
+    int kind = 0;            // 0: initial state, 1: tile pass, 2: observable (lambda = O psi), 3: QAOA co-state (lambda = H psi)
     int nv = 1;
     int layer = 0;           // layer whose rotations the pass applies (gate table, result slots)
     PassPlan pp;             // destination tile geometry; gbit = destination local bit of each gate slot (or -1)
@@ -171,6 +176,12 @@ struct XOp {
     int obs_peer_rank[QR_MAX_RANKS];   // physical rank holding logical shard value u
     // init
     int init_pop = 0;
+    int init_plus = 0;       // 1: |+..+> (QAOA) instead of the Ry(pi/4) product state
+    // QAOA diagonal phase exp(-i angle H) before the gates (forward) / generator inner product + un-phase after them (backward)
+    int pre_phase = 0, post_phase = 0;
+    double angle_pre = 0.0, angle_post = 0.0;
+    int ham_layout = -1;     // which of the two per-layout H tables (0 natural, 1 swapped) the pass / the co-state step uses
+    int lut_index = -1;      // phase look-up table of this (direction, layer)
     // ordering
     bool new_step = false;   // a pass that reads peer memory starts a step (and so does the pass after it)
     long long wait_done = 0; // asynchronous mode: wait for DONE >= this generation before launching (0: none)
@@ -183,7 +194,11 @@ struct SwapRun {
     int sigma = 0, h = 0, m = 0;
     int sweeps = 0, layers = 0;
     int slices = 1;
+    int circuit = 0;               // 0 McClean, 1 QAOA
+    int final_psi = 0;             // buffer that holds the state when the run ends
+    Layout lay[2];                 // QAOA: the natural and the swapped layout (H tables are built per layout)
     size_t tab_off = 0, n_results = 0;
+    size_t lut_off = 0;            // QAOA: phase look-up tables [2 L][ham_range] in d_small (0: none)
     bool lockstep = true;
     long long gen_base = 0;
     std::vector<cudaEvent_t> ev;   // two events per op (after its waits / after its kernels): per-kind device times at finish
@@ -191,10 +206,6 @@ struct SwapRun {
 };
 
 // layout bookkeeping -------------------------------------------------------------------------------------
-struct Layout {
-    Lin phi;         // physical (rho << nl | l) -> logical index
-    int nl, g;
-};
 
 // logical bit held by physical local bit k (-1 if the column is not a unit vector)
 static int layout_local_logical(const Layout& ly, int k) { return unit_bit(ly.phi.col[k]); }
@@ -216,6 +227,28 @@ static int layout_shard_value(const Layout& ly, int rho) {
     int u = 0;
     for (int b = 0; b < ly.g; ++b) u |= (int)((j >> held[b]) & 1) << b;
     return u;
+}
+
+// observable / Hamiltonian terms with their bit positions translated from the logical index to (u << nl) | l, where l is
+// this shard's local index in layout ly and u the logical value of the rank-held bits (bit b = logical bit held[b])
+static int layout_remap_terms(const Layout& ly, std::vector<ObsTerm>& terms, bool* needs_peer) {
+    int held[8];
+    layout_held(ly, held);
+    if (needs_peer) *needs_peer = false;
+    for (ObsTerm& t : terms) {
+        auto remap = [&](int p) -> int {
+            for (int k = 0; k < ly.nl; ++k)
+                if (layout_local_logical(ly, k) == p) return k;
+            for (int b = 0; b < ly.g; ++b)
+                if (held[b] == p) return ly.nl + b;
+            return -1;
+        };
+        t.bit_i = remap(t.bit_i);
+        if (t.kind == QR_TERM_ZZ) t.bit_j = remap(t.bit_j);
+        if (t.bit_i < 0 || (t.kind == QR_TERM_ZZ && t.bit_j < 0)) return fail(QR_ESTATE, "internal: observable qubit not found in the layout");
+        if (needs_peer && (t.kind == QR_TERM_X || t.kind == QR_TERM_Y) && t.bit_i >= ly.nl) *needs_peer = true;
+    }
+    return 0;
 }
 
 // fill the source description of a pass with destination geometry `pp` (k = 12) and source map M (dest -> source, physical)
@@ -372,9 +405,21 @@ static bool gather_is_local(const Layout& ly, const Lin& G) {
 //             also takes over the un-rotation of the CNOT's control qubit (which must follow the CNOT), so that pass's
 //             tile holds the swapped bits, the control bit right above them and 8 - g other local bits.
 // Every exchanged amplitude then crosses NVLink exactly once per layer and vector.
-static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const double* angles, const qr_obs* o, bool want_grad,
+struct SwapCircuit {
+    int kind;                                   // 0 McClean, 1 QAOA
+    int L;
+    const int32_t* axes; const double* angles;  // McClean [L * n]
+    const double* betas; const double* gammas;  // QAOA [L]
+};
+
+static int swap_build(qr_ctx* c, SwapRun* sr, const SwapCircuit& circ, const qr_obs* o, bool want_grad,
                       std::vector<GateP>* gate_tab) {
     const int nl = c->n, g = c->g, nt = c->n_total, G = 1 << g, me = c->rank;
+    const int L = circ.L;
+    const int32_t* axes = circ.axes;
+    const double* angles = circ.angles;
+    const bool qaoa = circ.kind == 1;
+    sr->circuit = circ.kind;
     const int m = 9 - g;                                   // local gate bits of an exchange pass
     // gate run of the exchange pass: [h, h+9) = [h, h+m) local + [sigma, sigma+g) swapped.  One local bit must stay above
     // it (the control of the peeled CNOT), and the peel needs that control to be an odd qubit (it then belongs to the
@@ -415,9 +460,11 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
                 const int p = layout_local_logical(dest_ly, op.pp.gbit[s]);
                 if (p < 0) return fail(QR_ESTATE, "internal: a gate bit does not hold a single logical qubit");
                 const int q = nt - 1 - p;
-                const double an = angles[(size_t)op.layer * nt + q];
-                gp.c = std::cos(0.5 * an); gp.s = sgn * std::sin(0.5 * an); gp.axis = axes[(size_t)op.layer * nt + q];
-                op.slot_qubit[s] = q;
+                if (op.layer >= 0) {
+                    const double an = qaoa ? circ.betas[op.layer] : angles[(size_t)op.layer * nt + q];
+                    gp.c = std::cos(0.5 * an); gp.s = sgn * std::sin(0.5 * an); gp.axis = qaoa ? 0 : axes[(size_t)op.layer * nt + q];
+                    op.slot_qubit[s] = q;
+                }
             }
             gate_tab->push_back(gp);
         }
@@ -443,12 +490,15 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
     // applied by the previous exchange pass, to be taken out of this ladder.  `next_stacking` (forward): the ladder of the
     // next layer, whose offending CNOT this layer's exchange pass may apply in advance.
     std::vector<Lin> pre;   // 0 or 1 entries
+    bool swapped = false;   // QAOA (no ladder, no relabelling): which of its two layouts is current
+    sr->lay[0] = ly;
+    sr->lay[1].nl = 0;
     auto add_layer = [&](int layer, int nv, int ladder_stacking, int next_stacking) -> int {
         bool owed = false;          // backward: a CNOT peeled off this layer's ladder, owed to this layer's exchange pass
         Lin owed_f = lin_identity(nt);
         // ---- the ladder in the current layout ----
         Lin M = lin_identity(nt);
-        if (ladder_stacking >= 0 && nt >= 2) {
+        if (ladder_stacking >= 0 && nt >= 2 && !qaoa) {
             Lin Gl = lin_ladder_gather(nt, ladder_stacking);
             if (!pre.empty()) { Gl = lin_mul(pre[0], Gl); pre.clear(); }          // G = F G_rest  =>  G_rest = F G
             int pc, pt;
@@ -501,10 +551,13 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
         }
         max_sweeps = std::max(max_sweeps, 2 + (int)strided.size());
         // ---- pass 0: contiguous tile, gather through the ladder ----
-        {
+        if (layer >= 0) {
             XOp op = new_op(layer, nv);
             QR_TRY(xop_set_geometry(op, low, true));
             QR_TRY(xop_set_map(c, op, M, nl, g));
+            if (qaoa && nv == 1 && layer >= 0) {   // exp(-i gamma H) before the mixer (qaoa.py:51), H in the current layout
+                op.pre_phase = 1; op.angle_pre = circ.gammas[layer]; op.ham_layout = swapped ? 1 : 0; op.lut_index = layer;
+            }
             const bool oop = op.xmap || op.gather;
             op.src_buf[0] = psi; op.src_buf[1] = lam;
             if (oop) {
@@ -519,9 +572,9 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
         // ---- strided local passes, in place ----
         // The last one and the exchange pass can be issued in slices of the index bits [9, 12) when those bits are tile-index
         // bits of both (rows below 9, gate runs from 12 up): the exchange of a slice then overlaps the local pass of the next.
-        bool slice_pair = sr->slices > 1 && !strided.empty() && xb.front() >= 12 && strided.back().front() >= 12 &&
+        bool slice_pair = sr->slices > 1 && !qaoa && layer >= 0 && !strided.empty() && xb.front() >= 12 && strided.back().front() >= 12 &&
                           (int)strided.back().size() >= 3 && nl - 12 >= 4;
-        for (size_t si = 0; si < strided.size(); ++si) {
+        for (size_t si = 0; si < strided.size() && layer >= 0; ++si) {
             XOp op = new_op(layer, nv);
             QR_TRY(xop_set_geometry(op, strided[si], false));
             QR_TRY(xop_set_map(c, op, lin_identity(nt), nl, g));
@@ -541,7 +594,7 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
             }
             Lin F = owed ? owed_f : lin_identity(nt);
             bool fold = owed;
-            if (!owed && nv == 1 && next_stacking >= 0 && peel_geometry) {
+            if (!owed && !qaoa && nv == 1 && next_stacking >= 0 && peel_geometry) {
                 // forward: would the next ladder read other shards in the new layout?  Then apply its offending CNOT here.
                 const Lin Gn = lin_ladder_gather(nt, next_stacking);
                 int pc, pt;
@@ -567,7 +620,12 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
                 if (!slice_pair) sr->ops.back().nslices = 1;   // (the local pass was already given result slots per slice: harmless)
             }
             if (slice_pair) op.nslices = sr->slices;
+            if (qaoa && nv == 2 && layer >= 0) {   // 2 Im<lambda|H|psi> and the un-phase after the un-mixing (qaoa.py:65-68), H in the NEW layout
+                op.post_phase = 1; op.angle_post = -circ.gammas[layer]; op.ham_layout = swapped ? 0 : 1; op.lut_index = L + layer;
+            }
             QR_TRY(finish_op(op, nw));
+            swapped = !swapped;
+            if (sr->lay[1].nl == 0 && swapped) sr->lay[1] = nw;
             if (slice_pair) sr->ops.back().pair_gen = op.gen;
             psi = d0; if (nv == 2) lam = d1;
             sr->ops.push_back(op);
@@ -581,31 +639,24 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
         op.kind = 0;
         op.dst_buf[0] = psi;
         op.init_pop = __builtin_popcount((unsigned)layout_shard_value(ly, me));
+        op.init_plus = qaoa ? 1 : 0;
         sr->ops.push_back(op);
     }
     for (int i = 0; i < L; ++i) QR_TRY(add_layer(i, 1, 0, i + 1 < L ? 0 : -1));
     pre.clear();
-    // ---- observable in the current layout ----
+    if (qaoa && !want_grad && swapped) {
+        // forward-only QAOA runs leave the state in the natural layout (rank r = amplitudes r * 2^nl ...), where the
+        // sharded sampler can scan it in index order: one more exchange pass without gates
+        QR_TRY(add_layer(-1, 1, -1, -1));
+    }
+    // ---- observable in the current layout (QAOA: the co-state H psi from the layout's H table) ----
     {
         XOp op;
-        op.kind = 2;
-        int held[8];
-        layout_held(ly, held);
+        op.kind = qaoa ? 3 : 2;
         op.terms = o->terms;
         bool needs_peer = false;
-        for (ObsTerm& t : op.terms) {
-            auto remap = [&](int p) -> int {   // logical bit position -> position in (u << nl | l)
-                for (int k = 0; k < nl; ++k)
-                    if (layout_local_logical(ly, k) == p) return k;
-                for (int b = 0; b < g; ++b)
-                    if (held[b] == p) return nl + b;
-                return -1;
-            };
-            t.bit_i = remap(t.bit_i);
-            if (t.kind == QR_TERM_ZZ) t.bit_j = remap(t.bit_j);
-            if (t.bit_i < 0 || (t.kind == QR_TERM_ZZ && t.bit_j < 0)) return fail(QR_ESTATE, "internal: observable qubit not found in the layout");
-            if ((t.kind == QR_TERM_X || t.kind == QR_TERM_Y) && t.bit_i >= nl) needs_peer = true;
-        }
+        QR_TRY(layout_remap_terms(ly, op.terms, &needs_peer));
+        if (qaoa) { needs_peer = false; op.ham_layout = swapped ? 1 : 0; }
         op.obs_base = (u64)layout_shard_value(ly, me) << nl;
         for (int rho = 0; rho < G; ++rho) op.obs_peer_rank[layout_shard_value(ly, rho)] = rho;
         op.src_buf[0] = psi;
@@ -629,7 +680,7 @@ static int swap_build(qr_ctx* c, SwapRun* sr, int L, const int32_t* axes, const 
     sr->sweeps = max_sweeps;
     sr->n_results = res;
     sr->gen_base = gen;
-    (void)psi;
+    sr->final_psi = want_grad ? lam : psi;   // what State.vec holds afterwards: psi_final, or the back-propagated co-state
     return 0;
 }
 
@@ -673,8 +724,12 @@ static int swap_launch_tile(qr_ctx* c, SwapRun* sr, const XOp& op, int slice, cu
         PassIO io = {c->buf[op.src_buf[0]], op.nv == 2 ? c->buf[op.src_buf[1]] : nullptr, c->buf[op.dst_buf[0]],
                      op.nv == 2 ? c->buf[op.dst_buf[1]] : nullptr};
         int units = 0;
-        return launch_pass(c, lp, 0, op.nv, io, d_tab, 0, -1, 1, (i64)c->N, 0, nullptr, 0, 0, 0, 0, &units,
-                           op.gather ? &op.spec : nullptr, final_out, nullptr, nullptr, &ex);
+        const bool ph = op.pre_phase || op.post_phase;
+        if (ph) ex.hidx = c->d_hidx_ly[op.ham_layout];
+        const double2* lut = (ph && c->ham_integer && c->opt_ham_lut && sr->lut_off) ?
+            (const double2*)((char*)c->d_small + sr->lut_off) + (size_t)op.lut_index * c->ham_range : nullptr;
+        return launch_pass(c, lp, 0, op.nv, io, d_tab, 0, -1, 1, (i64)c->N, 0, ph ? c->d_ham_ly[op.ham_layout] : nullptr, op.pre_phase,
+                           op.angle_pre, op.post_phase, op.angle_post, &units, op.gather ? &op.spec : nullptr, final_out, lut, nullptr, &ex);
     }
     const PassPlan& pp = op.pp;
     const u64 lmask = ((u64)1 << nl) - 1;
@@ -691,6 +746,18 @@ static int swap_launch_tile(qr_ctx* c, SwapRun* sr, const XOp& op, int slice, cu
     tp.final_out = final_out;
     tp.done_counter = ex.counter;
     tp.partials = ex.partials;
+    const bool ph = op.pre_phase || op.post_phase;
+    if (ph) {
+        tp.ham = c->d_ham_ly[op.ham_layout];
+        tp.pre_phase = op.pre_phase; tp.post_phase = op.post_phase;
+        tp.angle_pre = op.angle_pre; tp.angle_post = op.angle_post;
+        if (c->ham_integer && c->opt_ham_lut && sr->lut_off) {
+            tp.hidx = c->d_hidx_ly[op.ham_layout];
+            tp.lut = (const double2*)((char*)c->d_small + sr->lut_off) + (size_t)op.lut_index * c->ham_range;
+            tp.lut_size = c->ham_range;
+            tp.hmin = c->ham_min;
+        }
+    }
     Tile12X x;
     memset(&x, 0, sizeof(x));
     x.ngroups = pp.ngroups;
@@ -728,13 +795,10 @@ static int swap_launch_tile(qr_ctx* c, SwapRun* sr, const XOp& op, int slice, cu
     const int sms = max_sms > 0 ? std::min(max_sms, c->sm_count) : c->sm_count;
     const i64 grid = std::min<i64>(tp.num_tiles, (i64)sms * (op.nv == 1 ? 2 : 1));
     const size_t smem = (size_t)op.nv * (sizeof(double2) << 12);
-    if (op.nv == 1) {
-        QR_TRY(ensure_smem_attr(c, (const void*)k_tile12_x<1>, 27));
-        QR_LAUNCH(k_tile12_x<1>, (unsigned)grid, 512, smem, stream, tp, x, xm);
-    } else {
-        QR_TRY(ensure_smem_attr(c, (const void*)k_tile12_x<2>, 28));
-        QR_LAUNCH(k_tile12_x<2>, (unsigned)grid, 512, smem, stream, tp, x, xm);
-    }
+    typedef void (*xfn)(const TilePass, const Tile12X, const TileXMap);
+    const xfn fn = op.nv == 1 ? (ph ? k_tile12_x<1, true> : k_tile12_x<1, false>) : (ph ? k_tile12_x<2, true> : k_tile12_x<2, false>);
+    QR_TRY(ensure_smem_attr(c, (const void*)fn, 27 + (op.nv - 1) * 2 + (ph ? 1 : 0)));
+    QR_LAUNCH(fn, (unsigned)grid, 512, smem, stream, tp, x, xm);
     KERNEL_CHECK();
     c->tables_fresh = false;
     c->perf.kernel_launches++;
@@ -766,7 +830,19 @@ static int swap_launch_op(qr_ctx* c, SwapRun* sr, const XOp& op, int op_index) {
         for (size_t i = old; i < sr->ev.size(); ++i) cudaEventCreate(&sr->ev[i]);
     }
     CUDA_TRY(cudaEventRecord(sr->ev[2 * op_index], st));
-    if (op.kind == 0) {
+    if (op.kind == 0 && op.init_plus) {
+        QR_LAUNCH(k_init_basis, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[op.dst_buf[0]], c->N, 1, std::pow(2.0, -0.5 * c->n_total));
+        KERNEL_CHECK();
+        c->perf.kernel_launches++;
+    } else if (op.kind == 3) {
+        const int ogrid = grid_for(c, c->N);
+        QR_LAUNCH(k_ham_costate, ogrid, QR_BLOCK, 0, c->stream, (const double2*)c->buf[op.src_buf[0]],
+                  op.dst_buf[0] >= 0 ? c->buf[op.dst_buf[0]] : (double2*)nullptr, (const double*)c->d_ham_ly[op.ham_layout], c->N, c->d_scratch);
+        KERNEL_CHECK();
+        QR_LAUNCH(k_reduce_partials, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_scratch, ogrid, 1, c->d_result);
+        KERNEL_CHECK();
+        c->perf.kernel_launches += 2;
+    } else if (op.kind == 0) {
         const int nt = c->n_total;
         double table[48];
         const double cs = std::cos(M_PI / 8.0), sn = std::sin(M_PI / 8.0);

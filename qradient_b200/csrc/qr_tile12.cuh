@@ -262,7 +262,7 @@ __device__ __noinline__ double2 qr12_phase_slow(const double* __restrict__ ham, 
 // backward CTAs per SM, whose load / FP64 / exchange phases overlap; used where it does not cost a pass.
 template <int NV, bool PHASE, int STAGED, int K, bool XMAP>
 __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, const TileXMap* xmp) {
-    static_assert(!XMAP || (!PHASE && STAGED == 0 && K == 12), "XMAP passes: McClean, direct loads, 12-bit tiles");
+    static_assert(!XMAP || (STAGED == 0 && K == 12), "XMAP passes: direct loads, 12-bit tiles");
     constexpr int T = 1 << K;
     constexpr int LG = K - 3;   // first local bit of the register group held at load time
     QR_DYN_SMEM(double2, smem);
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
 }
 
 // sharded registers: general source map and source pointer table (exchange passes read the peers' shards over NVLink)
-template <int NV>
+template <int NV, bool PHASE = false>
 __global__ void __launch_bounds__(512, (NV == 1 ? 2 : 1)) k_tile12_x(const TilePass p, const Tile12X x, const TileXMap xm) {
-    qr12_body<NV, false, 0, 12, true>(p, x, &xm);
+    qr12_body<NV, PHASE, 0, 12, true>(p, x, &xm);
 }

@@ -241,3 +241,121 @@ class ShardedMcClean:
         for s in self.shards:
             s.close()
         self.shards = []
+
+
+class ShardedQaoa:
+    """QAOA circuit (circuit_logic/qaoa.py) on a register sharded over G = 2^g GPUs: `run_expec_val`, `grad_run` and
+    bitstring sampling with the signatures and return values of `Qaoa`; every rank calls the methods collectively with
+    identical arguments.  Swap engine only (>= 12 + log2 G local qubits); the observable has z / zz terms (qaoa.py:11-14)."""
+
+    def __init__(self, qubit_number, observable, layer_number, comm, device=None):
+        self.qnum, self.lnum, self.comm = int(qubit_number), int(layer_number), comm
+        g = int(np.log2(comm.world))
+        if 2 ** g != comm.world or g < 1:
+            raise ValueError('world size must be a power of two >= 2')
+        self.log2_world = g
+        self._lib = _lib.lib()
+        self.observable = Observable(self.qnum, observable)
+        if np.any(self.observable.term_kinds < 2):
+            raise ValueError('the classical Hamiltonian of a QAOA circuit has z / zz terms only')
+        self.shards = []
+        for r in comm.local_ranks():
+            dev = device if device is not None else (comm.devices[r] if hasattr(comm, 'devices') else 0)
+            self.shards.append(_Shard(self._lib, self.qnum, g, r, dev))
+        comm.barrier()
+        comm.exchange_handles(self.shards)
+        comm.barrier()
+        self.mode = 'swap'
+        for s in self.shards:
+            s.set_option('shard_mode', 2)
+            s.set_option('shard_lockstep', 1 if getattr(comm, 'lockstep', True) else 0)
+        self.perf = {}
+        self._sampled_state = False
+
+    def set_option(self, name, value):
+        for s in self.shards:
+            s.set_option(name, value)
+
+    def _check_parameters(self, betas, gammas):
+        betas, gammas = np.asarray(betas, dtype=np.float64), np.asarray(gammas, dtype=np.float64)
+        if (betas.size != self.lnum) or (gammas.size != self.lnum):   # qaoa.py:186-191
+            raise ValueError('Wrong amount of parameters. Expected {0} and {0}, found {1} and {2}.'.format(
+                self.lnum, betas.size, gammas.size))
+        return np.ascontiguousarray(betas).ravel(), np.ascontiguousarray(gammas).ravel()
+
+    def _run(self, betas, gammas, want_grad):
+        betas, gammas = self._check_parameters(betas, gammas)
+        nsteps = ctypes.c_int()
+        for s in self.shards:
+            self._lib.call('qr_shard_qaoa_begin', s.ctx, self.lnum, _lib.ptr(betas), _lib.ptr(gammas), self.observable._handle,
+                           int(want_grad), ctypes.byref(nsteps))
+        self.comm.barrier()
+        lockstep = getattr(self.comm, 'lockstep', True)
+        for step in range(nsteps.value):
+            for s in self.shards:
+                self._lib.call('qr_shard_step', s.ctx, step)
+            if lockstep:
+                self.comm.barrier()
+        parts = []
+        for s in self.shards:
+            e = ctypes.c_double()
+            grad = np.zeros(2 * self.lnum + 1, dtype=np.float64)
+            self._lib.call('qr_shard_mcclean_finish', s.ctx, ctypes.byref(e), _lib.ptr(grad[1:]) if want_grad else None)
+            grad[0] = e.value
+            parts.append(grad)
+        perf = _lib.QrPerf()
+        self._lib.call('qr_perf_last', self.shards[0].ctx, ctypes.byref(perf))
+        self.link_bytes = perf.link_bytes
+        self.perf = {'kernel_launches': int(perf.kernel_launches), 'link_bytes': float(perf.link_bytes),
+                     'sweeps_per_layer': int(perf.passes_per_layer), 'mode': self.mode, 'ms_total': perf.ms_total}
+        self._sampled_state = not want_grad
+        total = self.comm.allreduce_sum(parts)
+        return float(total[0]), np.array(total[1:]).reshape(self.lnum, 2)
+
+    def run_expec_val(self, betas, gammas, hide_progbar=True, exact_expec_val=True, shot_num=1, ini_state=None):
+        """qaoa.py:23-38 (exact expectation value; the state stays on the devices for `sample_bitstrings`)."""
+        if ini_state is not None or not exact_expec_val:
+            raise NotImplementedError('sharded QAOA: exact expectation values from |+..+> only')
+        return self._run(betas, gammas, False)[0]
+
+    def grad_run(self, betas, gammas, hide_progbar=True, ini_state=None):
+        """qaoa.py:40-70: (E, grad[p, 2]), column 0 = d/d beta, column 1 = d/d gamma."""
+        if ini_state is not None:
+            raise NotImplementedError('sharded QAOA starts from |+..+>')
+        return self._run(betas, gammas, True)
+
+    def sample_bitstrings(self, shot_num, uniforms=None):
+        """Indices drawn from |psi|^2 of the LAST run_expec_val by inverse CDF (qaoa.py:196-198): first k with
+        cumsum(|psi|^2)[k] >= u.  Every shard scans its own amplitudes; the shard totals are gathered, the shard whose range
+        of the cumulative sum holds u searches u minus the total of the shards before it, and the global index is the
+        shard's base plus the local one."""
+        if not self._sampled_state:
+            raise RuntimeError('sample_bitstrings needs the state of a preceding run_expec_val (grad_run leaves the co-state)')
+        u = np.random.uniform(size=shot_num) if uniforms is None else np.asarray(uniforms, dtype=np.float64)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        G, nl = self.comm.world, self.qnum - self.log2_world
+        totals = np.zeros(G)
+        for s in self.shards:
+            t = ctypes.c_double()
+            self._lib.call('qr_norm2', s.ctx, ctypes.byref(t))
+            totals[s.rank] = t.value
+        totals = np.asarray(self.comm.allreduce_sum([totals]))
+        ends = np.cumsum(totals)
+        owner = np.searchsorted(ends, u, side='left')          # first shard whose cumulative total reaches u
+        out = np.zeros(u.size, dtype=np.float64)
+        for s in self.shards:
+            mine = np.nonzero(owner == s.rank)[0]
+            if mine.size == 0:
+                continue
+            base = ends[s.rank] - totals[s.rank]
+            ul = np.ascontiguousarray(np.minimum(u[mine] - base, totals[s.rank]))
+            idx = np.empty(mine.size, dtype=np.int64)
+            self._lib.call('qr_sample_bitstrings', s.ctx, int(mine.size), _lib.ptr(ul), _lib.ptr(idx))
+            out[mine] = idx + float(s.rank) * 2.0 ** nl
+        out = np.asarray(self.comm.allreduce_sum([out]))       # u above the last total: no shard owns it, index 0 (scipy's argmax)
+        return out.astype(np.int64)
+
+    def close(self):
+        for s in self.shards:
+            s.close()
+        self.shards = []

@@ -21,6 +21,7 @@ ap.add_argument("--tile-bits", type=int, default=0)
 ap.add_argument("--check-single", action="store_true", help="compare with the single-GPU path on rank 0")
 ap.add_argument("--opt", action="append", default=[], help="library option name=value")
 ap.add_argument("--mode", default=None, help="sharded engine: swap | peer (default: auto)")
+ap.add_argument("--circuit", default="mcclean", choices=["mcclean", "qaoa"])
 args = ap.parse_args()
 
 import torch
@@ -39,9 +40,33 @@ else:
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = local_rank
-from qradient_b200.sharded import ShardedMcClean, TorchDistComm
+from qradient_b200.sharded import ShardedMcClean, ShardedQaoa, TorchDistComm
 
 n, L = args.n, args.L
+if args.circuit == "qaoa":
+    # Qaoa.grad_run + sampling on the sharded register, checked against the oracle (small n) on rank 0
+    rng = np.random.default_rng(5)
+    edges = [(i, i + 1) for i in range(n - 1)] + [(0, n - 1), (0, n // 2)]
+    from oracle import qr_oracle as orc
+    obs = orc.maxcut_observable(n, edges)
+    betas, gammas = rng.random(L), rng.random(L)
+    q = ShardedQaoa(n, obs, L, TorchDistComm(), device=device)
+    t0 = time.perf_counter()
+    e, g = q.grad_run(betas, gammas)
+    dt = time.perf_counter() - t0
+    e_fwd = q.run_expec_val(betas, gammas)
+    u = np.random.RandomState(0).uniform(size=40)
+    idx = q.sample_bitstrings(40, u)
+    if rank == 0:
+        print(json.dumps({"circuit": "qaoa", "n": n, "p": L, "world": world, "E": e, "s_per_gradient": dt, "perf": q.perf}))
+        if args.check:
+            e_ref, g_ref, psi = orc.qaoa_grad_run(n, obs, betas, gammas, return_state=True)
+            ok = abs(e - e_ref) < 1e-10 * len(edges) and np.allclose(g, g_ref, rtol=1e-10, atol=1e-10 * len(edges)) and \
+                abs(e_fwd - e_ref) < 1e-10 * len(edges) and np.array_equal(idx, orc.sample_bitstrings(psi, u))
+            print("PARITY OK" if ok else "PARITY FAIL")
+    q.close()
+    dist.destroy_process_group()
+    sys.exit(0)
 rng = np.random.default_rng(5)
 axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
 zz = np.full((n, n), None)

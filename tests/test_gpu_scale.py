@@ -174,6 +174,34 @@ def test_sharded_24_qubits_vs_oracle_fixture(G):
         assert_parity(e1, g1, float(d["e"]), d["grad"], 1.75, 1e-10)
 
 
+@pytest.mark.parametrize("G", [2, 8])
+def test_sharded_qaoa_24_qubits_matches_one_gpu(G):
+    """Sharded QAOA (swap engine without a ladder, per-layout H tables) against the one-GPU Qaoa on 24 qubits: E, gradient and
+    the sampled bitstring indices."""
+    from qradient_b200.circuit_logic import Qaoa
+    from qradient_b200.optimization_problems import MaxCut
+    from qradient_b200.sharded import ShardedQaoa, LocalComm
+    n, p = 24, 4
+    edges = MaxCut.random_regular(n, 3, seed=3)
+    obs = MaxCut(n, edge_set=edges).to_observable()
+    rng = np.random.default_rng(24)
+    betas, gammas = rng.random(p), rng.random(p)
+    one = Qaoa(n, obs, p)
+    e1, g1 = one.grad_run(betas, gammas)
+    one.run_expec_val(betas, gammas)
+    u = np.random.RandomState(1).uniform(size=100)
+    idx1 = one.sample_bitstrings(100, u)
+    q = ShardedQaoa(n, obs, p, LocalComm(G))
+    try:
+        e, g = q.grad_run(betas, gammas)
+        assert_parity(e, g, e1, g1, float(len(edges)), 1e-10)
+        assert abs(q.run_expec_val(betas, gammas) - e1) < 1e-10 * len(edges)
+        idx = q.sample_bitstrings(100, u)
+        assert np.mean(idx == idx1) >= 0.99
+    finally:
+        q.close()
+
+
 def test_mcclean_30_qubits_properties():
     """North-star size (16 GiB state).  No oracle can run here (31 history vectors of 16 GiB), so
     this is a property test by necessity: E consistency, unit norm, finite differences on two angles; bench.py compares

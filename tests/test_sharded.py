@@ -10,7 +10,7 @@ import pytest
 from backends import backend  # noqa: F401
 from conftest import assert_parity, obs_scale
 from oracle import qr_oracle as orc
-from qradient_b200.sharded import ShardedMcClean, LocalComm
+from qradient_b200.sharded import ShardedMcClean, ShardedQaoa, LocalComm
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -83,6 +83,47 @@ def test_swap_engine_virtual_shards_vs_oracle(backend, n, L, G, peeled):
         c.close()
 
 
+@pytest.mark.parametrize("n,p,G,weighted", [(14, 3, 2, False), (15, 2, 2, True), (16, 2, 4, False), (18, 3, 8, False)])
+def test_sharded_qaoa_and_sampling_vs_oracle(backend, n, p, G, weighted):
+    """Qaoa.grad_run / run_expec_val (qaoa.py:23-70) and inverse-CDF bitstring sampling (qaoa.py:196-198) on a sharded register:
+    the diagonal phase by the per-layout H tables (phase look-up table for integer weights, sincos otherwise), the beta /
+    gamma reductions of all passes, the shard-local scans + gathered totals of the sampler (indices equal to the oracle's)."""
+    rng = np.random.default_rng(n + G)
+    edges = [(i, i + 1) for i in range(n - 1)] + [(0, n - 1), (0, n // 2), (1, n - 2)]
+    if weighted:
+        zz = np.full((n, n), None)
+        for (a, b) in edges:
+            zz[a, b] = float(rng.uniform(0.5, 1.5))
+        obs = {"zz": zz, "z": np.array([0.3, None, -0.7] + [None] * (n - 3), dtype=object)}
+        scale = obs_scale(obs)
+    else:
+        obs = orc.maxcut_observable(n, edges)
+        scale = float(len(edges))
+    betas, gammas = rng.random(p), rng.random(p)
+    e_ref, g_ref, psi = orc.qaoa_grad_run(n, obs, betas, gammas, return_state=True)
+    q = ShardedQaoa(n, obs, p, LocalComm(G))
+    try:
+        e, g = q.grad_run(betas, gammas)
+        assert_parity(e, g, e_ref, g_ref, scale, 1e-10)
+        with pytest.raises(RuntimeError):
+            q.sample_bitstrings(5)                          # the devices hold the co-state now
+        assert abs(q.run_expec_val(betas, gammas) - e_ref) <= 1e-10 * scale
+        u = np.concatenate([np.random.RandomState(0).uniform(size=60), [0.0, 0.5]])
+        idx = q.sample_bitstrings(u.size, u)
+        ref = orc.sample_bitstrings(psi, u)
+        cdf = np.cumsum(np.abs(psi) ** 2)
+        for a, b, uu in zip(idx, ref, u):
+            if a != b:   # only where u sits within rounding of a cdf step
+                assert abs(cdf[min(a, b)] - uu) < 1e-13, (a, b, uu)
+        assert np.mean(idx == ref) > 0.95
+        with pytest.raises(ValueError):
+            q.grad_run(betas[:-1], gammas)                  # qaoa.py:186-191
+    finally:
+        q.close()
+    with pytest.raises(ValueError):
+        ShardedQaoa(n, {"x": np.array([1.0] + [None] * (n - 1), dtype=object)}, p, LocalComm(G))
+
+
 def test_swap_engine_needs_enough_local_qubits(backend):
     n, G = 13, 4      # 11 local qubits < 12 + 2
     c = ShardedMcClean(n, mixed_obs(n), 1, LocalComm(G), np.zeros((1, n), int), np.zeros((1, n)))
@@ -134,6 +175,17 @@ def test_sharded_argument_checks(backend):
     with pytest.raises(ValueError):
         c.grad_run()
     c.close()
+
+
+def test_gloo_world_size_2_sharded_qaoa_on_cpu():
+    """Two processes over gloo: ShardedQaoa.grad_run, run_expec_val and the sharded sampler (allreduced shard totals)."""
+    script = os.path.join(ROOT, "scripts", "shard_run.py")
+    env = dict(os.environ, QR_SHARD_BACKEND="emul", MASTER_ADDR="127.0.0.1", MASTER_PORT="29745")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29745", script, "--circuit", "qaoa", "--qubits", "14", "--layers", "3", "--check"]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "PARITY OK" in res.stdout, res.stdout + res.stderr
 
 
 @pytest.mark.parametrize("qubits,port", [(9, "29741"), (14, "29743")])
