@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libqradient_b200.so")
 SOURCES = ["qr_lib.cu"]
-HEADERS = ["qr_platform.cuh", "qr_kernels.cuh", "qr_tile.cuh", "qr_tile12.cuh", os.path.join("..", "..", "include", "qradient_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "qradient_b200.h")]   # every header of the single translation unit
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
