@@ -147,22 +147,22 @@ class McClean(ParametrizedCircuit):
         grad = np.ndarray([L, n], dtype='double')
         for q in range(n):
             st.yrot(np.pi / 4., q)
-        history = []
         for i in range(L):
             st.cnot_ladder(0)
             for q in range(n):
                 self._rot(i, q)
-            history.append(np.array(st.vec))            # mc_clean.py:132
+            st.save(i)                                  # mc_clean.py:132 state_history[i] (device snapshot, no host round trip)
         expec_val = self.expec_val() if exact_expec_val else self.sample_expec_val(shot_num)
         for i in range(L):
             for dq in range(n):
                 shifted = []
                 for shift in (np.pi / 2, -np.pi / 2):
-                    st.vec = history[i]
+                    st.load(i)
                     self._manual_rot(i, dq, shift)
                     self._forward_tail(i + 1)
                     shifted.append(self.sample_expec_val(shot_num))
                 grad[i, dq] = .5 * (shifted[0] - shifted[1])
+        st.free_snapshots()
         return expec_val, grad
 
     # -- mc_clean.py:158-198: the same with one observable component drawn per parameter --------

@@ -149,10 +149,19 @@ class State:
         """mc_clean.py:65 ``state.multiply_matrix(observable.matrix)``: vec = O vec on the device.
         Accepts an Observable or the host matrix obtained from ``Observable.matrix``."""
         obs = getattr(matrix, '_qr_observable', matrix)
-        if not hasattr(obs, '_handle'):
-            raise TypeError('multiply_matrix needs an Observable (or Observable.matrix); arbitrary host matrices '
-                            'have no device representation')
-        self._lib.call('qr_apply_observable', self._ctx, obs._handle)
+        if hasattr(obs, '_handle'):
+            self._lib.call('qr_apply_observable', self._ctx, obs._handle)
+            return
+        # any other 2^n x 2^n host matrix (dense or scipy.sparse): vec = M.dot(vec) as one dense matrix-vector product on
+        # the device -- an inspection aid for small registers, like the reference's own 2^n x 2^n matrices
+        if self.qnum > 12:
+            raise TypeError('multiply_matrix with an arbitrary host matrix is limited to 12 qubits (dense 2^n x 2^n product); '
+                            'pass an Observable (or Observable.matrix) for larger registers')
+        dense = matrix.toarray() if hasattr(matrix, 'toarray') else np.asarray(matrix)
+        if dense.shape != (self._N, self._N):
+            raise ValueError('matrix must have shape ({0}, {0})'.format(self._N))
+        self.load_dense(dense)
+        self.apply_dense()
 
     def exp_ham_classical(self, angle):            # state.py:299-301
         self._lib.call('qr_apply_exp_ham', self._ctx, float(angle))

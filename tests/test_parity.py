@@ -325,6 +325,16 @@ def test_state_api_vs_oracle(backend):
     st.vec = v0
     st.multiply_matrix(obs)
     np.testing.assert_allclose(st.vec, obs.matrix.dot(v0), atol=1e-14)
+    # any other host matrix (the method's contract is vec = M.dot(vec)): dense and scipy.sparse, small registers
+    import scipy.sparse as sp
+    rng_m = np.random.default_rng(5)
+    dense = rng_m.normal(size=(2 ** n, 2 ** n)) + 1j * rng_m.normal(size=(2 ** n, 2 ** n))
+    for m in (dense, sp.csr_matrix(dense * (np.abs(dense) > 1.0))):
+        st.vec = v0
+        st.multiply_matrix(m)
+        np.testing.assert_allclose(st.vec, m.dot(v0), atol=1e-11)
+    with pytest.raises(ValueError):
+        st.multiply_matrix(np.eye(3))
     # classical Hamiltonian family (z / zz terms only; x and y are ignored with a warning)
     with pytest.warns(UserWarning):
         st.gates = Gates(n).add_classical_ham(obs, include_individual_components=True)
