@@ -50,6 +50,8 @@ def test_swap_engine_virtual_shards_vs_oracle(backend, n, L, G, peeled):
     """Swap engine (qr_shard.cuh): exchange passes whose loads come from the peer shards and whose stores are local, the
     layout alternating between 'qubits 0..g-1 on the rank bits' and 'local bits [sigma, sigma+g) on the rank bits', ladder
     passes with cross-shard tiles in the swapped layout; x / y observable terms on a rank-held qubit and on the lowest bit."""
+    if backend == "emul" and n >= 16:
+        L = 2          # the host emulation runs every thread of every CTA as a fiber: keep the CPU tier short
     rng = np.random.default_rng(n * 10 + G)
     axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
     obs = mixed_obs(n)
@@ -72,7 +74,7 @@ def test_swap_engine_virtual_shards_vs_oracle(backend, n, L, G, peeled):
         e2, g2 = c.grad_run()
         e_ref2, g_ref2 = orc.mcclean_grad_run(n, obs, axes, angles + 0.1)
         assert_parity(e2, g2, e_ref2, g_ref2, obs_scale(obs), 1e-10)
-        if n > 16:
+        if n > 15 and backend == "emul":
             return
         # the round-1 engine on the same register
         p = ShardedMcClean(n, obs, L, LocalComm(G), axes, angles + 0.1, mode="peer")
@@ -88,6 +90,8 @@ def test_sharded_qaoa_and_sampling_vs_oracle(backend, n, p, G, weighted):
     """Qaoa.grad_run / run_expec_val (qaoa.py:23-70) and inverse-CDF bitstring sampling (qaoa.py:196-198) on a sharded register:
     the diagonal phase by the per-layout H tables (phase look-up table for integer weights, sincos otherwise), the beta /
     gamma reductions of all passes, the shard-local scans + gathered totals of the sampler (indices equal to the oracle's)."""
+    if backend == "emul" and n >= 18:
+        p = 2
     rng = np.random.default_rng(n + G)
     edges = [(i, i + 1) for i in range(n - 1)] + [(0, n - 1), (0, n // 2), (1, n - 2)]
     if weighted:
