@@ -151,6 +151,26 @@ def source_hash():
     return h.hexdigest()[:12]
 
 
+NVLINK_SM_PULL_GBPS = 673.0   # measured: SM loads from the peer, both directions busy (profiles/r2_p2pbench.log; copy engines: 777)
+
+
+def nvlink_block(perf, link_bytes, sec, nl, world, step_seconds):
+    """Link-side roofline of a sharded gradient: the exchange passes are the only kernels that cross NVLink; their rate
+    (bytes this rank pulls per pass / average duration of the pass, CUDA events on the launching stream) is compared with
+    what SM loads get from the link on this hardware."""
+    out = {"bytes_in_per_gpu_per_gradient": link_bytes, "achieved_GBps_in_per_gpu_whole_gradient": link_bytes / sec / 1e9,
+           "nominal_GBps_per_direction": 900.0, "measured_sm_pull_GBps": NVLINK_SM_PULL_GBPS,
+           "peak_source": "profiles/r2_p2pbench.log (scripts/p2pbench.cu, 2 GPUs, both directions)", "step_seconds": step_seconds}
+    per_pass = 16.0 * 2.0 ** nl * (world - 1) / world          # bytes of ONE vector crossing the link in one exchange pass
+    for key, nv in (("exchange_forward", 1), ("exchange_backward", 2)):
+        ms = perf.get("ms_%s_avg" % key, 0.0)
+        if ms:
+            gbs = nv * per_pass / (ms * 1e-3) / 1e9
+            out[key] = {"ms_per_pass": ms, "bytes_per_pass": nv * per_pass, "achieved_GBps": gbs, "frac_of_measured_pull": gbs / NVLINK_SM_PULL_GBPS,
+                        "frac_of_nominal": gbs / 900.0}
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # CPU arm
 # ------------------------------------------------------------------------------------------
@@ -445,8 +465,7 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": "whole gradient, per GPU (tile passes + exchange passes)", "achieved": b_hbm / sec / 1e9, "peak": peak,
                              "unit": "GB/s", "frac": b_hbm / sec / 1e9 / peak, "peak_source": peak_src, "traffic": None,
                              "bytes_per_gradient_per_gpu": b_hbm},
-                "nvlink": {"bytes_in_per_gpu_per_gradient": link, "achieved_GBps_in_per_gpu": link / sec / 1e9, "peak_GBps_per_direction": 900.0,
-                           "frac_if_serial": link / sec / 1e9 / 900.0, "step_seconds": sh.step_seconds}}
+                "nvlink": nvlink_block(perf, link, sec, n - g_, world, sh.step_seconds)}
         # ---- parity inside the run: the same circuit on ONE GPU (rank 0), compared with the sharded result ----
         sh.close()
         del sh
@@ -491,8 +510,7 @@ def main():
                     line["config5_33x20"] = {"workload": w5["name"] + ", sharded over 8 GPUs", "value": 1.0 / s5, "unit": "gradients/s", "seconds_per_gradient": s5,
                                              "E": e5, "sweeps_per_layer": p5["sweeps_per_layer"],
                                              "roofline": {"bound": "hbm", "achieved": b5 / s5 / 1e9, "peak": peak, "unit": "GB/s", "frac": b5 / s5 / 1e9 / peak},
-                                             "nvlink": {"bytes_in_per_gpu_per_gradient": p5["link_bytes"], "achieved_GBps_in_per_gpu": p5["link_bytes"] / s5 / 1e9,
-                                                        "step_seconds": sh5.step_seconds},
+                                             "nvlink": nvlink_block(p5, p5["link_bytes"], s5, 30, 8, sh5.step_seconds),
                                              "parity": "no oracle at 33 qubits: the sharded engine is compared with the one-GPU path at 30 qubits in this run and "
                                                        "with the oracle at <= 24 qubits in tests/"}
                     sh5.close()

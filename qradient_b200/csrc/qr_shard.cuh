@@ -125,9 +125,13 @@ __global__ void k_flag_wait(unsigned long long* flags, int nranks, int kind, uns
     if (r >= nranks) return;
 #ifndef QR_HOST_EMUL
     volatile unsigned long long* f = flags + kind * QR_MAX_RANKS + r;
+    volatile unsigned long long* err = flags + QR_FLAG_ERR * QR_MAX_RANKS;
     const long long t0 = clock64();
     while (*f < value) {
-        if (clock64() - t0 > 120000000000ll) { flags[QR_FLAG_ERR * QR_MAX_RANKS + r] = value; break; }   // ~60 s
+        bool dead = false;   // a wait that already timed out on this rank ends every later wait at once (reported at finish)
+        for (int q = 0; q < nranks; ++q) dead = dead || err[q] != 0;
+        if (dead) break;
+        if (clock64() - t0 > 60000000000ll) { err[r] = value; break; }   // ~30 s
         __nanosleep(200);
     }
     __threadfence_system();

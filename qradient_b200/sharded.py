@@ -183,8 +183,9 @@ class ShardedMcClean:
         self.comm.barrier()
         import time
         L = self.lnum
-        self.step_seconds = {'fwd_local': 0.0, 'fwd_global': 0.0, 'observable': 0.0, 'bwd_local': 0.0, 'bwd_global': 0.0}
         if self.mode == 'swap':
+            # swap engine: one process per GPU enqueues every step at once (device-side flags order the ranks); a process
+            # that drives several shards runs them in lockstep, one step after another
             t0 = time.perf_counter()
             lockstep = getattr(self.comm, 'lockstep', True)
             for step in range(nsteps.value):
@@ -193,19 +194,21 @@ class ShardedMcClean:
                 if lockstep:
                     self.comm.barrier()
             self.step_seconds = {'enqueue': time.perf_counter() - t0}
-            nsteps.value = 0
-        for step in range(nsteps.value):
-            t0 = time.perf_counter()
-            for s in self.shards:
-                self._lib.call('qr_shard_step', s.ctx, step)
-            self.comm.barrier()
-            if step < 2 * L:
-                kind = 'fwd_local' if step % 2 == 0 else 'fwd_global'
-            elif step == 2 * L:
-                kind = 'observable'
-            else:
-                kind = 'bwd_local' if (step - 2 * L - 1) % 2 == 0 else 'bwd_global'
-            self.step_seconds[kind] += time.perf_counter() - t0   # wall time of this rank incl. the barrier
+        else:
+            # peer engine: every step is stream-synchronised and followed by a barrier over the ranks
+            self.step_seconds = {'fwd_local': 0.0, 'fwd_global': 0.0, 'observable': 0.0, 'bwd_local': 0.0, 'bwd_global': 0.0}
+            for step in range(nsteps.value):
+                t0 = time.perf_counter()
+                for s in self.shards:
+                    self._lib.call('qr_shard_step', s.ctx, step)
+                self.comm.barrier()
+                if step < 2 * L:
+                    kind = 'fwd_local' if step % 2 == 0 else 'fwd_global'
+                elif step == 2 * L:
+                    kind = 'observable'
+                else:
+                    kind = 'bwd_local' if (step - 2 * L - 1) % 2 == 0 else 'bwd_global'
+                self.step_seconds[kind] += time.perf_counter() - t0   # wall time of this rank incl. the barrier
         parts = []
         for s in self.shards:
             e = ctypes.c_double()

@@ -202,6 +202,33 @@ def test_sharded_qaoa_24_qubits_matches_one_gpu(G):
         q.close()
 
 
+def test_two_devices_in_one_process():
+    """One process driving two GPUs (LocalComm(devices=[0, 1]) and the `device=` keyword): the dynamic shared-memory
+    opt-in of the tile kernels is per device (it used to be remembered per process).  Needs two visible devices."""
+    import ctypes
+    from qradient_b200 import _lib
+    from qradient_b200.circuit_logic import McClean
+    from qradient_b200.sharded import ShardedMcClean, LocalComm
+    ndev = ctypes.c_int(0)
+    _lib.lib().call("qr_device_count", ctypes.byref(ndev))
+    if ndev.value < 2:
+        pytest.skip("needs two CUDA devices")
+    n, L = 16, 3
+    rng = np.random.default_rng(2)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    e_ref, g_ref = orc.mcclean_grad_run(n, zz01(n), axes, angles)
+    for dev in (1, 0):      # device 1 FIRST: it must get its own opt-in
+        c = McClean(n, zz01(n), L, axes=axes, angles=angles, device=dev)
+        e, g = c.grad_run()
+        assert_parity(e, g, e_ref, g_ref, 1.0, 1e-10)
+    sh = ShardedMcClean(n, zz01(n), L, LocalComm(2, devices=[0, 1]), axes, angles)
+    try:
+        e, g = sh.grad_run()
+        assert_parity(e, g, e_ref, g_ref, 1.0, 1e-10)
+    finally:
+        sh.close()
+
+
 def test_mcclean_30_qubits_properties():
     """North-star size (16 GiB state).  No oracle can run here (31 history vectors of 16 GiB), so
     this is a property test by necessity: E consistency, unit norm, finite differences on two angles; bench.py compares
