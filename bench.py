@@ -130,7 +130,7 @@ def measured_peak():
 
 def ncu_traffic(n):
     """DRAM bytes per backward tile-pass launch from the committed ncu launch list of the current kernels
-    (profiles/r*_traffic_bwd_n<n>.json: written by scripts/ncu_summary.py from an `ncu --metrics dram__bytes_*` pass;
+    (profiles/r*_traffic_bwd_n<n>.json: written by scripts/ncu_traffic.py from an `ncu --metrics dram__bytes_*` pass;
     the file names the library source hash it was captured on).  None when no capture exists for this size."""
     cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic_bwd_n%d.json" % n)))
     if not cands:
