@@ -31,3 +31,9 @@ def test_hot_tile_kernels_compile_without_spills(tmp_path):
         staged = int(re.search(r"ELb0ELi(\d)E", name).group(1))
         limit = 64 if (nv == 1 and not staged) else 128     # forward: 2 x 512 (or 4 x 256) threads per SM; backward: 512 (2 x 256)
         assert int(regs) <= limit, (name, regs, k11)
+    # the exchange-pass instantiations of sharded registers (k_tile12_x<NV, PHASE = false>): same budgets, no spills
+    xhot = [b for b in blocks if b[0].startswith("_Z10k_tile12_xILi") and "ELb0E" in b[0]]
+    assert len(xhot) == 2, [b[0] for b in blocks if "tile12_x" in b[0]]
+    for name, stack, st, ld, regs in xhot:
+        assert int(st) == 0 and int(ld) == 0, (name, st, ld)
+        assert int(regs) <= (64 if "ILi1E" in name else 128), (name, regs)
