@@ -15,8 +15,10 @@
  *     vector psi, the co-state lambda of the adjoint sweep, ping-pong scratch, the diagonal
  *     Hamiltonian table, reduction scratch).  A context must not be used from two threads at
  *     once (same rule as the reference objects).
- *   - host pointers are caller-owned and only read/written during the call; every call is
- *     synchronous at return.
+ *   - host pointers are caller-owned and only read/written during the call.  Calls that take or return host data are
+ *     synchronous at return; calls that only launch kernels on the context's stream (single gates, ladders, diagonal
+ *     phases, snapshots) are stream ordered and return at once -- the next call that returns data synchronises
+ *     (qr_sync forces it).
  *   - amplitudes are complex128, interleaved (re, im); amplitude index j = sum_q b_q 2^(n-1-q)
  *     (qubit 0 is the most significant bit; physical_components/state.py:84-88,163).
  *   - there is NO CPU fallback: every compute entry point launches CUDA kernels.

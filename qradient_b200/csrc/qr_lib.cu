@@ -378,8 +378,7 @@ extern "C" int qr_state_init(qr_ctx* c, int which) {
     const double amp = std::pow(2.0, -0.5 * c->n);   // state.py:69
     QR_LAUNCH(k_init_basis, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[c->psi], c->N, which, amp);
     KERNEL_CHECK();
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return 0;
+    return 0;   // stream ordered: the next call that returns data to the host synchronises
 }
 
 extern "C" int qr_state_upload(qr_ctx* c, const double* re_im, size_t n_amps) {
@@ -417,8 +416,7 @@ extern "C" int qr_state_save(qr_ctx* c, int slot) {
         if (e != cudaSuccess) { c->snapshots[slot] = nullptr; return fail(QR_ENOMEM, "cannot allocate snapshot %d: %s", slot, cudaGetErrorString(e)); }
     }
     CUDA_TRY(cudaMemcpyAsync(c->snapshots[slot], c->buf[c->psi], c->N * sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return 0;
+    return 0;   // stream ordered: the next call that returns data to the host synchronises
 }
 
 extern "C" int qr_state_load(qr_ctx* c, int slot) {
@@ -426,8 +424,7 @@ extern "C" int qr_state_load(qr_ctx* c, int slot) {
     if (slot < 0 || (size_t)slot >= c->snapshots.size() || !c->snapshots[slot]) return fail(QR_EINVAL, "snapshot %d does not exist", slot);
     QR_TRY(use_device(c));
     CUDA_TRY(cudaMemcpyAsync(c->buf[c->psi], c->snapshots[slot], c->N * sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return 0;
+    return 0;   // stream ordered: the next call that returns data to the host synchronises
 }
 
 extern "C" int qr_state_free_snapshots(qr_ctx* c) {
@@ -490,8 +487,7 @@ extern "C" int qr_apply_rot(qr_ctx* c, int axis, double angle, int qubit) {
     QR_TRY(check_axis_qubit(c, axis, qubit));
     QR_TRY(use_device(c));
     QR_TRY(launch_1q(c, c->buf[c->psi], c->n - 1 - qubit, rot_matrix(axis, angle)));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return 0;
+    return 0;   // stream ordered: the next call that returns data to the host synchronises
 }
 
 extern "C" int qr_apply_drot(qr_ctx* c, int axis, double angle, int qubit) {
@@ -499,8 +495,7 @@ extern "C" int qr_apply_drot(qr_ctx* c, int axis, double angle, int qubit) {
     QR_TRY(check_axis_qubit(c, axis, qubit));
     QR_TRY(use_device(c));
     QR_TRY(launch_1q(c, c->buf[c->psi], c->n - 1 - qubit, drot_matrix(axis, angle)));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return 0;
+    return 0;   // stream ordered: the next call that returns data to the host synchronises
 }
 
 static int launch_cnot(qr_ctx* c, double2* v, int control, int target) {
@@ -516,8 +511,7 @@ extern "C" int qr_apply_cnot(qr_ctx* c, int control, int target) {
         return fail(QR_EINVAL, "Invalid CNOT indecies %d and %d, for %d qubits.", control, target, c->n);
     QR_TRY(use_device(c));
     QR_TRY(launch_cnot(c, c->buf[c->psi], control, target));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return 0;
+    return 0;   // stream ordered: the next call that returns data to the host synchronises
 }
 
 // scatter masks of ladder `stacking`; the gather for stacking s uses the
@@ -564,8 +558,7 @@ extern "C" int qr_apply_cnot_ladder(qr_ctx* c, int stacking, int periodic) {
             for (int i = start; i < n; i += 2) QR_TRY(launch_cnot(c, c->buf[c->psi], i, (i + 1) % n));
         }
     }
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return 0;
+    return 0;   // stream ordered: the next call that returns data to the host synchronises
 }
 
 extern "C" int qr_apply_x_summed(qr_ctx* c) {
@@ -576,8 +569,7 @@ extern "C" int qr_apply_x_summed(qr_ctx* c) {
     QR_LAUNCH(k_x_summed, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[c->psi], c->buf[dst], c->N, c->n);
     KERNEL_CHECK();
     c->psi = dst;
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return 0;
+    return 0;   // stream ordered: the next call that returns data to the host synchronises
 }
 
 extern "C" int qr_norm2(qr_ctx* c, double* out) {
@@ -756,8 +748,7 @@ extern "C" int qr_apply_exp_ham(qr_ctx* c, double angle) {
     QR_TRY(use_device(c));
     QR_LAUNCH(k_exp_ham, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[c->psi], (const double*)c->d_ham, c->N, angle);
     KERNEL_CHECK();
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return 0;
+    return 0;   // stream ordered: the next call that returns data to the host synchronises
 }
 
 extern "C" int qr_apply_exp_ham_component(qr_ctx* c, const qr_obs* o, int k, double angle) {
@@ -785,8 +776,7 @@ extern "C" int qr_apply_exp_ham_component(qr_ctx* c, const qr_obs* o, int k, dou
         QR_TRY(launch_1q(c, c->buf[c->psi], t.bit_j, m));
         QR_TRY(launch_cnot(c, c->buf[c->psi], qi, qj));
     }
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return 0;
+    return 0;   // stream ordered: the next call that returns data to the host synchronises
 }
 
 extern "C" int qr_apply_ham(qr_ctx* c, int mode) {
@@ -795,8 +785,7 @@ extern "C" int qr_apply_ham(qr_ctx* c, int mode) {
     QR_TRY(use_device(c));
     QR_LAUNCH(k_mul_ham, grid_for(c, c->N), QR_BLOCK, 0, c->stream, c->buf[c->psi], (const double*)c->d_ham, c->N, mode);
     KERNEL_CHECK();
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return 0;
+    return 0;   // stream ordered: the next call that returns data to the host synchronises
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1869,8 +1858,7 @@ extern "C" int qr_state_permute(qr_ctx* c) {
     QR_LAUNCH(k_permute_gather, grid_for(c, c->N), QR_BLOCK, 0, c->stream, (const double2*)c->buf[c->psi], (const i64*)c->d_perm, c->buf[dst], c->N);
     KERNEL_CHECK();
     c->psi = dst;
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return 0;
+    return 0;   // stream ordered: the next call that returns data to the host synchronises
 }
 
 // Dense basis change (observables with x / y terms are measured in the eigenbasis of the dense 2^n x 2^n observable,
@@ -1900,8 +1888,7 @@ extern "C" int qr_state_apply_dense(qr_ctx* c) {
     QR_LAUNCH(k_dense_matvec, grid, QR_BLOCK, 0, c->stream, (const double2*)c->d_dense, (const double2*)c->buf[c->psi], c->buf[dst], c->N);
     KERNEL_CHECK();
     c->psi = dst;
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return 0;
+    return 0;   // stream ordered: the next call that returns data to the host synchronises
 }
 
 extern "C" int qr_ham_gather(qr_ctx* c, int n, const int64_t* idx, double* out) {
