@@ -590,7 +590,7 @@ def main():
         "e2e": {"value": total_units / (t_wall / 1e3), "unit": "gradients/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": t_wall / args.steps},
         "gpu_launches": launches, "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_tile12<2,*> (backward tile pass: psi and lambda, qr_tile12.cuh)",
+        "roofline": {"bound": "hbm", "kernel": "k_tile12<2,*> / k_tile12_g<2,*> / k_tile12_gs<2> (backward tile passes: psi and lambda; contiguous pass, axis-aware strided passes; qr_tile12.cuh)",
                      "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak, "peak_source": peak_src,
                      "bytes_per_launch": perf["bwd_pass_bytes"], "ms_per_launch": perf["bwd_pass_ms_avg"],
                      "traffic": traffic, "traffic_source": traffic_src,
@@ -608,6 +608,16 @@ def main():
         line["self_check"] = {"abs_E_grad_minus_E_forward": abs(e_grad - e_fwd), "norm_error": float(abs(circ.state.norm_error())),
                               "note": "no oracle exists at this size (SURVEY.md section 6); oracle parity is asserted on the extra configurations below"}
         assert abs(e_grad - e_fwd) <= 1e-10, "grad_run and run_expec_val disagree on E"
+        if world == 1 and not args.no_extras and hasattr(circ, "state"):
+            # the timed runs use the per-layer axis-aware plans (QR_OPT_AXIS_PLAN); one more gradient with the static plan
+            # (every index bit a tile bit of some pass) must give the same numbers
+            g_axis = np.array(res[1])
+            circ.state.set_option("axis_plan", 0)
+            e_static, g_static = circ.grad_run()
+            circ.state.set_option("axis_plan", dict(opts).get("axis_plan", 15))
+            line["self_check"]["axis_plan_vs_static_plan"] = {"abs_dE": abs(e_grad - float(e_static)), "max_abs_dgrad": float(np.abs(g_axis - np.array(g_static)).max()),
+                                                              "tol": 1e-10, "ms_static_plan": circ.perf()["ms_total"]}
+            assert abs(e_grad - float(e_static)) <= 1e-10 and np.abs(g_axis - np.array(g_static)).max() <= 1e-10, "axis-aware and static plans disagree"
     del circ
     if rank == 0 and world == 1 and args.workload == "mcclean30" and not args.no_extras:
         for key, fn in (("config2_20x20", lambda: check_config2(McClean, local_rank)), ("config3_qaoa26", lambda: check_config3(local_rank))):

@@ -13,7 +13,9 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -62,6 +64,9 @@ struct PassPlan {
     bool lean;                 // lean static kernel k_tile12 (k == 12 or 11): slot = local bit
     int ngroups;               // lean: active register groups (1..4)
     int m1, h2;                // lean: two-segment geometry (Geo12); single segment: m1 = k - c, h2 = h + m1
+    bool gx;                   // axis-aware pass (plan_axis_layer): general geometry lbit[], out-of-tile Rz gates in the row slots
+    int lbit[QR_MAX_TILE_BITS];   // gx: global index bit of local bit b
+    unsigned zmask;            // gx: slots (local bits < c) that hold an Rz on an index bit outside the tile
 };
 
 struct LayerPlan {
@@ -108,6 +113,7 @@ struct qr_ctx {
     long long opt_staged_min_bit = 21;   // auto mode: strided backward passes whose lowest gate bit is >= this are staged
     long long opt_defer_reduce = 1; // single circuits: one reduction launch per gradient instead of a last-CTA reduction in every backward pass
     long long opt_pdl = 1;         // k_tile12 passes launched with programmatic stream serialization: 0 off, 1 auto (n <= 22), 2 always
+    long long opt_axis_plan = 15;  // single McClean circuits: bit 0 per-layer plans from the axes (plan_axis_layer); bit 1 pass 0 trades Rz-only bits for high X / Y bits where that saves a round; bit 2 passes without an exchange run the two-round program; bit 3 split barriers in two-round backward passes
     long long opt_shard_zskip = 1; // sharded states: Rz on a global qubit is applied as a per-subgroup phase, without the exchange
     bool tables_fresh = true;      // gate / phase tables were (re)written since the last tile pass: see launch_pass
     qr_perf perf;
@@ -318,6 +324,7 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
         case QR_OPT_BATCH_CHUNK_MB: if (v < 0 || v > 65536) return fail(QR_EINVAL, "bad batch chunk"); c->opt_batch_chunk_mb = v; break;
         case QR_OPT_DEFER_REDUCE: c->opt_defer_reduce = v ? 1 : 0; break;
         case QR_OPT_SHARD_ZSKIP: c->opt_shard_zskip = v ? 1 : 0; break;
+        case QR_OPT_AXIS_PLAN: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad axis-plan mode"); c->opt_axis_plan = v; break;
         case QR_OPT_PDL: if (v < 0 || v > 2) return fail(QR_EINVAL, "bad PDL mode"); c->opt_pdl = v; break;
         case QR_OPT_SHARD_MODE: if (v < 0 || v > 2) return fail(QR_EINVAL, "bad shard mode"); c->opt_shard_mode = v; break;
         case QR_OPT_SHARD_LOCKSTEP: c->opt_shard_lockstep = v ? 1 : 0; break;
@@ -345,6 +352,7 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_STAGED_MIN_BIT: *v = c->opt_staged_min_bit; break;
         case QR_OPT_PDL: *v = c->opt_pdl; break;
         case QR_OPT_SHARD_ZSKIP: *v = c->opt_shard_zskip; break;
+        case QR_OPT_AXIS_PLAN: *v = c->opt_axis_plan; break;
         case QR_OPT_DEFER_REDUCE: *v = c->opt_defer_reduce; break;
         case QR_OPT_SHARD_MODE: *v = c->opt_shard_mode; break;
         case QR_OPT_SHARD_LOCKSTEP: *v = c->opt_shard_lockstep; break;
@@ -863,7 +871,7 @@ static int make_plan(int n, int tile_bits, LayerPlan* lp, int tile_bits_x = 0, i
     lp->R = R;
     int np = 0;
     PassPlan& p0 = lp->pass[np++];
-    p0.k = k; p0.c = k; p0.h = k; p0.lean = false; p0.ngroups = 0; p0.m1 = 0; p0.h2 = k;
+    p0.k = k; p0.c = k; p0.h = k; p0.lean = false; p0.ngroups = 0; p0.m1 = 0; p0.h2 = k; p0.gx = false; p0.zmask = 0;
     const bool lean_k = (k == 12 || k == 11) && (tile_bits_x == 0 || tile_bits_x == k) && (k == 12 || min_row_bits >= 2);
     if (lean_k) plan_lean(p0, 0); else plan_rounds(p0, 0, R);
     const int rem = n - k;
@@ -876,7 +884,7 @@ static int make_plan(int n, int tile_bits, LayerPlan* lp, int tile_bits_x = 0, i
         for (int i = 0; i < nx; ++i) {
             const int m = rem / nx + (i < rem % nx ? 1 : 0);
             PassPlan& pp = lp->pass[np++];
-            pp.k = kx; pp.c = kx - m; pp.h = h; pp.lean = false; pp.ngroups = 0;
+            pp.k = kx; pp.c = kx - m; pp.h = h; pp.lean = false; pp.ngroups = 0; pp.gx = false; pp.zmask = 0;
             pp.m1 = m; pp.h2 = h + m;
             if (lean_k) plan_lean(pp, pp.c); else plan_rounds(pp, pp.c, R);
             h += m;
@@ -889,6 +897,168 @@ static int make_plan(int n, int tile_bits, LayerPlan* lp, int tile_bits_x = 0, i
     return 0;
 }
 
+
+// ---- axis-aware plans (QR_OPT_AXIS_PLAN) ----------------------------------------------------------------------------
+// The static plan gives every index bit a tile bit in some pass.  A diagonal gate does not need one: k_tile12_g applies
+// an Rz whose index bit lies outside the tile as a phase factor of the tile and takes its gradient from the tile's total
+// of Im(conj(lambda) psi).  So the strided passes of a layer only need tile bits for the layer's X / Y rotations above
+// the contiguous tile: with k of them in a pass the tile keeps 2^(K-k) contiguous amplitudes per row (K = 12, k = 6:
+// 1 KiB rows and ONE shared-memory exchange instead of 128 B rows and two), and a register with few high bits may need
+// fewer passes.  Pass 0 (contiguous tile, ladder gather) is unchanged.
+// Estimated cost of a strided pass with k X / Y gate bits (two-vector pass at n = 30, ms; measured, profiles/README.md):
+#define QR_AXIS_MAX_ROW_BITS 7   // rows of 2 KiB; 8 KiB rows (c = 9, no exchange at all) ran at 15 ms against 13.3 ms for c = 6..7
+static double axis_pass_cost(int k, int K) {
+    // measured back to back at n = 30 (QR_TRACE_PASSES, profiles/r2_axis_trace.log): one exchange round costs ~3.4 ms in
+    // the two-vector pass whatever the row width -- k <= 6: 13.2-14.0 ms; k = 7, 8 (256 / 512 B rows): 17.0-17.5 ms;
+    // k = 9 (128 B rows, staged loads like the static plan): 15.7-16.9 ms
+    (void)K;
+    return k <= 6 ? 13.5 : (k <= 8 ? 17.2 : 20.0);   // k = 9: 128 B rows on 9 scattered high bits ran at 18-22 ms
+}
+
+// cheapest composition of k X / Y bits into m parts of at most maxk (parts descending in split[]); 1e30 if none
+static double axis_best_split(int k, int m, int maxk, int K, int* split_out) {
+    double best = 1e30;
+    int split[8];
+    std::function<void(int, int, double)> rec = [&](int i, int left, double cost) {
+        if (i == m - 1) {
+            if (left > maxk) return;
+            split[i] = left;
+            const double cst = cost + axis_pass_cost(left, K);
+            if (cst < best) { best = cst; for (int j = 0; j < m; ++j) split_out[j] = split[j]; }
+            return;
+        }
+        for (int a = std::min(left, maxk); a >= 0; --a) {
+            if ((m - 1 - i) * maxk < left - a) break;
+            split[i] = a;
+            rec(i + 1, left - a, cost + axis_pass_cost(a, K));
+        }
+    };
+    rec(0, k, 0.0);
+    if (best < 1e29) std::sort(split_out, split_out + m, [](int a, int b) { return a > b; });
+    return best;
+}
+
+// plan of one layer from its axes (ax[q], qubit q <-> index bit n-1-q); false: keep the static plan.
+// Strided passes: tile = rows + the X / Y bits given to the pass (+ fillers); the Rz gates of index bits outside the
+// tile go to the slots of the row bits.  Pass 0 keeps the contiguous tile unless a strided pass would need a second
+// exchange round for one or two bits: then pass 0 trades Rz-only bits of [7, K) (never row bits of a strided tile) for
+// the lowest high X / Y bits (allow_absorb); its ladder gather works on any tile by linearity of the ladder map.
+static bool plan_axis_layer(const LayerPlan& base, const int32_t* ax, LayerPlan* out, int allow_absorb) {
+    const int n = base.n, K = base.k;
+    if (base.npasses < 2 || !base.pass[0].lean || (K != 12 && K != 11)) return false;
+    const int H = n - K, maxk = K - 3, maxm = base.npasses - 1;
+    if (H < 3) return false;   // every strided tile has at least 3 high bits (the register bits at load time)
+    int nz[64], zs[64], k = 0, nzs = 0;
+    for (int b = K; b < n; ++b) {
+        if (ax[n - 1 - b] == 2) zs[nzs++] = b; else nz[k++] = b;
+    }
+    int lowz[16], nlowz = 0;   // Rz-only bits of pass 0 that it may trade away, highest first
+    for (int b = K - 1; b >= QR_AXIS_MAX_ROW_BITS && allow_absorb; --b)
+        if (ax[n - 1 - b] == 2) lowz[nlowz++] = b;
+    // choose the number of absorbed bits e and the pass count m by estimated cost
+    double best_total = 1e30;
+    int best_e = -1, best_m = 0, best_split[8];
+    for (int e = 0; e <= std::min(nlowz, k); ++e)
+        for (int m = 1; m <= maxm; ++m) {
+            if (m * maxk < k - e) continue;
+            int split[8];
+            const double cst = axis_best_split(k - e, m, maxk, K, split) + (e ? 0.6 + 0.1 * e : 0.0);
+            if (cst < best_total - 1e-9) { best_total = cst; best_e = e; best_m = m; for (int j = 0; j < m; ++j) best_split[j] = split[j]; }
+        }
+    if (best_e < 0 || best_total >= 16.0 * maxm) return false;   // the static plan's strided passes run at ~16 ms each
+    // try the chosen (e, m); when the Rz capacity does not suffice fall back to e = 0 with growing m
+    for (int attempt = 0; attempt < 1 + maxm; ++attempt) {
+        int e = best_e, m = best_m, splitv[8];
+        if (attempt == 0) { for (int j = 0; j < m; ++j) splitv[j] = best_split[j]; }
+        else {
+            e = 0; m = attempt;
+            if (m * maxk < k || axis_best_split(k, m, maxk, K, splitv) > 1e29) continue;
+        }
+        bool used_z[64] = {};
+        int nzpos = e, tbits[8][QR_MAX_TILE_BITS], tgate[8][QR_MAX_TILE_BITS], tn[8], cs[8];   // nz[0..e) go to pass 0
+        for (int i = 0; i < m; ++i) {
+            cs[i] = std::max(std::min(std::min(K - 3, QR_AXIS_MAX_ROW_BITS), K - splitv[i]), K - H);   // small registers: the tile takes every high bit
+            tn[i] = 0;
+            for (int j = 0; j < splitv[i]; ++j) { tgate[i][tn[i]] = 1; tbits[i][tn[i]++] = nz[nzpos++]; }
+        }
+        // fillers (tiles with few X / Y bits): unassigned Rz bits first (applied in the tile), then any other high bit
+        bool ok = true;
+        for (int i = 0; i < m && ok; ++i) {
+            const int want = K - cs[i];
+            for (int z = 0; z < nzs && tn[i] < want; ++z)
+                if (!used_z[z]) { used_z[z] = true; tgate[i][tn[i]] = 1; tbits[i][tn[i]++] = zs[z]; }
+            for (int b = K; b < n && tn[i] < want; ++b) {
+                bool in = false;
+                for (int j = 0; j < tn[i]; ++j) in = in || tbits[i][j] == b;
+                if (!in) { tgate[i][tn[i]] = 0; tbits[i][tn[i]++] = b; }
+            }
+            ok = tn[i] == want;
+        }
+        // remaining Rz bits (and the bits pass 0 traded away) -> the slots of the row bits, spread evenly
+        int zbits[8][QR_GX_ZSLOTS], zn[8];
+        for (int i = 0; i < m; ++i) zn[i] = 0;
+        auto place_z = [&](int bit) {
+            int at = -1;
+            for (int i = 0; i < m; ++i)
+                if (zn[i] < std::min(cs[i], QR_GX_ZSLOTS) && (at < 0 || zn[i] < zn[at])) at = i;
+            if (at < 0) return false;
+            zbits[at][zn[at]++] = bit;
+            return true;
+        };
+        for (int z = 0; z < nzs && ok; ++z)
+            if (!used_z[z]) ok = place_z(zs[z]);
+        for (int j = 0; j < e && ok; ++j) ok = place_z(lowz[j]);
+        if (!ok) continue;
+        *out = base;
+        out->npasses = 1 + m;
+        if (e > 0) {   // pass 0 on a general tile: bits [0, K) without the traded Rz bits, plus the e lowest high X / Y bits
+            PassPlan& p0 = out->pass[0];
+            p0.gx = true; p0.zmask = 0;
+            u64 traded = 0;
+            for (int j = 0; j < e; ++j) traded |= (u64)1 << lowz[j];
+            int lb = 0;
+            for (int b = 0; b < K; ++b)
+                if (!((traded >> b) & 1)) { p0.lbit[lb] = b; p0.gbit[lb] = b; ++lb; }
+            p0.c = 0;
+            while (p0.c < lb && p0.lbit[p0.c] == p0.c) ++p0.c;   // contiguous amplitudes per row
+            for (int j = 0; j < e; ++j, ++lb) { p0.lbit[lb] = nz[j]; p0.gbit[lb] = nz[j]; }
+            p0.ngroups = 4; p0.nrounds = 4;
+        }
+        for (int i = 0; i < m; ++i) {
+            PassPlan& pp = out->pass[1 + i];
+            pp = PassPlan();
+            pp.k = K; pp.c = cs[i]; pp.h = K; pp.m1 = K - cs[i]; pp.h2 = pp.h + pp.m1;
+            pp.lean = true; pp.gx = true; pp.zmask = 0;
+            for (int j = 0; j < QR_MAXROUNDS; ++j) pp.g[j] = 0;
+            for (int j = 0; j < QR_GATE_SLOTS; ++j) pp.gbit[j] = -1;
+            for (int b = 0; b < QR_MAX_TILE_BITS; ++b) pp.lbit[b] = b;
+            // local order above the rows: the bits without an X / Y gate first (they need no round), then the X / Y bits
+            const int ki = splitv[i];
+            int lb = cs[i];
+            for (int j = ki; j < tn[i]; ++j, ++lb) {
+                pp.lbit[lb] = tbits[i][j];
+                if (tgate[i][j]) pp.gbit[lb] = tbits[i][j];
+            }
+            const int first = ki > 0 ? lb : K;
+            for (int j = 0; j < ki; ++j, ++lb) { pp.lbit[lb] = tbits[i][j]; pp.gbit[lb] = tbits[i][j]; }
+            for (int j = 0; j < zn[i]; ++j) { pp.gbit[j] = zbits[i][j]; pp.zmask |= 1u << j; }
+            pp.ngroups = first < 3 ? 4 : (first < 6 ? 3 : (first < K - 3 ? 2 : 1));
+            pp.nrounds = pp.ngroups;
+            pp.g[0] = K - 3;
+        }
+        return true;
+    }
+    return false;
+}
+
+// global index bits of a tile-local index in a gx pass
+static u64 gx_local(const PassPlan& pp, u64 l) {
+    u64 m = 0;
+    for (int b = 0; b < pp.k; ++b)
+        if ((l >> b) & 1) m |= (u64)1 << pp.lbit[b];
+    return m;
+}
+
 // gate table entries of one (layer, pass): QR_MAXROUNDS*QR_R GateP, from per-qubit (axis, cos, sin)
 template <class F>
 static void fill_gates(const LayerPlan& lp, int pass, GateP* out, F gate_of_qubit) {
@@ -897,6 +1067,7 @@ static void fill_gates(const LayerPlan& lp, int pass, GateP* out, F gate_of_qubi
         GateP g;
         g.c = 1.0; g.s = 0.0; g.axis = -1; g.pad = 0;
         if (pp.gbit[i] >= 0) g = gate_of_qubit(lp.n - 1 - pp.gbit[i]);
+        if (pp.gx && ((pp.zmask >> i) & 1)) g.pad = 1 + pp.gbit[i];   // Rz applied through the tile's own index bit
         out[i] = g;
     }
 }
@@ -930,9 +1101,9 @@ struct PassExtra {
 
 // opt in to > 48 KiB of dynamic shared memory: the attribute is PER DEVICE, so remember it per (kernel, device)
 static int ensure_smem_attr(qr_ctx* c, const void* fn, int slot) {
-    static bool done[64][32] = {};   // [device][kernel slot]
+    static bool done[64][44] = {};   // [device][kernel slot]
     const int dev = c->device & 63;
-    if (slot < 0 || slot >= 32) return fail(QR_EINVAL, "internal: kernel slot %d", slot);
+    if (slot < 0 || slot >= 44) return fail(QR_EINVAL, "internal: kernel slot %d", slot);
     if (!done[dev][slot]) {
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (int)sizeof(double2) << QR_MAX_TILE_BITS));
         done[dev][slot] = true;
@@ -989,31 +1160,52 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         int staged = (nv == 2 ? (c->opt_staged & 1) : (c->opt_staged & 2)) ? 1 : 0;
         {   // auto: strided backward passes most of whose gate bits are high-stride bits (two-run tiles: count them)
             int nbits = 0, nhigh = 0;
-            for (int sb = 0; sb < QR_GATE_SLOTS; ++sb)
+            for (int sb = pp.gx ? pp.c : 0; sb < QR_GATE_SLOTS; ++sb)
                 if (pp.gbit[sb] >= 0) { ++nbits; if (pp.gbit[sb] >= c->opt_staged_min_bit) ++nhigh; }
-            const bool single_run = pp.h2 == pp.h + pp.m1;
+            const bool single_run = !pp.gx && pp.h2 == pp.h + pp.m1;
             const bool high = single_run ? pp.h >= c->opt_staged_min_bit : (nbits > 0 && 2 * nhigh > nbits);
             if (nv == 2 && (c->opt_staged & 4) && pp.c < pp.k && high) staged = 1;
         }
         const int K = pp.k;   // 12, or 11 (half-size tiles, direct loads only)
+        if (pp.gx) staged = 0;   // staged loads measured at 20-25 ms per backward pass on these tiles (13-17.5 ms direct)
         if (K == 11) staged = 0;
         lean_fn lfn;
-        if (K == 11) lfn = nv == 1 ? (ph ? k_tile12<1, true, 0, 11> : k_tile12<1, false, 0, 11>) : (ph ? k_tile12<2, true, 0, 11> : k_tile12<2, false, 0, 11>);
+        if (pp.gx) {
+            if (ph || tp.hole || spec) return fail(QR_ESTATE, "internal: axis-aware pass with a phase, a slice or a sharded gather");
+            if (K == 11) lfn = nv == 1 ? k_tile12_g<1, 0, 11> : k_tile12_g<2, 0, 11>;
+            else lfn = nv == 1 ? k_tile12_g<1, 0> : k_tile12_g<2, 0>;
+        } else if (K == 11) lfn = nv == 1 ? (ph ? k_tile12<1, true, 0, 11> : k_tile12<1, false, 0, 11>) : (ph ? k_tile12<2, true, 0, 11> : k_tile12<2, false, 0, 11>);
         else if (staged) lfn = nv == 1 ? (ph ? k_tile12<1, true, 1> : k_tile12<1, false, 1>) : (ph ? k_tile12<2, true, 1> : k_tile12<2, false, 1>);
         else lfn = nv == 1 ? (ph ? k_tile12<1, true, 0> : k_tile12<1, false, 0>) : (ph ? k_tile12<2, true, 0> : k_tile12<2, false, 0>);
-        QR_TRY(ensure_smem_attr(c, (const void*)lfn, ((K - 11) * 2 + (nv - 1)) * 6 + ph * 3 + staged));
+        QR_TRY(ensure_smem_attr(c, (const void*)lfn, pp.gx ? 32 + ((K - 11) * 2 + (nv - 1)) * 2 : ((K - 11) * 2 + (nv - 1)) * 6 + ph * 3 + staged));
         if (staged == 1) tp.prefetch = 0;
         Tile12X x;
         memset(&x, 0, sizeof(x));
         x.ngroups = pp.ngroups;
+        if (pp.gx && (c->opt_axis_plan & 4) && x.ngroups == 1 && K == 12) x.ngroups = 2;   // experiment: keep the warps of a tile together
+        if (pp.gx && (c->opt_axis_plan & 8) && x.ngroups == 2 && K == 12 && nv == 2 && !staged) {
+            // the halves of the CTA synchronise separately (measured 13.3-14.2 -> 12.2-12.8 ms per backward pass at n = 30;
+            // the one-vector kernel spills with it and is slower)
+            lfn = k_tile12_gs<2>;
+            QR_TRY(ensure_smem_attr(c, (const void*)lfn, 40));
+        }
         const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2, K, 0};
-        x.last_group = pp.ngroups == 1 ? K - 3 : (pp.ngroups == 5 ? 5 : 6);
+        x.last_group = x.ngroups == 1 ? K - 3 : (x.ngroups == 5 ? 5 : 6);
         for (int r = 0; r < 8; ++r) {
             const u64 lf = (u64)r << (K - 3);
             const u64 ll = (u64)r << x.last_group;
-            x.droff_first[r] = geo12_local(geo, lf);
+            x.droff_first[r] = pp.gx ? gx_local(pp, lf) : geo12_local(geo, lf);
             x.roff_first[r] = tp.ladder ? ladder_map(x.droff_first[r], tp.M1, tp.M2) : x.droff_first[r];
-            x.roff_last[r] = geo12_local(geo, ll);
+            x.roff_last[r] = pp.gx ? gx_local(pp, ll) : geo12_local(geo, ll);
+        }
+        if (pp.gx) {   // general geometry: index bit of every local bit, and of every tile-index bit (the rest, ascending)
+            u64 in_tile = 0;
+            for (int b = 0; b < K; ++b) { x.lpos[b] = (unsigned char)pp.lbit[b]; in_tile |= (u64)1 << pp.lbit[b]; }
+            int j = 0;
+            for (int b = 0; b < lp.n; ++b)
+                if (!((in_tile >> b) & 1)) x.tpos[j++] = (unsigned char)b;
+            if (j != lp.n - K || j > 24) return fail(QR_ESTATE, "internal: axis-aware tile geometry");
+            for (; j < 24; ++j) x.tpos[j] = 63;   // never selected: tile indices have n - K bits
         }
         const long long lctas = K == 11 ? (nv == 1 ? 4 : 2) : ((nv == 1 && !staged) ? std::min<long long>(2, c->opt_ctas_fwd) : 1);
         const i64 lgrid = std::min<i64>(tp.num_tiles, (i64)sms * lctas);
@@ -1026,7 +1218,7 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         const bool strided_pass = pp.c < K;
         // L2 prefetch of the next tile: opt_prefetch bit 4 = contiguous passes only
         if ((c->opt_prefetch & 16) && strided_pass) tp.prefetch = 0;
-        const size_t lsmem = staged ? (size_t)(nv + 1) * tile_bytes : (pp.ngroups > 1 ? (size_t)nv * tile_bytes : 0);
+        const size_t lsmem = staged ? (size_t)(nv + 1) * tile_bytes : (x.ngroups > 1 ? (size_t)nv * tile_bytes : 0);
         // programmatic dependent launch: the next pass's CTAs queue up while this one drains.  Auto (1): only where a
         // pass is short enough for the launch ramp to matter (states that fit in L2); 2: every pass.
         // The first pass after the gate / phase tables were written is launched fully serialized: k_tile12 reads the
@@ -1178,7 +1370,12 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     const int n = c->n;
     c->tables_fresh = true;
     LayerPlan lpf, lp;   // forward / backward plans: same tile geometry, different register blocking
-    QR_TRY(make_plan(n, pick_tile_bits(c, n), &lpf, (int)c->opt_tile_bits_x, pick_min_row_bits(c, n)));
+    // axis-aware plans apply to single circuits whose axes the host knows; with them 12-bit tiles win from n = 23 on
+    // (measured, profiles/r2_axis_ab.log: n = 24: 30.1 -> 25.3 ms per 30 layers, n = 26: 127 -> 118 ms; n = 22: 4.45 vs 4.57 ms)
+    const bool axis_ok = c->opt_axis_plan && batch == 1 && dev == nullptr;
+    int tile_bits = pick_tile_bits(c, n);
+    if (axis_ok && c->opt_tile_bits == 0 && n >= 23 && n <= 26 && tile_bits == 11) tile_bits = 12;
+    QR_TRY(make_plan(n, tile_bits, &lpf, (int)c->opt_tile_bits_x, tile_bits == pick_tile_bits(c, n) ? pick_min_row_bits(c, n) : (int)c->opt_min_row_bits));
     lp = lpf;
     const int P = lp.npasses;
     const int GS = QR_GATE_SLOTS;                 // gate entries per (layer, pass)
@@ -1193,6 +1390,12 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     const size_t tab_off = (terms_bytes + 255) & ~(size_t)255;
     const size_t raw_off = (tab_off + tab_bytes + 1024 + 255) & ~(size_t)255;   // batched: raw axes/angles/qmap staging
     const bool dev_tables = batch > 1 || dev != nullptr;   // build the gate tables on the device from raw axes / angles
+    // per-layer plans from the axes (QR_OPT_AXIS_PLAN): pass counts may differ between layers (<= P), the table and
+    // result layouts keep P entries per layer
+    std::vector<LayerPlan> plans((size_t)L, lpf);
+    int n_axis_layers = 0;
+    if (axis_ok && uniform_lean_plan(lpf))
+        for (int i = 0; i < L; ++i) n_axis_layers += plan_axis_layer(lpf, axes + (size_t)i * n, &plans[i], (c->opt_axis_plan & 2) ? 1 : 0) ? 1 : 0;
     const size_t raw_bytes = dev_tables ? (size_t)batch * L * n * (sizeof(double) + sizeof(int32_t)) + 2 * (size_t)P * GS * sizeof(int) + 1024 : 0;
     QR_TRY(ensure_small(c, raw_off + raw_bytes + 1024));
     QR_TRY(ensure_pin(c, dev_tables ? std::max((size_t)1 << 16, (size_t)batch * (1 + (size_t)L * P * QR_SLOTS) * sizeof(double) + 8192)
@@ -1234,8 +1437,8 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
                     const int32_t* ax = axes + ((size_t)b * L + i) * n;
                     const double* an = angles + ((size_t)b * L + i) * n;
                     const double sgn = dir == 0 ? 1.0 : -1.0;
-                    for (int p = 0; p < P; ++p)
-                        fill_gates(dir == 0 ? lpf : lp, p, tb + ((size_t)lay * P + p) * GS, [&](int q) {
+                    for (int p = 0; p < plans[i].npasses; ++p)
+                        fill_gates(plans[i], p, tb + ((size_t)lay * P + p) * GS, [&](int q) {
                             GateP g; g.c = std::cos(0.5 * an[q]); g.s = sgn * std::sin(0.5 * an[q]); g.axis = ax[q]; g.pad = 0; return g; });
                 }
         }
@@ -1246,6 +1449,18 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     const i64 stride = (i64)c->N;
     const int flush = batch > 1 ? 1 : 0;
 
+    // QR_TRACE_PASSES=1 (environment): one CUDA event per tile pass, per-pass device times on stderr after the run
+    static const bool trace = getenv("QR_TRACE_PASSES") != nullptr;
+    struct TraceRec { cudaEvent_t ev; int layer, pass, nv, c, ng, gx; };
+    std::vector<TraceRec> trace_recs;
+    auto trace_mark = [&](int layer, int pass, int nv, const PassPlan* pp) {
+        if (!trace) return;
+        TraceRec r;
+        cudaEventCreate(&r.ev);
+        cudaEventRecord(r.ev, c->stream);
+        r.layer = layer; r.pass = pass; r.nv = nv; r.c = pp ? pp->c : 0; r.ng = pp ? pp->ngroups : 0; r.gx = pp ? (int)pp->gx : 0;
+        trace_recs.push_back(r);
+    };
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     // ---- forward ----
     int lay = 0;
@@ -1276,17 +1491,20 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
         }
         ++lay;
     }
+    int n_fwd_pass = ry_layer ? P : 0;
     for (int i = 0; i < L; ++i, ++lay) {
-        for (int p = 0; p < P; ++p) {
+        for (int p = 0; p < plans[i].npasses; ++p, ++n_fwd_pass) {
             int dst = c->psi;
             int lad = -1;
             if (p == 0 && has_ladder(i)) { dst = other_buf(c, c->psi); QR_TRY(ensure_buf(c, dst)); lad = 0; }
             PassIO io = {c->buf[c->psi], nullptr, c->buf[dst], nullptr};
-            QR_TRY(launch_pass(c, lpf, p, 1, io, d_tab + ((size_t)lay * P + p) * GS, gate_stride, lad, batch, stride, 0,
+            trace_mark(i, p, 1, &plans[i].pass[p]);
+            QR_TRY(launch_pass(c, plans[i], p, 1, io, d_tab + ((size_t)lay * P + p) * GS, gate_stride, lad, batch, stride, 0,
                                nullptr, 0, 0, 0, 0, nullptr));
             c->psi = dst;
         }
     }
+    trace_mark(-1, -1, 0, nullptr);
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     // ---- observable: lambda = O psi, E = Re<psi|lambda> ----
     const ObsTerm* d_terms;
@@ -1322,7 +1540,9 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
         for (int i = L - 1; i >= 0; --i, ++lay) {
             // table index of backward layer i: forward tables come first, backward tables are stored in layer order
             const int tlay = (ry_layer ? 1 : 0) + L + i;
-            for (int p = 0; p < P; ++p) {
+            for (int p = plans[i].npasses; p < P && defer; ++p)   // a pass this layer does not need: its slice of partials reads as zero
+                CUDA_TRY(cudaMemsetAsync(c->d_scratch + ((size_t)i * P + p) * unit_cap * QR_SLOTS, 0, unit_cap * QR_SLOTS * sizeof(double), c->stream));
+            for (int p = 0; p < plans[i].npasses; ++p) {
                 int dpsi = c->psi, dlam = lam, lad = -1;
                 if (p == 0 && i < L - 1 && has_ladder(i + 1)) {
                     dpsi = other_buf(c, c->psi, lam);
@@ -1333,7 +1553,8 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
                 }
                 PassIO io = {c->buf[c->psi], c->buf[lam], c->buf[dpsi], c->buf[dlam]};
                 int units = 0;
-                QR_TRY(launch_pass(c, lp, p, 2, io, d_tab + ((size_t)tlay * P + p) * GS, gate_stride, lad, batch, stride,
+                trace_mark(i, p, 2, &plans[i].pass[p]);
+                QR_TRY(launch_pass(c, plans[i], p, 2, io, d_tab + ((size_t)tlay * P + p) * GS, gate_stride, lad, batch, stride,
                                    flush, nullptr, 0, 0, 0, 0, &units, nullptr,
                                    (batch == 1 && !defer) ? d_slots + ((size_t)i * P + p) * QR_SLOTS : nullptr, nullptr,
                                    defer ? c->d_scratch + ((size_t)i * P + p) * unit_cap * QR_SLOTS : nullptr));
@@ -1346,7 +1567,7 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
                 ++n_bwd_pass;
                 if (batch == 1) continue;   // second-stage reduction is fused into the pass (last CTA)
                 {
-                    const int tiles_per_state = 1 << (n - lp.pass[p].k);
+                    const int tiles_per_state = 1 << (n - plans[i].pass[p].k);
                     QR_LAUNCH(k_reduce_partials_grouped, (unsigned)batch, 32, 0, c->stream, (const double*)c->d_scratch,
                               tiles_per_state, QR_SLOTS, d_slots + ((size_t)i * P + p) * QR_SLOTS, slots_per_state);
                 }
@@ -1368,7 +1589,19 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
             lam = d;
         }
     }
+    trace_mark(-1, -1, 0, nullptr);
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    if (trace) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (size_t t = 0; t + 1 < trace_recs.size(); ++t) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, trace_recs[t].ev, trace_recs[t + 1].ev);
+            if (trace_recs[t].nv)
+                fprintf(stderr, "[qr trace] layer %d pass %d nv %d %s rows 2^%d groups %d: %.3f ms\n", trace_recs[t].layer, trace_recs[t].pass,
+                        trace_recs[t].nv, trace_recs[t].gx ? "axis" : "static", trace_recs[t].c, trace_recs[t].ng, ms);
+        }
+        for (auto& r : trace_recs) cudaEventDestroy(r.ev);
+    }
     if (dev) {   // results stay on the device; tell the caller how to read the slot sums
         for (int p = 0; p < P; ++p)
             for (int s2 = 0; s2 < GS; ++s2) {
@@ -1391,16 +1624,21 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
         // (slot offset within a layer, qubit) of the n gradient slots, once per call: the scatter below runs
         // batch * L * n times (1.6 M for BASELINE config 4)
         int soff[64], sq[64], ns = 0;
-        for (int p = 0; p < P; ++p)
-            for (int s = 0; s < GS; ++s) {
-                const int gb = lp.pass[p].gbit[s];
-                if (gb < 0 || ns >= 64) continue;
-                soff[ns] = p * QR_SLOTS + s;
-                sq[ns] = n - 1 - gb;
-                ++ns;
-            }
+        auto slot_map = [&](const LayerPlan& pl) {
+            ns = 0;
+            for (int p = 0; p < pl.npasses; ++p)
+                for (int s = 0; s < GS; ++s) {
+                    const int gb = pl.pass[p].gbit[s];
+                    if (gb < 0 || ns >= 64) continue;
+                    soff[ns] = p * QR_SLOTS + s;
+                    sq[ns] = n - 1 - gb;
+                    ++ns;
+                }
+        };
+        slot_map(lp);
         for (i64 b = 0; b < batch; ++b)
             for (int i = 0; i < L; ++i) {
+                if (n_axis_layers) slot_map(plans[i]);
                 const double* src = slots + (size_t)b * slots_per_state + (size_t)i * P * QR_SLOTS;
                 double* dst = grad + ((size_t)b * L + i) * n;
                 for (int k = 0; k < ns; ++k) dst[sq[k]] = src[soff[k]];
@@ -1418,7 +1656,6 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     c->perf.tile_bits = lp.k;
     c->perf.fwd_pass_bytes = 32.0 * amps;
     c->perf.bwd_pass_bytes = 64.0 * amps;
-    const int n_fwd_pass = (L + (ry_layer ? 1 : 0)) * P;
     c->perf.fwd_pass_ms_avg = n_fwd_pass ? c->perf.ms_forward / n_fwd_pass : 0.0;
     c->perf.bwd_pass_ms_avg = n_bwd_pass ? c->perf.ms_backward / n_bwd_pass : 0.0;
     // B_sched: init write 16, forward 32 per pass, observable 32 (+16 read-only if no grad), backward 64 per pass

@@ -64,6 +64,10 @@ struct Tile12X {
     u64 roff_first[8];      // global offset of register r at load time (group G3), gather map applied
     u64 roff_last[8];       // global offset of register r at store time (G2, or G3 when ngroups == 1)
     u64 droff_first[8];     // same as roff_first without the gather map (destination index: phase tables)
+    // GX passes (axis-aware plans): general tile geometry -- local bit b is global index bit lpos[b] (rows: lpos[b] = b),
+    // tile-index bit j is global index bit tpos[j] (the index bits outside the tile, ascending)
+    unsigned char lpos[QR_MAX_TILE_BITS];
+    unsigned char tpos[24];
 };
 
 // XMAP passes (sharded registers, qr_shard.cuh): the source of a tile is given by a general GF(2)-linear map instead of
@@ -169,9 +173,23 @@ __device__ __forceinline__ int qr12_sbase(int tid) {
 template <int G>
 __device__ __forceinline__ constexpr int qr12_cr(int r) { return (r << G) ^ (((r << G) >> 3) & 7); }
 
+// Barrier of one half of the CTA (even / odd warps): an exchange between the register groups 9-11 and 6-8 only moves data
+// between threads that agree in tile-local bits 0-5, i.e. in thread-id bit 5 = the lowest warp-index bit, so the even and
+// the odd warps of a 12-bit tile never exchange anything in a pass with two rounds.  With their own barriers the halves
+// drift apart and one loads / stores while the other computes (TilePass::split_bar).
+#ifndef QR_HOST_EMUL
+__device__ __forceinline__ void qr12_bar(int split, int tid) {
+    if (!split) __syncthreads();
+    else if ((tid >> 5) & 1) asm volatile("bar.sync 2, 256;" ::: "memory");   // warp-uniform branch; 512-thread CTAs only (K = 12)
+    else asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+#else
+__device__ __forceinline__ void qr12_bar(int, int) { __syncthreads(); }
+#endif
+
 // registers of group GP -> shared memory -> registers of group GN (one block barrier)
 template <int NV, int GP, int GN, int K = QR_MAX_TILE_BITS>
-__device__ __forceinline__ void qr12_exchange(double2 (&a)[NV][8], double2* smem, int tid) {
+__device__ __forceinline__ void qr12_exchange(double2 (&a)[NV][8], double2* smem, int tid, int split = 0) {
     constexpr int T = 1 << K;
     const int bp = qr12_sbase<GP>(tid), bn = qr12_sbase<GN>(tid);
 #pragma unroll
@@ -180,7 +198,7 @@ __device__ __forceinline__ void qr12_exchange(double2 (&a)[NV][8], double2* smem
 #pragma unroll
         for (int v = 0; v < NV; ++v) smem[v * T + l] = a[v][r];
     }
-    __syncthreads();
+    qr12_bar(split, tid);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const int l = bn ^ qr12_cr<GN>(r);
@@ -192,16 +210,16 @@ __device__ __forceinline__ void qr12_exchange(double2 (&a)[NV][8], double2* smem
 // same exchange through ONE tile-sized buffer: the vectors take turns (staged kernel: the other
 // 128 KiB of shared memory hold the next tile).  The buffer holds vector NV-1 when it returns.
 template <int NV, int GP, int GN>
-__device__ __forceinline__ void qr12_exchange_1buf(double2 (&a)[NV][8], double2* xbuf, int tid) {
+__device__ __forceinline__ void qr12_exchange_1buf(double2 (&a)[NV][8], double2* xbuf, int tid, int split = 0) {
     const int bp = qr12_sbase<GP>(tid), bn = qr12_sbase<GN>(tid);
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
         // safe without a barrier: this thread overwrites only the slots it read itself last time
         // (v == 0: its GP slots of the previous exchange's last vector; v > 0: needs the barrier below)
-        if (v > 0) __syncthreads();
+        if (v > 0) qr12_bar(split, tid);
 #pragma unroll
         for (int r = 0; r < 8; ++r) xbuf[bp ^ qr12_cr<GP>(r)] = a[v][r];
-        __syncthreads();
+        qr12_bar(split, tid);
 #pragma unroll
         for (int r = 0; r < 8; ++r) a[v][r] = xbuf[bn ^ qr12_cr<GN>(r)];
     }
@@ -260,9 +278,20 @@ __device__ __noinline__ double2 qr12_phase_slow(const double* __restrict__ ham, 
 // instead of only reaching L2 (prefetch) or being waited for (direct loads).
 // K = 11: half-size tiles (2048 amplitudes, 256 threads, 64 KiB of shared memory for the backward pass): two
 // backward CTAs per SM, whose load / FP64 / exchange phases overlap; used where it does not cost a pass.
-template <int NV, bool PHASE, int STAGED, int K, bool XMAP>
+//
+// GX (axis-aware plans of single McClean circuits, qr_lib.cu: plan_axis_layer): the tile's index bits are an arbitrary
+// subset (rows + any high bits, Tile12X::lpos / tpos; tile base from three byte tables in shared memory), and an Rz
+// whose index bit lies OUTSIDE the tile is applied without a tile bit: its phase is a factor of the tile (selected by
+// the tile's own index bit) and its gradient is +- the tile's total of w.  Such gates sit in the gate slots of the row
+// bits (local bits < c, which carry no gates in a strided pass) with GateP::pad = 1 + index bit.  Diagonal gates thus
+// never cost tile capacity: the strided passes of a layer only need tile bits for its X / Y rotations, which buys wider
+// rows (DRAM efficiency) and fewer exchange rounds.
+#define QR_GX_ZSLOTS 6    // more slots spill (the two-vector kernel sits at 128 registers)
+template <int NV, bool PHASE, int STAGED, int K, bool XMAP, bool GX = false, bool SPLIT = false>
 __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, const TileXMap* xmp) {
     static_assert(!XMAP || (STAGED == 0 && K == 12), "XMAP passes: direct loads, 12-bit tiles");
+    static_assert(!GX || (!XMAP && !PHASE), "GX passes: McClean layers of one register");
+    static_assert(!SPLIT || (GX && K == 12), "split barriers: two-round passes of 12-bit tiles");
     constexpr int T = 1 << K;
     constexpr int LG = K - 3;   // first local bit of the register group held at load time
     QR_DYN_SMEM(double2, smem);
@@ -271,9 +300,34 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
     __shared__ double2 szr[8];                  // Z phases of the G3 register bits (times nothing else)
     __shared__ double2 szb[QR_GATE_SLOTS][2];   // per gate bit: Z phase for bit value 0 / 1 (identity if not Z)
     __shared__ int s_flags[2];                  // [0]: the pass needs its diagonal (an Rz, or an odd number of sign flips)
-    __shared__ double2 lut_sm[QR_LUT_MAX];
+    __shared__ double2 lut_sm[PHASE ? QR_LUT_MAX : 1];
+    __shared__ u64 gx_tab[GX ? 3 : 1][GX ? 256 : 1];   // GX: tile-index byte -> global index bits
+    __shared__ int s_zq[GX ? QR_GX_ZSLOTS : 1];        // GX: index bit of the out-of-tile Rz in slot j, or -1
     const int tid = threadIdx.x;
     const Geo12 geo = {p.c, p.h, p.m1, p.h2, K, p.hole};
+    if (GX) {
+        for (int i = tid; i < 3 * 256; i += blockDim.x) {
+            const int j = i >> 8, v = i & 255;
+            u64 m = 0;
+            for (int b = 0; b < 8; ++b)
+                if ((v >> b) & 1) m |= (u64)1 << x.tpos[8 * j + b];
+            gx_tab[j][v] = m;
+        }
+        __syncthreads();
+    }
+    // global index bits of a tile-local index / of a tile index
+    auto local_bits = [&](u64 l) -> u64 {
+        if (!GX) return geo12_local(geo, l);
+        u64 m = 0;
+#pragma unroll
+        for (int b = 0; b < K; ++b)
+            if ((l >> b) & 1) m |= (u64)1 << x.lpos[b];
+        return m;
+    };
+    auto tile_bits = [&](u64 t) -> u64 {
+        if (GX) return gx_tab[0][t & 255] | gx_tab[1][(t >> 8) & 255] | gx_tab[2][(t >> 16) & 255];
+        return geo12_tile(geo, t) | p.tile_or;
+    };
     const u64 tmask = ((u64)1 << p.tiles_log2) - 1;
     const int ng = x.ngroups;
 
@@ -283,7 +337,7 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
     double wtot = 0.0;   // running sum of Im(conj(lambda) psi) over this thread's amplitudes
 
     // per-thread global offsets (local bits 0-8 at load time; the last group's thread bits at store time)
-    const u64 toff_d = geo12_local(geo, (u64)tid);                                  // destination index bits
+    const u64 toff_d = local_bits((u64)tid);                                  // destination index bits
     u64 toff_s = p.ladder ? ladder_map(toff_d, p.M1, p.M2) : toff_d;                // gathered source bits
     __shared__ u64 xm_tab[XMAP ? 3 : 1][XMAP ? 256 : 1];                            // XMAP: tile index byte -> source index bits
     if (XMAP) {
@@ -314,11 +368,12 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
         return s;
     };
     const int tbl = ng > 1 ? qr12_tb(tid, K == 12 ? 6 : x.last_group) : tid;        // K = 12: the last group is always 6
-    const u64 toff_l = geo12_local(geo, (u64)tbl);
+    const u64 toff_l = local_bits((u64)tbl);
 
     const i64 nworkers = (i64)gridDim.x, worker = (i64)blockIdx.x;
     const int iters = (int)((p.num_tiles + nworkers - 1) / nworkers);   // tiles per CTA (32-bit loop state: the kernel sits at its register budget)
-    auto tile_at = [&](int it) -> i64 { return worker + (i64)it * nworkers; };
+    // GX passes are never batched: tile indices fit 32 bits (n - K <= 24)
+    auto tile_at = [&](int it) -> i64 { return GX ? (i64)((int)blockIdx.x + it * (int)gridDim.x) : worker + (i64)it * nworkers; };
     int cur_b = -1;
     double2 zt = make_double2(1.0, 0.0);   // thread factor of the merged diagonal (includes F)
     bool has_z = false;       // apply the diagonal zt * zr after the load
@@ -340,10 +395,11 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
                 o.sig = ss;
                 o.mode = g.axis;
             } else if (g.axis == 2) {   // Rz: (c - i s) on bit value 0, (c + i s) on bit value 1 (state.py:168-170)
-                o.mode = 4;
+                o.mode = (GX && g.pad > 0) ? 5 : 4;   // 5: the index bit lies outside the tile (GX)
                 z0 = make_double2(g.c, -g.s);
                 z1 = make_double2(g.c, g.s);
             }
+            if (GX && tid < QR_GX_ZSLOTS) s_zq[tid] = o.mode == 5 ? g.pad - 1 : -1;
             sg[tid] = o;
             szb[tid][0] = z0;
             szb[tid][1] = z1;
@@ -351,7 +407,7 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
         __syncthreads();
         if (tid == 0) {
             int z = 0, neg = 0;
-            for (int i = 0; i < QR_GATE_SLOTS; ++i) { z |= (sg[i].mode == 4); neg ^= sg[i].neg; }
+            for (int i = 0; i < QR_GATE_SLOTS; ++i) { z |= (sg[i].mode >= 4); neg ^= sg[i].neg; }
             s_flags[0] = z | neg;
             s_flags[1] = neg;
         }
@@ -365,10 +421,11 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
         has_z = s_flags[0] != 0;
         has_zgate = false;
 #pragma unroll
-        for (int j = 0; j < QR_GATE_SLOTS; ++j) has_zgate = has_zgate || sg[j].mode == 4;
+        for (int j = 0; j < QR_GATE_SLOTS; ++j) has_zgate = has_zgate || sg[j].mode >= 4;
         zt = make_double2(s_flags[1] ? -1.0 : 1.0, 0.0);
 #pragma unroll
-        for (int j = 0; j < LG; ++j) zt = cmul(zt, szb[j][(tid >> j) & 1]);
+        for (int j = 0; j < LG; ++j)
+            if (!GX || sg[j].mode != 5) zt = cmul(zt, szb[j][(tid >> j) & 1]);
         cur_b = b;
     };
 
@@ -400,7 +457,7 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
     // pull tile `nt` into L2: one 128 B line per thread and vector
     auto prefetch_tile = [&](i64 nt) {
 #ifndef QR_HOST_EMUL
-        const i64 nb = nt >> p.tiles_log2;
+        const i64 nb = GX ? 0 : (nt >> p.tiles_log2);   // GX passes are never batched
         if (XMAP) {   // line tid of the tile: tile-local bits 3..11 = tid bits 0..8 (bits 9-11 are the load-time register bits)
             const u64 t2 = (u64)nt & tmask;
             u64 s = xm_base(t2) ^ xmp->src_const ^ x.roff_first[tid >> 6];
@@ -412,9 +469,9 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
             if (NV == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(xmp->src[1][sl][tid >> 6] + s));
             return;
         }
-        const u64 nbase = geo12_tile(geo, (u64)nt & tmask) | p.tile_or;
+        const u64 nbase = tile_bits((u64)nt & tmask);
         const int l = tid << 3;
-        const u64 d = nbase | geo12_local(geo, (u64)l);
+        const u64 d = nbase | local_bits((u64)l);
         const u64 s = p.ladder ? (ladder_map(d, p.M1, p.M2) ^ p.src_xor) : d;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src0 + nb * p.state_stride + s));
         if (NV == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src1 + nb * p.state_stride + s));
@@ -422,8 +479,8 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
     };
     // issue the asynchronous copies of this thread's amplitudes of tile `tl` into its stage slots
     auto issue_stage = [&](i64 tl) {
-        const i64 nb = tl >> p.tiles_log2;
-        const u64 nbase = geo12_tile(geo, (u64)tl & tmask) | p.tile_or;
+        const i64 nb = GX ? 0 : (tl >> p.tiles_log2);
+        const u64 nbase = tile_bits((u64)tl & tmask);
         const u64 sb = (p.ladder ? (ladder_map(nbase, p.M1, p.M2) ^ p.src_xor) : nbase) ^ toff_s;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -439,12 +496,12 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
     for (int it = 0; it < iters; ++it) {
         const i64 tile = tile_at(it);
         if (tile >= p.num_tiles) continue;
-        const int b = (int)(tile >> p.tiles_log2);
-        const u64 t = (u64)tile & tmask;
-        const u64 tbase = geo12_tile(geo, t) | p.tile_or;
+        const int b = GX ? 0 : (int)(tile >> p.tiles_log2);
+        const u64 t = GX ? (u64)tile : ((u64)tile & tmask);
+        const u64 tbase = tile_bits(t);
         if (b != cur_b) convert_gates(b);   // block-uniform: a persistent CTA of a batched pass moves on to the next circuit
         // batch element offset: state_stride is a multiple of 2^n, so it can be OR-ed into the index bits
-        const u64 boff = (u64)b * (u64)p.state_stride;
+        const u64 boff = GX ? (u64)0 : (u64)b * (u64)p.state_stride;
 
         // ---- global -> registers (group G3; ladder gather folded into the load addresses) ----
         const u64 sbt = XMAP ? (xm_base(t) ^ toff_s) : (((p.ladder ? (ladder_map(tbase, p.M1, p.M2) ^ p.src_xor) : tbase) ^ toff_s) | boff);
@@ -486,6 +543,14 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
             const double e2 = w[4] + w[5], o2 = w[4] - w[5], e3 = w[6] + w[7], o3 = w[6] - w[7];
             const double ee0 = e0 + e1, eo0 = e0 - e1, ee1 = e2 + e3, eo1 = e2 - e3;
             wtot += ee0 + ee1;
+            if (GX) {   // Rz on an index bit outside the tile: the sign is the tile's
+                const double wt = ee0 + ee1;
+#pragma unroll
+                for (int j = 0; j < QR_GX_ZSLOTS; ++j) {
+                    const int q = s_zq[j];
+                    if (q >= 0) acc_all[j] += ((tbase >> q) & 1) ? -wt : wt;
+                }
+            }
             if (sg[LG].mode == 4) acc_all[LG] += (o0 + o1) + (o2 + o3);
             if (sg[LG + 1].mode == 4) acc_all[LG + 1] += eo0 + eo1;
             if (sg[LG + 2].mode == 4) acc_all[LG + 2] += ee0 - ee1;
@@ -506,9 +571,17 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
         }
         // ---- merged diagonal (all Rz of the pass) and the pass scale F ----
         if (has_z) {
+            double2 ztt = zt;
+            if (GX) {   // phases of the out-of-tile Rz gates: one factor per tile
+#pragma unroll
+                for (int j = 0; j < QR_GX_ZSLOTS; ++j) {
+                    const int q = s_zq[j];
+                    if (q >= 0) ztt = cmul(ztt, szb[j][(tbase >> q) & 1]);
+                }
+            }
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const double2 ph = cmul(zt, szr[r]);
+                const double2 ph = cmul(ztt, szr[r]);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) a[v][r] = cmul(a[v][r], ph);
             }
@@ -527,11 +600,14 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
             qr12_round<NV, 3>(a, sg, acc_all);
             QR12_X(3, 6);
         } else if (ng == 2) {
-            QR12_X(LG, 6);
+            if (SPLIT) {   // the halves of the CTA run apart
+                if (STAGED == 1) qr12_exchange_1buf<NV, LG, 6>(a, smem, tid, 1); else qr12_exchange<NV, LG, 6, K>(a, smem, tid, 1);
+            } else QR12_X(LG, 6);
         }
         if (K == 12 ? ng >= 2 : (ng >= 2 && ng <= 4)) {
             qr12_round<NV, 6, (K == 12 ? 3 : 2)>(a, sg, acc_all);   // K = 11: bit 8 belongs to the load group
-            __syncthreads();   // every thread has read its last exchange: smem is free for the next tile
+            if (SPLIT) qr12_bar(1, tid);
+            else __syncthreads();   // every thread has read its last exchange: smem is free for the next tile
         }
         if (K == 11 && ng == 5) {   // 64 B rows: gate bits 2-10 = groups 8 | 2 | 5
             QR12_X(LG, 2);
@@ -607,6 +683,18 @@ template <int NV, bool PHASE, int STAGED, int K = QR_MAX_TILE_BITS>
 __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 1 ? 4 : 2)) : ((NV == 1 && !STAGED) ? 2 : 1)))
     k_tile12(const TilePass p, const Tile12X x) {
     qr12_body<NV, PHASE, STAGED, K, false>(p, x, nullptr);
+}
+
+// axis-aware plans (GX): general tile geometry, out-of-tile Rz gates
+template <int NV, int STAGED, int K = QR_MAX_TILE_BITS>
+__global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 1 ? 4 : 2)) : ((NV == 1 && !STAGED) ? 2 : 1)))
+    k_tile12_g(const TilePass p, const Tile12X x) {
+    qr12_body<NV, false, STAGED, K, false, true>(p, x, nullptr);
+}
+// two-round passes (one exchange, between the register groups 9-11 and 6-8): the even and the odd warps synchronise separately
+template <int NV>
+__global__ void __launch_bounds__(512, 1) k_tile12_gs(const TilePass p, const Tile12X x) {
+    qr12_body<NV, false, 0, 12, false, true, true>(p, x, nullptr);
 }
 
 // sharded registers: general source map and source pointer table (exchange passes read the peers' shards over NVLink)

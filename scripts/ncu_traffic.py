@@ -13,8 +13,9 @@ rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 14 and r[0].isdigit
 per = {}
 for r in rows:
     per.setdefault(int(r[0]), {"name": r[4]})[r[12]] = float(r[14].replace(",", ""))
-bwd = [v for v in per.values() if "k_tile12<2" in v["name"] or "k_tile12ILi2" in v["name"]]
-fwd = [v for v in per.values() if "k_tile12<1" in v["name"] or "k_tile12ILi1" in v["name"]]
+import re  # noqa: E402
+bwd = [v for v in per.values() if re.search(r"k_tile12(_gs?)?(<|ILi)2", v["name"])]   # static, axis-aware and split-barrier passes
+fwd = [v for v in per.values() if re.search(r"k_tile12(_gs?)?(<|ILi)1", v["name"])]
 h = hashlib.sha1()
 for f in sorted(glob.glob(os.path.join(ROOT, "qradient_b200", "csrc", "*"))):
     h.update(open(f, "rb").read())

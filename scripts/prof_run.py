@@ -14,9 +14,10 @@ ap.add_argument("--n", type=int, default=28)
 ap.add_argument("--L", type=int, default=2)
 ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--shards", type=int, default=1)
+ap.add_argument("--seed", type=int, default=None)
 ap.add_argument("--opt", action="append", default=[], help="name=value library option")
 args = ap.parse_args()
-rng = np.random.default_rng(args.n)
+rng = np.random.default_rng(args.n if args.seed is None else args.seed)
 zz = np.full((args.n, args.n), None)
 zz[0, 1] = 1.0
 axes, angles = rng.integers(0, 3, (args.L, args.n)), rng.uniform(0, 2 * np.pi, (args.L, args.n))

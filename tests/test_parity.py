@@ -192,6 +192,7 @@ def test_lean_tile_kernel_group_counts(backend, n, L):
     obs = mixed_obs(n)
     c = McClean(n, obs, L, axes=axes, angles=angles)
     c.state.set_option("tile_bits", 12)
+    c.state.set_option("axis_plan", 0)   # the static plan (axis-aware plans: test_axis_aware_plans)
     e1, g1 = c.grad_run()
     v1 = np.array(c.state.vec)
     c.state.set_option("tile_bits", 10)
@@ -234,6 +235,50 @@ def test_lean_tile_kernel_half_size_tiles(backend, n, L, min_row_bits):
         q.state.set_option("min_row_bits", min_row_bits)
         e1, g1 = q.grad_run(b, gm)
         assert_parity(e1, g1, e0, g0, float(n - 1), 1e-12)
+
+
+def _axis_case(case, n, L, rng):
+    """Axes (L, n) of the named pattern; index bit b <-> qubit n-1-b."""
+    axes = rng.integers(0, 3, (L, n))
+    if case == "few_xy":            # one or two X / Y rotations above the contiguous tile: tiles padded with fillers
+        axes[:, :n - 12] = 2
+        axes[:, 0] = 0
+        axes[1:, 3] = 1
+    elif case == "all_z_high":      # nothing but Rz above the contiguous tile
+        axes[:, :n - 12] = 2
+    elif case == "all_xy":          # no Rz at all
+        axes = rng.integers(0, 2, (L, n))
+    elif case == "absorb":          # 7 X / Y bits above the tile, Rz on bits 7..11: the contiguous pass trades bits for them
+        for b in range(n):
+            axes[:, n - 1 - b] = (b % 2) if b >= 12 else (2 if b >= 7 else b % 3)
+        axes[1:, n - 1 - 9] = 1
+    return axes
+
+
+@pytest.mark.parametrize("n,L,tile_bits,case", [(15, 3, 12, "random"), (16, 2, 12, "random"), (17, 2, 11, "random"), (18, 2, 12, "few_xy"),
+                                                 (16, 2, 12, "all_z_high"), (17, 2, 12, "all_xy"), (19, 2, 12, "absorb"), (18, 1, 11, "absorb")])
+def test_axis_aware_plans(backend, n, L, tile_bits, case):
+    """QR_OPT_AXIS_PLAN: per-layer plans from the axes (general tile geometry, Rz gates of index bits outside the tile
+    applied through the tile's own index bits, split barriers, the contiguous pass on a general tile with the ladder
+    gather) against the static plan and the oracle."""
+    rng = np.random.default_rng(31 * n + L)
+    axes = _axis_case(case, n, L, rng)
+    angles = rng.uniform(0, 2 * np.pi, (L, n))
+    obs = mixed_obs(n)
+    c = McClean(n, obs, L, axes=axes, angles=angles)
+    c.state.set_option("tile_bits", tile_bits)
+    c.state.set_option("axis_plan", 0)
+    e0, g0 = c.grad_run()
+    v0 = np.array(c.state.vec)
+    if n <= 17:
+        e_ref, g_ref = orc.mcclean_grad_run(n, obs, axes, angles)
+        assert_parity(e0, g0, e_ref, g_ref, obs_scale(obs), TOL)
+    for mode in (1, 13, 15):
+        c.state.set_option("axis_plan", mode)
+        e1, g1 = c.grad_run()
+        assert_parity(e1, g1, e0, g0, obs_scale(obs), 1e-12)
+        np.testing.assert_allclose(c.state.vec, v0, atol=1e-13)
+        np.testing.assert_allclose(c.run_expec_val(), e0, atol=1e-12 * obs_scale(obs))
 
 
 @pytest.mark.parametrize("case", ["all_x", "all_y", "all_z", "special_angles"])
