@@ -468,6 +468,7 @@ static int swap_build(qr_ctx* c, SwapRun* sr, const SwapCircuit& circ, const qr_
                     const double an = qaoa ? circ.betas[op.layer] : angles[(size_t)op.layer * nt + q];
                     gp.c = std::cos(0.5 * an); gp.s = sgn * std::sin(0.5 * an); gp.axis = qaoa ? 0 : axes[(size_t)op.layer * nt + q];
                     op.slot_qubit[s] = q;
+                    if (op.pp.gx && ((op.pp.zmask >> s) & 1)) gp.pad = 1 + op.pp.gbit[s];   // Rz applied through the tile's own index bit
                 }
             }
             gate_tab->push_back(gp);
@@ -544,7 +545,25 @@ static int swap_build(qr_ctx* c, SwapRun* sr, const SwapCircuit& circ, const qr_
             (k < 12 ? low : high).push_back(k);
         }
         std::vector<std::vector<int>> strided;
-        if (!high.empty()) {
+        std::vector<PassPlan> strided_gx;   // axis-aware plans of the strided local passes (McClean; qr_lib.cu: plan_axis_layer)
+        if (!high.empty() && !qaoa && layer >= 0 && c->opt_axis_plan && sr->slices <= 1 && nl - 12 >= 3) {
+            int nzb[64], zsb[64], k = 0, nzs = 0;
+            for (int kb : high) {
+                const int p = layout_local_logical(ly, kb);
+                if (p < 0) { k = -1; break; }
+                if (axes[(size_t)layer * nt + (nt - 1 - p)] == 2) zsb[nzs++] = kb; else nzb[k++] = kb;
+            }
+            const int nx = ((int)high.size() + 8) / 9;
+            for (int mm = 1; mm <= nx && k >= 0 && strided_gx.empty(); ++mm) {
+                int split[8];
+                if (mm * 9 < k) continue;
+                const double cst = axis_best_split(k, mm, 9, 12, split);
+                if (cst > 1e29 || (mm == nx && cst >= 16.0 * nx)) continue;
+                PassPlan outp[8];
+                if (axis_build_strided(12, nl, 12, nzb, k, zsb, nzs, mm, split, outp)) strided_gx.assign(outp, outp + mm);
+            }
+        }
+        if (!high.empty() && strided_gx.empty()) {
             const int nx = ((int)high.size() + 8) / 9;
             size_t pos = 0;
             for (int i = 0; i < nx; ++i) {
@@ -553,7 +572,8 @@ static int swap_build(qr_ctx* c, SwapRun* sr, const SwapCircuit& circ, const qr_
                 pos += sz;
             }
         }
-        max_sweeps = std::max(max_sweeps, 2 + (int)strided.size());
+        const size_t n_strided = strided_gx.empty() ? strided.size() : strided_gx.size();
+        max_sweeps = std::max(max_sweeps, 2 + (int)n_strided);
         // ---- pass 0: contiguous tile, gather through the ladder ----
         if (layer >= 0) {
             XOp op = new_op(layer, nv);
@@ -576,14 +596,15 @@ static int swap_build(qr_ctx* c, SwapRun* sr, const SwapCircuit& circ, const qr_
         // ---- strided local passes, in place ----
         // The last one and the exchange pass can be issued in slices of the index bits [9, 12) when those bits are tile-index
         // bits of both (rows below 9, gate runs from 12 up): the exchange of a slice then overlaps the local pass of the next.
-        bool slice_pair = sr->slices > 1 && !qaoa && layer >= 0 && !strided.empty() && xb.front() >= 12 && strided.back().front() >= 12 &&
+        bool slice_pair = sr->slices > 1 && strided_gx.empty() && !qaoa && layer >= 0 && !strided.empty() && xb.front() >= 12 && strided.back().front() >= 12 &&
                           (int)strided.back().size() >= 3 && nl - 12 >= 4;
-        for (size_t si = 0; si < strided.size() && layer >= 0; ++si) {
+        for (size_t si = 0; si < n_strided && layer >= 0; ++si) {
             XOp op = new_op(layer, nv);
-            QR_TRY(xop_set_geometry(op, strided[si], false));
+            if (!strided_gx.empty()) op.pp = strided_gx[si];
+            else QR_TRY(xop_set_geometry(op, strided[si], false));
             QR_TRY(xop_set_map(c, op, lin_identity(nt), nl, g));
             op.src_buf[0] = psi; op.src_buf[1] = lam; op.dst_buf[0] = psi; op.dst_buf[1] = lam;
-            if (slice_pair && si + 1 == strided.size()) op.nslices = sr->slices;
+            if (slice_pair && si + 1 == n_strided) op.nslices = sr->slices;
             QR_TRY(finish_op(op, ly));
             sr->ops.push_back(op);
         }

@@ -35,3 +35,5 @@ else:
 for _ in range(args.reps):
     e, g = c.grad_run()
 print("E = %.15g" % e)
+perf = c.perf if args.shards > 1 else c.state.perf()
+print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in perf.items()})
