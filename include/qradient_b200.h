@@ -181,6 +181,11 @@ int qr_qaoa_grad(qr_ctx* ctx, int n_layers, const double* betas, const double* g
 int qr_mcclean_optimize(qr_ctx* ctx, int n_layers, const int32_t* axes, double* angles, const qr_obs* obs, int rule,
                         double* hyper, int* iter_inout, double* m_inout, double* v_inout, int steps,
                         double* cost_history, double* param_history);
+/* QaoaOpt.step x steps (optimization.py:113-129): params [n_layers][2] = rows (beta_i, gamma_i), in/out; m / v [n_layers*2];
+ * param_history [steps][n_layers*2].  Needs an integer-valued Hamiltonian (MaxCut: the phase look-up tables are rebuilt on
+ * the device from the updated gammas); QR_EINVAL otherwise -- the caller keeps the host loop. */
+int qr_qaoa_optimize(qr_ctx* ctx, int n_layers, double* params, int rule, double* hyper, int* iter_inout, double* m_inout,
+                     double* v_inout, int steps, double* cost_history, double* param_history);
 
 /* ---- finite-shot sampling (qaoa.py:196-198, mc_clean.py:259-261) ------------------------ */
 /* index = first k with cumsum(|vec|^2)[k] >= u  (scipy rv_discrete inverse CDF); uniforms are

@@ -75,6 +75,7 @@ _SIGNATURES = {
     "qr_ham_gather": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "qr_mcclean_optimize": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                     c_void_p, c_void_p]),
+    "qr_qaoa_optimize": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "qr_perm_load": (c_int, [c_void_p, c_void_p, c_size_t]),
     "qr_state_permute": (c_int, [c_void_p]),
     "qr_dense_load": (c_int, [c_void_p, c_void_p, c_size_t]),

@@ -65,6 +65,31 @@ class Qaoa(ParametrizedCircuit):
                        ctypes.byref(e), _lib.ptr(grad))
         return e.value, grad
 
+    # -- optimiser loop on the device (optimization.py:113-129 QaoaOpt.step, repeated) ----------
+    def optimize_on_device(self, rule, hyper, iteration, steps, params, m=None, v=None, keep_param_history=True):
+        """`steps` x (grad_run, parameter update) enqueued back to back on the device.
+
+        params: float64[p, 2] = rows (beta_i, gamma_i), updated in place; rule / hyper / m / v as in
+        `McClean.optimize_on_device`.  Needs an integer-valued Hamiltonian (MaxCut); raises ValueError otherwise.
+        Returns (cost_history float64[steps], param_history float64[steps, p, 2] or None, iteration, hyper)."""
+        par = np.ascontiguousarray(params, dtype=np.float64)
+        if par.shape != (self.lnum, 2):
+            raise ValueError('params must have shape ({}, 2)'.format(self.lnum))
+        hyper = np.ascontiguousarray(hyper, dtype=np.float64)
+        cost = np.zeros(steps, dtype=np.float64)
+        hist = np.zeros((steps, self.lnum, 2), dtype=np.float64) if keep_param_history else None
+        it = ctypes.c_int(int(iteration))
+        mm = np.ascontiguousarray(m, dtype=np.float64) if m is not None else None
+        vv = np.ascontiguousarray(v, dtype=np.float64) if v is not None else None
+        self._lib.call('qr_qaoa_optimize', self.state._ctx, self.lnum, _lib.ptr(par), int(rule), _lib.ptr(hyper), ctypes.byref(it),
+                       _lib.ptr(mm) if mm is not None else None, _lib.ptr(vv) if vv is not None else None, int(steps), _lib.ptr(cost),
+                       _lib.ptr(hist) if hist is not None else None)
+        params[...] = par
+        if m is not None:
+            m[...] = mm
+            v[...] = vv
+        return cost, hist, it.value, hyper
+
     # -- qaoa.py:72-81 ------------------------------------------------------------------------
     def sample_grad(self, betas, gammas, shot_num=1, hide_progbar=True, exact_expec_val=True, ini_state=None):
         warnings.warn('Not implemented yet.')

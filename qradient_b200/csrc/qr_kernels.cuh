@@ -429,7 +429,9 @@ struct GatePOut { double c, s; int axis; int pad; };   // same layout as GateP (
 
 __global__ void k_build_gates(const int* __restrict__ axes, const double* __restrict__ angles,
                               const int* __restrict__ qmap, GatePOut* __restrict__ tab, i64 batch, int L, int n,
-                              int P, int GS, int ndir) {
+                              int P, int GS, int ndir, int qmap_per_layer) {
+    // qmap[dir][layer or 0][pass][slot] = qubit + 64 * pad (pad > 0: Rz applied through the tile's index bit pad - 1,
+    // axis-aware plans) or -1
     const i64 per_batch = (i64)ndir * L * P * GS;
     const i64 total = batch * per_batch;
     for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
@@ -439,9 +441,10 @@ __global__ void k_build_gates(const int* __restrict__ axes, const double* __rest
         const int p = (int)(r % P); r /= P;
         const int lay = (int)r;
         const int dir = lay / L, i = lay - dir * L;
-        const int q = qmap[((size_t)dir * P + p) * GS + s];
+        const int qm = qmap[(((size_t)dir * (qmap_per_layer ? L : 1) + (qmap_per_layer ? i : 0)) * P + p) * GS + s];
+        const int q = qm < 0 ? -1 : (qm & 63);
         GatePOut g;
-        g.c = 1.0; g.s = 0.0; g.axis = -1; g.pad = 0;
+        g.c = 1.0; g.s = 0.0; g.axis = -1; g.pad = qm < 0 ? 0 : (qm >> 6);
         if (q >= 0) {
             const double th = 0.5 * angles[((size_t)b * L + i) * n + q];
             double sn, cs;
@@ -468,18 +471,13 @@ struct OptDev {
     double step_size, beta1, beta2, eps, decay_rate, cost;
 };
 
-__global__ void k_opt_step(const double* __restrict__ result, const int* __restrict__ slot_qubit, int L, int n, int P, int GS, int SL,
-                           double* __restrict__ params, double* __restrict__ m, double* __restrict__ v, double* __restrict__ grad,
-                           OptDev* st, double* __restrict__ cost_hist, double* __restrict__ param_hist, int it) {
+// the update of one optimiser step on np_ parameters whose gradient is in grad[] (shared tail of both loops)
+__device__ __forceinline__ void qr_opt_update(int np_, double e, double* __restrict__ params, double* __restrict__ m, double* __restrict__ v,
+                                              const double* __restrict__ grad, OptDev* st, double* __restrict__ cost_hist,
+                                              double* __restrict__ param_hist, int it) {
     __shared__ double sh[3];   // step size of this step, 1 - beta1^iter, 1 - beta2^iter
-    const int total_slots = L * P * GS, np_ = L * n;
-    for (int idx = threadIdx.x; idx < total_slots; idx += blockDim.x) {
-        const int s = idx % GS, p = (idx / GS) % P, i = idx / (GS * P);
-        const int q = slot_qubit[p * GS + s];
-        if (q >= 0) grad[i * n + q] = result[1 + (size_t)(i * P + p) * SL + s];
-    }
+    __syncthreads();           // grad[] was written by this block
     if (threadIdx.x == 0) {
-        const double e = result[0];
         cost_hist[it] = e;
         st->iter += 1;
         if (st->rule == 2) {               // optimization.py:183-192
@@ -511,6 +509,62 @@ __global__ void k_opt_step(const double* __restrict__ result, const int* __restr
         }
         params[k] = x;
         if (param_hist) param_hist[(size_t)it * np_ + k] = x;
+    }
+}
+
+// McClean: gradient [L][n] from the slot sums of the backward passes, then the update (optimization.py:41-91)
+__global__ void k_opt_step(const double* __restrict__ result, const int* __restrict__ slot_qubit, int L, int n, int P, int GS, int SL,
+                           double* __restrict__ params, double* __restrict__ m, double* __restrict__ v, double* __restrict__ grad,
+                           OptDev* st, double* __restrict__ cost_hist, double* __restrict__ param_hist, int it) {
+    // slot_qubit[layer][pass][slot]: the plans (hence the slot maps) differ between layers with the axis-aware plans
+    const int total_slots = L * P * GS, np_ = L * n;
+    for (int idx = threadIdx.x; idx < total_slots; idx += blockDim.x) {
+        const int i = idx / (GS * P);
+        const int q = slot_qubit[idx];
+        if (q >= 0) grad[i * n + q] = result[1 + (size_t)(idx / GS) * SL + idx % GS];
+    }
+    qr_opt_update(np_, result[0], params, m, v, grad, st, cost_hist, param_hist, it);
+}
+
+// QAOA: gradient rows (d/d beta_i, d/d gamma_i) from the slot sums (qaoa.py:62-68), then the update (optimization.py:113-129)
+__global__ void k_qaoa_opt_step(const double* __restrict__ result, const int* __restrict__ slot_qubit, int L, int P, int GS, int SL,
+                                double* __restrict__ params, double* __restrict__ m, double* __restrict__ v, double* __restrict__ grad,
+                                OptDev* st, double* __restrict__ cost_hist, double* __restrict__ param_hist, int it) {
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        double gb = 0.0;
+        for (int p = 0; p < P; ++p)
+            for (int s = 0; s < GS; ++s)
+                if (slot_qubit[p * GS + s] >= 0) gb += result[1 + (size_t)(i * P + p) * SL + s];
+        grad[2 * i] = gb;
+        grad[2 * i + 1] = 2.0 * result[1 + (size_t)(i * P + (P - 1)) * SL + (SL - 1)];
+    }
+    qr_opt_update(2 * L, result[0], params, m, v, grad, st, cost_hist, param_hist, it);
+}
+
+// QAOA gate tables and phase look-up tables from device-resident parameter rows (beta_i, gamma_i):
+// tab[dir][layer][pass][slot] = X rotation by +-beta_i on every slot that holds a qubit; lut[dir][layer][v] = exp(-+ i gamma_i (hmin + v))
+__global__ void k_qaoa_tables(const double* __restrict__ params, const int* __restrict__ slot_qubit, int L, int P, int GS, int dirs,
+                              double hmin, int range, GatePOut* __restrict__ tab, double2* __restrict__ lut) {
+    const i64 ntab = (i64)dirs * L * P * GS, nlut = (i64)2 * L * range;
+    for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < ntab + nlut; idx += (i64)gridDim.x * blockDim.x) {
+        if (idx < ntab) {
+            const int s = (int)(idx % GS), p = (int)((idx / GS) % P), i = (int)((idx / ((i64)GS * P)) % L), dir = (int)(idx / ((i64)GS * P * L));
+            GatePOut g;
+            g.c = 1.0; g.s = 0.0; g.axis = -1; g.pad = 0;
+            if (slot_qubit[p * GS + s] >= 0) {
+                double sn, cs;
+                sincos(0.5 * params[2 * i], &sn, &cs);
+                g.c = cs; g.s = dir == 0 ? sn : -sn; g.axis = 0;
+            }
+            tab[idx] = g;
+        } else {
+            const i64 j = idx - ntab;
+            const int v = (int)(j % range), i = (int)((j / range) % L), dir = (int)(j / ((i64)range * L));
+            const double ang = (dir == 0 ? params[2 * i + 1] : -params[2 * i + 1]) * (hmin + (double)v);
+            double sn, cs;
+            sincos(ang, &sn, &cs);
+            lut[j] = make_double2(cs, -sn);
+        }
     }
 }
 

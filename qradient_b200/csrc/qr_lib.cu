@@ -1377,7 +1377,7 @@ struct GradLayout {   // where the per-(layer, pass) slot sums land in d_result
 // ([E][L][P][QR_SLOTS]) for the update kernel that is enqueued next.
 struct DevParams {
     const double* d_angles;      // [L * n] on the device
-    int* slot_qubit_out;         // host [P * QR_GATE_SLOTS]: qubit of each backward gradient slot (or -1)
+    int* slot_qubit_out;         // host [L * P * QR_GATE_SLOTS]: qubit of each backward gradient slot (or -1), per layer
     int* passes_out;             // host: P
 };
 
@@ -1389,7 +1389,7 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     LayerPlan lpf, lp;   // forward / backward plans: same tile geometry, different register blocking
     // axis-aware plans apply to single circuits whose axes the host knows; with them 12-bit tiles win from n = 23 on
     // (measured, profiles/r2_axis_ab.log: n = 24: 30.1 -> 25.3 ms per 30 layers, n = 26: 127 -> 118 ms; n = 22: 4.45 vs 4.57 ms)
-    const bool axis_ok = c->opt_axis_plan && batch == 1 && dev == nullptr;
+    const bool axis_ok = c->opt_axis_plan && batch == 1;
     int tile_bits = pick_tile_bits(c, n);
     if (axis_ok && c->opt_tile_bits == 0 && n >= 23 && n <= 26 && tile_bits == 11) tile_bits = 12;
     QR_TRY(make_plan(n, tile_bits, &lpf, (int)c->opt_tile_bits_x, tile_bits == pick_tile_bits(c, n) ? pick_min_row_bits(c, n) : (int)c->opt_min_row_bits));
@@ -1413,9 +1413,11 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     int n_axis_layers = 0;
     if (axis_ok && uniform_lean_plan(lpf))
         for (int i = 0; i < L; ++i) n_axis_layers += plan_axis_layer(lpf, axes + (size_t)i * n, &plans[i], (c->opt_axis_plan & 2) ? 1 : 0) ? 1 : 0;
-    const size_t raw_bytes = dev_tables ? (size_t)batch * L * n * (sizeof(double) + sizeof(int32_t)) + 2 * (size_t)P * GS * sizeof(int) + 1024 : 0;
+    const bool qmap_per_layer = dev != nullptr;   // one circuit: slot -> qubit maps per layer (axis-aware plans)
+    const size_t qmap_ints = 2 * (size_t)(qmap_per_layer ? L : 1) * P * GS;
+    const size_t raw_bytes = dev_tables ? (size_t)batch * L * n * (sizeof(double) + sizeof(int32_t)) + qmap_ints * sizeof(int) + 1024 : 0;
     QR_TRY(ensure_small(c, raw_off + raw_bytes + 1024));
-    QR_TRY(ensure_pin(c, dev_tables ? std::max((size_t)1 << 16, (size_t)batch * (1 + (size_t)L * P * QR_SLOTS) * sizeof(double) + 8192)
+    QR_TRY(ensure_pin(c, dev_tables ? std::max((size_t)1 << 16, (size_t)batch * (1 + (size_t)L * P * QR_SLOTS) * sizeof(double) + 8192) + tab_off + qmap_ints * sizeof(int)
                                     : tab_off + tab_bytes + 1024));
     if (dev_tables) {
         // device-side table build: upload raw parameters + the slot->qubit maps of both directions
@@ -1425,17 +1427,20 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
         int* d_qmap = d_axes + (size_t)batch * L * n;
         int* qmap = (int*)(c->h_pin + tab_off);   // own staging slot: offset 0 is reused for the observable terms below
         for (int dir = 0; dir < 2; ++dir)
-            for (int p = 0; p < P; ++p)
-                for (int s2 = 0; s2 < GS; ++s2) {
-                    const int gb = (dir == 0 ? lpf : lp).pass[p].gbit[s2];
-                    qmap[((size_t)dir * P + p) * GS + s2] = gb < 0 ? -1 : n - 1 - gb;
-                }
-        CUDA_TRY(cudaMemcpyAsync(d_qmap, qmap, 2 * (size_t)P * GS * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            for (int i = 0; i < (qmap_per_layer ? L : 1); ++i)
+                for (int p = 0; p < P; ++p)
+                    for (int s2 = 0; s2 < GS; ++s2) {
+                        const LayerPlan& pl = qmap_per_layer ? plans[i] : lp;
+                        const int gb = p < pl.npasses ? pl.pass[p].gbit[s2] : -1;
+                        const int pad = (gb >= 0 && pl.pass[p].gx && ((pl.pass[p].zmask >> s2) & 1)) ? 1 + gb : 0;
+                        qmap[(((size_t)dir * (qmap_per_layer ? L : 1) + i) * P + p) * GS + s2] = gb < 0 ? -1 : (n - 1 - gb) + 64 * pad;
+                    }
+        CUDA_TRY(cudaMemcpyAsync(d_qmap, qmap, qmap_ints * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         if (!dev) CUDA_TRY(cudaMemcpyAsync(d_angles, angles, (size_t)batch * L * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaMemcpyAsync(d_axes, axes, (size_t)batch * L * n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         const i64 total = (i64)batch * per_batch;
         QR_LAUNCH(k_build_gates, grid_for(c, (u64)total), QR_BLOCK, 0, c->stream, (const int*)d_axes, dev ? dev->d_angles : (const double*)d_angles,
-                  (const int*)d_qmap, (GatePOut*)((char*)c->d_small + tab_off), batch, L, n, P, GS, want_grad ? 2 : 1);
+                  (const int*)d_qmap, (GatePOut*)((char*)c->d_small + tab_off), batch, L, n, P, GS, want_grad ? 2 : 1, qmap_per_layer ? 1 : 0);
         KERNEL_CHECK();
         c->perf.kernel_launches++;
     } else {
@@ -1620,11 +1625,12 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
         for (auto& r : trace_recs) cudaEventDestroy(r.ev);
     }
     if (dev) {   // results stay on the device; tell the caller how to read the slot sums
-        for (int p = 0; p < P; ++p)
-            for (int s2 = 0; s2 < GS; ++s2) {
-                const int gb = lp.pass[p].gbit[s2];
-                dev->slot_qubit_out[p * GS + s2] = gb < 0 ? -1 : n - 1 - gb;
-            }
+        for (int i = 0; i < L; ++i)
+            for (int p = 0; p < P; ++p)
+                for (int s2 = 0; s2 < GS; ++s2) {
+                    const int gb = p < plans[i].npasses ? plans[i].pass[p].gbit[s2] : -1;
+                    dev->slot_qubit_out[((size_t)i * P + p) * GS + s2] = gb < 0 ? -1 : n - 1 - gb;
+                }
         *dev->passes_out = P;
         c->psi = lam;
         return 0;
@@ -1776,7 +1782,7 @@ extern "C" int qr_mcclean_optimize(qr_ctx* c, int L, const int32_t* axes, double
     const size_t np_ = (size_t)L * c->n;
     // device block: params | m | v | grad | cost history | parameter history | slot map | state
     const size_t doubles = 4 * np_ + (size_t)steps + (param_history ? (size_t)steps * np_ : 0);
-    const size_t map_ints = 16 * QR_GATE_SLOTS;
+    const size_t map_ints = (size_t)L * 16 * QR_GATE_SLOTS;
     char* d_blk = nullptr;
     CUDA_TRY(cudaMalloc((void**)&d_blk, doubles * sizeof(double) + map_ints * sizeof(int) + sizeof(OptDev) + 64));
     double* d_params = (double*)d_blk;
@@ -1790,7 +1796,7 @@ extern "C" int qr_mcclean_optimize(qr_ctx* c, int L, const int32_t* axes, double
     st.step_size = hyper[0]; st.beta1 = hyper[1]; st.beta2 = hyper[2]; st.eps = hyper[3];
     st.plateau_length = (int)hyper[4]; st.decay_rate = hyper[5]; st.cost = hyper[6]; st.plateau_counter = (int)hyper[7];
     int rc = 0;
-    std::vector<int> slot_q(16 * QR_GATE_SLOTS, -1);
+    std::vector<int> slot_q((size_t)L * 16 * QR_GATE_SLOTS, -1);
     int P = 0;
     do {
         cudaError_t e;
@@ -1812,7 +1818,7 @@ extern "C" int qr_mcclean_optimize(qr_ctx* c, int L, const int32_t* axes, double
             if (rc) break;
             if (it == 0) {   // the slot map is the same for every step
                 if (P > 16) { rc = fail(QR_EINVAL, "internal: too many passes"); break; }
-                if ((e = cudaMemcpyAsync(d_map, slot_q.data(), (size_t)P * QR_GATE_SLOTS * sizeof(int), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
+                if ((e = cudaMemcpyAsync(d_map, slot_q.data(), (size_t)L * P * QR_GATE_SLOTS * sizeof(int), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
                     (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { rc = fail(QR_ECUDA, "optimiser: %s", cudaGetErrorString(e)); break; }
             }
             QR_LAUNCH(k_opt_step, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_result, (const int*)d_map, L, c->n, P, QR_GATE_SLOTS, QR_SLOTS,
@@ -1896,8 +1902,17 @@ static int qaoa_unfused(qr_ctx* c, int p, const double* betas, const double* gam
     return 0;
 }
 
+// Device-resident parameters (optimiser loop, qr_qaoa_optimize): rows (beta_i, gamma_i) in device memory; the gate tables
+// and the phase look-up tables are built on the device (integer-valued Hamiltonians only: a general H takes its angle as a
+// kernel argument), nothing is read back -- E and the slot sums stay in d_result for the update kernel.
+struct QaoaDev {
+    const double* d_params;      // [p][2] on the device
+    int* slot_qubit_out;         // host [P * QR_GATE_SLOTS]: qubit of each gradient slot (or -1)
+    int* passes_out;             // host: P
+};
+
 static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gammas, int use_current, double* e_out,
-                      double* grad) {
+                      double* grad, const QaoaDev* dev = nullptr) {
     const int n = c->n;
     c->tables_fresh = true;
     LayerPlan lpf, lp;
@@ -1909,9 +1924,28 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
     const int nlay_tab = p * (want_grad ? 2 : 1);
     const size_t tab_bytes = (size_t)nlay_tab * P * GS * sizeof(GateP);
     const size_t lut_space = (size_t)2 * p * QR_LUT_MAX * sizeof(double2) + 2048;   // reserved up front: no realloc mid-stream
-    QR_TRY(ensure_small(c, tab_bytes + 1024 + lut_space));
+    QR_TRY(ensure_small(c, tab_bytes + 1024 + lut_space + (dev ? (size_t)P * GS * sizeof(int) + 2048 : 0)));
     QR_TRY(ensure_pin(c, std::max(tab_bytes + 1024 + lut_space, (size_t)(1 + (size_t)p * P * QR_SLOTS) * sizeof(double) + 1024)));
-    {
+    if (dev && !(c->ham_integer && c->opt_ham_lut)) return fail(QR_EINVAL, "the device optimiser loop needs an integer-valued Hamiltonian (phase look-up tables)");
+    if (dev) {
+        // tables from the device-resident parameters: slot map up, one kernel for gate tables + look-up tables
+        const size_t lut_off = (tab_bytes + 1024 + 255) & ~(size_t)255;
+        const size_t map_off = (lut_off + lut_space + 255) & ~(size_t)255;
+        int* qmap = (int*)c->h_pin;
+        for (int q = 0; q < P; ++q)
+            for (int s2 = 0; s2 < GS; ++s2) {
+                const int gb = lp.pass[q].gbit[s2];
+                qmap[q * GS + s2] = gb < 0 ? -1 : n - 1 - gb;
+                dev->slot_qubit_out[q * GS + s2] = qmap[q * GS + s2];
+            }
+        *dev->passes_out = P;
+        CUDA_TRY(cudaMemcpyAsync((char*)c->d_small + map_off, qmap, (size_t)P * GS * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        const i64 total = (i64)nlay_tab * P * GS + (i64)2 * p * c->ham_range;
+        QR_LAUNCH(k_qaoa_tables, grid_for(c, (u64)total), QR_BLOCK, 0, c->stream, dev->d_params, (const int*)((char*)c->d_small + map_off), p, P, GS,
+                  want_grad ? 2 : 1, c->ham_min, c->ham_range, (GatePOut*)c->d_small, (double2*)((char*)c->d_small + lut_off));
+        KERNEL_CHECK();
+        c->perf.kernel_launches++;
+    } else {
         GateP* tab = (GateP*)c->h_pin;
         int lay = 0;
         for (int dir = 0; dir < (want_grad ? 2 : 1); ++dir)
@@ -1927,7 +1961,8 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
     // phase look-up tables exp(-i gamma_i h) (forward) and exp(+i gamma_i h) (backward), host libm values
     const bool lut_on = c->ham_integer && c->opt_ham_lut;
     const double2* d_lut = nullptr;
-    if (lut_on) {
+    if (dev) d_lut = (const double2*)((char*)c->d_small + ((tab_bytes + 1024 + 255) & ~(size_t)255));
+    else if (lut_on) {
         const size_t lut_off = (tab_bytes + 1024 + 255) & ~(size_t)255;
         const size_t lut_bytes = (size_t)2 * p * c->ham_range * sizeof(double2);
         double2* lut = (double2*)(c->h_pin + lut_off);
@@ -1950,7 +1985,7 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
         for (int q = 0; q < P; ++q) {
             PassIO io = {c->buf[c->psi], nullptr, c->buf[c->psi], nullptr};
             QR_TRY(launch_pass(c, lpf, q, 1, io, d_tab + ((size_t)i * P + q) * GS, 0, -1, 1, stride, 0, c->d_ham, q == 0 ? 1 : 0,
-                               gammas[i], 0, 0.0, nullptr, nullptr, nullptr, d_lut ? d_lut + (size_t)i * c->ham_range : nullptr));
+                               dev ? 0.0 : gammas[i], 0, 0.0, nullptr, nullptr, nullptr, d_lut ? d_lut + (size_t)i * c->ham_range : nullptr));
         }
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     const int g = grid_for(c, c->N);
@@ -1976,7 +2011,7 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
                 PassIO io = {c->buf[c->psi], c->buf[lam], c->buf[c->psi], c->buf[lam]};
                 int units = 0;
                 QR_TRY(launch_pass(c, lp, q, 2, io, d_tab + ((size_t)(p + i) * P + q) * GS, 0, -1, 1, stride, 0, c->d_ham, 0, 0.0,
-                                   q == P - 1 ? 1 : 0, -gammas[i], &units, nullptr, defer ? nullptr : d_slots + ((size_t)i * P + q) * QR_SLOTS,
+                                   q == P - 1 ? 1 : 0, dev ? 0.0 : -gammas[i], &units, nullptr, defer ? nullptr : d_slots + ((size_t)i * P + q) * QR_SLOTS,
                                    d_lut ? d_lut + (size_t)(p + i) * c->ham_range : nullptr,
                                    defer ? c->d_scratch + ((size_t)i * P + q) * unit_cap * QR_SLOTS : nullptr));
                 if (defer) {
@@ -1993,6 +2028,10 @@ static int qaoa_fused(qr_ctx* c, int p, const double* betas, const double* gamma
         }
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    if (dev) {   // results stay on the device
+        if (want_grad) c->psi = lam;
+        return 0;
+    }
     const size_t nres = 1 + (want_grad ? (size_t)p * P * QR_SLOTS : 0);
     QR_TRY(ensure_pin(c, nres * sizeof(double)));
     CUDA_TRY(cudaMemcpyAsync(c->h_pin, c->d_result, nres * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -2052,6 +2091,82 @@ extern "C" int qr_qaoa_grad(qr_ctx* c, int p, const double* betas, const double*
     double dummy[2];
     if (use_fused(c)) return qaoa_fused(c, p, betas, gammas, use_current_state, e_out, grad_out ? grad_out : dummy);
     return qaoa_unfused(c, p, betas, gammas, use_current_state, e_out, grad_out ? grad_out : dummy);
+}
+
+// QaoaOpt.step x steps on the device (optimization.py:113-129): params = rows (beta_i, gamma_i), same rules and state
+// hand-over as qr_mcclean_optimize
+extern "C" int qr_qaoa_optimize(qr_ctx* c, int p, double* params, int rule, double* hyper, int* iter_inout, double* m_inout,
+                                double* v_inout, int steps, double* cost_history, double* param_history) {
+    QR_TRY(check_qaoa_args(c, p, params, params));
+    if (!use_fused(c)) return fail(QR_EINVAL, "the device optimiser loop needs the fused path (>= 4 qubits, QR_OPT_FUSION)");
+    if (rule < 0 || rule > 2 || !hyper || !iter_inout || steps < 0 || (steps > 0 && !cost_history)) return fail(QR_EINVAL, "bad optimiser arguments");
+    if (rule == 0 && (!m_inout || !v_inout)) return fail(QR_EINVAL, "Adam needs the moment arrays");
+    if (!(c->ham_integer && c->opt_ham_lut)) return fail(QR_EINVAL, "the device optimiser loop needs an integer-valued Hamiltonian (phase look-up tables)");
+    if (steps == 0 || p == 0) return 0;
+    QR_TRY(use_device(c));
+    perf_reset(c);
+    const size_t np_ = (size_t)2 * p;
+    const size_t doubles = 4 * np_ + (size_t)steps + (param_history ? (size_t)steps * np_ : 0);
+    const size_t map_ints = 16 * QR_GATE_SLOTS;
+    char* d_blk = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_blk, doubles * sizeof(double) + map_ints * sizeof(int) + sizeof(OptDev) + 64));
+    double* d_params = (double*)d_blk;
+    double *d_m = d_params + np_, *d_v = d_m + np_, *d_grad = d_v + np_, *d_cost = d_grad + np_;
+    double* d_hist = param_history ? d_cost + steps : nullptr;
+    int* d_map = (int*)(d_params + doubles);
+    OptDev* d_st = (OptDev*)(d_map + map_ints);
+    OptDev st;
+    memset(&st, 0, sizeof(st));
+    st.rule = rule; st.iter = *iter_inout;
+    st.step_size = hyper[0]; st.beta1 = hyper[1]; st.beta2 = hyper[2]; st.eps = hyper[3];
+    st.plateau_length = (int)hyper[4]; st.decay_rate = hyper[5]; st.cost = hyper[6]; st.plateau_counter = (int)hyper[7];
+    int rc = 0;
+    std::vector<int> slot_q(16 * QR_GATE_SLOTS, -1);
+    int P = 0;
+    do {
+        cudaError_t e;
+        if ((e = cudaMemcpyAsync(d_params, params, np_ * sizeof(double), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
+            (e = cudaMemsetAsync(d_m, 0, 3 * np_ * sizeof(double), c->stream)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(d_st, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) {
+            rc = fail(QR_ECUDA, "optimiser setup: %s", cudaGetErrorString(e));
+            break;
+        }
+        if (rule == 0) {
+            cudaMemcpyAsync(d_m, m_inout, np_ * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+            cudaMemcpyAsync(d_v, v_inout, np_ * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+        }
+        if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { rc = fail(QR_ECUDA, "optimiser setup: %s", cudaGetErrorString(e)); break; }
+        double dummy_grad[2] = {0.0, 0.0}, dummy_e = 0.0;
+        for (int it = 0; it < steps && rc == 0; ++it) {
+            QaoaDev dev = {d_params, slot_q.data(), &P};
+            rc = qaoa_fused(c, p, nullptr, nullptr, 0, &dummy_e, dummy_grad, &dev);
+            if (rc) break;
+            if (it == 0) {   // the slot map is the same for every step
+                if (P > 16) { rc = fail(QR_EINVAL, "internal: too many passes"); break; }
+                if ((e = cudaMemcpyAsync(d_map, slot_q.data(), (size_t)P * QR_GATE_SLOTS * sizeof(int), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
+                    (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { rc = fail(QR_ECUDA, "optimiser: %s", cudaGetErrorString(e)); break; }
+            }
+            QR_LAUNCH(k_qaoa_opt_step, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_result, (const int*)d_map, p, P, QR_GATE_SLOTS, QR_SLOTS,
+                      d_params, d_m, d_v, d_grad, d_st, d_cost, d_hist, it);
+            if ((e = cudaGetLastError()) != cudaSuccess) { rc = fail(QR_ECUDA, "optimiser step: %s", cudaGetErrorString(e)); break; }
+            c->perf.kernel_launches++;
+        }
+        if (rc) break;
+        cudaMemcpyAsync(params, d_params, np_ * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(cost_history, d_cost, (size_t)steps * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (param_history) cudaMemcpyAsync(param_history, d_hist, (size_t)steps * np_ * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (rule == 0) {
+            cudaMemcpyAsync(m_inout, d_m, np_ * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+            cudaMemcpyAsync(v_inout, d_v, np_ * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        }
+        cudaMemcpyAsync(&st, d_st, sizeof(st), cudaMemcpyDeviceToHost, c->stream);
+        if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { rc = fail(QR_ECUDA, "optimiser loop: %s", cudaGetErrorString(e)); break; }
+        *iter_inout = st.iter;
+        hyper[0] = st.step_size; hyper[6] = st.cost; hyper[7] = (double)st.plateau_counter;
+    } while (0);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_blk);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -207,6 +207,44 @@ class QaoaOpt(ParametrizedCircuitOptimizer):
         self.iter += 1
         self.param_history[self.iter] = self.optimizer.parameters
 
+    def run(self, steps):
+        """`steps` exact-gradient steps as ONE device-side loop (`Qaoa.optimize_on_device`, qr_qaoa_optimize) where the
+        update rule and the Hamiltonian allow it (Adam, constant-step GradientDescent, RateDecayOnPlateau; integer-valued
+        H such as MaxCut); the same sequence as `steps` calls of `step()`, which is also the fallback."""
+        opt = self.optimizer
+        steps = int(min(steps, self.max_iter - 1 - self.iter))
+        rule = {Adam: 0, GradientDescent: 1, RateDecayOnPlateau: 2}.get(type(opt))
+        device_ok = (steps > 0 and rule is not None and hasattr(self.circuit, 'optimize_on_device')
+                     and self.circuit.qnum >= 4 and (rule != 1 or opt.constant_step))
+        if device_ok:
+            hyper = np.array([opt.step_size, getattr(opt, 'beta1', 0.), getattr(opt, 'beta2', 0.), getattr(opt, 'eps', 0.),
+                              getattr(opt, 'plateau_length', 0), getattr(opt, 'decay_rate', 0.), getattr(opt, 'cost', 0.),
+                              getattr(opt, 'plateau_counter', 0)], dtype=np.float64)
+            params = np.ascontiguousarray(opt.parameters, dtype=np.float64)
+            m = opt.m if rule == 0 else None
+            v = opt.v if rule == 0 else None
+            try:
+                cost, hist, it, hyper = self.circuit.optimize_on_device(rule, hyper, opt.iter, steps, params, m=m, v=v)
+            except ValueError as exc:
+                if 'integer-valued' not in str(exc):
+                    raise
+                device_ok = False          # a Hamiltonian with non-integer values: host loop below
+        if not device_ok:
+            for _ in range(max(steps, 0)):
+                self.step()
+            return
+        self.cost_history[self.iter:self.iter + steps] = cost
+        self.param_history[self.iter + 1:self.iter + 1 + steps] = hist
+        self.iter += steps
+        opt.iter = it
+        opt.step_size = hyper[0]
+        if rule == 0:
+            opt.m_hat = opt.m / (1 - opt.beta1 ** opt.iter)
+            opt.v_hat = opt.v / (1 - opt.beta2 ** opt.iter)
+        if rule == 2:
+            opt.cost, opt.plateau_counter = hyper[6], int(hyper[7])
+        opt.parameters[...] = params
+
     def reset(self, **kwargs):
         if 'betas' in kwargs and 'gammas' in kwargs:
             self.param_history[0] = np.array([kwargs['betas'], kwargs['gammas']]).transpose()
