@@ -16,7 +16,7 @@ QR_OK, QR_EINVAL, QR_ECUDA, QR_ENOMEM, QR_ESTATE = 0, 1, 2, 3, 4
 TERM_KIND = {"x": 0, "y": 1, "z": 2, "zz": 3}
 OPT = {"fusion": 0, "tile_bits": 1, "prefetch": 2, "ctas_per_sm_fwd": 3, "ctas_per_sm_bwd": 4,
        "final_ladder": 5, "ham_lut": 6, "tile_bits_strided": 11, "min_row_bits": 12, "batch_chunk_mb": 13,
-       "staged": 19, "staged_min_bit": 20, "pdl": 26, "defer_reduce": 28, "shard_zskip": 29, "shard_mode": 30, "shard_lockstep": 31, "shard_slices": 32, "shard_xsms": 33, "axis_plan": 34}
+       "staged": 19, "staged_min_bit": 20, "pdl": 26, "defer_reduce": 28, "shard_zskip": 29, "shard_mode": 30, "shard_lockstep": 31, "shard_slices": 32, "shard_xsms": 33, "axis_plan": 34, "loop_graph": 35}
 
 c_int, c_double, c_void_p, c_size_t, c_ll = ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_longlong
 P = ctypes.POINTER

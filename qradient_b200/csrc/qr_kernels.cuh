@@ -469,16 +469,22 @@ struct OptDev {
     int iter;
     int plateau_length, plateau_counter;
     double step_size, beta1, beta2, eps, decay_rate, cost;
+    int step;              // index of the next history entry: kept on the device so that every step is the same launch sequence (CUDA graph replay)
+    int pad_;
 };
 
 // the update of one optimiser step on np_ parameters whose gradient is in grad[] (shared tail of both loops)
 __device__ __forceinline__ void qr_opt_update(int np_, double e, double* __restrict__ params, double* __restrict__ m, double* __restrict__ v,
                                               const double* __restrict__ grad, OptDev* st, double* __restrict__ cost_hist,
-                                              double* __restrict__ param_hist, int it) {
+                                              double* __restrict__ param_hist) {
     __shared__ double sh[3];   // step size of this step, 1 - beta1^iter, 1 - beta2^iter
+    __shared__ int s_it;
+    if (threadIdx.x == 0) s_it = st->step;
     __syncthreads();           // grad[] was written by this block
+    const int it = s_it;
     if (threadIdx.x == 0) {
         cost_hist[it] = e;
+        st->step = it + 1;
         st->iter += 1;
         if (st->rule == 2) {               // optimization.py:183-192
             if (e > st->cost) {
@@ -515,7 +521,7 @@ __device__ __forceinline__ void qr_opt_update(int np_, double e, double* __restr
 // McClean: gradient [L][n] from the slot sums of the backward passes, then the update (optimization.py:41-91)
 __global__ void k_opt_step(const double* __restrict__ result, const int* __restrict__ slot_qubit, int L, int n, int P, int GS, int SL,
                            double* __restrict__ params, double* __restrict__ m, double* __restrict__ v, double* __restrict__ grad,
-                           OptDev* st, double* __restrict__ cost_hist, double* __restrict__ param_hist, int it) {
+                           OptDev* st, double* __restrict__ cost_hist, double* __restrict__ param_hist) {
     // slot_qubit[layer][pass][slot]: the plans (hence the slot maps) differ between layers with the axis-aware plans
     const int total_slots = L * P * GS, np_ = L * n;
     for (int idx = threadIdx.x; idx < total_slots; idx += blockDim.x) {
@@ -523,13 +529,13 @@ __global__ void k_opt_step(const double* __restrict__ result, const int* __restr
         const int q = slot_qubit[idx];
         if (q >= 0) grad[i * n + q] = result[1 + (size_t)(idx / GS) * SL + idx % GS];
     }
-    qr_opt_update(np_, result[0], params, m, v, grad, st, cost_hist, param_hist, it);
+    qr_opt_update(np_, result[0], params, m, v, grad, st, cost_hist, param_hist);
 }
 
 // QAOA: gradient rows (d/d beta_i, d/d gamma_i) from the slot sums (qaoa.py:62-68), then the update (optimization.py:113-129)
 __global__ void k_qaoa_opt_step(const double* __restrict__ result, const int* __restrict__ slot_qubit, int L, int P, int GS, int SL,
                                 double* __restrict__ params, double* __restrict__ m, double* __restrict__ v, double* __restrict__ grad,
-                                OptDev* st, double* __restrict__ cost_hist, double* __restrict__ param_hist, int it) {
+                                OptDev* st, double* __restrict__ cost_hist, double* __restrict__ param_hist) {
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
         double gb = 0.0;
         for (int p = 0; p < P; ++p)
@@ -538,7 +544,7 @@ __global__ void k_qaoa_opt_step(const double* __restrict__ result, const int* __
         grad[2 * i] = gb;
         grad[2 * i + 1] = 2.0 * result[1 + (size_t)(i * P + (P - 1)) * SL + (SL - 1)];
     }
-    qr_opt_update(2 * L, result[0], params, m, v, grad, st, cost_hist, param_hist, it);
+    qr_opt_update(2 * L, result[0], params, m, v, grad, st, cost_hist, param_hist);
 }
 
 // QAOA gate tables and phase look-up tables from device-resident parameter rows (beta_i, gamma_i):

@@ -115,6 +115,8 @@ struct qr_ctx {
     long long opt_pdl = 1;         // k_tile12 passes launched with programmatic stream serialization: 0 off, 1 auto (n <= 22), 2 always
     long long opt_axis_plan = 15;  // single McClean circuits: bit 0 per-layer plans from the axes (plan_axis_layer); bit 1 pass 0 trades Rz-only bits for high X / Y bits where that saves a round; bit 2 passes without an exchange run the two-round program; bit 3 split barriers in two-round backward passes
     long long opt_shard_zskip = 1; // sharded states: Rz on a global qubit is applied as a per-subgroup phase, without the exchange
+    long long opt_loop_graph = 1;  // device optimiser loops: steps 2..N replay a CUDA graph captured from the second step
+    bool capturing = false;        // a step of a device optimiser loop is being captured into a graph: no tracing
     bool tables_fresh = true;      // gate / phase tables were (re)written since the last tile pass: see launch_pass
     qr_perf perf;
     // ---- sharded states: this context holds one shard of an n_total-qubit register ----
@@ -324,6 +326,7 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
         case QR_OPT_BATCH_CHUNK_MB: if (v < 0 || v > 65536) return fail(QR_EINVAL, "bad batch chunk"); c->opt_batch_chunk_mb = v; break;
         case QR_OPT_DEFER_REDUCE: c->opt_defer_reduce = v ? 1 : 0; break;
         case QR_OPT_SHARD_ZSKIP: c->opt_shard_zskip = v ? 1 : 0; break;
+        case QR_OPT_LOOP_GRAPH: c->opt_loop_graph = v ? 1 : 0; break;
         case QR_OPT_AXIS_PLAN: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad axis-plan mode"); c->opt_axis_plan = v; break;
         case QR_OPT_PDL: if (v < 0 || v > 2) return fail(QR_EINVAL, "bad PDL mode"); c->opt_pdl = v; break;
         case QR_OPT_SHARD_MODE: if (v < 0 || v > 2) return fail(QR_EINVAL, "bad shard mode"); c->opt_shard_mode = v; break;
@@ -353,6 +356,7 @@ extern "C" int qr_get_option(qr_ctx* c, int key, long long* v) {
         case QR_OPT_PDL: *v = c->opt_pdl; break;
         case QR_OPT_SHARD_ZSKIP: *v = c->opt_shard_zskip; break;
         case QR_OPT_AXIS_PLAN: *v = c->opt_axis_plan; break;
+        case QR_OPT_LOOP_GRAPH: *v = c->opt_loop_graph; break;
         case QR_OPT_DEFER_REDUCE: *v = c->opt_defer_reduce; break;
         case QR_OPT_SHARD_MODE: *v = c->opt_shard_mode; break;
         case QR_OPT_SHARD_LOCKSTEP: *v = c->opt_shard_lockstep; break;
@@ -1417,7 +1421,7 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     const size_t qmap_ints = 2 * (size_t)(qmap_per_layer ? L : 1) * P * GS;
     const size_t raw_bytes = dev_tables ? (size_t)batch * L * n * (sizeof(double) + sizeof(int32_t)) + qmap_ints * sizeof(int) + 1024 : 0;
     QR_TRY(ensure_small(c, raw_off + raw_bytes + 1024));
-    QR_TRY(ensure_pin(c, dev_tables ? std::max((size_t)1 << 16, (size_t)batch * (1 + (size_t)L * P * QR_SLOTS) * sizeof(double) + 8192) + tab_off + qmap_ints * sizeof(int)
+    QR_TRY(ensure_pin(c, dev_tables ? std::max((size_t)1 << 16, (size_t)batch * (1 + (size_t)L * P * QR_SLOTS) * sizeof(double) + 8192) + tab_off + qmap_ints * sizeof(int) + (dev ? (size_t)L * n * sizeof(int32_t) + 64 : 0)
                                     : tab_off + tab_bytes + 1024));
     if (dev_tables) {
         // device-side table build: upload raw parameters + the slot->qubit maps of both directions
@@ -1437,7 +1441,11 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
                     }
         CUDA_TRY(cudaMemcpyAsync(d_qmap, qmap, qmap_ints * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         if (!dev) CUDA_TRY(cudaMemcpyAsync(d_angles, angles, (size_t)batch * L * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(d_axes, axes, (size_t)batch * L * n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        if (dev) {   // through pinned memory: the step may be captured into a graph (device optimiser loop)
+            int32_t* ax_pin = (int32_t*)(c->h_pin + tab_off + qmap_ints * sizeof(int) + (dev ? (size_t)L * n * sizeof(int32_t) + 64 : 0));
+            memcpy(ax_pin, axes, (size_t)L * n * sizeof(int32_t));
+            CUDA_TRY(cudaMemcpyAsync(d_axes, ax_pin, (size_t)L * n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        } else CUDA_TRY(cudaMemcpyAsync(d_axes, axes, (size_t)batch * L * n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         const i64 total = (i64)batch * per_batch;
         QR_LAUNCH(k_build_gates, grid_for(c, (u64)total), QR_BLOCK, 0, c->stream, (const int*)d_axes, dev ? dev->d_angles : (const double*)d_angles,
                   (const int*)d_qmap, (GatePOut*)((char*)c->d_small + tab_off), batch, L, n, P, GS, want_grad ? 2 : 1, qmap_per_layer ? 1 : 0);
@@ -1472,7 +1480,8 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     const int flush = batch > 1 ? 1 : 0;
 
     // QR_TRACE_PASSES=1 (environment): one CUDA event per tile pass, per-pass device times on stderr after the run
-    static const bool trace = getenv("QR_TRACE_PASSES") != nullptr;
+    static const bool trace_env = getenv("QR_TRACE_PASSES") != nullptr;
+    const bool trace = trace_env && !c->capturing && dev == nullptr;
     struct TraceRec { cudaEvent_t ev; int layer, pass, nv, c, ng, gx; };
     std::vector<TraceRec> trace_recs;
     auto trace_mark = [&](int layer, int pass, int nv, const PassPlan* pp) {
@@ -1769,6 +1778,49 @@ extern "C" int qr_mcclean_grad_batch(qr_ctx* c, int batch, int L, const int32_t*
 
 // Optimiser loop on the device (optimization.py:41-91 McCleanOpt.step repeated `steps` times):
 // gradient -> parameter update -> gate tables -> next gradient, all stream ordered, one synchronisation at the end.
+// Device optimiser loops: `steps` identical launch sequences.  The first step runs eagerly (it settles every allocation and
+// kernel attribute), the second is captured into a CUDA graph and steps 2..N are replays of it -- one launch per step instead
+// of ~4 per layer, which is what a small register's step costs on the host.  Any failure while capturing falls back to eager
+// launches.  body() must enqueue on c->stream only, read host data only from pinned staging it wrote itself, and not
+// depend on the step index (the history index lives on the device, OptDev::step).
+template <class F>
+static int run_steps_graphed(qr_ctx* c, int steps, F body) {
+#ifndef QR_HOST_EMUL
+    bool use_graph = c->opt_loop_graph != 0 && steps > 2;
+    cudaGraphExec_t exec = nullptr;
+    int rc = 0;
+    for (int it = 0; it < steps && rc == 0; ++it) {
+        if (it == 0 || !use_graph) { rc = body(it); continue; }
+        if (!exec) {
+            c->capturing = true;
+            cudaGraph_t graph = nullptr;
+            const cudaError_t e0 = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+            const int rc2 = e0 == cudaSuccess ? body(it) : -1;
+            const cudaError_t e1 = e0 == cudaSuccess ? cudaStreamEndCapture(c->stream, &graph) : e0;
+            c->capturing = false;
+            if (rc2 == 0 && e1 == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                cudaGraphDestroy(graph);
+            } else {   // not capturable here: eager launches for the rest
+                if (graph) cudaGraphDestroy(graph);
+                exec = nullptr;
+                use_graph = false;
+                cudaGetLastError();
+                g_err.clear();
+                rc = body(it);
+                continue;
+            }
+        }
+        if (cudaGraphLaunch(exec, c->stream) != cudaSuccess) rc = fail(QR_ECUDA, "optimiser loop: graph launch failed");
+    }
+    if (exec) { cudaStreamSynchronize(c->stream); cudaGraphExecDestroy(exec); }
+    return rc;
+#else
+    int rc = 0;
+    for (int it = 0; it < steps && rc == 0; ++it) rc = body(it);
+    return rc;
+#endif
+}
+
 extern "C" int qr_mcclean_optimize(qr_ctx* c, int L, const int32_t* axes, double* angles, const qr_obs* o, int rule,
                                    double* hyper, int* iter_inout, double* m_inout, double* v_inout, int steps,
                                    double* cost_history, double* param_history) {
@@ -1812,20 +1864,24 @@ extern "C" int qr_mcclean_optimize(qr_ctx* c, int L, const int32_t* axes, double
         }
         if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { rc = fail(QR_ECUDA, "optimiser setup: %s", cudaGetErrorString(e)); break; }
         double dummy_grad = 0.0, dummy_e = 0.0;
-        for (int it = 0; it < steps && rc == 0; ++it) {
+        long long launches = 0;
+        rc = run_steps_graphed(c, steps, [&](int it) -> int {
+            const long long before = c->perf.kernel_launches;
             DevParams dev = {d_params, slot_q.data(), &P};
-            rc = mcclean_fused(c, 1, L, axes, nullptr, o, 0, &dummy_e, &dummy_grad, &dev);
-            if (rc) break;
+            QR_TRY(mcclean_fused(c, 1, L, axes, nullptr, o, 0, &dummy_e, &dummy_grad, &dev));
             if (it == 0) {   // the slot map is the same for every step
-                if (P > 16) { rc = fail(QR_EINVAL, "internal: too many passes"); break; }
-                if ((e = cudaMemcpyAsync(d_map, slot_q.data(), (size_t)L * P * QR_GATE_SLOTS * sizeof(int), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
-                    (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { rc = fail(QR_ECUDA, "optimiser: %s", cudaGetErrorString(e)); break; }
+                if (P > 16) return fail(QR_EINVAL, "internal: too many passes");
+                CUDA_TRY(cudaMemcpyAsync(d_map, slot_q.data(), (size_t)L * P * QR_GATE_SLOTS * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                CUDA_TRY(cudaStreamSynchronize(c->stream));
             }
             QR_LAUNCH(k_opt_step, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_result, (const int*)d_map, L, c->n, P, QR_GATE_SLOTS, QR_SLOTS,
-                      d_params, d_m, d_v, d_grad, d_st, d_cost, d_hist, it);
-            if ((e = cudaGetLastError()) != cudaSuccess) { rc = fail(QR_ECUDA, "optimiser step: %s", cudaGetErrorString(e)); break; }
+                      d_params, d_m, d_v, d_grad, d_st, d_cost, d_hist);
+            KERNEL_CHECK();
             c->perf.kernel_launches++;
-        }
+            launches = c->perf.kernel_launches - before;
+            return 0;
+        });
+        c->perf.kernel_launches = launches * steps;   // replayed steps launch the same kernels from the graph
         if (rc) break;
         cudaMemcpyAsync(angles, d_params, np_ * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
         cudaMemcpyAsync(cost_history, d_cost, (size_t)steps * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
@@ -2137,20 +2193,24 @@ extern "C" int qr_qaoa_optimize(qr_ctx* c, int p, double* params, int rule, doub
         }
         if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { rc = fail(QR_ECUDA, "optimiser setup: %s", cudaGetErrorString(e)); break; }
         double dummy_grad[2] = {0.0, 0.0}, dummy_e = 0.0;
-        for (int it = 0; it < steps && rc == 0; ++it) {
+        long long launches = 0;
+        rc = run_steps_graphed(c, steps, [&](int it) -> int {
+            const long long before = c->perf.kernel_launches;
             QaoaDev dev = {d_params, slot_q.data(), &P};
-            rc = qaoa_fused(c, p, nullptr, nullptr, 0, &dummy_e, dummy_grad, &dev);
-            if (rc) break;
+            QR_TRY(qaoa_fused(c, p, nullptr, nullptr, 0, &dummy_e, dummy_grad, &dev));
             if (it == 0) {   // the slot map is the same for every step
-                if (P > 16) { rc = fail(QR_EINVAL, "internal: too many passes"); break; }
-                if ((e = cudaMemcpyAsync(d_map, slot_q.data(), (size_t)P * QR_GATE_SLOTS * sizeof(int), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
-                    (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { rc = fail(QR_ECUDA, "optimiser: %s", cudaGetErrorString(e)); break; }
+                if (P > 16) return fail(QR_EINVAL, "internal: too many passes");
+                CUDA_TRY(cudaMemcpyAsync(d_map, slot_q.data(), (size_t)P * QR_GATE_SLOTS * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                CUDA_TRY(cudaStreamSynchronize(c->stream));
             }
             QR_LAUNCH(k_qaoa_opt_step, 1, QR_BLOCK, 0, c->stream, (const double*)c->d_result, (const int*)d_map, p, P, QR_GATE_SLOTS, QR_SLOTS,
-                      d_params, d_m, d_v, d_grad, d_st, d_cost, d_hist, it);
-            if ((e = cudaGetLastError()) != cudaSuccess) { rc = fail(QR_ECUDA, "optimiser step: %s", cudaGetErrorString(e)); break; }
+                      d_params, d_m, d_v, d_grad, d_st, d_cost, d_hist);
+            KERNEL_CHECK();
             c->perf.kernel_launches++;
-        }
+            launches = c->perf.kernel_launches - before;
+            return 0;
+        });
+        c->perf.kernel_launches = launches * steps;
         if (rc) break;
         cudaMemcpyAsync(params, d_params, np_ * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
         cudaMemcpyAsync(cost_history, d_cost, (size_t)steps * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
