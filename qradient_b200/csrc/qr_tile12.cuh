@@ -177,9 +177,13 @@ __device__ __forceinline__ constexpr int qr12_cr(int r) { return (r << G) ^ (((r
 // between threads that agree in tile-local bits 0-5, i.e. in thread-id bit 5 = the lowest warp-index bit, so the even and
 // the odd warps of a 12-bit tile never exchange anything in a pass with two rounds.  With their own barriers the halves
 // drift apart and one loads / stores while the other computes (TilePass::split_bar).
+// split = 2: the exchange between the register groups 0-2 and 3-5 stays inside aligned groups of 8 threads (a thread that
+// holds local bits 3-11 = tid with bits 0-2 in registers hands over to the threads with the same tid >> 3): a warp barrier
+// is all it needs.
 #ifndef QR_HOST_EMUL
 __device__ __forceinline__ void qr12_bar(int split, int tid) {
-    if (!split) __syncthreads();
+    if (split == 0) __syncthreads();
+    else if (split == 2) __syncwarp();
     else if ((tid >> 5) & 1) asm volatile("bar.sync 2, 256;" ::: "memory");   // warp-uniform branch; 512-thread CTAs only (K = 12)
     else asm volatile("bar.sync 1, 256;" ::: "memory");
 }
@@ -592,7 +596,7 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
         if (ng == 4) {
             QR12_X(LG, 0);
             qr12_round<NV, 0>(a, sg, acc_all);
-            QR12_X(0, 3);
+            if (STAGED == 1) qr12_exchange_1buf<NV, 0, 3>(a, smem, tid, 2); else qr12_exchange<NV, 0, 3, K>(a, smem, tid, 2);
         } else if (ng == 3) {
             QR12_X(LG, 3);
         }
