@@ -61,7 +61,7 @@ enum {
     QR_OPT_SHARD_LOCKSTEP = 31, /* swap engine: 1 (default) the caller runs qr_shard_step in lockstep over the ranks; 0: all steps are enqueued at once and device-side flags order the ranks */
     QR_OPT_SHARD_SLICES = 32, /* swap engine: the last local pass and the exchange pass of a layer are issued in 1 (default), 2, 4 or 8 slices of the index bits 9..11; asynchronous mode runs the exchange pass of a slice on a second stream while the local pass works on the next slice */
     QR_OPT_LOOP_GRAPH = 35,   /* 1 (default): the device optimiser loops (qr_mcclean_optimize, qr_qaoa_optimize) replay a CUDA graph captured from their second step; 0: every step is launched kernel by kernel */
-    QR_OPT_AXIS_PLAN = 34,    /* single McClean circuits, bit mask (default 15): bit 0 plan the strided passes of every layer from its axes -- an Rz needs no tile bit, so the tiles keep wider rows and fewer exchange rounds; bit 1 the contiguous pass trades Rz-only bits for high X / Y bits where that saves an exchange round; bit 2 passes without an exchange run the two-round program; bit 3 the even / odd warps of a two-round backward pass synchronise separately; 0: one static plan */
+    QR_OPT_AXIS_PLAN = 34,    /* single McClean circuits, bit mask (default 15, applied from 20 qubits on unless the option is set explicitly): bit 0 plan the strided passes of every layer from its axes -- an Rz needs no tile bit, so the tiles keep wider rows and fewer exchange rounds; bit 1 the contiguous pass trades Rz-only bits for high X / Y bits where that saves an exchange round; bit 2 passes without an exchange run the two-round program; bit 3 the even / odd warps of a two-round backward pass synchronise separately; 0: one static plan */
     QR_OPT_SHARD_XSMS = 33,   /* asynchronous mode: SMs given to the exchange pass of a slice (default 60); the concurrent local pass uses the others */
     QR_OPT_SHARD_ZSKIP = 29   /* 1 (default): sharded states apply an Rz on a global qubit as a per-subgroup phase without the NVLink exchange (only X / Y rotations are exchanged) */
 };

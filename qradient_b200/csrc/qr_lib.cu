@@ -115,6 +115,7 @@ struct qr_ctx {
     long long opt_pdl = 1;         // k_tile12 passes launched with programmatic stream serialization: 0 off, 1 auto (n <= 22), 2 always
     long long opt_axis_plan = 15;  // single McClean circuits: bit 0 per-layer plans from the axes (plan_axis_layer); bit 1 pass 0 trades Rz-only bits for high X / Y bits where that saves a round; bit 2 passes without an exchange run the two-round program; bit 3 split barriers in two-round backward passes
     long long opt_shard_zskip = 1; // sharded states: Rz on a global qubit is applied as a per-subgroup phase, without the exchange
+    bool axis_plan_forced = false; // QR_OPT_AXIS_PLAN was set explicitly: the plans apply at every size; by default only from 20 qubits on (n = 16: +5 % with them, the per-launch table set-up; n = 20: -3 %)
     long long opt_loop_graph = 1;  // device optimiser loops: steps 2..N replay a CUDA graph captured from the second step
     bool capturing = false;        // a step of a device optimiser loop is being captured into a graph: no tracing
     bool tables_fresh = true;      // gate / phase tables were (re)written since the last tile pass: see launch_pass
@@ -327,7 +328,7 @@ extern "C" int qr_set_option(qr_ctx* c, int key, long long v) {
         case QR_OPT_DEFER_REDUCE: c->opt_defer_reduce = v ? 1 : 0; break;
         case QR_OPT_SHARD_ZSKIP: c->opt_shard_zskip = v ? 1 : 0; break;
         case QR_OPT_LOOP_GRAPH: c->opt_loop_graph = v ? 1 : 0; break;
-        case QR_OPT_AXIS_PLAN: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad axis-plan mode"); c->opt_axis_plan = v; break;
+        case QR_OPT_AXIS_PLAN: if (v < 0 || v > 15) return fail(QR_EINVAL, "bad axis-plan mode"); c->opt_axis_plan = v; c->axis_plan_forced = true; break;
         case QR_OPT_PDL: if (v < 0 || v > 2) return fail(QR_EINVAL, "bad PDL mode"); c->opt_pdl = v; break;
         case QR_OPT_SHARD_MODE: if (v < 0 || v > 2) return fail(QR_EINVAL, "bad shard mode"); c->opt_shard_mode = v; break;
         case QR_OPT_SHARD_LOCKSTEP: c->opt_shard_lockstep = v ? 1 : 0; break;
@@ -1201,11 +1202,10 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
         memset(&x, 0, sizeof(x));
         x.ngroups = pp.ngroups;
         if (pp.gx && (c->opt_axis_plan & 4) && x.ngroups == 1 && K == 12) x.ngroups = 2;   // experiment: keep the warps of a tile together
-        if (pp.gx && (c->opt_axis_plan & 8) && x.ngroups == 2 && K == 12 && nv == 2 && !staged) {
-            // the halves of the CTA synchronise separately (measured 13.3-14.2 -> 12.2-12.8 ms per backward pass at n = 30;
-            // the one-vector kernel spills with it and is slower)
-            lfn = k_tile12_gs<2>;
-            QR_TRY(ensure_smem_attr(c, (const void*)lfn, 40));
+        if (pp.gx && (c->opt_axis_plan & 8) && x.ngroups == 2 && K == 12 && !staged) {
+            // the halves of the CTA synchronise separately (measured 13.3-14.2 -> 12.2-12.8 ms per backward pass at n = 30)
+            lfn = nv == 1 ? k_tile12_gs<1> : k_tile12_gs<2>;
+            QR_TRY(ensure_smem_attr(c, (const void*)lfn, 40 + (nv - 1)));
         }
         const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2, K, 0};
         x.last_group = x.ngroups == 1 ? K - 3 : (x.ngroups == 5 ? 5 : 6);
@@ -1393,7 +1393,7 @@ static int mcclean_fused(qr_ctx* c, i64 batch, int L, const int32_t* axes, const
     LayerPlan lpf, lp;   // forward / backward plans: same tile geometry, different register blocking
     // axis-aware plans apply to single circuits whose axes the host knows; with them 12-bit tiles win from n = 23 on
     // (measured, profiles/r2_axis_ab.log: n = 24: 30.1 -> 25.3 ms per 30 layers, n = 26: 127 -> 118 ms; n = 22: 4.45 vs 4.57 ms)
-    const bool axis_ok = c->opt_axis_plan && batch == 1;
+    const bool axis_ok = c->opt_axis_plan && batch == 1 && (n >= 20 || c->axis_plan_forced);
     int tile_bits = pick_tile_bits(c, n);
     if (axis_ok && c->opt_tile_bits == 0 && n >= 23 && n <= 26 && tile_bits == 11) tile_bits = 12;
     QR_TRY(make_plan(n, tile_bits, &lpf, (int)c->opt_tile_bits_x, tile_bits == pick_tile_bits(c, n) ? pick_min_row_bits(c, n) : (int)c->opt_min_row_bits));

@@ -546,7 +546,7 @@ static int swap_build(qr_ctx* c, SwapRun* sr, const SwapCircuit& circ, const qr_
         }
         std::vector<std::vector<int>> strided;
         std::vector<PassPlan> strided_gx;   // axis-aware plans of the strided local passes (McClean; qr_lib.cu: plan_axis_layer)
-        if (!high.empty() && !qaoa && layer >= 0 && c->opt_axis_plan && sr->slices <= 1 && nl - 12 >= 3) {
+        if (!high.empty() && !qaoa && layer >= 0 && c->opt_axis_plan && (nl >= 20 || c->axis_plan_forced) && sr->slices <= 1 && nl - 12 >= 3) {
             int nzb[64], zsb[64], k = 0, nzs = 0;
             for (int kb : high) {
                 const int p = layout_local_logical(ly, kb);

@@ -184,8 +184,7 @@ __device__ __forceinline__ constexpr int qr12_cr(int r) { return (r << G) ^ (((r
 __device__ __forceinline__ void qr12_bar(int split, int tid) {
     if (split == 0) __syncthreads();
     else if (split == 2) __syncwarp();
-    else if ((tid >> 5) & 1) asm volatile("bar.sync 2, 256;" ::: "memory");   // warp-uniform branch; 512-thread CTAs only (K = 12)
-    else asm volatile("bar.sync 1, 256;" ::: "memory");
+    else __barrier_sync_count(1 + ((tid >> 5) & 1), 256);   // 512-thread CTAs only (K = 12)
 }
 #else
 __device__ __forceinline__ void qr12_bar(int, int) { __syncthreads(); }
@@ -697,7 +696,7 @@ __global__ void __launch_bounds__(1 << (K - 3), (K == 11 ? (STAGED ? 1 : (NV == 
 }
 // two-round passes (one exchange, between the register groups 9-11 and 6-8): the even and the odd warps synchronise separately
 template <int NV>
-__global__ void __launch_bounds__(512, 1) k_tile12_gs(const TilePass p, const Tile12X x) {
+__global__ void __launch_bounds__(512, (NV == 1 ? 2 : 1)) k_tile12_gs(const TilePass p, const Tile12X x) {
     qr12_body<NV, false, 0, 12, false, true, true>(p, x, nullptr);
 }
 
