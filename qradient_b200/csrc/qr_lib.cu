@@ -1025,6 +1025,11 @@ static bool plan_axis_layer(const LayerPlan& base, const int32_t* ax, LayerPlan*
     int lowz[16], nlowz = 0;   // Rz-only bits of pass 0 that it may trade away, highest first
     for (int b = K - 1; b >= QR_AXIS_MAX_ROW_BITS && allow_absorb; --b)
         if (ax[n - 1 - b] == 2) lowz[nlowz++] = b;
+    // The contiguous pass runs the chain L | 0 | 3 (two exchanges instead of three, ~2.5 ms) when the tile positions 6-8
+    // can be given to bits without an X / Y gate, i.e. when at most 4 of its bits above bit 4 carry one (allow_absorb).
+    int cnt5 = 0;
+    for (int b = 5; b < K; ++b) cnt5 += ax[n - 1 - b] != 2 ? 1 : 0;
+    auto three_rounds = [&](int e) { return allow_absorb && K == 12 && cnt5 + e <= 4; };
     // choose the number of absorbed bits e and the pass count m by estimated cost
     double best_total = 1e30;
     int best_e = -1, best_m = 0, best_split[8];
@@ -1032,10 +1037,10 @@ static bool plan_axis_layer(const LayerPlan& base, const int32_t* ax, LayerPlan*
         for (int m = 1; m <= maxm; ++m) {
             if (m * maxk < k - e) continue;
             int split[8];
-            const double cst = axis_best_split(k - e, m, maxk, K, split) + (e ? 0.6 + 0.1 * e : 0.0);
+            const double cst = axis_best_split(k - e, m, maxk, K, split) + (e ? 0.6 + 0.1 * e : 0.0) - (three_rounds(e) ? 2.5 : 0.0);
             if (cst < best_total - 1e-9) { best_total = cst; best_e = e; best_m = m; for (int j = 0; j < m; ++j) best_split[j] = split[j]; }
         }
-    if (best_e < 0 || best_total >= 16.0 * maxm) return false;   // the static plan's strided passes run at ~16 ms each
+    if (best_e < 0 || best_total >= 16.0 * maxm) return false;   // the static plan's strided passes run at ~16 ms each (layers that keep it also keep the four-round contiguous pass)
     // try the chosen (e, m); when the Rz capacity does not suffice fall back to e = 0 with growing m
     for (int attempt = 0; attempt < 1 + maxm; ++attempt) {
         int e = best_e, m = best_m, splitv[8];
@@ -1052,18 +1057,42 @@ static bool plan_axis_layer(const LayerPlan& base, const int32_t* ax, LayerPlan*
         *out = base;
         out->npasses = 1 + m;
         for (int i = 0; i < m; ++i) out->pass[1 + i] = strided[i];
-        if (e > 0) {   // pass 0 on a general tile: bits [0, K) without the traded Rz bits, plus the e lowest high X / Y bits
+        if (e > 0 || three_rounds(e)) {   // pass 0 on a general tile: bits [0, K) without the traded Rz bits, plus the e lowest high X / Y bits
             PassPlan& p0 = out->pass[0];
             p0.gx = true; p0.zmask = 0;
             u64 traded = 0;
             for (int j = 0; j < e; ++j) traded |= (u64)1 << lowz[j];
             int lb = 0;
-            for (int b = 0; b < K; ++b)
-                if (!((traded >> b) & 1)) { p0.lbit[lb] = b; p0.gbit[lb] = b; ++lb; }
+            if (!three_rounds(e)) {
+                for (int b = 0; b < K; ++b)
+                    if (!((traded >> b) & 1)) { p0.lbit[lb] = b; p0.gbit[lb] = b; ++lb; }
+                for (int j = 0; j < e; ++j, ++lb) { p0.lbit[lb] = nz[j]; p0.gbit[lb] = nz[j]; }
+                p0.ngroups = 4; p0.nrounds = 4;
+            } else {
+                // local 0-4 = index bits 0-4; the X / Y bits above go to the positions 9, 10, 11, 5 (register groups L and 3),
+                // Rz-only bits to 6, 7, 8 and to what is left
+                int xy[8], nxy = 0, zz[8], nzz = 0;
+                for (int b = 5; b < K; ++b) {
+                    if ((traded >> b) & 1) continue;
+                    if (ax[n - 1 - b] != 2) xy[nxy++] = b; else zz[nzz++] = b;
+                }
+                for (int j = 0; j < e; ++j) xy[nxy++] = nz[j];
+                for (int b = 0; b < 5; ++b) p0.lbit[b] = b;
+                const int xy_pos[4] = {9, 10, 11, 5};
+                int pos_used[QR_MAX_TILE_BITS] = {1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0};
+                for (int j = 0; j < nxy; ++j) { p0.lbit[xy_pos[j]] = xy[j]; pos_used[xy_pos[j]] = 1; }
+                int zi = 0;
+                for (int pos = 6; pos < K; ++pos) {           // 6, 7, 8 first, then the free ones of 9-11
+                    if (pos_used[pos]) continue;
+                    p0.lbit[pos] = zz[zi++]; pos_used[pos] = 1;
+                }
+                if (!pos_used[5]) p0.lbit[5] = zz[zi++];
+                if (zi != nzz || nxy > 4) return false;   // cannot happen: 7 positions, cnt5 + e <= 4
+                for (int b = 0; b < K; ++b) p0.gbit[b] = p0.lbit[b];
+                p0.ngroups = 6; p0.nrounds = 3;
+            }
             p0.c = 0;
-            while (p0.c < lb && p0.lbit[p0.c] == p0.c) ++p0.c;   // contiguous amplitudes per row
-            for (int j = 0; j < e; ++j, ++lb) { p0.lbit[lb] = nz[j]; p0.gbit[lb] = nz[j]; }
-            p0.ngroups = 4; p0.nrounds = 4;
+            while (p0.c < K && p0.lbit[p0.c] == p0.c) ++p0.c;   // leading index bits in place
         }
         return true;
     }
@@ -1208,7 +1237,7 @@ static int launch_pass(qr_ctx* c, const LayerPlan& lp, int pass, int nv, const P
             QR_TRY(ensure_smem_attr(c, (const void*)lfn, 40 + (nv - 1)));
         }
         const Geo12 geo = {pp.c, pp.h, pp.m1, pp.h2, K, 0};
-        x.last_group = x.ngroups == 1 ? K - 3 : (x.ngroups == 5 ? 5 : 6);
+        x.last_group = x.ngroups == 1 ? K - 3 : (x.ngroups == 5 ? 5 : (x.ngroups == 6 ? 3 : 6));
         for (int r = 0; r < 8; ++r) {
             const u64 lf = (u64)r << (K - 3);
             const u64 ll = (u64)r << x.last_group;

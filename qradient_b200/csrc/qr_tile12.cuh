@@ -59,7 +59,7 @@ __host__ __device__ __forceinline__ u64 geo12_tile(const Geo12 g, u64 t) {
 
 struct Tile12X {
     int ngroups;            // chain of register groups (first local bit of each; K = tile bits, L = K-3):
-                            // 1 = L; 2 = L,6; 3 = L,3,6; 4 = L,0,3,6; 5 (K = 11, 64 B rows) = L,2,5
+                            // 1 = L; 2 = L,6; 3 = L,3,6; 4 = L,0,3,6; 5 (K = 11, 64 B rows) = L,2,5; 6 (K = 12, GX) = L,0,3
     int last_group;         // first local bit of the register group held at store time
     u64 roff_first[8];      // global offset of register r at load time (group G3), gather map applied
     u64 roff_last[8];       // global offset of register r at store time (G2, or G3 when ngroups == 1)
@@ -370,7 +370,7 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
         if (xmp->sel_bit[1] >= 0) s |= (int)((t >> xmp->sel_bit[1]) & 1) << 1;
         return s;
     };
-    const int tbl = ng > 1 ? qr12_tb(tid, K == 12 ? 6 : x.last_group) : tid;        // K = 12: the last group is always 6
+    const int tbl = ng > 1 ? qr12_tb(tid, K == 12 ? (GX && ng == 6 ? 3 : 6) : x.last_group) : tid;   // K = 12: the last group is 6 (3 for the chain L | 0 | 3)
     const u64 toff_l = local_bits((u64)tbl);
 
     const i64 nworkers = (i64)gridDim.x, worker = (i64)blockIdx.x;
@@ -592,6 +592,15 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
         // ---- rounds ----
 #define QR12_X(GP, GN) do { if (STAGED == 1) qr12_exchange_1buf<NV, GP, GN>(a, smem, tid); else qr12_exchange<NV, GP, GN, K>(a, smem, tid); } while (0)
         qr12_round<NV, LG>(a, sg, acc_all);
+        if (GX && K == 12 && ng == 6) {
+            // chain L | 0 | 3 (axis-aware contiguous pass whose local bits 6-8 carry no X / Y gate): two exchanges instead of
+            // three, the second one warp local; stores from the group-3 layout (a warp writes four 128 B segments)
+            QR12_X(LG, 0);
+            qr12_round<NV, 0>(a, sg, acc_all);
+            if (STAGED == 1) qr12_exchange_1buf<NV, 0, 3>(a, smem, tid, 2); else qr12_exchange<NV, 0, 3, K>(a, smem, tid, 2);
+            qr12_round<NV, 3>(a, sg, acc_all);
+            __syncthreads();   // every thread has read its last exchange: smem is free for the next tile
+        } else
         if (ng == 4) {
             QR12_X(LG, 0);
             qr12_round<NV, 0>(a, sg, acc_all);
@@ -599,7 +608,7 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
         } else if (ng == 3) {
             QR12_X(LG, 3);
         }
-        if (K == 12 ? ng >= 3 : (ng == 3 || ng == 4)) {
+        if (K == 12 ? (ng >= 3 && ng <= 4) : (ng == 3 || ng == 4)) {
             qr12_round<NV, 3>(a, sg, acc_all);
             QR12_X(3, 6);
         } else if (ng == 2) {
@@ -607,7 +616,7 @@ __device__ __forceinline__ void qr12_body(const TilePass& p, const Tile12X& x, c
                 if (STAGED == 1) qr12_exchange_1buf<NV, LG, 6>(a, smem, tid, 1); else qr12_exchange<NV, LG, 6, K>(a, smem, tid, 1);
             } else QR12_X(LG, 6);
         }
-        if (K == 12 ? ng >= 2 : (ng >= 2 && ng <= 4)) {
+        if (ng >= 2 && ng <= 4) {
             qr12_round<NV, 6, (K == 12 ? 3 : 2)>(a, sg, acc_all);   // K = 11: bit 8 belongs to the load group
             if (SPLIT) qr12_bar(1, tid);
             else __syncthreads();   // every thread has read its last exchange: smem is free for the next tile
