@@ -248,6 +248,11 @@ def _axis_case(case, n, L, rng):
         axes[:, :n - 12] = 2
     elif case == "all_xy":          # no Rz at all
         axes = rng.integers(0, 2, (L, n))
+    elif case == "three_rounds":    # at most 4 X / Y gates on bits 5..11: the contiguous pass runs the chain L | 0 | 3
+        for b in range(5, 12):
+            axes[:, n - 1 - b] = 2
+        axes[0, n - 1 - 5], axes[0, n - 1 - 9] = 0, 1
+        axes[1:, n - 1 - 6], axes[1:, n - 1 - 7], axes[1:, n - 1 - 10], axes[1:, n - 1 - 11] = 1, 0, 0, 1
     elif case == "absorb":          # 7 X / Y bits above the tile, Rz on bits 7..11: the contiguous pass trades bits for them
         for b in range(n):
             axes[:, n - 1 - b] = (b % 2) if b >= 12 else (2 if b >= 7 else b % 3)
@@ -256,7 +261,7 @@ def _axis_case(case, n, L, rng):
 
 
 @pytest.mark.parametrize("n,L,tile_bits,case", [(15, 2, 12, "random"), (17, 2, 11, "random"), (17, 1, 12, "few_xy"),
-                                                 (16, 2, 12, "all_z_high"), (16, 1, 12, "all_xy"), (19, 1, 12, "absorb"), (18, 1, 11, "absorb")])
+                                                 (16, 2, 12, "all_z_high"), (16, 1, 12, "all_xy"), (19, 1, 12, "absorb"), (18, 1, 11, "absorb"), (16, 2, 12, "three_rounds")])
 def test_axis_aware_plans(backend, n, L, tile_bits, case):
     """QR_OPT_AXIS_PLAN: per-layer plans from the axes (general tile geometry, Rz gates of index bits outside the tile
     applied through the tile's own index bits, split barriers, the contiguous pass on a general tile with the ladder
@@ -273,7 +278,7 @@ def test_axis_aware_plans(backend, n, L, tile_bits, case):
     if n <= 17:
         e_ref, g_ref = orc.mcclean_grad_run(n, obs, axes, angles)
         assert_parity(e0, g0, e_ref, g_ref, obs_scale(obs), TOL)
-    for mode in ((1, 15) if case in ("random", "absorb") else (15,)):   # 1: block barriers, no trade with the contiguous pass
+    for mode in ((1, 15) if case in ("random", "absorb", "three_rounds") else (15,)):   # 1: block barriers, no trade with the contiguous pass
         c.state.set_option("axis_plan", mode)
         e1, g1 = c.grad_run()
         assert_parity(e1, g1, e0, g0, obs_scale(obs), 1e-12)
