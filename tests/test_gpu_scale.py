@@ -254,6 +254,35 @@ def test_mcclean_30_qubits_properties():
         assert abs((ep - em) / (2 * eps) - g[i, q]) < 1e-7
 
 
+@pytest.mark.parametrize("n,L", [(21, 6), (23, 6), (24, 6), (26, 4)])
+@pytest.mark.parametrize("p_z", [0.0, 0.15, 1.0 / 3.0, 0.6, 0.9, 1.0])
+def test_axis_aware_plans_many_axis_patterns(n, L, p_z):
+    """Planner stress: layers from all-X/Y to all-Rz (pass counts, splits, fillers, Rz slots, trades with the contiguous pass,
+    the three-round contiguous pass and the fallback to the static plan all occur) -- axis-aware plans against the static plan
+    of the same library, 12- and 11-bit tiles."""
+    from qradient_b200.circuit_logic import McClean
+    rng = np.random.default_rng(int(1000 * p_z) + n)
+    axes = np.where(rng.random((L, n)) < p_z, 2, rng.integers(0, 2, (L, n)))
+    angles = rng.uniform(0, 2 * np.pi, (L, n))
+    zz = np.full((n, n), None)
+    zz[0, 1], zz[2, n - 1] = 1.0, -0.7
+    obs = {"zz": zz, "x": np.array([0.3] + [None] * (n - 1)), "y": np.array([None] * (n - 1) + [0.2])}
+    c = McClean(n, obs, L, axes=axes, angles=angles)
+    for tile_bits in (12, 11):
+        c.state.set_option("tile_bits", tile_bits)
+        c.state.set_option("axis_plan", 0)
+        e0, g0 = c.grad_run()
+        v0 = np.array(c.state.vec) if n <= 23 else None
+        for mode in (15, 13, 1):
+            c.state.set_option("axis_plan", mode)
+            e1, g1 = c.grad_run()
+            assert_parity(e1, g1, e0, g0, 2.2, 1e-12)
+            assert abs(c.run_expec_val() - e0) <= 1e-12
+            if v0 is not None and mode == 15:
+                c.grad_run()
+                np.testing.assert_allclose(c.state.vec, v0, atol=1e-13)
+
+
 def test_batched_14_qubits_matches_single():
     from qradient_b200.circuit_logic import McClean
     n, L, B = 14, 4, 64
