@@ -676,12 +676,14 @@ def test_options_and_permutation_api_validation(backend):
     """Argument checks of the kernel-selection options and of qr_perm_load / qr_state_permute."""
     n = 6
     st = State(n)
-    for name, bad in (("tile_bits", 3), ("tile_bits", 13), ("prefetch", 32), ("staged", 16), ("pdl", 3), ("min_row_bits", 12)):
+    for name, bad in (("tile_bits", 3), ("tile_bits", 13), ("prefetch", 32), ("staged", 16), ("pdl", 3), ("min_row_bits", 12), ("axis_plan", 16), ("axis_plan", -1)):
         with pytest.raises(ValueError):
             st.set_option(name, bad)
     with pytest.raises(ValueError):                   # retired round-1 experiment key (decoupled exchange)
         st._lib.call("qr_set_option", st._ctx, 14, 1)
     st.set_option("tile_bits", 0)                     # auto
+    st.set_option("loop_graph", 0)
+    st.set_option("axis_plan", 15)
     with pytest.raises(ValueError):
         st.load_permutation(np.arange(2 ** n - 1))    # wrong length
     with pytest.raises(ValueError):
