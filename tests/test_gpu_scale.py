@@ -283,6 +283,26 @@ def test_axis_aware_plans_many_axis_patterns(n, L, p_z):
                 np.testing.assert_allclose(c.state.vec, v0, atol=1e-13)
 
 
+@pytest.mark.parametrize("n", [20, 22, 24])
+def test_classifier_sublayers_with_axis_aware_plans(n):
+    """Layered circuits (qr_layered_grad: sub-layers of one axis each, a ladder before every third one): all-Rz sub-layers,
+    contiguous passes on general tiles without a ladder gather -- axis-aware plans against the static plan."""
+    from qradient_b200.circuit_logic import MeynardClassifier
+    rng = np.random.default_rng(n)
+    Le, Lc = 1, 2
+    data, enc, cls = rng.uniform(0, np.pi, (Le, n)), rng.uniform(0, 2 * np.pi, (Le, n, 2)), rng.uniform(0, 2 * np.pi, (Lc, n, 3))
+    c = MeynardClassifier(n, Le, Lc)
+    c.state.set_option("axis_plan", 0)
+    e0, ge0, gc0 = c.grad_run(data, enc, cls)
+    for mode in (15, 1):
+        c.state.set_option("axis_plan", mode)
+        e1, ge1, gc1 = c.grad_run(data, enc, cls)
+        assert abs(e1 - e0) <= 1e-12
+        np.testing.assert_allclose(ge1, ge0, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(gc1, gc0, rtol=0, atol=1e-12)
+        assert abs(c.run_expec_val(data, enc, cls) - e0) <= 1e-12
+
+
 def test_batched_14_qubits_matches_single():
     from qradient_b200.circuit_logic import McClean
     n, L, B = 14, 4, 64
