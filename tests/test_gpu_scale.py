@@ -303,6 +303,26 @@ def test_classifier_sublayers_with_axis_aware_plans(n):
         assert abs(c.run_expec_val(data, enc, cls) - e0) <= 1e-12
 
 
+def test_ini_state_with_axis_aware_plans():
+    """`ini_state` given (mc_clean.py:30-36: the Ry(pi/4) layer is applied as gates, on the static plan) followed by layers on
+    the axis-aware plans."""
+    from qradient_b200.circuit_logic import McClean
+    n, L = 21, 3
+    rng = np.random.default_rng(21)
+    axes, angles = rng.integers(0, 3, (L, n)), rng.uniform(0, 2 * np.pi, (L, n))
+    ini = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    ini /= np.linalg.norm(ini)
+    zz = np.full((n, n), None)
+    zz[0, 1], zz[4, n - 1] = 1.0, 0.5
+    c = McClean(n, {"zz": zz}, L, axes=axes, angles=angles)
+    c.state.set_option("axis_plan", 0)
+    e0, g0 = c.grad_run(ini_state=ini)
+    c.state.set_option("axis_plan", 15)
+    e1, g1 = c.grad_run(ini_state=ini)
+    assert_parity(e1, g1, e0, g0, 1.5, 1e-12)
+    assert abs(c.run_expec_val(ini_state=ini) - e0) <= 1e-12
+
+
 def test_batched_14_qubits_matches_single():
     from qradient_b200.circuit_logic import McClean
     n, L, B = 14, 4, 64
